@@ -1,0 +1,198 @@
+"""ctypes front-end of the CPU parity oracle (oracle/udales_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
+--impl reference legs of bench.py.  Never imported by the product package.
+
+Arrays are exposed as numpy views in Fortran order with the reference's shapes
+(src/modfields.f90:440-474): ``o.u0[i + ih - 1, j + jh - 1, k + kh - 1]`` is Fortran ``u0(i,j,k)``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("itot", C.c_int), ("jtot", C.c_int), ("ktot", C.c_int), ("nsv", C.c_int),
+                ("BCtopm", C.c_int), ("lles", C.c_int), ("lvreman", C.c_int), ("lsmagorinsky", C.c_int),
+                ("iadv_sv", C.c_int),
+                ("xlen", C.c_double), ("ylen", C.c_double),
+                ("numol", C.c_double), ("prandtlmoli", C.c_double), ("prandtli", C.c_double),
+                ("c_vreman", C.c_double), ("cs", C.c_double), ("Uinf", C.c_double), ("Vinf", C.c_double),
+                ("zf", C.POINTER(C.c_double))]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "udales_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.POINTER(_Cfg)]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_field.restype = C.POINTER(C.c_double)
+        L.orc_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
+        L.orc_metric.restype = C.POINTER(C.c_double)
+        L.orc_metric.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        for f in ("orc_advection", "orc_closure", "orc_subgrid", "orc_tderive", "orc_halos", "orc_boundary"):
+            getattr(L, f).argtypes = [C.c_void_p]
+            getattr(L, f).restype = None
+        for f in ("orc_fillps", "orc_poisson", "orc_tstep_integrate"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_double, C.c_int]
+            getattr(L, f).restype = None
+        L.orc_poisson_solve.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.orc_tstep_update.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double,
+                                       C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_chkdiv.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3
+        L.orc_randomize.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_double, C.c_int]
+        L.orc_substep.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_double, C.c_int,
+                                  C.c_double, C.c_double]
+        L.orc_rfft_packed.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def equidistant_zf(ktot: int, zsize: float) -> np.ndarray:
+    dz = zsize / ktot
+    return (np.arange(ktot) + 0.5) * dz
+
+
+def stretched_zf(ktot: int, zsize: float, ratio: float = 1.03) -> np.ndarray:
+    """geometric stretching: dzf(k+1) = ratio*dzf(k); exercises every dzf/dzh weight."""
+    dz = ratio ** np.arange(ktot)
+    dz *= zsize / dz.sum()
+    zh = np.concatenate([[0.0], np.cumsum(dz)])
+    return 0.5 * (zh[:-1] + zh[1:])
+
+
+FIELDS = ("u0", "v0", "w0", "um", "vm", "wm", "pres0", "p", "ekm", "ekh",
+          "up", "vp", "wp", "pup", "pvp", "pwp", "rhs", "sv0", "svm", "svp")
+
+
+class Oracle:
+    """One single-pencil uDALES dynamics state on the CPU."""
+
+    def __init__(self, itot, jtot, ktot, xlen=None, ylen=None, zf=None, nsv=0, BCtopm=1,
+                 lvreman=True, lsmagorinsky=False, lles=None, iadv_sv=7,
+                 numol=1.5e-5, prandtlmol=0.71, prandtl=0.333, c_vreman=0.07, cs=-1.0,
+                 Uinf=0.0, Vinf=0.0):
+        self.L = lib()
+        xlen = float(xlen if xlen is not None else itot / 2.0)
+        ylen = float(ylen if ylen is not None else jtot / 2.0)
+        if zf is None:
+            zf = equidistant_zf(ktot, ktot * xlen / itot)
+        self.zf = np.ascontiguousarray(zf, dtype=np.float64)
+        assert self.zf.size == ktot
+        if lles is None:
+            lles = bool(lvreman or lsmagorinsky)
+        self.cfg = _Cfg(itot, jtot, ktot, nsv, BCtopm, int(lles), int(lvreman), int(lsmagorinsky), iadv_sv,
+                        xlen, ylen, numol, 1.0 / prandtlmol, 1.0 / prandtl, c_vreman, cs, Uinf, Vinf,
+                        self.zf.ctypes.data_as(C.POINTER(C.c_double)))
+        self.h = C.c_void_p(self.L.orc_create(C.byref(self.cfg)))
+        self.itot, self.jtot, self.ktot, self.nsv = itot, jtot, ktot, nsv
+        self.ih = self.jh = self.kh = 1
+        self.ihc = self.jhc = self.khc = 2 if (nsv > 0 and iadv_sv == 7) else 1
+        self.dx, self.dy = xlen / itot, ylen / jtot
+        for name in FIELDS:
+            dims = (C.c_int * 4)()
+            ptr = self.L.orc_field(self.h, name.encode(), dims)
+            if not ptr:
+                setattr(self, name, None)
+                continue
+            shape = tuple(dims[:3]) + ((dims[3],) if name.startswith("sv") else ())
+            n = int(np.prod(shape))
+            arr = np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape, order="F")
+            setattr(self, name, arr)
+        self.rk3step = 0
+        self.dt = 0.0
+
+    def metric(self, name):
+        lo, n = C.c_int(), C.c_int()
+        ptr = self.L.orc_metric(self.h, name.encode(), C.byref(lo), C.byref(n))
+        return np.ctypeslib.as_array(ptr, shape=(n.value,)), lo.value
+
+    def __del__(self):
+        try:
+            self.L.orc_destroy(self.h)
+        except Exception:
+            pass
+
+    # reference call surface -------------------------------------------------
+    def advection(self): self.L.orc_advection(self.h)
+    def closure(self): self.L.orc_closure(self.h)
+    def subgrid(self): self.L.orc_subgrid(self.h)
+    def fillps(self, dt, rk3step): self.L.orc_fillps(self.h, dt, rk3step)
+    def tderive(self): self.L.orc_tderive(self.h)
+    def poisson(self, dt, rk3step): self.L.orc_poisson(self.h, dt, rk3step)
+    def tstep_integrate(self, dt, rk3step): self.L.orc_tstep_integrate(self.h, dt, rk3step)
+    def halos(self): self.L.orc_halos(self.h)
+    def boundary(self): self.L.orc_boundary(self.h)
+
+    def poisson_solve(self, rhs: np.ndarray) -> np.ndarray:
+        pz = np.array(rhs, dtype=np.float64, order="F", copy=True)
+        assert pz.shape == (self.itot, self.jtot, self.ktot)
+        self.L.orc_poisson_solve(self.h, pz.ctypes.data_as(C.POINTER(C.c_double)))
+        return pz
+
+    def tstep_update(self, dt, rk3step, courant=1.0, diffnr=0.25, dtmax=1e9, ladaptive=True):
+        d, r = C.c_double(dt), C.c_int(rk3step)
+        ct, dn = C.c_double(0), C.c_double(0)
+        self.L.orc_tstep_update(self.h, C.byref(d), courant, diffnr, dtmax, int(ladaptive), C.byref(r),
+                                C.byref(ct), C.byref(dn))
+        return d.value, r.value, ct.value, dn.value
+
+    def chkdiv(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self.L.orc_chkdiv(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def randomize(self, name, ampl, ir=43, n=0):
+        self.L.orc_randomize(self.h, name.encode(), n, ampl, ir)
+
+    def substep(self, dtmax, ladaptive=False, courant=1.0, diffnr=0.25):
+        d, r = C.c_double(self.dt), C.c_int(self.rk3step)
+        self.L.orc_substep(self.h, C.byref(d), C.byref(r), dtmax, int(ladaptive), courant, diffnr)
+        self.dt, self.rk3step = d.value, r.value
+
+    # synthetic channel of SURVEY.md §8d --------------------------------------
+    def init_channel(self, ubase=1.0, ampl=0.05, ir=43):
+        """u = ubase + LCG noise, v, w = LCG noise; ghosts as A.5; then one projection-free ghost fill."""
+        for f in (self.u0, self.v0, self.w0, self.pres0):
+            f[...] = 0.0
+        self.u0[1:-1, 1:-1, 1:-1] = ubase
+        self.randomize("u0", ampl, ir)
+        self.randomize("v0", ampl, ir + 1)
+        self.randomize("w0", ampl, ir + 2)
+        self.w0[:, :, 1] = 0.0
+        for n in range(self.nsv):
+            self.sv0[..., n] = 0.0
+            self.sv0[2:-2, 2:-2, 2:-2, n] = 1.0
+            self.randomize("sv0", 0.1, ir + 10 + n, n)
+        self.halos()
+        self.boundary()
+        self.um[...] = self.u0
+        self.vm[...] = self.v0
+        self.wm[...] = self.w0
+        if self.nsv:
+            self.svm[...] = self.sv0
+        for f in (self.up, self.vp, self.wp):
+            f[...] = 0.0
+
+
+def rfft_packed(line: np.ndarray, inverse: bool = False) -> np.ndarray:
+    x = np.array(line, dtype=np.float64, copy=True)
+    lib().orc_rfft_packed(x.size, x.ctypes.data_as(C.POINTER(C.c_double)), int(inverse))
+    return x

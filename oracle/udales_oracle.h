@@ -1,0 +1,76 @@
+/* udales_oracle.h — CPU restatement (parity ORACLE) of the uDALES dynamics hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (u-dales_b200/, include/)
+ * may include, link or call this.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py use it, and only as the checker
+ * or as the timed CPU baseline.
+ *
+ * Every function cites the reference file:line (relative to /root/reference) whose
+ * loop nest, operand order and boundary handling it restates.  The reference is
+ * Fortran (1-based, column-major, halos); the macros below reproduce its index
+ * space so the loop bodies can be compared line by line.
+ *
+ * Single pencil (nprocx = nprocy = 1): lateral periodicity is applied by the local
+ * wrap routines, exactly what the reference does when a direction is unsplit
+ * (src/modboundary.f90:95-107).  Decomposition invariance (1e-9, reference's own
+ * tolerance) lets this serve as the oracle for multi-GPU runs too.
+ */
+#ifndef UDALES_ORACLE_H
+#define UDALES_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_cfg {
+  int itot, jtot, ktot;
+  int nsv;            /* passive scalars (kappa advection, halo 2)              */
+  int BCtopm;         /* 1 freeslip, 2 noslip   (src/modglobal.f90:140-142)     */
+  int lles;           /* .true. when any SGS model is on (modsubgrid.f90:118)   */
+  int lvreman, lsmagorinsky;
+  int iadv_sv;        /* 7 kappa (forced by modglobal.f90:556-559), 2 cd2, 1 upw */
+  double xlen, ylen;
+  double numol, prandtlmoli, prandtli, c_vreman, cs;
+  double Uinf, Vinf;
+  const double *zf;   /* ktot cell-centre heights (column 1 of prof.inp)        */
+} orc_cfg;
+
+typedef struct orc orc_t;
+
+orc_t *orc_create(const orc_cfg *cfg);
+void orc_destroy(orc_t *o);
+
+/* field access: returns pointer to the first element of the Fortran array (incl. halos)
+ * and its three extents.  Names: u0 v0 w0 um vm wm up vp wp pres0 p ekm ekh rhs
+ * pup pvp pwp sv0 svm svp (scalar arrays have a 4th extent nsv). */
+double *orc_field(orc_t *o, const char *name, int dims[4]);
+/* 1-D metric arrays: dzf dzh dzfi dzhi xrt yrt a b c ; returns pointer to Fortran index
+ * lo (written to *lo) */
+double *orc_metric(orc_t *o, const char *name, int *lo, int *n);
+
+/* hot-path routines, named after the reference procedures */
+void orc_advection(orc_t *o);                       /* modadvection.f90:36   */
+void orc_closure(orc_t *o);                         /* modsubgrid.f90:159 (+closurebc) */
+void orc_subgrid(orc_t *o);                         /* modsubgrid.f90:128   */
+void orc_fillps(orc_t *o, double dt, int rk3step);  /* modpois.f90:911      */
+void orc_poisson_solve(orc_t *o, double *pz);       /* modpois.f90:440-712 on an (itot,jtot,ktot) array */
+void orc_tderive(orc_t *o);                         /* modpois.f90:1001     */
+void orc_poisson(orc_t *o, double dt, int rk3step); /* modpois.f90:419      */
+void orc_tstep_update(orc_t *o, double *dt, double courant, double diffnr, double dtmax,
+                      int ladaptive, int *rk3step, double *courtot, double *diffnrtot); /* modtstep.f90:49 */
+void orc_tstep_integrate(orc_t *o, double dt, int rk3step);  /* modtstep.f90:171 */
+void orc_halos(orc_t *o);                           /* modboundary.f90:67   */
+void orc_boundary(orc_t *o);                        /* modboundary.f90:115  */
+void orc_chkdiv(orc_t *o, double *divmax, double *divtot, double *divrms); /* modchecksim.f90:161 */
+void orc_randomize(orc_t *o, const char *name, int n4, double ampl, int ir); /* modstartup.f90:2367 (all k = 1..ktot) */
+/* one pass of program.f90:132-207 restricted to the in-scope calls */
+void orc_substep(orc_t *o, double *dt, int *rk3step, double dtmax, int ladaptive,
+                 double courant, double diffnr);
+
+/* stand-alone real FFT helpers (FFTW r2c/c2r conventions + the reference's packing) */
+void orc_rfft_packed(int n, double *line, int inverse);  /* modpois.f90:478-490 / 669-679 on one line */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
