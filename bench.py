@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native uDALES dynamics core.
+
+Metric (BASELINE.json): cell-updates/s = grid cells advanced through one RK3 substep
+(tstep_update, advection, subgrid, poisson, tstep_integrate, halos, boundary — one pass of
+src/program.f90:132-207 restricted to the in-scope calls) per second, whole job.
+Workload at N=1: BASELINE config 2, neutral periodic channel 256^3, stencil + Poisson only.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA through the C-ABI)
+  python bench.py --impl reference --gpus N ...            # CPU arm: the oracle port on host cores
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+B_PER_CELL = {  # algorithmic (compulsory) fp64 bytes per cell, SURVEY.md §8d / DESIGN.md
+    "mom_tend": 64.0, "closure": 40.0, "poisson_core": 80.0, "fillps": 56.0, "tderive_integrate": 168.0, "halos": 0.0,
+}
+PROF_NAMES = ["mom_tend", "closure", "poisson_core", "fillps", "tderive_integrate", "halos"]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, dev=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.dev = dev
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.dev)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def channel_state(n_i, n_j, n_k, seed=0):
+    """synthetic periodic channel of SURVEY.md §8d: u = 1 + noise, v, w noise, halo-consistent."""
+    rng = np.random.default_rng(seed)
+    shp = (n_i + 2, n_j + 2, n_k + 2)
+    u = np.zeros(shp, order="F"); v = np.zeros(shp, order="F"); w = np.zeros(shp, order="F")
+    u[1:-1, 1:-1, 1:-1] = 1.0 + 0.05 * (rng.random((n_i, n_j, n_k)) - 0.5)
+    v[1:-1, 1:-1, 1:-1] = 0.05 * (rng.random((n_i, n_j, n_k)) - 0.5)
+    w[1:-1, 1:-1, 2:-1] = 0.05 * (rng.random((n_i, n_j, n_k - 1)) - 0.5)
+    return u, v, w
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (C/OpenMP restatement of the reference loops — the Fortran/MPI binary
+    cannot be built here: no Fortran compiler, MPI or FFTW).  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle
+    n = args.size
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    o = Oracle(n, n, n)
+    o.init_channel()
+    dt = 0.25 * o.dx / 1.1
+    o.dt = dt
+    for _ in range(args.warmup):
+        o.substep(dt)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.substep(dt)
+    el = time.perf_counter() - t0
+    val = n ** 3 * args.steps / el
+    line = {
+        "impl": "reference", "metric": "cell-updates/s", "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"neutral periodic channel {n}^3, stencil+Poisson only, no IBM/scalars (BASELINE config 2)",
+                   "grid": [n, n, n], "substeps_per_step": 1},
+        "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} RK3 substeps of the full {n}^3 workload, C/OpenMP restatement of the reference loops "
+                                   "(not the Fortran/MPI binary; in-tree radix-2 FFT instead of FFTW)"},
+        "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, world):
+    import torch
+    import udales_b200 as U
+    if world > 1:
+        raise SystemExit("multi-GPU slabs are not wired into bench.py yet")
+    n = args.size
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    g = U.UdalesGPU(n, n, n, device=dev)
+    u, v, w = channel_state(n, n, n)
+    for nm, f in (("u0", u), ("v0", v), ("w0", w)):
+        g.push(nm, f)
+    g.halos(); g.boundary()
+    for nm in ("u0", "v0", "w0"):
+        g.push(nm.replace("0", "m"), g.pull(nm))
+    dt = 0.25 * 0.5 / 1.1
+    g.dt = dt
+    st = torch.cuda.ExternalStream(g.stream(), device=dev)
+    ncell = n ** 3
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(max(args.warmup, 3)):
+        g.substep(dt)
+    g.sync()
+    sampler = ClockSampler(dev); sampler.start()
+    l0 = g.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for _ in range(args.steps):
+        g.substep(dt)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = g.launch_count() - l0
+    clocks = sampler.stop()
+    value = ncell * args.steps / (ms * 1e-3)
+    dmax, dtot, drms = g.divergence()
+
+    # ---- per-kernel-family device times (CUDA events on the library stream, live) ----
+    g.profile_enable(True); g.profile_reset()
+    nprof = min(args.steps, 10)
+    for _ in range(nprof):
+        g.substep(dt)
+    fam = {}
+    for i, nm in enumerate(PROF_NAMES):
+        t, cnt = g.profile_get(i)
+        fam[nm] = t / nprof
+    g.profile_enable(False)
+    hbm, how = peaks()
+    roof_all = {}
+    for nm, t in fam.items():
+        if t > 0 and B_PER_CELL[nm] > 0:
+            ach = B_PER_CELL[nm] * ncell / (t * 1e-3) / 1e9
+            roof_all[nm] = {"ms": t, "achieved_gbs": ach, "frac": ach / hbm}
+    dom = max(roof_all, key=lambda k: roof_all[k]["ms"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": roof_all[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": roof_all[dom]["frac"], "traffic": None, "peak_source": how,
+                "bytes_per_cell": B_PER_CELL[dom], "families": roof_all}
+
+    # ---- end to end through the C-ABI with HOST buffers (state lives on the host, literal drop-in) ----
+    names_in = ("u0", "v0", "w0", "um", "vm", "wm", "pres0")
+    names_out = ("u0", "v0", "w0", "pres0")
+    host = {nm: torch.empty((n + 2) ** 3, dtype=torch.float64).pin_memory() for nm in names_in}
+    for nm in names_in:
+        g.pull_raw(nm, host[nm].data_ptr())
+    g.sync()
+    ne2e = max(3, min(args.steps, 10))
+    rk = g.rk3step
+    for it in range(2 + ne2e):
+        if it == 2:
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+        for nm in names_in:
+            g.push_raw(nm, host[nm].data_ptr())
+        g.substep(dt)
+        for nm in names_out:
+            g.pull_raw(nm, host[nm].data_ptr())
+        g.sync()
+    t_e2e = (time.perf_counter() - t0) / ne2e
+    bi = len(names_in) * (n + 2) ** 3 * 8
+    bo = len(names_out) * (n + 2) ** 3 * 8
+
+    # ---- CPU baseline beside it (oracle port, bounded sample) ----
+    cpu = None
+    if not args.no_cpu:
+        from oracle.oracle import Oracle
+        cores = os.cpu_count() or 1
+        o = Oracle(n, n, n)
+        o.init_channel()
+        o.dt = dt
+        o.substep(dt)
+        nsub = 12
+        t0 = time.perf_counter()
+        for _ in range(nsub):
+            o.substep(dt)
+        el = time.perf_counter() - t0
+        cpu = {"value": ncell * nsub / el, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+               "sample": f"{nsub} RK3 substeps of the same {n}^3 workload; C/OpenMP restatement of the reference loops, "
+                         "in-tree radix-2 FFT (FFTW absent) — not the Fortran/MPI binary"}
+
+    line = {
+        "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"neutral periodic channel {n}^3, stencil+Poisson only, no IBM/scalars (BASELINE config 2)",
+                   "grid": [n, n, n], "substeps_per_step": 1, "l2": "working set (13 fields x 134 MB) >> 126 MB L2, no flush needed",
+                   "sgs": "vreman", "poisson": "FFT2D x,y + tridiagonal z"},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": ncell / t_e2e, "unit": "cell-updates/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
+                "ms_per_step": 1e3 * t_e2e, "note": "state pushed from / pulled to pinned host arrays every substep"},
+        "gpu_launches": launches, "clocks": clocks,
+        "poisson_solves_per_s": (1e3 / fam["poisson_core"]) if fam.get("poisson_core") else None,
+        "divergence_rms": drms,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if args.steps > 40:
+            args.steps = 40
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

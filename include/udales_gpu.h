@@ -1,0 +1,168 @@
+/* udales_gpu.h — C-ABI of the B200-native uDALES dynamics core (libudales_gpu.so).
+ *
+ * This is the drop-in boundary for the per-RK3-substep hot path of uDALES
+ * (reference = /root/reference @ 2fe4df1; file:line citations are relative to it).
+ * The reference has no plugin API: the boundary is the set of argument-less Fortran
+ * module procedures called from src/program.f90:134-207 which talk through public
+ * module arrays (src/modfields.f90) and namelist switches (src/modglobal.f90).
+ * Each entry point below replaces one of those procedures; the ISO_C_BINDING shim a
+ * maintainer adds on the Fortran side is u-dales_b200/fortran/modgpu.f90 and the
+ * patch points are listed in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C: ints, doubles, pointers, sizes.  No C++/torch types.
+ *  - every function returns 0 on success, a negative UDGPU_E* code on failure and
+ *    never aborts; udgpu_last_error() gives the text.  The Fortran shim turns a
+ *    non-zero code into `write(0,*) ...; stop 1`, the reference's error convention
+ *    (e.g. src/modpois.f90:896-898).
+ *  - all 3-D arrays are Fortran column-major fp64 with the reference's halo shapes
+ *    (src/modfields.f90:440-474): the pointer addresses element (ib-ih, jb-jh, klo).
+ *  - one host thread per GPU/rank; calls are collective across ranks and ordered,
+ *    like the MPI ranks of the reference.
+ *  - the library owns all device memory and streams; host arrays stay owned by the
+ *    caller and are touched only inside udgpu_push / udgpu_pull.
+ *  - there is NO CPU fallback: without a CUDA device udgpu_init fails with
+ *    UDGPU_ENODEV.
+ */
+#ifndef UDALES_GPU_H
+#define UDALES_GPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UDGPU_ABI_VERSION 1
+
+/* error codes */
+#define UDGPU_OK 0
+#define UDGPU_EINVAL (-1)   /* bad argument / unsupported switch combination          */
+#define UDGPU_ENODEV (-2)   /* no CUDA device / wrong architecture                    */
+#define UDGPU_ECUDA (-3)    /* CUDA runtime or driver error                           */
+#define UDGPU_ENCCL (-4)    /* NCCL error                                             */
+#define UDGPU_ESTATE (-5)   /* call order violated (e.g. poisson before init)         */
+#define UDGPU_ENOMEM (-6)
+
+/* field ids for push / pull / device_ptr (names = src/modfields.f90, src/modpois.f90:41,
+ * src/modsubgriddata.f90) */
+enum udgpu_field {
+  UDGPU_U0 = 0, UDGPU_V0, UDGPU_W0,          /* (ib-ih:ie+ih, jb-jh:je+jh, kb-kh:ke+kh) */
+  UDGPU_UM, UDGPU_VM, UDGPU_WM,              /* same                                    */
+  UDGPU_UP, UDGPU_VP, UDGPU_WP,              /* (.., .., kb:ke+kh)  tendencies          */
+  UDGPU_PRES0,                               /* as u0                                   */
+  UDGPU_P,                                   /* as u0   (src/modpois.f90:83)            */
+  UDGPU_EKM, UDGPU_EKH,                      /* as u0   (src/modsubgrid.f90:54-55)      */
+  UDGPU_RHS,                                 /* (imax,jmax,ktot) no halo (modpois.f90:84) */
+  UDGPU_SV0, UDGPU_SVM,                      /* (ib-ihc:.., jb-jhc:.., kb-khc:ke+khc, nsv) */
+  UDGPU_SVP,                                 /* (.., .., kb:ke+khc, nsv)                */
+  UDGPU_NFIELDS
+};
+
+/* Everything the hot path reads from modglobal / modsubgriddata / decomp_2d at init.
+ * Filled by the Fortran shim right after `call initpois` (src/program.f90:89). */
+typedef struct udgpu_cfg {
+  int abi_version;               /* = UDGPU_ABI_VERSION                                  */
+  int itot, jtot, ktot;          /* global grid            (namelist DOMAIN)             */
+  int imax, jmax, kmax;          /* local z-pencil = zsize (src/modglobal.f90:613-636)   */
+  int ih, jh, kh;                /* momentum halo          (src/modglobal.f90:586-599)   */
+  int ihc, jhc, khc;             /* scalar halo            (src/modglobal.f90:602-609)   */
+  int nsv;                       /* passive scalars        (namelist SCALARS)            */
+  int zstart[3];                 /* 1-based global index of local (1,1,1) (decomp_2d zstart) */
+  int nprocx, nprocy;            /* p_row, p_col           (src/modstartup.f90:676)      */
+  int myidx, myidy;              /* pencil coordinates     (src/modmpi.f90)              */
+  int BCxm, BCym;                /* 1 periodic             (src/modglobal.f90:97,121)    */
+  int BCtopm;                    /* 1 freeslip 2 noslip    (src/modglobal.f90:140-142)   */
+  int BCzp;                      /* 1 = tridiagonal solve in z (src/modpois.f90:146)     */
+  int ipoiss;                    /* 0 = POISS_FFT2D        (src/modglobal.f90:389)       */
+  int iadv_mom;                  /* 2 = cd2                (src/modglobal.f90:398)       */
+  int iadv_sv;                   /* 7 kappa, 2 cd2         (src/modglobal.f90:397-399)   */
+  int lles, lvreman, lsmagorinsky, loneeqn;  /* src/modsubgriddata.f90:39-42            */
+  int ltempeq, lmoist;           /* must be 0 (out of scope)              */
+  double dx, dy;                 /* src/modglobal.f90:710-711                            */
+  const double *dzf;             /* dzf(kb-kh:ke+kh): ktot+2 values (src/modglobal.f90:751-755) */
+  const double *dzh;             /* dzh(kb:ke+kh):   ktot+1 values (src/modglobal.f90:757-760)  */
+  const double *delta;           /* delta(kb:ke+kh) at any i (x uniform) ktot+1 values (:793-797); may be NULL (computed) */
+  double numol, prandtlmoli, prandtli;   /* src/modglobal.f90:300-303, modsubgrid.f90:117 */
+  double c_vreman, cs;           /* src/modsubgriddata.f90:55,61 ; cs = -1 -> (cm^3/ceps)^1/4 */
+  double Uinf, Vinf;             /* noslip top velocity    (src/modglobal.f90)           */
+  double e12min;
+  int device;                    /* CUDA device ordinal, -1 = LOCAL_RANK / current        */
+  int flags;                     /* UDGPU_F_* */
+} udgpu_cfg;
+
+#define UDGPU_F_NO_LAZY_FUSION 1  /* run every call eagerly as its own kernel(s) (debug / parity bisecting) */
+#define UDGPU_F_NO_GRAPH 2        /* do not capture the substep into a CUDA graph                          */
+#define UDGPU_F_P2P_TRANSPOSE 4   /* multi-GPU: peer-store pack+transfer kernels instead of ncclSend/Recv  */
+
+typedef struct udgpu udgpu_t;     /* opaque */
+
+/* ---- life cycle -------------------------------------------------------------------- */
+/* replaces: allocation part of initfields/initpois/initsubgrid on the device
+ * (src/modfields.f90:422, src/modpois.f90:66, src/modsubgrid.f90:44).
+ * nccl_uid: 128-byte ncclUniqueId obtained from udgpu_nccl_unique_id on rank 0 and broadcast by
+ * the host (MPI_Bcast in Fortran, torch.distributed in the tests); NULL when nprocx*nprocy == 1. */
+int udgpu_nccl_unique_id(void *uid128);
+int udgpu_init(const udgpu_cfg *cfg, const void *nccl_uid, udgpu_t **out);
+int udgpu_finalize(udgpu_t *h);
+const char *udgpu_last_error(void);
+int udgpu_abi_version(void);
+
+/* ---- residency control ------------------------------------------------------------- */
+/* host <-> device copies of one field in the reference's own array shape.  n4 selects the
+ * scalar index for SV0/SVM/SVP (0-based), ignored otherwise.  Asynchronous on the library
+ * stream when host memory is pinned; udgpu_sync waits. */
+int udgpu_push(udgpu_t *h, int field, int n4, const double *host);
+int udgpu_pull(udgpu_t *h, int field, int n4, double *host);
+int udgpu_field_count(udgpu_t *h, int field, size_t *count, int dims[3]);
+int udgpu_device_ptr(udgpu_t *h, int field, int n4, void **dptr);   /* zero-copy interop */
+int udgpu_sync(udgpu_t *h);
+int udgpu_host_register(void *ptr, size_t bytes);    /* pin a Fortran array once (cudaHostRegister) */
+int udgpu_host_unregister(void *ptr);
+
+/* ---- the hot path: one entry point per reference procedure ------------------------- */
+/* src/modtstep.f90:49  tstep_update.  In/out: dt, rk3step.  Also returns the two global maxima. */
+int udgpu_tstep_update(udgpu_t *h, double *dt, double courant, double diffnr, double dtmax,
+                       int ladaptive, int *rk3step, double *courtot, double *diffnrtot);
+/* src/modadvection.f90:36  advection (advecu/v/w_2nd + per-scalar advecc_kappa / advecc_2nd) */
+int udgpu_advection(udgpu_t *h);
+/* src/modsubgrid.f90:128  subgrid (closure + closurebc + diffu/v/w + diffc) */
+int udgpu_subgrid(udgpu_t *h);
+/* src/modsubgrid.f90:159  closure only (ekm, ekh incl. ghost cells) */
+int udgpu_closure(udgpu_t *h);
+/* src/modpois.f90:419  poisson = fillps + FFT2D solve + tderive */
+int udgpu_poisson(udgpu_t *h, double dt, int rk3step);
+/* src/modpois.f90:440-712 core only: rhs (imax,jmax,ktot) z-pencil in, p same shape out (host
+ * pointers; rhs == p allowed).  The "Poisson solves/s" unit of BASELINE.json. */
+int udgpu_poisson_solve(udgpu_t *h, const double *rhs, double *p);
+/* same on the resident UDGPU_RHS buffer, no host traffic */
+int udgpu_poisson_solve_resident(udgpu_t *h);
+/* src/modpois.f90:911 fillps (+bcpup) -> UDGPU_RHS and p interior ; src/modpois.f90:1001 tderive (+bcp) */
+int udgpu_fillps(udgpu_t *h, double dt, int rk3step);
+int udgpu_tderive(udgpu_t *h);
+/* src/modtstep.f90:171  tstep_integrate */
+int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step);
+/* src/modboundary.f90:67  halos ; src/modboundary.f90:115  boundary (periodic / freeslip / noslip subset) */
+int udgpu_halos(udgpu_t *h);
+int udgpu_boundary(udgpu_t *h);
+/* src/modchecksim.f90:161  chkdiv: max |div|, sum div*dV, and RMS(div) (parity metric) */
+int udgpu_divergence(udgpu_t *h, double *divmax, double *divtot, double *divrms);
+/* one pass of src/program.f90:132-207 restricted to the calls above, in the reference's order:
+ * tstep_update, advection, subgrid, poisson, tstep_integrate, halos, boundary. */
+int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax, int ladaptive,
+                  double courant, double diffnr);
+
+/* ---- measurement hooks (used by bench.py; no effect on results) --------------------- */
+/* device time in ms of the most recent launch group of one hot-path kernel family, measured
+ * with CUDA events on the library stream.  which: 0 mom_tend, 1 closure, 2 poisson core,
+ * 3 fillps, 4 tderive+integrate, 5 halos+boundary. */
+int udgpu_profile_enable(udgpu_t *h, int on);
+int udgpu_profile_get(udgpu_t *h, int which, double *ms_total, long *launches);
+int udgpu_profile_reset(udgpu_t *h);
+long udgpu_launch_count(udgpu_t *h);          /* kernels launched by this library so far */
+int udgpu_stream(udgpu_t *h, void **cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UDALES_GPU_H */

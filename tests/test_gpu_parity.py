@@ -1,0 +1,146 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances (fp64, stated by BASELINE.md §4): stencil tendencies rel-L_inf <= 1e-12, pressure
+rel-L_inf <= 1e-10, post-projection divergence RMS far below north_star's 1e-6.
+"""
+import numpy as np
+import pytest
+
+from helpers import interior, make_pair, push_state, relerr, tend_interior
+
+pytestmark = pytest.mark.gpu
+
+TOL_STENCIL = 1e-12
+TOL_PRES = 1e-10
+
+SIZES = [(16, 16, 16), (32, 24, 20), (64, 64, 64), (48, 40, 33), (20, 36, 7)]
+
+
+@pytest.mark.parametrize("shape", SIZES)
+@pytest.mark.parametrize("model", ["vreman", "smag", "dns"])
+def test_closure(shape, model):
+    kw = dict(vreman=dict(), smag=dict(lvreman=False, lsmagorinsky=True), dns=dict(lvreman=False, lsmagorinsky=False))[model]
+    o, g = make_pair(*shape, **kw)
+    o.closure(); g.closure()
+    for name in ("ekm", "ekh"):
+        a, b = g.pull(name), getattr(o, name)
+        assert relerr(a, b) < TOL_STENCIL, name          # whole array incl. all ghost cells
+    # reassure_fluxtop touched the top ghosts of u0/v0
+    assert relerr(g.pull("u0"), o.u0) == 0.0
+
+
+@pytest.mark.parametrize("shape", SIZES)
+@pytest.mark.parametrize("kw", [dict(), dict(lvreman=False, lsmagorinsky=False), dict(BCtopm=2, Uinf=1.0, Vinf=0.2)])
+def test_advection_and_subgrid(shape, kw):
+    o, g = make_pair(*shape, **kw)
+    o.advection(); g.advection()
+    for n in ("up", "vp", "wp"):
+        assert relerr(tend_interior(g.pull(n)), tend_interior(getattr(o, n))) < TOL_STENCIL, n
+    o.subgrid(); g.subgrid()
+    for n in ("up", "vp", "wp"):
+        assert relerr(tend_interior(g.pull(n)), tend_interior(getattr(o, n))) < TOL_STENCIL, n
+
+
+@pytest.mark.parametrize("shape", SIZES + [(12, 10, 8), (30, 18, 9), (128, 64, 32)])
+def test_poisson_solve(shape):
+    o, g = make_pair(*shape)
+    rng = np.random.default_rng(5)
+    rhs = rng.standard_normal(shape)
+    p_ref = o.poisson_solve(rhs)
+    p = g.poisson_solve(rhs)
+    assert relerr(p, p_ref) < TOL_PRES
+
+
+@pytest.mark.parametrize("shape", SIZES)
+@pytest.mark.parametrize("rk3step", [1, 2, 3])
+def test_poisson_fillps_tderive(shape, rk3step):
+    o, g = make_pair(*shape)
+    o.advection(); o.subgrid()
+    g.advection(); g.subgrid()
+    dt = 0.03
+    o.fillps(dt, rk3step); g.fillps(dt, rk3step)
+    rhs_ref = interior(o.p)
+    assert relerr(g.pull("rhs"), rhs_ref) < 1e-11
+    o2, g2 = o, g
+    # full poisson from the same tendencies
+    o2.poisson(dt, rk3step); g2.poisson(dt, rk3step)
+    assert relerr(interior(g2.pull("p")), interior(o2.p)) < TOL_PRES
+    for n in ("up", "vp", "wp"):
+        assert relerr(tend_interior(g2.pull(n)), tend_interior(getattr(o2, n))) < 1e-10, n
+    pr, pr_ref = g2.pull("pres0"), o2.pres0
+    assert relerr(pr[:, 1:-1, 1:-1], pr_ref[:, 1:-1, 1:-1]) < TOL_PRES     # interior + x-face halos
+    assert relerr(pr[1:-1, :, 1:-1], pr_ref[1:-1, :, 1:-1]) < TOL_PRES     # interior + y-face halos
+
+
+@pytest.mark.parametrize("shape", [(32, 24, 20), (64, 64, 64), (20, 36, 7)])
+@pytest.mark.parametrize("kw", [dict(), dict(lvreman=False, lsmagorinsky=True), dict(BCtopm=2, Uinf=1.0)])
+def test_substeps_track_oracle(shape, kw):
+    """six RK3 substeps (two full time steps) through the reference call surface."""
+    o, g = make_pair(*shape, **kw)
+    dt = 0.02
+    o.dt = g.dt = dt
+    for s in range(6):
+        o.substep(dt); g.substep(dt)
+        assert o.rk3step == g.rk3step
+        for n in ("u0", "v0", "w0", "um", "vm", "wm"):
+            assert relerr(g.pull(n), getattr(o, n)) < 1e-11, (s, n)       # whole arrays incl. halos/ghosts
+        dmax, dtot, drms = g.divergence()
+        omax, otot, orms = o.chkdiv()
+        assert drms < 1e-12 and dmax < 1e-11
+        assert abs(drms - orms) < 1e-13
+
+
+def test_tstep_update_adaptive():
+    o, g = make_pair(32, 24, 20)
+    o.closure(); g.closure()
+    d_ref, r_ref, ct_ref, dn_ref = o.tstep_update(0.05, 0, courant=1.1, diffnr=0.25, dtmax=2.0, ladaptive=True)
+    d, r, ct, dn = g.tstep_update(0.05, 0, courant=1.1, diffnr=0.25, dtmax=2.0, ladaptive=True)
+    assert r == r_ref == 1
+    assert ct == pytest.approx(ct_ref, rel=1e-14) and dn == pytest.approx(dn_ref, rel=1e-14)
+    assert d == pytest.approx(d_ref, rel=1e-14)
+    # rk3step 2, 3: dt untouched
+    d2, r2, _, _ = g.tstep_update(d, r, dtmax=2.0)
+    assert (d2, r2) == (d, 2)
+
+
+def test_pull_after_integrate_gives_zero_tendencies():
+    o, g = make_pair(16, 16, 16)
+    g.dt = 0.02
+    g.substep(0.02)
+    for n in ("up", "vp", "wp"):
+        assert np.abs(g.pull(n)).max() == 0.0      # src/modtstep.f90:322-324
+
+
+def test_full_size_properties_256():
+    """BASELINE config 2 (256^3): size-independent properties instead of the (slow) oracle."""
+    import udales_b200 as U
+    n = 256
+    g = U.UdalesGPU(n, n, n)
+    rng = np.random.default_rng(0)
+    # linearity + operator inversion of the Poisson solve
+    a = rng.standard_normal((n, n, n)); b = rng.standard_normal((n, n, n))
+    pa, pb, pab = g.poisson_solve(a), g.poisson_solve(b), g.poisson_solve(a + 2 * b)
+    assert relerr(pab, pa + 2 * pb) < 1e-11
+    dx = 0.5
+    lap = sum((np.roll(pa, -1, ax) - 2 * pa + np.roll(pa, 1, ax)) for ax in (0, 1)) / dx ** 2
+    pk = np.concatenate([pa[:, :, :1], pa, pa[:, :, -1:]], axis=2)
+    lap += (pk[:, :, 2:] - 2 * pk[:, :, 1:-1] + pk[:, :, :-2]) / dx ** 2
+    res = (lap - a)[:, :, :-1]
+    assert np.abs(res).max() < 1e-9 * np.abs(a).max()
+    # projection property after substeps from an LCG-perturbed channel
+    F = lambda: np.zeros((n + 2, n + 2, n + 2), order="F")
+    u = F(); v = F(); w = F()
+    u[1:-1, 1:-1, 1:-1] = 1.0 + 0.05 * rng.standard_normal((n, n, n))
+    v[1:-1, 1:-1, 1:-1] = 0.05 * rng.standard_normal((n, n, n))
+    w[1:-1, 1:-1, 2:-1] = 0.05 * rng.standard_normal((n, n, n - 1))
+    for nm, f in (("u0", u), ("v0", v), ("w0", w)):
+        g.push(nm, f)
+    g.halos(); g.boundary()
+    for nm in ("u0", "v0", "w0"):
+        g.push(nm.replace("0", "m"), g.pull(nm))
+    g.dt = 0.05
+    for s in range(3):
+        g.substep(0.05)
+        dmax, dtot, drms = g.divergence()
+        assert drms < 1e-12, (s, drms)
+    assert np.isfinite(g.pull("u0")).all()

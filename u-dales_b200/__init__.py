@@ -1,0 +1,274 @@
+"""udales_b200 — host-side mirror of the uDALES dynamics call surface over the sm_100a C-ABI.
+
+The product is ``libudales_gpu.so`` (include/udales_gpu.h).  This module is the thin ctypes
+binding used by the tests, bench.py and Python drivers; its method names are the reference's
+procedure names (src/program.f90:134-207): ``tstep_update, advection, subgrid, poisson,
+tstep_integrate, halos, boundary``.  There is no CPU fallback: if the library is missing or no
+B200 is visible, construction raises.
+
+The directory name contains a hyphen (``u-dales_b200``), so the importable alias is the
+top-level ``udales_b200.py`` shim.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libudales_gpu.so")
+ABI_VERSION = 1
+
+FIELD_IDS = {"u0": 0, "v0": 1, "w0": 2, "um": 3, "vm": 4, "wm": 5, "up": 6, "vp": 7, "wp": 8,
+             "pres0": 9, "p": 10, "ekm": 11, "ekh": 12, "rhs": 13, "sv0": 14, "svm": 15, "svp": 16}
+
+EXPORTS = [
+    "udgpu_nccl_unique_id", "udgpu_init", "udgpu_finalize", "udgpu_last_error", "udgpu_abi_version",
+    "udgpu_push", "udgpu_pull", "udgpu_field_count", "udgpu_device_ptr", "udgpu_sync",
+    "udgpu_host_register", "udgpu_host_unregister",
+    "udgpu_tstep_update", "udgpu_advection", "udgpu_subgrid", "udgpu_closure", "udgpu_poisson",
+    "udgpu_poisson_solve", "udgpu_poisson_solve_resident", "udgpu_fillps", "udgpu_tderive",
+    "udgpu_tstep_integrate", "udgpu_halos", "udgpu_boundary", "udgpu_divergence", "udgpu_substep",
+    "udgpu_profile_enable", "udgpu_profile_get", "udgpu_profile_reset", "udgpu_launch_count", "udgpu_stream",
+]
+
+
+class Cfg(C.Structure):
+    """ctypes image of ``udgpu_cfg`` (include/udales_gpu.h)."""
+    _fields_ = [("abi_version", C.c_int),
+                ("itot", C.c_int), ("jtot", C.c_int), ("ktot", C.c_int),
+                ("imax", C.c_int), ("jmax", C.c_int), ("kmax", C.c_int),
+                ("ih", C.c_int), ("jh", C.c_int), ("kh", C.c_int),
+                ("ihc", C.c_int), ("jhc", C.c_int), ("khc", C.c_int),
+                ("nsv", C.c_int), ("zstart", C.c_int * 3),
+                ("nprocx", C.c_int), ("nprocy", C.c_int), ("myidx", C.c_int), ("myidy", C.c_int),
+                ("BCxm", C.c_int), ("BCym", C.c_int), ("BCtopm", C.c_int), ("BCzp", C.c_int),
+                ("ipoiss", C.c_int), ("iadv_mom", C.c_int), ("iadv_sv", C.c_int),
+                ("lles", C.c_int), ("lvreman", C.c_int), ("lsmagorinsky", C.c_int), ("loneeqn", C.c_int),
+                ("ltempeq", C.c_int), ("lmoist", C.c_int),
+                ("dx", C.c_double), ("dy", C.c_double),
+                ("dzf", C.POINTER(C.c_double)), ("dzh", C.POINTER(C.c_double)), ("delta", C.POINTER(C.c_double)),
+                ("numol", C.c_double), ("prandtlmoli", C.c_double), ("prandtli", C.c_double),
+                ("c_vreman", C.c_double), ("cs", C.c_double), ("Uinf", C.c_double), ("Vinf", C.c_double),
+                ("e12min", C.c_double), ("device", C.c_int), ("flags", C.c_int)]
+
+
+class UdalesGPUError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libudales_gpu.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", _HERE, "libudales_gpu.so"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise UdalesGPUError("nvcc build failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib():
+    """Load the C-ABI library.  Fails loudly when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise UdalesGPUError(f"{LIB_PATH} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        L.udgpu_last_error.restype = C.c_char_p
+        L.udgpu_launch_count.restype = C.c_long
+        L.udgpu_launch_count.argtypes = [C.c_void_p]
+        L.udgpu_init.argtypes = [C.POINTER(Cfg), C.c_void_p, C.POINTER(C.c_void_p)]
+        L.udgpu_finalize.argtypes = [C.c_void_p]
+        L.udgpu_push.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.udgpu_pull.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.udgpu_field_count.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+        L.udgpu_device_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.udgpu_sync.argtypes = [C.c_void_p]
+        L.udgpu_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.udgpu_host_unregister.argtypes = [C.c_void_p]
+        L.udgpu_tstep_update.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double,
+                                         C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        for f in ("udgpu_advection", "udgpu_subgrid", "udgpu_closure", "udgpu_poisson_solve_resident",
+                  "udgpu_tderive", "udgpu_halos", "udgpu_boundary"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        for f in ("udgpu_poisson", "udgpu_fillps", "udgpu_tstep_integrate"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.udgpu_poisson_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.udgpu_divergence.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3
+        L.udgpu_substep.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_double, C.c_int,
+                                    C.c_double, C.c_double]
+        L.udgpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.udgpu_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
+        L.udgpu_profile_reset.argtypes = [C.c_void_p]
+        L.udgpu_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.udgpu_nccl_unique_id.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def grid_metrics(zf: np.ndarray):
+    """dzf(kb-kh:ke+kh), dzh(kb:ke+kh) from cell-centre heights, src/modglobal.f90:746-760."""
+    K = zf.size
+    zfx = np.zeros(K + 2)          # 1-based: zfx[k] = zf(k)
+    zfx[1:K + 1] = zf
+    zh1 = np.zeros(K + 3)
+    zh1[1] = 0.0
+    for k in range(1, K + 1):
+        zh1[k + 1] = zh1[k] + 2.0 * (zfx[k] - zh1[k])
+    zfx[K + 1] = zfx[K] + 2.0 * (zh1[K + 1] - zfx[K])
+    dzf = np.zeros(K + 2)          # index k = 0..K+1
+    for k in range(1, K + 1):
+        dzf[k] = zh1[k + 1] - zh1[k]
+    dzf[K + 1] = dzf[K]
+    dzf[0] = dzf[1]
+    dzh = np.zeros(K + 1)          # index k = 1..K+1 -> dzh[k-1]
+    dzh[0] = 2 * zfx[1]
+    for k in range(2, K + 2):
+        dzh[k - 1] = zfx[k] - zfx[k - 1]
+    return dzf, dzh
+
+
+class UdalesGPU:
+    """One z-pencil of the uDALES dynamics core resident on one B200."""
+
+    def __init__(self, itot, jtot, ktot, xlen=None, ylen=None, zf=None, nsv=0, BCtopm=1,
+                 lvreman=True, lsmagorinsky=False, lles=None, iadv_sv=7,
+                 numol=1.5e-5, prandtlmol=0.71, prandtl=0.333, c_vreman=0.07, cs=-1.0,
+                 Uinf=0.0, Vinf=0.0, device=-1, flags=0):
+        self.L = lib()
+        xlen = float(xlen if xlen is not None else itot / 2.0)
+        ylen = float(ylen if ylen is not None else jtot / 2.0)
+        if zf is None:
+            dz = xlen / itot
+            zf = (np.arange(ktot) + 0.5) * dz
+        zf = np.ascontiguousarray(zf, dtype=np.float64)
+        self._dzf, self._dzh = grid_metrics(zf)
+        if lles is None:
+            lles = bool(lvreman or lsmagorinsky)
+        hc = 2 if (nsv > 0 and iadv_sv == 7) else 1
+        c = Cfg()
+        c.abi_version = ABI_VERSION
+        c.itot, c.jtot, c.ktot = itot, jtot, ktot
+        c.imax, c.jmax, c.kmax = itot, jtot, ktot
+        c.ih = c.jh = c.kh = 1
+        c.ihc = c.jhc = c.khc = hc
+        c.nsv = nsv
+        c.zstart[0] = c.zstart[1] = c.zstart[2] = 1
+        c.nprocx = c.nprocy = 1
+        c.myidx = c.myidy = 0
+        c.BCxm = c.BCym = 1
+        c.BCtopm = BCtopm
+        c.BCzp = 1
+        c.ipoiss = 0
+        c.iadv_mom = 2
+        c.iadv_sv = iadv_sv
+        c.lles, c.lvreman, c.lsmagorinsky, c.loneeqn = int(lles), int(lvreman), int(lsmagorinsky), 0
+        c.ltempeq = c.lmoist = 0
+        c.dx, c.dy = xlen / itot, ylen / jtot
+        c.dzf = self._dzf.ctypes.data_as(C.POINTER(C.c_double))
+        c.dzh = self._dzh.ctypes.data_as(C.POINTER(C.c_double))
+        c.delta = None
+        c.numol, c.prandtlmoli, c.prandtli = numol, 1.0 / prandtlmol, 1.0 / prandtl
+        c.c_vreman, c.cs, c.Uinf, c.Vinf, c.e12min = c_vreman, cs, Uinf, Vinf, 5e-5
+        c.device, c.flags = device, flags
+        self.cfg = c
+        self.h = C.c_void_p()
+        self._chk(self.L.udgpu_init(C.byref(c), None, C.byref(self.h)))
+        self.itot, self.jtot, self.ktot, self.nsv = itot, jtot, ktot, nsv
+        self.dt, self.rk3step = 0.0, 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise UdalesGPUError(f"udgpu error {rc}: {self.L.udgpu_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.udgpu_finalize(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # residency ---------------------------------------------------------------
+    def shape(self, name):
+        cnt, dims = C.c_size_t(), (C.c_int * 3)()
+        self._chk(self.L.udgpu_field_count(self.h, FIELD_IDS[name], C.byref(cnt), dims))
+        return tuple(dims)
+
+    def push(self, name, arr, n4=0):
+        a = np.asfortranarray(arr, dtype=np.float64)
+        assert a.shape[:3] == self.shape(name), (name, a.shape, self.shape(name))
+        self._chk(self.L.udgpu_push(self.h, FIELD_IDS[name], n4, a.ctypes.data))
+        self._chk(self.L.udgpu_sync(self.h))
+
+    def pull(self, name, n4=0, out=None):
+        if out is None:
+            out = np.empty(self.shape(name), dtype=np.float64, order="F")
+        self._chk(self.L.udgpu_pull(self.h, FIELD_IDS[name], n4, out.ctypes.data))
+        return out
+
+    def push_raw(self, name, ptr, n4=0):
+        self._chk(self.L.udgpu_push(self.h, FIELD_IDS[name], n4, ptr))
+
+    def pull_raw(self, name, ptr, n4=0):
+        self._chk(self.L.udgpu_pull(self.h, FIELD_IDS[name], n4, ptr))
+
+    def sync(self): self._chk(self.L.udgpu_sync(self.h))
+
+    # reference call surface ----------------------------------------------------
+    def tstep_update(self, dt, rk3step, courant=1.0, diffnr=0.25, dtmax=1e9, ladaptive=True):
+        d, r, ct, dn = C.c_double(dt), C.c_int(rk3step), C.c_double(0), C.c_double(0)
+        self._chk(self.L.udgpu_tstep_update(self.h, C.byref(d), courant, diffnr, dtmax, int(ladaptive),
+                                            C.byref(r), C.byref(ct), C.byref(dn)))
+        return d.value, r.value, ct.value, dn.value
+
+    def advection(self): self._chk(self.L.udgpu_advection(self.h))
+    def subgrid(self): self._chk(self.L.udgpu_subgrid(self.h))
+    def closure(self): self._chk(self.L.udgpu_closure(self.h))
+    def fillps(self, dt, rk3step): self._chk(self.L.udgpu_fillps(self.h, dt, rk3step))
+    def tderive(self): self._chk(self.L.udgpu_tderive(self.h))
+    def poisson(self, dt, rk3step): self._chk(self.L.udgpu_poisson(self.h, dt, rk3step))
+    def tstep_integrate(self, dt, rk3step): self._chk(self.L.udgpu_tstep_integrate(self.h, dt, rk3step))
+    def halos(self): self._chk(self.L.udgpu_halos(self.h))
+    def boundary(self): self._chk(self.L.udgpu_boundary(self.h))
+    def poisson_solve_resident(self): self._chk(self.L.udgpu_poisson_solve_resident(self.h))
+
+    def poisson_solve(self, rhs):
+        a = np.array(rhs, dtype=np.float64, order="F", copy=True)
+        assert a.shape == (self.itot, self.jtot, self.ktot)
+        self._chk(self.L.udgpu_poisson_solve(self.h, a.ctypes.data, a.ctypes.data))
+        return a
+
+    def divergence(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._chk(self.L.udgpu_divergence(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def substep(self, dtmax, ladaptive=False, courant=1.0, diffnr=0.25):
+        d, r = C.c_double(self.dt), C.c_int(self.rk3step)
+        self._chk(self.L.udgpu_substep(self.h, C.byref(d), C.byref(r), dtmax, int(ladaptive), courant, diffnr))
+        self.dt, self.rk3step = d.value, r.value
+
+    # measurement ---------------------------------------------------------------
+    def profile_enable(self, on=True): self._chk(self.L.udgpu_profile_enable(self.h, int(on)))
+    def profile_reset(self): self._chk(self.L.udgpu_profile_reset(self.h))
+
+    def profile_get(self, which):
+        ms, n = C.c_double(), C.c_long()
+        self._chk(self.L.udgpu_profile_get(self.h, which, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launch_count(self): return int(self.L.udgpu_launch_count(self.h))
+
+    def stream(self):
+        s = C.c_void_p()
+        self._chk(self.L.udgpu_stream(self.h, C.byref(s)))
+        return s.value

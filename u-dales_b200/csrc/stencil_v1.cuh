@@ -1,0 +1,402 @@
+// stencil_v1.cuh — direct (one thread per cell, operands through L1/L2) forms of the stencil
+// routines.  They are the always-available general path (any tile-unfriendly size, any switch
+// combination) and the in-library cross-check for the TMA-staged kernels in momtend_tma.cuh.
+// Operand order follows the reference expressions so that differences to the oracle are pure
+// FMA-contraction rounding.
+#pragma once
+#include "common.cuh"
+
+namespace udg {
+
+// ---------------------------------------------------------------------------------------------
+// closure: src/modsubgrid.f90:159-412.  MODEL 0 = DNS (:401-404), 1 = Vreman (:269-360),
+// 2 = Smagorinsky (:208-267).  Writes interior ekm/ekh including "+ numol" (:263-264,359-360).
+// Ghost cells are produced by k_closurebc_*.
+template <int MODEL>
+__global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
+                                                 const double *__restrict__ w0, double *__restrict__ ekm,
+                                                 double *__restrict__ ekh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long c = offF(g, i, j, k);
+  const long long sj = g.pi, sk = g.pk;
+  double e;
+  if (MODEL == 0) {
+    e = 0.0;
+  } else {
+    const double dzfk = g.dzf[k], dzfkp = g.dzf[k + 1], dzfkm = g.dzf[k - 1];
+    const double dzhik = g.dzhi[k], dzhikp = g.dzhi[k + 1];
+#define U(di, dj, dk) __ldg(u0 + c + (di) + (dj)*sj + (dk)*sk)
+#define V(di, dj, dk) __ldg(v0 + c + (di) + (dj)*sj + (dk)*sk)
+#define W(di, dj, dk) __ldg(w0 + c + (di) + (dj)*sj + (dk)*sk)
+    if (MODEL == 1) {
+      const double a11 = (U(1, 0, 0) - U(0, 0, 0)) * g.dxi;
+      const double a12 = (V(1, 1, 0) + V(1, 0, 0) - V(-1, 1, 0) - V(-1, 0, 0)) * g.dxiq;
+      const double a13 = (W(1, 0, 1) + W(1, 0, 0) - W(-1, 0, 1) - W(-1, 0, 0)) * g.dxiq;
+      const double a21 = (U(1, 1, 0) + U(0, 1, 0) - U(1, -1, 0) - U(0, -1, 0)) * g.dyiq;
+      const double a22 = (V(0, 1, 0) - V(0, 0, 0)) * g.dyi;
+      const double a23 = (W(0, 1, 1) + W(0, 1, 0) - W(0, -1, 1) - W(0, -1, 0)) * g.dyiq;
+      const double a31 = (((U(1, 0, 1) + U(0, 0, 1)) * dzfk + (U(1, 0, 0) + U(0, 0, 0)) * dzfkp) * dzhikp -
+                          ((U(1, 0, 0) + U(0, 0, 0)) * dzfkm + (U(1, 0, -1) + U(0, 0, -1)) * dzfk) * dzhik) *
+                         g.dzfiq[k];
+      const double a32 = (((V(0, 1, 1) + V(0, 0, 1)) * dzfk + (V(0, 1, 0) + V(0, 0, 0)) * dzfkp) * dzhikp -
+                          ((V(0, 1, 0) + V(0, 0, 0)) * dzfkm + (V(0, 1, -1) + V(0, 0, -1)) * dzfk) * dzhik) *
+                         g.dzfiq[k];
+      const double a33 = (W(0, 0, 1) - W(0, 0, 0)) * g.dzfi[k];
+      const double aa = a11 * a11 + a21 * a21 + a31 * a31 + a12 * a12 + a22 * a22 + a32 * a32 + a13 * a13 +
+                        a23 * a23 + a33 * a33;
+      const double dzf2 = g.dzf2[k];
+      const double b11 = g.dx2 * a11 * a11 + g.dy2 * a21 * a21 + dzf2 * a31 * a31;
+      const double b22 = g.dx2 * a12 * a12 + g.dy2 * a22 * a22 + dzf2 * a32 * a32;
+      const double b12 = g.dx2 * a11 * a12 + g.dy2 * a21 * a22 + dzf2 * a31 * a32;
+      const double b33 = g.dx2 * a13 * a13 + g.dy2 * a23 * a23 + dzf2 * a33 * a33;
+      const double b13 = g.dx2 * a11 * a13 + g.dy2 * a21 * a23 + dzf2 * a31 * a33;
+      const double b23 = g.dx2 * a12 * a13 + g.dy2 * a22 * a23 + dzf2 * a32 * a33;
+      const double bb = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
+      e = (bb < 1.e-8) ? 0.0 : g.c_vreman * sqrt(bb / aa);
+    } else {
+      const double mlen = g.csz * g.delta[k];
+      double t, s2;
+#define SQ(x) (t = (x), t * t)
+      s2 = SQ((U(1, 0, 0) - U(0, 0, 0)) * g.dxi) + SQ((V(0, 1, 0) - V(0, 0, 0)) * g.dyi) +
+           SQ((W(0, 0, 1) - W(0, 0, 0)) * g.dzfi[k]);
+      s2 = s2 + 0.125 * (SQ((W(0, 0, 1) - W(-1, 0, 1)) * g.dxi + (U(0, 0, 1) - U(0, 0, 0)) * dzhikp) +
+                         SQ((W(0, 0, 0) - W(-1, 0, 0)) * g.dxi + (U(0, 0, 0) - U(0, 0, -1)) * dzhik) +
+                         SQ((W(1, 0, 0) - W(0, 0, 0)) * g.dxi + (U(1, 0, 0) - U(1, 0, -1)) * dzhik) +
+                         SQ((W(1, 0, 1) - W(0, 0, 1)) * g.dxi + (U(1, 0, 1) - U(1, 0, 0)) * dzhikp));
+      s2 = s2 + 0.125 * (SQ((U(0, 1, 0) - U(0, 0, 0)) * g.dyi + (V(0, 1, 0) - V(-1, 1, 0)) * g.dxi) +
+                         SQ((U(0, 0, 0) - U(0, -1, 0)) * g.dyi + (V(0, 0, 0) - V(-1, 0, 0)) * g.dxi) +
+                         SQ((U(1, 0, 0) - U(1, -1, 0)) * g.dyi + (V(1, 0, 0) - V(0, 0, 0)) * g.dxi) +
+                         SQ((U(1, 1, 0) - U(1, 0, 0)) * g.dyi + (V(1, 1, 0) - V(0, 1, 0)) * g.dxi));
+      s2 = s2 + 0.125 * (SQ((V(0, 0, 1) - V(0, 0, 0)) * dzhikp + (W(0, 0, 1) - W(0, -1, 1)) * g.dyi) +
+                         SQ((V(0, 0, 0) - V(0, 0, -1)) * dzhik + (W(0, 0, 0) - W(0, -1, 0)) * g.dyi) +
+                         SQ((V(0, 1, 0) - V(0, 1, -1)) * dzhik + (W(0, 1, 0) - W(0, 0, 0)) * g.dyi) +
+                         SQ((V(0, 1, 1) - V(0, 1, 0)) * dzhikp + (W(0, 1, 1) - W(0, 0, 1)) * g.dyi));
+#undef SQ
+      e = (mlen * mlen) * sqrt(2. * s2);
+    }
+#undef U
+#undef V
+#undef W
+  }
+  ekm[c] = e + g.numol;
+  ekh[c] = e * g.prandtli + g.numol * g.prandtlmoli;
+}
+
+// closurebc part 1: src/modboundary.f90:447-465 top/bottom ghost levels on (0..imax+1, 0..jmax+1).
+// Run AFTER the lateral halo fill of the interior levels so the ghost levels of the lateral halo
+// are consistent (the reference gets the same values through its :476-500 wraps).
+__global__ void k_closurebc_topbot(Geo g, double *__restrict__ ekm, double *__restrict__ ekh) {
+  const int si = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sj = blockIdx.y;
+  if (si >= g.pi) return;
+  const long long b = (long long)si + (long long)g.pi * sj;
+  const long long k1 = b + g.pk * g.kh, kK = b + g.pk * (g.ktot + g.kh - 1);
+  const double tm = 2. * g.numol, th = 2. * g.numol * g.prandtlmoli;
+  if (g.BCtopm == 2) {
+    ekm[kK + g.pk] = tm - ekm[kK];
+    ekh[kK + g.pk] = th - ekh[kK];
+  } else {
+    ekm[kK + g.pk] = ekm[kK];
+    ekh[kK + g.pk] = ekh[kK];
+  }
+  ekm[k1 - g.pk] = tm - ekm[k1];
+  ekh[k1 - g.pk] = th - ekh[k1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// periodic wraps of N momentum-halo arrays (xm_periodic/ym_periodic src/modboundary.f90:508-626,
+// closurebc :476-500, bcp :1362-1408).  nlev = number of stored k levels, width = halo width.
+struct PtrPack { double *p[8]; int n; };
+
+__global__ void k_wrap_x(PtrPack a, int pi, int pj, int nlev, int imax, int h) {
+  // all (j,k) incl. halos; one thread per (j,k,m)
+  const long long jk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (jk >= (long long)pj * nlev) return;
+  const long long row = jk * pi;
+  for (int f = 0; f < a.n; f++) {
+    double *q = a.p[f] + row;
+    for (int m = 1; m <= h; m++) {
+      q[h - m] = q[h + imax - m];          // (ib-m) = (ie+1-m)
+      q[h + imax - 1 + m] = q[h - 1 + m];  // (ie+m) = (ib-1+m)
+    }
+  }
+}
+__global__ void k_wrap_y(PtrPack a, int pi, int pj, int nlev, int jmax, int h) {
+  const int si = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lev = blockIdx.y;
+  if (si >= pi) return;
+  const long long base = (long long)lev * pi * pj + si;
+  for (int f = 0; f < a.n; f++) {
+    double *q = a.p[f] + base;
+    for (int m = 1; m <= h; m++) {
+      q[(long long)(h - m) * pi] = q[(long long)(h + jmax - m) * pi];
+      q[(long long)(h + jmax - 1 + m) * pi] = q[(long long)(h - 1 + m) * pi];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// momentum tendencies, direct form.  advecu/v/w_2nd src/modadvection.f90:158-314 and
+// diffu/v/w src/modsubgrid.f90:672-997.  ACC: add to the existing tendency (drop-in semantics)
+// or overwrite (tendencies are zero on entry, src/modtstep.f90:322-324).
+template <bool ADV, bool DIFF, bool ACC, bool LES>
+__global__ void __launch_bounds__(256) k_momtend_v1(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
+                                                    const double *__restrict__ w0, const double *__restrict__ pres0,
+                                                    const double *__restrict__ ekm, double *__restrict__ up,
+                                                    double *__restrict__ vp, double *__restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long c = offF(g, i, j, k);
+  const long long t = offT(g, i, j, k);
+  const long long sj = g.pi, sk = g.pk;
+#define U(di, dj, dk) __ldg(u0 + c + (di) + (dj)*sj + (dk)*sk)
+#define V(di, dj, dk) __ldg(v0 + c + (di) + (dj)*sj + (dk)*sk)
+#define W(di, dj, dk) __ldg(w0 + c + (di) + (dj)*sj + (dk)*sk)
+#define P(di, dj, dk) __ldg(pres0 + c + (di) + (dj)*sj + (dk)*sk)
+#define E(di, dj, dk) (LES ? __ldg(ekm + c + (di) + (dj)*sj + (dk)*sk) : g.numol)
+  const double dzfk = g.dzf[k], dzfkp = g.dzf[k + 1], dzfkm = g.dzf[k - 1];
+  const double dzhik = g.dzhi[k], dzhikp = g.dzhi[k + 1];
+  const double dzfik = g.dzfi[k], dzfi5k = g.dzfi5[k];
+  const double dxi = g.dxi, dyi = g.dyi;
+  double ru = ACC ? up[t] : 0.0, rv = ACC ? vp[t] : 0.0;
+  if (ADV) {
+    ru = ru - (((U(0, 0, 0) + U(1, 0, 0)) * (U(0, 0, 0) + U(1, 0, 0)) - (U(0, 0, 0) + U(-1, 0, 0)) * (U(0, 0, 0) + U(-1, 0, 0))) * g.dxiq +
+               ((U(0, 0, 0) + U(0, 1, 0)) * (V(0, 1, 0) + V(-1, 1, 0)) - (U(0, 0, 0) + U(0, -1, 0)) * (V(0, 0, 0) + V(-1, 0, 0))) * g.dyiq) -
+         ((P(0, 0, 0) - P(-1, 0, 0)) * dxi);
+    ru = ru - ((U(0, 0, 1) * dzfk + U(0, 0, 0) * dzfkp) * dzhikp * (W(0, 0, 1) + W(-1, 0, 1)) -
+               (U(0, 0, 0) * dzfkm + U(0, 0, -1) * dzfk) * dzhik * (W(0, 0, 0) + W(-1, 0, 0))) * 0.5 * dzfi5k;
+    rv = rv - (((U(1, 0, 0) + U(1, -1, 0)) * (V(0, 0, 0) + V(1, 0, 0)) - (U(0, 0, 0) + U(0, -1, 0)) * (V(0, 0, 0) + V(-1, 0, 0))) * g.dxiq +
+               ((V(0, 1, 0) + V(0, 0, 0)) * (V(0, 0, 0) + V(0, 1, 0)) - (V(0, -1, 0) + V(0, 0, 0)) * (V(0, 0, 0) + V(0, -1, 0))) * g.dyiq) -
+         ((P(0, 0, 0) - P(0, -1, 0)) * dyi);
+    rv = rv - ((W(0, 0, 1) + W(0, -1, 1)) * (V(0, 0, 1) * dzfk + V(0, 0, 0) * dzfkp) * dzhikp -
+               (W(0, 0, 0) + W(0, -1, 0)) * (V(0, 0, -1) * dzfk + V(0, 0, 0) * dzfkm) * dzhik) * 0.5 * dzfi5k;
+  }
+  if (DIFF) {
+    const double dzhiqk = g.dzhiq[k], dzhiqkp = g.dzhiq[k + 1];
+    {
+      const double emom = LES ? (dzfkm * (E(0, 0, 0) + E(-1, 0, 0)) + dzfk * (E(0, 0, -1) + E(-1, 0, -1))) * dzhiqk : g.numol;
+      const double emop = LES ? (dzfkp * (E(0, 0, 0) + E(-1, 0, 0)) + dzfk * (E(0, 0, 1) + E(-1, 0, 1))) * dzhiqkp : g.numol;
+      const double empo = LES ? 0.25 * ((E(0, 0, 0) + E(0, 1, 0)) + (E(-1, 0, 0) + E(-1, 1, 0))) : g.numol;
+      const double emmo = LES ? 0.25 * ((E(0, 0, 0) + E(0, -1, 0)) + (E(-1, -1, 0) + E(-1, 0, 0))) : g.numol;
+      ru = ru + (E(0, 0, 0) * (U(1, 0, 0) - U(0, 0, 0)) - E(-1, 0, 0) * (U(0, 0, 0) - U(-1, 0, 0))) * 2. * g.dx2i +
+           (empo * ((U(0, 1, 0) - U(0, 0, 0)) * dyi + (V(0, 1, 0) - V(-1, 1, 0)) * dxi) -
+            emmo * ((U(0, 0, 0) - U(0, -1, 0)) * dyi + (V(0, 0, 0) - V(-1, 0, 0)) * dxi)) * dyi +
+           (emop * ((U(0, 0, 1) - U(0, 0, 0)) * dzhikp + (W(0, 0, 1) - W(-1, 0, 1)) * dxi) -
+            emom * ((U(0, 0, 0) - U(0, 0, -1)) * dzhik + (W(0, 0, 0) - W(-1, 0, 0)) * dxi)) * dzfik;
+    }
+    {
+      const double eomm = LES ? (dzfkm * (E(0, 0, 0) + E(0, -1, 0)) + dzfk * (E(0, 0, -1) + E(0, -1, -1))) * dzhiqk : g.numol;
+      const double eomp = LES ? (dzfkp * (E(0, 0, 0) + E(0, -1, 0)) + dzfk * (E(0, 0, 1) + E(0, -1, 1))) * dzhiqkp : g.numol;
+      const double emmo = LES ? 0.25 * (E(0, 0, 0) + E(0, -1, 0) + E(-1, -1, 0) + E(-1, 0, 0)) : g.numol;
+      const double epmo = LES ? 0.25 * (E(0, 0, 0) + E(0, -1, 0) + E(1, -1, 0) + E(1, 0, 0)) : g.numol;
+      rv = rv + (epmo * ((V(1, 0, 0) - V(0, 0, 0)) * dxi + (U(1, 0, 0) - U(1, -1, 0)) * dyi) -
+                 emmo * ((V(0, 0, 0) - V(-1, 0, 0)) * dxi + (U(0, 0, 0) - U(0, -1, 0)) * dyi)) * dxi +
+           (E(0, 0, 0) * (V(0, 1, 0) - V(0, 0, 0)) - E(0, -1, 0) * (V(0, 0, 0) - V(0, -1, 0))) * 2. * g.dy2i +
+           (eomp * ((V(0, 0, 1) - V(0, 0, 0)) * dzhikp + (W(0, 0, 1) - W(0, -1, 1)) * dyi) -
+            eomm * ((V(0, 0, 0) - V(0, 0, -1)) * dzhik + (W(0, 0, 0) - W(0, -1, 0)) * dyi)) * dzfik;
+    }
+  }
+  up[t] = ru;
+  vp[t] = rv;
+  if (k >= 2) {
+    double rw = ACC ? wp[t] : 0.0;
+    if (ADV) {
+      rw = rw - (((W(1, 0, 0) + W(0, 0, 0)) * (dzfkm * U(1, 0, 0) + dzfk * U(1, 0, -1)) -
+                  (W(0, 0, 0) + W(-1, 0, 0)) * (dzfkm * U(0, 0, 0) + dzfk * U(0, 0, -1))) * g.dxiq * dzhik +
+                 ((W(0, 1, 0) + W(0, 0, 0)) * (dzfkm * V(0, 1, 0) + dzfk * V(0, 1, -1)) -
+                  (W(0, 0, 0) + W(0, -1, 0)) * (dzfkm * V(0, 0, 0) + dzfk * V(0, 0, -1))) * g.dyiq * dzhik +
+                 ((W(0, 0, 0) + W(0, 0, 1)) * (W(0, 0, 0) + W(0, 0, 1)) - (W(0, 0, 0) + W(0, 0, -1)) * (W(0, 0, 0) + W(0, 0, -1))) * g.dzhiq[k]) -
+           ((P(0, 0, 0) - P(0, 0, -1)) * dzhik);
+    }
+    if (DIFF) {
+      const double dzhiqk = g.dzhiq[k];
+      const double emom = LES ? (dzfkm * (E(0, 0, 0) + E(-1, 0, 0)) + dzfk * (E(0, 0, -1) + E(-1, 0, -1))) * dzhiqk : g.numol;
+      const double eomm = LES ? (dzfkm * (E(0, 0, 0) + E(0, -1, 0)) + dzfk * (E(0, 0, -1) + E(0, -1, -1))) * dzhiqk : g.numol;
+      const double eopm = LES ? (dzfkm * (E(0, 0, 0) + E(0, 1, 0)) + dzfk * (E(0, 0, -1) + E(0, 1, -1))) * dzhiqk : g.numol;
+      const double epom = LES ? (dzfkm * (E(0, 0, 0) + E(1, 0, 0)) + dzfk * (E(0, 0, -1) + E(1, 0, -1))) * dzhiqk : g.numol;
+      rw = rw + (epom * ((W(1, 0, 0) - W(0, 0, 0)) * dxi + (U(1, 0, 0) - U(1, 0, -1)) * dzhik) -
+                 emom * ((W(0, 0, 0) - W(-1, 0, 0)) * dxi + (U(0, 0, 0) - U(0, 0, -1)) * dzhik)) * dxi +
+           (eopm * ((W(0, 1, 0) - W(0, 0, 0)) * dyi + (V(0, 1, 0) - V(0, 1, -1)) * dzhik) -
+            eomm * ((W(0, 0, 0) - W(0, -1, 0)) * dyi + (V(0, 0, 0) - V(0, 0, -1)) * dzhik)) * dyi +
+           (E(0, 0, 0) * (W(0, 0, 1) - W(0, 0, 0)) * dzfik - E(0, 0, -1) * (W(0, 0, 0) - W(0, 0, -1)) * g.dzfi[k - 1]) * 2. * dzhik;
+    }
+    wp[t] = rw;
+  } else if (!ACC) {
+    wp[t] = 0.0;
+  }
+#undef U
+#undef V
+#undef W
+#undef P
+#undef E
+}
+
+// ---------------------------------------------------------------------------------------------
+// fillps + bcpup: src/modpois.f90:911-973, src/modboundary.f90:1191-1255,1307-1315.
+// pup/pvp/pwp are never materialised: p = d/dx(up+um/c) + ... evaluated on the fly.  The +1
+// neighbour in x / y is taken from the periodic image when the direction is unsplit (XWRAP /
+// YWRAP), otherwise from the halo cell (filled by the halo exchange of up+um/c's inputs).
+// Output: halo-free rhs(imax,jmax,ktot).
+template <bool XWRAP, bool YWRAP>
+__global__ void __launch_bounds__(256) k_fillps(Geo g, double rk3coefi, const double *__restrict__ up, const double *__restrict__ vp,
+                                                const double *__restrict__ wp, const double *__restrict__ um,
+                                                const double *__restrict__ vm, const double *__restrict__ wm,
+                                                double *__restrict__ rhs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const int ip = (XWRAP && i == g.imax) ? 1 : i + 1;
+  const int jp = (YWRAP && j == g.jmax) ? 1 : j + 1;
+  const double pu0 = up[offT(g, i, j, k)] + um[offF(g, i, j, k)] * rk3coefi;
+  const double pu1 = up[offT(g, ip, j, k)] + um[offF(g, ip, j, k)] * rk3coefi;
+  const double pv0 = vp[offT(g, i, j, k)] + vm[offF(g, i, j, k)] * rk3coefi;
+  const double pv1 = vp[offT(g, i, jp, k)] + vm[offF(g, i, jp, k)] * rk3coefi;
+  const double pw0 = (k == 1) ? 0.0 : wp[offT(g, i, j, k)] + wm[offF(g, i, j, k)] * rk3coefi;
+  const double pw1 = (k == g.ktot) ? 0.0 : wp[offT(g, i, j, k + 1)] + wm[offF(g, i, j, k + 1)] * rk3coefi;
+  rhs[offR(g, i, j, k)] = (pu1 - pu0) * g.dxi + (pv1 - pv0) * g.dyi + (pw1 - pw0) * g.dzfi[k];
+}
+
+// tderive: src/modpois.f90:1046-1056 (velocity tendencies) on a halo'd p.
+__global__ void __launch_bounds__(256) k_tderive(Geo g, const double *__restrict__ p, double *__restrict__ up,
+                                                 double *__restrict__ vp, double *__restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long c = offF(g, i, j, k), t = offT(g, i, j, k);
+  const double pc = p[c];
+  up[t] = up[t] - (pc - p[c - 1]) * g.dxi;
+  vp[t] = vp[t] - (pc - p[c - g.pi]) * g.dyi;
+  if (k >= 2) wp[t] = wp[t] - (pc - p[c - g.pk]) * g.dzhi[k];
+}
+// pres0 += p on (ib-1:ie+1, jb-1:je+1, kb-1:ke+1): src/modpois.f90:1096-1102
+__global__ void k_pres_update(long long n, const double *__restrict__ p, double *__restrict__ pres0) {
+  long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; q < n; q += stride) pres0[q] = pres0[q] + p[q];
+}
+
+// tstep_integrate: src/modtstep.f90:171-340 for u,v,w.  ZERO: also zero the tendencies (:322-324);
+// STEP3: um = u0 on the interior (halos are refreshed by the following halos call, :330-338).
+template <bool ZERO, bool STEP3>
+__global__ void __launch_bounds__(256) k_integrate(Geo g, double rk3coef, double *__restrict__ u0, double *__restrict__ v0,
+                                                   double *__restrict__ w0, double *__restrict__ um, double *__restrict__ vm,
+                                                   double *__restrict__ wm, double *__restrict__ up, double *__restrict__ vp,
+                                                   double *__restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long c = offF(g, i, j, k), t = offT(g, i, j, k);
+  const double a = um[c] + rk3coef * up[t];
+  const double b = vm[c] + rk3coef * vp[t];
+  const double d = wm[c] + rk3coef * wp[t];
+  u0[c] = a; v0[c] = b; w0[c] = d;
+  if (STEP3) { um[c] = a; vm[c] = b; wm[c] = d; }
+  if (ZERO) { up[t] = 0.; vp[t] = 0.; wp[t] = 0.; }
+}
+
+// boundary (periodic x/y subset): src/modboundary.f90:163-204.  One thread per (si,sj) incl. halos.
+__global__ void k_boundary_topbot(Geo g, double *__restrict__ u0, double *__restrict__ v0, double *__restrict__ w0,
+                                  double *__restrict__ um, double *__restrict__ vm, double *__restrict__ wm) {
+  const int si = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sj = blockIdx.y;
+  if (si >= g.pi) return;
+  const long long b = (long long)si + (long long)g.pi * sj;
+  const long long k1 = b + g.pk * g.kh, kK = b + g.pk * (g.ktot + g.kh - 1), kT = kK + g.pk;
+  wm[k1] = 0.; w0[k1] = 0.;
+  if (g.BCtopm == 2) {
+    um[kT] = 2 * g.Uinf - um[kK]; u0[kT] = 2 * g.Uinf - u0[kK];
+    vm[kT] = 2 * g.Vinf - vm[kK]; v0[kT] = 2 * g.Vinf - v0[kK];
+  } else {
+    um[kT] = um[kK]; u0[kT] = u0[kK];
+    vm[kT] = vm[kK]; v0[kT] = v0[kK];
+  }
+  w0[kT] = 0.; wm[kT] = 0.;
+}
+// reassure_fluxtop_boundary (src/modboundary.f90:392-431) for freeslip: u,v top ghost = top level
+__global__ void k_fluxtop_uv(Geo g, double *__restrict__ u0, double *__restrict__ v0, double *__restrict__ um,
+                             double *__restrict__ vm) {
+  const int si = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sj = blockIdx.y;
+  if (si >= g.pi) return;
+  const long long b = (long long)si + (long long)g.pi * sj;
+  const long long kK = b + g.pk * (g.ktot + g.kh - 1), kT = kK + g.pk;
+  um[kT] = um[kK]; u0[kT] = u0[kK]; vm[kT] = vm[kK]; v0[kT] = v0[kK];
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions.  Block-level max/sum in shared memory, then one atomic per block on doubles
+// encoded so that atomicMax on the bit pattern works (all candidates are >= 0).
+__device__ __forceinline__ double warp_max(double v) {
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
+  atomicMax((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
+}
+
+// tstep_update maxima: src/modtstep.f90:113-127.  out[0] = courant, out[1] = diffusion number
+// (both divided by dt later on the host side: they are linear in dt).
+__global__ void __launch_bounds__(256) k_cfl(Geo g, const double *__restrict__ um, const double *__restrict__ vm,
+                                             const double *__restrict__ wm, const double *__restrict__ ekm,
+                                             const double *__restrict__ ekh, double dt, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  double c = 0., d = 0.;
+  if (i <= g.imax && j <= g.jmax) {
+    const long long q = offF(g, i, j, k);
+    c = (fabs(um[q]) * g.dxi + fabs(vm[q]) * g.dyi + fabs(wm[q]) / g.dzh[k]) * dt;
+    const double m = (g.dzh2i[k] + g.dx2i + g.dy2i) * dt;
+    d = fmax(ekm[q] * m, ekh[q] * m);
+  }
+  c = warp_max(c); d = warp_max(d);
+  __shared__ double sc[8], sd[8];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if ((tid & 31) == 0) { sc[tid >> 5] = c; sd[tid >> 5] = d; }
+  __syncthreads();
+  if (tid < 32) {
+    const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+    c = tid < nw ? sc[tid] : 0.; d = tid < nw ? sd[tid] : 0.;
+    c = warp_max(c); d = warp_max(d);
+    if (tid == 0) { atomic_max_nonneg(out, c); atomic_max_nonneg(out + 1, d); }
+  }
+}
+
+// chkdiv: src/modchecksim.f90:161-203.  out[0] = max|div|, out[1] = sum div*dx*dy*dzf, out[2] = sum div^2
+__global__ void __launch_bounds__(256) k_div(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
+                                             const double *__restrict__ w0, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  double m = 0., s = 0., s2 = 0.;
+  if (i <= g.imax && j <= g.jmax) {
+    const long long q = offF(g, i, j, k);
+    const double div = (u0[q + 1] - u0[q]) * g.dxi + (v0[q + g.pi] - v0[q]) * g.dyi + (w0[q + g.pk] - w0[q]) * g.dzfi[k];
+    m = fabs(div); s = div * g.dx * g.dy * g.dzf[k]; s2 = div * div;
+  }
+  m = warp_max(m); s = warp_sum(s); s2 = warp_sum(s2);
+  __shared__ double sm[8], ss[8], ss2[8];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if ((tid & 31) == 0) { sm[tid >> 5] = m; ss[tid >> 5] = s; ss2[tid >> 5] = s2; }
+  __syncthreads();
+  if (tid < 32) {
+    const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+    m = tid < nw ? sm[tid] : 0.; s = tid < nw ? ss[tid] : 0.; s2 = tid < nw ? ss2[tid] : 0.;
+    m = warp_max(m); s = warp_sum(s); s2 = warp_sum(s2);
+    if (tid == 0) { atomic_max_nonneg(out, m); atomicAdd(out + 1, s); atomicAdd(out + 2, s2); }
+  }
+}
+
+}  // namespace udg

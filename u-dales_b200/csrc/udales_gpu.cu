@@ -1,0 +1,668 @@
+// udales_gpu.cu — C-ABI implementation (include/udales_gpu.h) of the B200-native uDALES
+// dynamics core.  One instance = one z-pencil on one GPU.  sm_100a only, no CPU fallback.
+#include "../../include/udales_gpu.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "poisson_v1.cuh"
+#include "stencil_v1.cuh"
+
+using namespace udg;
+
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int set_err(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(x)                                                                                         \
+  do {                                                                                                \
+    cudaError_t e_ = (x);                                                                             \
+    if (e_ != cudaSuccess)                                                                            \
+      return set_err(UDGPU_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+  } while (0)
+#define KCHECK() CU(cudaGetLastError())
+#define RET(x)                \
+  do {                        \
+    int r_ = (x);             \
+    if (r_ != UDGPU_OK) return r_; \
+  } while (0)
+
+enum { PROF_MOM = 0, PROF_CLOSURE, PROF_POIS, PROF_FILLPS, PROF_INTEG, PROF_HALO, PROF_N };
+
+struct ProfSlot {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pend;
+  double ms = 0;
+  long n = 0;
+};
+
+struct udgpu {
+  udgpu_cfg cfg;
+  Geo g;
+  int dev = 0;
+  cudaStream_t st = nullptr;
+  double *f[UDGPU_NFIELDS] = {};
+  size_t cnt[UDGPU_NFIELDS] = {};  // elements per scalar slice
+  int dims[UDGPU_NFIELDS][3] = {};
+  int nslices[UDGPU_NFIELDS] = {};
+  std::vector<void *> allocs;
+  // metrics on device (base pointers, un-offset)
+  double *m_base = nullptr;
+  // poisson
+  double *d_scr = nullptr;  // Thomas d scratch
+  double *d_xrt = nullptr, *d_yrt = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;
+  double b_top_D = 0;
+  FftPlan px, py;
+  // reductions
+  double *d_red = nullptr, *h_red = nullptr;
+  // state
+  bool tend_zero = false;
+  bool prof = false;
+  ProfSlot ps[PROF_N];
+  long launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+static int dev_alloc(udgpu *h, void **p, size_t bytes) {
+  CU(cudaMalloc(p, bytes ? bytes : 8));
+  CU(cudaMemsetAsync(*p, 0, bytes ? bytes : 8, h->st));
+  h->allocs.push_back(*p);
+  return UDGPU_OK;
+}
+
+static void prof_begin(udgpu *h, int which, cudaEvent_t *a, cudaEvent_t *b) {
+  if (!h->prof) return;
+  cudaEventCreate(a);
+  cudaEventCreate(b);
+  cudaEventRecord(*a, h->st);
+  (void)which;
+}
+static void prof_end(udgpu *h, int which, cudaEvent_t a, cudaEvent_t b) {
+  if (!h->prof) return;
+  cudaEventRecord(b, h->st);
+  h->ps[which].pend.push_back({a, b});
+}
+struct ProfScope {
+  udgpu *h; int which; cudaEvent_t a, b;
+  ProfScope(udgpu *h_, int w) : h(h_), which(w) { prof_begin(h, which, &a, &b); }
+  ~ProfScope() { prof_end(h, which, a, b); }
+};
+
+static std::vector<int> factor_radices(int hlen) {
+  std::vector<int> r;
+  const int cand[] = {4, 2, 3, 5, 7, 11, 13};
+  for (int c : cand)
+    while (hlen % c == 0) { r.push_back(c); hlen /= c; }
+  if (hlen != 1) r.clear();
+  return r;
+}
+
+static int make_plan(udgpu *h, int n, FftPlan *pl) {
+  if (n < 2 || (n & 1)) return set_err(UDGPU_EINVAL, "FFT length %d must be even (reference packing assumes it, src/modpois.f90:482-487)", n);
+  pl->n = n;
+  pl->h = n / 2;
+  std::vector<int> r = factor_radices(pl->h);
+  if (pl->h > 1 && r.empty()) return set_err(UDGPU_EINVAL, "FFT length %d: n/2 has a prime factor > 13 (unsupported)", n);
+  if (r.size() > 24) return set_err(UDGPU_EINVAL, "FFT length %d too composite", n);
+  pl->nst = (int)r.size();
+  for (int s = 0; s < pl->nst; s++) pl->radix[s] = r[s];
+  pl->fac = 1. / sqrt((double)n * 1.);
+  std::vector<double2> tw(n);
+  for (int q = 0; q < n; q++) {
+    // exact octant symmetry is not needed: cos/sin of a correctly rounded argument are < 1 ulp
+    const double ang = -2.0 * M_PI * (double)q / (double)n;
+    tw[q] = make_double2(cos(ang), sin(ang));
+  }
+  double2 *d;
+  RET(dev_alloc(h, (void **)&d, sizeof(double2) * n));
+  CU(cudaMemcpyAsync(d, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  pl->tw = d;
+  return UDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" const char *udgpu_last_error(void) { return g_err; }
+extern "C" int udgpu_abi_version(void) { return UDGPU_ABI_VERSION; }
+
+extern "C" int udgpu_nccl_unique_id(void *uid128) {
+  (void)uid128;
+  return set_err(UDGPU_ENCCL, "multi-GPU support not compiled in yet");
+}
+
+extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **out) {
+  (void)nccl_uid;
+  if (!c || !out) return set_err(UDGPU_EINVAL, "null argument");
+  if (c->abi_version != UDGPU_ABI_VERSION) return set_err(UDGPU_EINVAL, "ABI version mismatch: header %d, caller %d", UDGPU_ABI_VERSION, c->abi_version);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_err(UDGPU_ENODEV, "no CUDA device visible: this library has no CPU fallback");
+  }
+  // supported switch set (everything else is the reference's business)
+  if (c->ipoiss != 0) return set_err(UDGPU_EINVAL, "ipoiss=%d: only POISS_FFT2D (0) is supported (src/modglobal.f90:389)", c->ipoiss);
+  if (c->iadv_mom != 2) return set_err(UDGPU_EINVAL, "iadv_mom=%d: only cd2 (2) exists in the reference (src/modadvection.f90:47-54)", c->iadv_mom);
+  if (c->BCxm != 1 || c->BCym != 1) return set_err(UDGPU_EINVAL, "only periodic lateral BCs (BCxm=BCym=1) are in scope");
+  if (c->BCtopm != 1 && c->BCtopm != 2) return set_err(UDGPU_EINVAL, "BCtopm=%d: freeslip (1) / noslip (2) only", c->BCtopm);
+  if (c->BCzp != 1) return set_err(UDGPU_EINVAL, "BCzp=%d: only the tridiagonal z solve (1) is in scope", c->BCzp);
+  if (c->ltempeq || c->lmoist || c->loneeqn) return set_err(UDGPU_EINVAL, "ltempeq/lmoist/loneeqn are out of scope (neutral configs)");
+  if (c->ih != 1 || c->jh != 1 || c->kh != 1) return set_err(UDGPU_EINVAL, "momentum halo must be 1 (cd2, src/modglobal.f90:592-599)");
+  if (c->nprocx * c->nprocy != 1) return set_err(UDGPU_EINVAL, "multi-GPU pencils not available in this build");
+  if (c->imax != c->itot || c->jmax != c->jtot || c->kmax != c->ktot) return set_err(UDGPU_EINVAL, "single pencil requires imax=itot, jmax=jtot, kmax=ktot");
+  if (c->nsv != 0) return set_err(UDGPU_EINVAL, "nsv > 0 not available in this build");
+  if (!c->dzf || !c->dzh) return set_err(UDGPU_EINVAL, "dzf/dzh missing");
+
+  udgpu *h = new udgpu();
+  h->cfg = *c;
+  h->dev = c->device;
+  if (h->dev < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    h->dev = lr ? atoi(lr) % ndev : 0;
+  }
+  CU(cudaSetDevice(h->dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, h->dev));
+  if (prop.major < 10) {
+    const int dv = h->dev;
+    delete h;
+    return set_err(UDGPU_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", dv, prop.major, prop.minor);
+  }
+  CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+
+  Geo &g = h->g;
+  memset(&g, 0, sizeof(g));
+  g.imax = c->imax; g.jmax = c->jmax; g.ktot = c->ktot; g.itot = c->itot; g.jtot = c->jtot;
+  g.ih = c->ih; g.jh = c->jh; g.kh = c->kh;
+  g.pi = g.imax + 2 * g.ih; g.pj = g.jmax + 2 * g.jh; g.pk = (long long)g.pi * g.pj;
+  g.ihc = c->ihc; g.jhc = c->jhc; g.khc = c->khc;
+  g.pic = g.imax + 2 * g.ihc; g.pjc = g.jmax + 2 * g.jhc; g.pkc = (long long)g.pic * g.pjc;
+  g.i0g = c->zstart[0] - 1; g.j0g = c->zstart[1] - 1;
+  g.dx = c->dx; g.dy = c->dy;
+  g.dxi = 1. / g.dx; g.dyi = 1. / g.dy;                       // src/modglobal.f90:805-808
+  g.dx2 = g.dx * g.dx; g.dy2 = g.dy * g.dy;
+  g.dxiq = 0.25 * g.dxi; g.dyiq = 0.25 * g.dyi;               // :816-817
+  g.dx2i = g.dxi * g.dxi; g.dy2i = g.dyi * g.dyi;             // :821-822
+  g.dxi5 = 0.5 * g.dxi; g.dyi5 = 0.5 * g.dyi;                 // :826-827
+  g.numol = c->numol; g.prandtlmoli = c->prandtlmoli; g.prandtli = c->prandtli;
+  g.c_vreman = c->c_vreman;
+  {
+    // csz: src/modsubgrid.f90:65-77
+    const double pi = 3.141592653589793116, cf = 2.5, alpha_kolm = 1.5;
+    const double cm = cf / (2. * pi) * pow(1.5 * alpha_kolm, -1.5);
+    const double ceps = 2. * pi / cf * pow(1.5 * alpha_kolm, -1.5);
+    g.csz = (c->cs == -1.) ? pow(cm * cm * cm / ceps, 0.25) : c->cs;
+  }
+  g.Uinf = c->Uinf; g.Vinf = c->Vinf; g.BCtopm = c->BCtopm; g.lles = c->lles;
+
+  // ---- metric tables: index k in [-1, ktot+2], 13 tables ----
+  const int K = g.ktot, NM = K + 4, OFF = 1;
+  std::vector<double> tab(13 * (size_t)NM, 0.0);
+  auto T = [&](int t, int k) -> double & { return tab[(size_t)t * NM + k + OFF]; };
+  enum { tDZF, tDZH, tDZFI, tDZHI, tDZHIQ, tDZFIQ, tDZH2I, tDZF2, tDZFI5, tDELTA, tDZFC, tDZFCI, tDZHCI };
+  for (int k = 0; k <= K + 1; k++) T(tDZF, k) = c->dzf[k];
+  for (int k = 1; k <= K + 1; k++) T(tDZH, k) = c->dzh[k - 1];
+  for (int k = 0; k <= K + 1; k++) {
+    T(tDZFI, k) = 1. / T(tDZF, k);
+    T(tDZF2, k) = T(tDZF, k) * T(tDZF, k);
+    T(tDZFIQ, k) = 0.25 * T(tDZFI, k);
+    T(tDZFI5, k) = 0.5 * T(tDZFI, k);
+    T(tDZFC, k) = T(tDZF, k);
+  }
+  for (int k = 1; k <= K + 1; k++) {
+    T(tDZHI, k) = 1. / T(tDZH, k);
+    T(tDZHIQ, k) = 0.25 * T(tDZHI, k);
+    T(tDZH2I, k) = T(tDZHI, k) * T(tDZHI, k);
+    T(tDELTA, k) = c->delta ? c->delta[k - 1] : pow(g.dx * g.dy * T(tDZF, k), 1. / 3.);
+    T(tDZHCI, k) = T(tDZHI, k);
+  }
+  T(tDZFC, -1) = T(tDZFC, 0); T(tDZFC, K + 2) = T(tDZFC, K + 1);      // src/modglobal.f90:849-851
+  for (int k = -1; k <= K + 2; k++) T(tDZFCI, k) = 1. / T(tDZFC, k);
+  T(tDZHCI, 0) = T(tDZHCI, 1); T(tDZHCI, K + 2) = T(tDZHCI, K + 1);   // :857-859
+  RET(dev_alloc(h, (void **)&h->m_base, tab.size() * sizeof(double)));
+  CU(cudaMemcpyAsync(h->m_base, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  auto MP = [&](int t) { return (const double *)(h->m_base + (size_t)t * NM + OFF); };
+  g.dzf = MP(tDZF); g.dzh = MP(tDZH); g.dzfi = MP(tDZFI); g.dzhi = MP(tDZHI); g.dzhiq = MP(tDZHIQ);
+  g.dzfiq = MP(tDZFIQ); g.dzh2i = MP(tDZH2I); g.dzf2 = MP(tDZF2); g.dzfi5 = MP(tDZFI5); g.delta = MP(tDELTA);
+  g.dzfc = MP(tDZFC); g.dzfci = MP(tDZFCI); g.dzhci = MP(tDZHCI);
+
+  // ---- fields ----
+  const size_t nF = (size_t)g.pi * g.pj * (K + 2 * g.kh), nT = (size_t)g.pi * g.pj * (K + g.kh);
+  const size_t nR = (size_t)g.imax * g.jmax * K;
+  for (int f = 0; f < UDGPU_NFIELDS; f++) {
+    size_t n = 0;
+    int d3 = 0, sl = 1;
+    switch (f) {
+      case UDGPU_UP: case UDGPU_VP: case UDGPU_WP: n = nT; d3 = K + g.kh; break;
+      case UDGPU_RHS: n = nR; d3 = K; break;
+      case UDGPU_SV0: case UDGPU_SVM: case UDGPU_SVP: n = 0; sl = 0; break;
+      default: n = nF; d3 = K + 2 * g.kh; break;
+    }
+    h->cnt[f] = n; h->nslices[f] = sl;
+    h->dims[f][0] = (f == UDGPU_RHS) ? g.imax : g.pi;
+    h->dims[f][1] = (f == UDGPU_RHS) ? g.jmax : g.pj;
+    h->dims[f][2] = d3;
+    if (n) RET(dev_alloc(h, (void **)&h->f[f], n * sl * sizeof(double)));
+  }
+  RET(dev_alloc(h, (void **)&h->d_scr, nR * sizeof(double)));
+  RET(dev_alloc(h, (void **)&h->d_red, 16 * sizeof(double)));
+  CU(cudaMallocHost((void **)&h->h_red, 16 * sizeof(double)));
+
+  // ---- Poisson coefficients: src/modpois.f90:98-176 (periodic x,y; BCzp = 1; rhobf = rhobh = 1) ----
+  {
+    const double pi = 3.141592653589793116;
+    std::vector<double> xrt(g.itot), yrt(g.jtot), a(K), b(K), cc(K);
+    double fac = 1. / (2. * g.itot);
+    for (int i = 3; i <= g.itot; i += 2) {
+      const double s = sin((double)(i - 1) * pi * fac);
+      xrt[i - 2] = -4. * g.dxi * g.dxi * (s * s);
+      xrt[i - 1] = xrt[i - 2];
+    }
+    xrt[0] = 0.; xrt[g.itot - 1] = -4. * g.dxi * g.dxi;
+    fac = 1. / (2. * g.jtot);
+    for (int j = 3; j <= g.jtot; j += 2) {
+      const double s = sin((double)(j - 1) * pi * fac);
+      yrt[j - 2] = -4. * g.dyi * g.dyi * (s * s);
+      yrt[j - 1] = yrt[j - 2];
+    }
+    yrt[0] = 0.; yrt[g.jtot - 1] = -4. * g.dyi * g.dyi;
+    for (int k = 1; k <= K; k++) {
+      a[k - 1] = 1. / (T(tDZF, k) * T(tDZH, k));
+      cc[k - 1] = 1. / (T(tDZF, k) * T(tDZH, k + 1));
+      b[k - 1] = -(a[k - 1] + cc[k - 1]);
+    }
+    b[0] = b[0] + a[0];
+    const double b_top_N = b[K - 1] + cc[K - 1];
+    h->b_top_D = b[K - 1] - cc[K - 1];
+    b[K - 1] = b_top_N;
+    a[0] = 0.; cc[K - 1] = 0.;
+    RET(dev_alloc(h, (void **)&h->d_xrt, g.itot * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_yrt, g.jtot * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_a, K * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_b, K * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_c, K * sizeof(double)));
+    CU(cudaMemcpyAsync(h->d_xrt, xrt.data(), g.itot * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_yrt, yrt.data(), g.jtot * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_a, a.data(), K * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_b, b.data(), K * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_c, cc.data(), K * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
+  }
+  RET(make_plan(h, g.itot, &h->px));
+  RET(make_plan(h, g.jtot, &h->py));
+  {
+    const int hmax = (h->px.h > h->py.h ? h->px.h : h->py.h);
+    const size_t smem = (size_t)hmax * FFT_BP * sizeof(double2);
+    if (smem > 227 * 1024) return set_err(UDGPU_EINVAL, "FFT length too large for the shared-memory tile (%zu B)", smem);
+    CU(cudaFuncSetAttribute(k_rfft<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_rfft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  CU(cudaStreamSynchronize(h->st));
+  *out = h;
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_finalize(udgpu_t *h) {
+  if (!h) return UDGPU_OK;
+  cudaSetDevice(h->dev);
+  cudaStreamSynchronize(h->st);
+  for (void *p : h->allocs) cudaFree(p);
+  if (h->h_red) cudaFreeHost(h->h_red);
+  for (int w = 0; w < PROF_N; w++)
+    for (auto &e : h->ps[w].pend) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  cudaStreamDestroy(h->st);
+  delete h;
+  return UDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+static int check_field(udgpu *h, int field, int n4) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (field < 0 || field >= UDGPU_NFIELDS) return set_err(UDGPU_EINVAL, "bad field id %d", field);
+  if (!h->f[field]) return set_err(UDGPU_EINVAL, "field %d not allocated in this configuration", field);
+  if (n4 < 0 || n4 >= h->nslices[field]) return set_err(UDGPU_EINVAL, "scalar index %d out of range", n4);
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_field_count(udgpu_t *h, int field, size_t *count, int dims[3]) {
+  if (!h || field < 0 || field >= UDGPU_NFIELDS) return set_err(UDGPU_EINVAL, "bad field id %d", field);
+  if (count) *count = h->cnt[field];
+  if (dims) for (int d = 0; d < 3; d++) dims[d] = h->dims[field][d];
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
+  RET(check_field(h, field, n4));
+  CU(cudaSetDevice(h->dev));
+  CU(cudaMemcpyAsync(h->f[field] + (size_t)n4 * h->cnt[field], host, h->cnt[field] * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP) h->tend_zero = false;
+  return UDGPU_OK;
+}
+extern "C" int udgpu_pull(udgpu_t *h, int field, int n4, double *host) {
+  RET(check_field(h, field, n4));
+  CU(cudaSetDevice(h->dev));
+  CU(cudaMemcpyAsync(host, h->f[field] + (size_t)n4 * h->cnt[field], h->cnt[field] * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return UDGPU_OK;
+}
+extern "C" int udgpu_device_ptr(udgpu_t *h, int field, int n4, void **dptr) {
+  RET(check_field(h, field, n4));
+  *dptr = h->f[field] + (size_t)n4 * h->cnt[field];
+  return UDGPU_OK;
+}
+extern "C" int udgpu_sync(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  CU(cudaStreamSynchronize(h->st));
+  return UDGPU_OK;
+}
+extern "C" int udgpu_host_register(void *ptr, size_t bytes) {
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return UDGPU_OK;
+}
+extern "C" int udgpu_host_unregister(void *ptr) {
+  CU(cudaHostUnregister(ptr));
+  return UDGPU_OK;
+}
+extern "C" int udgpu_stream(udgpu_t *h, void **s) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  *s = (void *)h->st;
+  return UDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+static dim3 grid3(const Geo &g, dim3 b) { return dim3((g.imax + b.x - 1) / b.x, (g.jmax + b.y - 1) / b.y, g.ktot); }
+static const dim3 B3(64, 4, 1);
+
+static int wrap_xy(udgpu *h, std::initializer_list<double *> fields, int nlev) {
+  const Geo &g = h->g;
+  PtrPack pp; pp.n = 0;
+  for (double *p : fields) pp.p[pp.n++] = p;
+  const long long rows = (long long)g.pj * nlev;
+  k_wrap_x<<<(unsigned)((rows + 127) / 128), 128, 0, h->st>>>(pp, g.pi, g.pj, nlev, g.imax, g.ih);
+  KCHECK();
+  k_wrap_y<<<dim3((g.pi + 127) / 128, nlev), 128, 0, h->st>>>(pp, g.pi, g.pj, nlev, g.jmax, g.jh);
+  KCHECK();
+  h->launches += 2;
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_closure(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const Geo &g = h->g;
+  ProfScope ps(h, PROF_CLOSURE);
+  const dim3 gr = grid3(g, B3);
+  // model selection order of the reference: smagorinsky first, then vreman, else DNS (modsubgrid.f90:208,269,401)
+  if (h->cfg.lsmagorinsky) k_closure<2><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
+  else if (h->cfg.lvreman) k_closure<1><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
+  else k_closure<0><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
+  KCHECK();
+  h->launches++;
+  // closurebc: lateral wraps on all levels, then top/bottom ghost levels over the full halo'd plane
+  RET(wrap_xy(h, {h->f[UDGPU_EKM], h->f[UDGPU_EKH]}, g.ktot + 2 * g.kh));
+  k_closurebc_topbot<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
+  KCHECK();
+  h->launches++;
+  if (g.BCtopm == 1) {  // reassure_fluxtop_boundary
+    k_fluxtop_uv<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_UM], h->f[UDGPU_VM]);
+    KCHECK();
+    h->launches++;
+  }
+  return UDGPU_OK;
+}
+
+template <bool ADV, bool DIFF>
+static int launch_momtend(udgpu *h, bool acc) {
+  const Geo &g = h->g;
+  const dim3 gr = grid3(g, B3);
+  const bool les = g.lles != 0;
+#define LAUNCH(ACC, LES)                                                                                          \
+  k_momtend_v1<ADV, DIFF, ACC, LES><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0],      \
+                                                          h->f[UDGPU_PRES0], h->f[UDGPU_EKM], h->f[UDGPU_UP],     \
+                                                          h->f[UDGPU_VP], h->f[UDGPU_WP])
+  if (acc) { if (les) LAUNCH(true, true); else LAUNCH(true, false); }
+  else { if (les) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_advection(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  ProfScope ps(h, PROF_MOM);
+  RET((launch_momtend<true, false>(h, !h->tend_zero)));
+  h->tend_zero = false;
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_subgrid(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(udgpu_closure(h));
+  ProfScope ps(h, PROF_MOM);
+  RET((launch_momtend<false, true>(h, !h->tend_zero)));
+  h->tend_zero = false;
+  return UDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *out, bool out_halo) {
+  const Geo &g = h->g;
+  LineDesc di, dd;
+  const long long pr = g.imax, pp = (long long)g.imax * g.jmax;
+  if (xdir) {
+    di = {1, pr, pp, g.jmax, g.ktot};
+    dd = di;
+    if (out_halo) { dd.s1 = g.pi; dd.s2 = g.pk; }
+    const size_t smem = (size_t)h->px.h * FFT_BP * sizeof(double2);
+    k_rfft<true><<<dim3((g.jmax + FFT_B - 1) / FFT_B, g.ktot), dim3(FFT_B, FFT_TY), smem, h->st>>>(h->px, inverse, in, di, out, dd);
+  } else {
+    di = {pr, 1, pp, g.imax, g.ktot};
+    dd = di;
+    if (out_halo) { dd.sp = g.pi; dd.s2 = g.pk; }
+    const size_t smem = (size_t)h->py.h * FFT_BP * sizeof(double2);
+    k_rfft<false><<<dim3((g.imax + FFT_B - 1) / FFT_B, g.ktot), dim3(FFT_B, FFT_TY), smem, h->st>>>(h->py, inverse, in, di, out, dd);
+  }
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+
+// rhs (halo-free work array) -> solution.  Final pass writes either in place or into the interior of
+// the halo'd p array.  Order x, y, z, y^-1, x^-1 as in src/modpois.f90:478-679.
+static int poisson_core(udgpu *h, double *work, double *p_halo) {
+  const Geo &g = h->g;
+  ProfScope ps(h, PROF_POIS);
+  RET(fft_pass(h, true, 0, work, work, false));
+  RET(fft_pass(h, false, 0, work, work, false));
+  k_solmpj<<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, work, h->d_scr, h->d_xrt, h->d_yrt, h->d_a, h->d_b, h->d_c, h->b_top_D);
+  KCHECK();
+  h->launches++;
+  RET(fft_pass(h, false, 1, work, work, false));
+  if (p_halo) RET(fft_pass(h, true, 1, work, p_halo + offF(g, 1, 1, 1), true));
+  else RET(fft_pass(h, true, 1, work, work, false));
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_poisson_solve_resident(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  return poisson_core(h, h->f[UDGPU_RHS], nullptr);
+}
+
+extern "C" int udgpu_poisson_solve(udgpu_t *h, const double *rhs, double *p) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const size_t bytes = h->cnt[UDGPU_RHS] * sizeof(double);
+  CU(cudaMemcpyAsync(h->f[UDGPU_RHS], rhs, bytes, cudaMemcpyHostToDevice, h->st));
+  RET(poisson_core(h, h->f[UDGPU_RHS], nullptr));
+  CU(cudaMemcpyAsync(p, h->f[UDGPU_RHS], bytes, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const Geo &g = h->g;
+  ProfScope ps(h, PROF_FILLPS);
+  const double rk3coef = (rk3step == 0) ? 1. : dt / (4. - (double)rk3step);
+  const double rk3coefi = 1. / rk3coef;
+  k_fillps<true, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
+                                                       h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS]);
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_tderive(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const Geo &g = h->g;
+  ProfScope ps(h, PROF_INTEG);
+  RET(wrap_xy(h, {h->f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
+  k_tderive<<<grid3(g, B3), B3, 0, h->st>>>(g, h->f[UDGPU_P], h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP]);
+  KCHECK();
+  k_pres_update<<<148 * 8, 256, 0, h->st>>>((long long)h->cnt[UDGPU_PRES0], h->f[UDGPU_P], h->f[UDGPU_PRES0]);
+  KCHECK();
+  h->launches += 2;
+  h->tend_zero = false;
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_poisson(udgpu_t *h, double dt, int rk3step) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(udgpu_fillps(h, dt, rk3step));
+  RET(poisson_core(h, h->f[UDGPU_RHS], h->f[UDGPU_P]));
+  RET(udgpu_tderive(h));
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const Geo &g = h->g;
+  ProfScope ps(h, PROF_INTEG);
+  const double rk3coef = dt / (4. - (double)rk3step);
+  double **f = h->f;
+  if (rk3step == 3)
+    k_integrate<true, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM],
+                                                            f[UDGPU_WM], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP]);
+  else
+    k_integrate<true, false><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM],
+                                                             f[UDGPU_WM], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP]);
+  KCHECK();
+  h->launches++;
+  h->tend_zero = true;
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_halos(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const Geo &g = h->g;
+  ProfScope ps(h, PROF_HALO);
+  double **f = h->f;
+  RET(wrap_xy(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_boundary(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const Geo &g = h->g;
+  ProfScope ps(h, PROF_HALO);
+  double **f = h->f;
+  k_boundary_topbot<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]);
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_tstep_update(udgpu_t *h, double *dt, double courant, double diffnr, double dtmax, int ladaptive,
+                                  int *rk3step, double *courtot, double *diffnrtot) {
+  if (!h || !dt || !rk3step) return set_err(UDGPU_ESTATE, "null argument");
+  const Geo &g = h->g;
+  *rk3step = (*rk3step % 3) + 1;
+  if (*rk3step != 1) return UDGPU_OK;
+  if (ladaptive) {
+    double **f = h->f;
+    CU(cudaMemsetAsync(h->d_red, 0, 2 * sizeof(double), h->st));
+    k_cfl<<<grid3(g, B3), B3, 0, h->st>>>(g, f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_EKM], f[UDGPU_EKH], *dt, h->d_red);
+    KCHECK();
+    h->launches++;
+    CU(cudaMemcpyAsync(h->h_red, h->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    const double ct = h->h_red[0], dn = fmax(1e-5, h->h_red[1]);  // src/modtstep.f90:114-115
+    if (courtot) *courtot = ct;
+    if (diffnrtot) *diffnrtot = dn;
+    *dt = fmin(dtmax, fmin((*dt) * courant / ct, (*dt) * diffnr / dn));  // :135
+  } else {
+    *dt = dtmax;  // :143
+  }
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_divergence(udgpu_t *h, double *divmax, double *divtot, double *divrms) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const Geo &g = h->g;
+  double **f = h->f;
+  CU(cudaMemsetAsync(h->d_red + 4, 0, 3 * sizeof(double), h->st));
+  k_div<<<grid3(g, B3), B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], h->d_red + 4);
+  KCHECK();
+  h->launches++;
+  CU(cudaMemcpyAsync(h->h_red + 4, h->d_red + 4, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  if (divmax) *divmax = h->h_red[4];
+  if (divtot) *divtot = h->h_red[5];
+  if (divrms) *divrms = sqrt(h->h_red[6] / ((double)g.itot * g.jtot * g.ktot));
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax, int ladaptive, double courant, double diffnr) {
+  RET(udgpu_tstep_update(h, dt, courant, diffnr, dtmax, ladaptive, rk3step, nullptr, nullptr));
+  RET(udgpu_advection(h));
+  RET(udgpu_subgrid(h));
+  RET(udgpu_poisson(h, *dt, *rk3step));
+  RET(udgpu_tstep_integrate(h, *dt, *rk3step));
+  RET(udgpu_halos(h));
+  RET(udgpu_boundary(h));
+  return UDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int udgpu_profile_enable(udgpu_t *h, int on) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  h->prof = on != 0;
+  return UDGPU_OK;
+}
+static void prof_collect(udgpu *h) {
+  cudaStreamSynchronize(h->st);
+  for (int w = 0; w < PROF_N; w++) {
+    for (auto &e : h->ps[w].pend) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) { h->ps[w].ms += ms; h->ps[w].n++; }
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+    h->ps[w].pend.clear();
+  }
+}
+extern "C" int udgpu_profile_get(udgpu_t *h, int which, double *ms_total, long *launches) {
+  if (!h || which < 0 || which >= PROF_N) return set_err(UDGPU_EINVAL, "bad profile slot");
+  prof_collect(h);
+  if (ms_total) *ms_total = h->ps[which].ms;
+  if (launches) *launches = h->ps[which].n;
+  return UDGPU_OK;
+}
+extern "C" int udgpu_profile_reset(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  prof_collect(h);
+  for (int w = 0; w < PROF_N; w++) { h->ps[w].ms = 0; h->ps[w].n = 0; }
+  return UDGPU_OK;
+}
+extern "C" long udgpu_launch_count(udgpu_t *h) { return h ? h->launches : 0; }

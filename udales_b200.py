@@ -1,0 +1,11 @@
+"""Importable alias of the ``u-dales_b200/`` package (its directory name has a hyphen)."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "u-dales_b200")
+_spec = _u.spec_from_file_location("udales_b200", _os.path.join(_dir, "__init__.py"),
+                                   submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules["udales_b200"] = _mod
+_spec.loader.exec_module(_mod)
