@@ -481,6 +481,8 @@ static void closurebc(orc_t *o) {
   /* nsv > 0 with BCtops flux (default, wsvtop = 0): fluxtopscal, see orc_boundary */
 }
 
+static inline double sq_(double x) { return x * x; }
+
 /* closure: src/modsubgrid.f90:159-412 (Smagorinsky :208-267, Vreman :269-360, DNS :401-404) */
 void orc_closure(orc_t *o) {
   const double *u0 = o->u0, *v0 = o->v0, *w0 = o->w0;
@@ -503,8 +505,8 @@ void orc_closure(orc_t *o) {
         for (int i = 1; i <= o->itot; i++) {
           const int ip = i + 1, im = i - 1;
           const double damp = 1.;
-          double strain2, t;
-#define SQ(x) (t = (x), t * t)
+          double strain2;
+#define SQ(x) sq_(x)
           strain2 = SQ((F(u0, ip, j, k) - F(u0, i, j, k)) * dxi)
                   + SQ((F(v0, i, jp, k) - F(v0, i, j, k)) * dyi)
                   + SQ((F(w0, i, j, kp) - F(w0, i, j, k)) * M(dzfi, k));

@@ -9,6 +9,8 @@
 namespace udg {
 
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sq_(double x) { return x * x; }
+
 // closure: src/modsubgrid.f90:159-412.  MODEL 0 = DNS (:401-404), 1 = Vreman (:269-360),
 // 2 = Smagorinsky (:208-267).  Writes interior ekm/ekh including "+ numol" (:263-264,359-360).
 // Ghost cells are produced by k_closurebc_*.
@@ -58,8 +60,8 @@ __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict
       e = (bb < 1.e-8) ? 0.0 : g.c_vreman * sqrt(bb / aa);
     } else {
       const double mlen = g.csz * g.delta[k];
-      double t, s2;
-#define SQ(x) (t = (x), t * t)
+      double s2;
+#define SQ(x) sq_(x)
       s2 = SQ((U(1, 0, 0) - U(0, 0, 0)) * g.dxi) + SQ((V(0, 1, 0) - V(0, 0, 0)) * g.dyi) +
            SQ((W(0, 0, 1) - W(0, 0, 0)) * g.dzfi[k]);
       s2 = s2 + 0.125 * (SQ((W(0, 0, 1) - W(-1, 0, 1)) * g.dxi + (U(0, 0, 1) - U(0, 0, 0)) * dzhikp) +
