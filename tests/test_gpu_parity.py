@@ -29,10 +29,29 @@ def test_closure(shape, model):
     assert relerr(g.pull("u0"), o.u0) == 0.0
 
 
+F_NO_LAZY, F_V1 = 1, 8
+
+
+@pytest.mark.parametrize("shape", SIZES + [(96, 40, 12), (34, 18, 5)])
+@pytest.mark.parametrize("kw", [dict(), dict(lvreman=False, lsmagorinsky=False), dict(BCtopm=2, Uinf=1.0, Vinf=0.2)])
+@pytest.mark.parametrize("flags", [0, F_V1])
+def test_fused_advection_subgrid(shape, kw, flags):
+    """advection(); subgrid() back to back = ONE fused TMA kernel (flags 0) vs the direct kernels (V1)."""
+    o, g = make_pair(*shape, gpu_flags=flags, **kw)
+    o.advection(); o.subgrid()
+    g.advection(); g.subgrid()
+    for n in ("up", "vp", "wp"):
+        assert relerr(tend_interior(g.pull(n)), tend_interior(getattr(o, n))) < TOL_STENCIL, n
+    # top ghost level of the tendencies is never touched (stays 0)
+    assert np.abs(g.pull("wp")[:, :, -1]).max() == 0.0
+
+
 @pytest.mark.parametrize("shape", SIZES)
 @pytest.mark.parametrize("kw", [dict(), dict(lvreman=False, lsmagorinsky=False), dict(BCtopm=2, Uinf=1.0, Vinf=0.2)])
-def test_advection_and_subgrid(shape, kw):
-    o, g = make_pair(*shape, **kw)
+@pytest.mark.parametrize("flags", [0, F_NO_LAZY, F_V1])
+def test_advection_and_subgrid(shape, kw, flags):
+    """operator-by-operator (a pull between the calls forces the un-fused, accumulating kernels)."""
+    o, g = make_pair(*shape, gpu_flags=flags, **kw)
     o.advection(); g.advection()
     for n in ("up", "vp", "wp"):
         assert relerr(tend_interior(g.pull(n)), tend_interior(getattr(o, n))) < TOL_STENCIL, n

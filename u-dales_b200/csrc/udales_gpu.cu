@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "momtend_tma.cuh"
 #include "poisson_v1.cuh"
 #include "stencil_v1.cuh"
 
@@ -67,7 +68,14 @@ struct udgpu {
   FftPlan px, py;
   // reductions
   double *d_red = nullptr, *h_red = nullptr;
+  // TMA path of the fused momentum kernel
+  bool use_tma = false;
+  CUtensorMap tm[5];
+  MomTmaParams mtp;
+  int mt_grid = 0;
+  int nsm = 148;
   // state
+  bool adv_pending = false;   // advection() was called, its work is fused into the next subgrid()
   bool tend_zero = false;
   bool prof = false;
   ProfSlot ps[PROF_N];
@@ -75,6 +83,7 @@ struct udgpu {
 };
 
 // ------------------------------------------------------------------------------------------
+static int flush_pending(udgpu *h);
 static int dev_alloc(udgpu *h, void **p, size_t bytes) {
   CU(cudaMalloc(p, bytes ? bytes : 8));
   CU(cudaMemsetAsync(*p, 0, bytes ? bytes : 8, h->st));
@@ -130,6 +139,68 @@ static int make_plan(udgpu *h, int n, FftPlan *pl) {
   CU(cudaMemcpyAsync(d, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, h->st));
   CU(cudaStreamSynchronize(h->st));
   pl->tw = d;
+  return UDGPU_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// TMA descriptors for the fused momentum kernel: 3-D tiled maps over the Fortran-shaped arrays
+// (dims pi x pj x nlev, box 34 x 18 x 1).  cuTensorMapEncodeTiled is fetched through the runtime so
+// the library has no link-time dependency on libcuda.
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int setup_momtend_tma(udgpu *h) {
+  const Geo &g = h->g;
+  h->use_tma = false;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, h->dev));
+  h->nsm = prop.multiProcessorCount;
+  if (h->cfg.flags & UDGPU_F_V1_KERNELS) return UDGPU_OK;
+  if (g.pi % 2 != 0) return UDGPU_OK;  // TMA needs 16-byte strides: odd row pitch -> direct kernels
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return set_err(UDGPU_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  PFN_encodeTiled enc = (PFN_encodeTiled)fn;
+  const int ids[5] = {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_PRES0, UDGPU_EKM};
+  for (int f = 0; f < 5; f++) {
+    cuuint64_t dims[3] = {(cuuint64_t)g.pi, (cuuint64_t)g.pj, (cuuint64_t)(g.ktot + 2 * g.kh)};
+    cuuint64_t strides[2] = {(cuuint64_t)g.pi * 8, (cuuint64_t)g.pk * 8};
+    cuuint32_t box[3] = {(cuuint32_t)MT_BX, (cuuint32_t)MT_BY, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&h->tm[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->f[ids[f]], dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(UDGPU_ECUDA, "cuTensorMapEncodeTiled failed for field %d: CUresult %d", ids[f], (int)r);
+  }
+  MomTmaParams &P = h->mtp;
+  P.g = g;
+  P.ntx = (g.imax + MT_TX - 1) / MT_TX;
+  P.nty = (g.jmax + MT_TY - 1) / MT_TY;
+  // k-chunks: balance (items over SMs, one CTA per SM) against the one redundant plane per chunk
+  const int ntile = P.ntx * P.nty, G = h->nsm;
+  int best = 1; double beste = -1;
+  for (int c = 1; c <= g.ktot && c <= 64; c++) {
+    const double L = (double)g.ktot / c;
+    if (L < 4 && c > 1) break;
+    const long items = (long)ntile * c;
+    const double rounds = ceil((double)items / G);
+    const double eff = (double)items / (G * rounds) * L / (L + 1.0);
+    if (eff > beste + 1e-9) { beste = eff; best = c; }
+  }
+  P.nchunk = best;
+  P.nitems = ntile * best;
+  P.up = h->f[UDGPU_UP]; P.vp = h->f[UDGPU_VP]; P.wp = h->f[UDGPU_WP];
+  h->mt_grid = P.nitems < G ? P.nitems : G;
+#define SETATTR(A, D, L, C) CU(cudaFuncSetAttribute(k_momtend_tma<A, D, L, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM))
+  // exactly the variants launch_momtend can pick: <ADV, DIFF, DIFF && LES, ACC>
+  SETATTR(true, true, true, false); SETATTR(true, true, true, true); SETATTR(true, true, false, false); SETATTR(true, true, false, true);
+  SETATTR(true, false, false, false); SETATTR(true, false, false, true);
+  SETATTR(false, true, true, true); SETATTR(false, true, true, false); SETATTR(false, true, false, true); SETATTR(false, true, false, false);
+#undef SETATTR
+  h->use_tma = true;
   return UDGPU_OK;
 }
 
@@ -302,6 +373,7 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
   }
   RET(make_plan(h, g.itot, &h->px));
   RET(make_plan(h, g.jtot, &h->py));
+  RET(setup_momtend_tma(h));
   {
     const int hmax = (h->px.h > h->py.h ? h->px.h : h->py.h);
     const size_t smem = (size_t)hmax * FFT_BP * sizeof(double2);
@@ -345,6 +417,7 @@ extern "C" int udgpu_field_count(udgpu_t *h, int field, size_t *count, int dims[
 
 extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
   RET(check_field(h, field, n4));
+  RET(flush_pending(h));
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(h->f[field] + (size_t)n4 * h->cnt[field], host, h->cnt[field] * sizeof(double), cudaMemcpyHostToDevice, h->st));
   if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP) h->tend_zero = false;
@@ -352,6 +425,7 @@ extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
 }
 extern "C" int udgpu_pull(udgpu_t *h, int field, int n4, double *host) {
   RET(check_field(h, field, n4));
+  RET(flush_pending(h));
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(host, h->f[field] + (size_t)n4 * h->cnt[field], h->cnt[field] * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
@@ -400,6 +474,7 @@ static int wrap_xy(udgpu *h, std::initializer_list<double *> fields, int nlev) {
 
 extern "C" int udgpu_closure(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(flush_pending(h));
   const Geo &g = h->g;
   ProfScope ps(h, PROF_CLOSURE);
   const dim3 gr = grid3(g, B3);
@@ -423,7 +498,7 @@ extern "C" int udgpu_closure(udgpu_t *h) {
 }
 
 template <bool ADV, bool DIFF>
-static int launch_momtend(udgpu *h, bool acc) {
+static int launch_momtend_v1(udgpu *h, bool acc) {
   const Geo &g = h->g;
   const dim3 gr = grid3(g, B3);
   const bool les = g.lles != 0;
@@ -439,19 +514,57 @@ static int launch_momtend(udgpu *h, bool acc) {
   return UDGPU_OK;
 }
 
-extern "C" int udgpu_advection(udgpu_t *h) {
-  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+template <bool ADV, bool DIFF>
+static int launch_momtend(udgpu *h, bool acc) {
+  const Geo &g = h->g;
+  const bool les = g.lles != 0;
+  if (h->use_tma) {
+    const MomTmaParams &P = h->mtp;
+#define LAUNCH(ACC, LES) \
+  k_momtend_tma<ADV, DIFF, (DIFF && LES), ACC><<<h->mt_grid, MT_THREADS, MT_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->tm[3], h->tm[4], P)
+    if (acc) { if (les) LAUNCH(true, true); else LAUNCH(true, false); }
+    else { if (les) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+  } else {
+    const dim3 gr = grid3(g, B3);
+    if (ADV && DIFF) {  // the direct kernels are instantiated per operator only
+      RET((launch_momtend_v1<true, false>(h, acc)));
+      return launch_momtend_v1<false, true>(h, true);
+    }
+    (void)gr;
+    return launch_momtend_v1<ADV, DIFF>(h, acc);
+  }
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+
+// run a deferred advection() on its own (something needs the tendencies before subgrid())
+static int flush_pending(udgpu *h) {
+  if (!h->adv_pending) return UDGPU_OK;
+  h->adv_pending = false;
   ProfScope ps(h, PROF_MOM);
   RET((launch_momtend<true, false>(h, !h->tend_zero)));
   h->tend_zero = false;
   return UDGPU_OK;
 }
 
+extern "C" int udgpu_advection(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(flush_pending(h));
+  h->adv_pending = true;   // fused into subgrid() (closure must run first: the fused kernel needs ekm)
+  if (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION) RET(flush_pending(h));
+  return UDGPU_OK;
+}
+
 extern "C" int udgpu_subgrid(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const bool fuse = h->adv_pending;
+  h->adv_pending = false;
   RET(udgpu_closure(h));
   ProfScope ps(h, PROF_MOM);
-  RET((launch_momtend<false, true>(h, !h->tend_zero)));
+  if (fuse) RET((launch_momtend<true, true>(h, !h->tend_zero)));
+  else RET((launch_momtend<false, true>(h, !h->tend_zero)));
   h->tend_zero = false;
   return UDGPU_OK;
 }
@@ -497,6 +610,7 @@ static int poisson_core(udgpu *h, double *work, double *p_halo) {
 
 extern "C" int udgpu_poisson_solve_resident(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(flush_pending(h));
   return poisson_core(h, h->f[UDGPU_RHS], nullptr);
 }
 
@@ -512,6 +626,7 @@ extern "C" int udgpu_poisson_solve(udgpu_t *h, const double *rhs, double *p) {
 
 extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(flush_pending(h));
   const Geo &g = h->g;
   ProfScope ps(h, PROF_FILLPS);
   const double rk3coef = (rk3step == 0) ? 1. : dt / (4. - (double)rk3step);
@@ -525,6 +640,7 @@ extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
 
 extern "C" int udgpu_tderive(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(flush_pending(h));
   const Geo &g = h->g;
   ProfScope ps(h, PROF_INTEG);
   RET(wrap_xy(h, {h->f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
@@ -547,6 +663,7 @@ extern "C" int udgpu_poisson(udgpu_t *h, double dt, int rk3step) {
 
 extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(flush_pending(h));
   const Geo &g = h->g;
   ProfScope ps(h, PROF_INTEG);
   const double rk3coef = dt / (4. - (double)rk3step);
@@ -565,6 +682,7 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
 
 extern "C" int udgpu_halos(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(flush_pending(h));
   const Geo &g = h->g;
   ProfScope ps(h, PROF_HALO);
   double **f = h->f;
@@ -574,6 +692,7 @@ extern "C" int udgpu_halos(udgpu_t *h) {
 
 extern "C" int udgpu_boundary(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(flush_pending(h));
   const Geo &g = h->g;
   ProfScope ps(h, PROF_HALO);
   double **f = h->f;
@@ -609,6 +728,7 @@ extern "C" int udgpu_tstep_update(udgpu_t *h, double *dt, double courant, double
 
 extern "C" int udgpu_divergence(udgpu_t *h, double *divmax, double *divtot, double *divrms) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(flush_pending(h));
   const Geo &g = h->g;
   double **f = h->f;
   CU(cudaMemsetAsync(h->d_red + 4, 0, 3 * sizeof(double), h->st));
