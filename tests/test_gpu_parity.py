@@ -32,7 +32,7 @@ def test_closure(shape, model):
 F_NO_LAZY, F_V1 = 1, 8
 
 
-@pytest.mark.parametrize("shape", SIZES + [(96, 40, 12), (34, 18, 5)])
+@pytest.mark.parametrize("shape", SIZES + [(96, 40, 12), (36, 18, 5)])
 @pytest.mark.parametrize("kw", [dict(), dict(lvreman=False, lsmagorinsky=False), dict(BCtopm=2, Uinf=1.0, Vinf=0.2)])
 @pytest.mark.parametrize("flags", [0, F_V1])
 def test_fused_advection_subgrid(shape, kw, flags):
