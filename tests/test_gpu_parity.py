@@ -13,6 +13,8 @@ pytestmark = pytest.mark.gpu
 TOL_STENCIL = 1e-12
 TOL_PRES = 1e-10
 
+F_NO_LAZY, F_V1 = 1, 8
+
 SIZES = [(16, 16, 16), (32, 24, 20), (64, 64, 64), (48, 40, 33), (20, 36, 7)]
 
 
@@ -27,9 +29,6 @@ def test_closure(shape, model):
         assert relerr(a, b) < TOL_STENCIL, name          # whole array incl. all ghost cells
     # reassure_fluxtop touched the top ghosts of u0/v0
     assert relerr(g.pull("u0"), o.u0) == 0.0
-
-
-F_NO_LAZY, F_V1 = 1, 8
 
 
 @pytest.mark.parametrize("shape", SIZES + [(96, 40, 12), (36, 18, 5)])
@@ -60,9 +59,11 @@ def test_advection_and_subgrid(shape, kw, flags):
         assert relerr(tend_interior(g.pull(n)), tend_interior(getattr(o, n))) < TOL_STENCIL, n
 
 
-@pytest.mark.parametrize("shape", SIZES + [(12, 10, 8), (30, 18, 9), (128, 64, 32)])
-def test_poisson_solve(shape):
-    o, g = make_pair(*shape)
+@pytest.mark.parametrize("shape", SIZES + [(12, 10, 8), (30, 18, 9), (128, 64, 32), (256, 64, 8), (64, 256, 9), (512, 128, 4),
+                                           (128, 512, 5), (1024, 64, 3), (64, 1024, 4), (96, 64, 16), (256, 100, 6)])
+@pytest.mark.parametrize("flags", [0, F_V1])
+def test_poisson_solve(shape, flags):
+    o, g = make_pair(*shape, gpu_flags=flags)
     rng = np.random.default_rng(5)
     rhs = rng.standard_normal(shape)
     p_ref = o.poisson_solve(rhs)

@@ -1,0 +1,355 @@
+// poisson_fast.cuh — tuned Poisson kernels for power-of-two line lengths (64..1024):
+//   * k_rfft_fast: batched real FFT with the reference's half-complex packing and 1/sqrt(n) scaling
+//     (src/modpois.f90:478-490, :522-534 forward; :615-625, :669-679 inverse).  A length-n real line is
+//     a length-h = n/2 complex FFT of z[m] = x[2m] + i x[2m+1] plus a split (forward) / merge
+//     (inverse) pass.  h = R1*R2: every thread does one radix-R1 DFT entirely in registers, a twiddle,
+//     ONE shared-memory exchange, then radix-R2 DFTs in registers (four-step FFT).  Lanes of a warp
+//     run over the batch (32 neighbouring lines), so all index arithmetic is warp-uniform and every
+//     shared-memory access is conflict-free; y lines (stride = row pitch) are read/written straight
+//     from/to global memory, coalesced over the lanes; x lines (contiguous) are staged through a
+//     padded shared-memory tile so global traffic stays coalesced along the line.
+//   * k_zfactor / k_zsolve: the tridiagonal solve of solmpj (src/modpois.f90:1107-1166).  The Thomas
+//     factors 1/(b_k + lambda - a_k d_{k-1}) depend only on the eigenvalue lambda = xrt(i) + yrt(j) and
+//     the packed slots (2m, 2m+1) share eigenvalues (src/modpois.f90:100-107), so they are tabulated
+//     once per distinct (lambda_x, lambda_y) pair (N/4 values).  The per-solve sweeps are then pure
+//     FMA recurrences streamed with deep software prefetch, no divisions, no d scratch array.
+#pragma once
+#include "common.cuh"
+#include "poisson_v1.cuh"
+
+namespace udg {
+
+// exp(-2 pi i k / 32) = (w32c(k), -w32s(k)); octant table, exactly symmetric
+__host__ __device__ constexpr double w32q(int k) {
+  return k == 0 ? 1.0 : k == 1 ? 0.9807852804032304 : k == 2 ? 0.9238795325112867 : k == 3 ? 0.8314696123025452
+       : k == 4 ? 0.7071067811865476 : k == 5 ? 0.5555702330196022 : k == 6 ? 0.3826834323650898
+       : k == 7 ? 0.1950903220161283 : 0.0;
+}
+__host__ __device__ constexpr double w32c(int k) {  // cos(2 pi k / 32), 0 <= k < 32
+  return k <= 8 ? w32q(k) : k <= 16 ? -w32q(16 - k) : k <= 24 ? -w32q(k - 16) : w32q(32 - k);
+}
+__host__ __device__ constexpr double w32s(int k) {  // sin(2 pi k / 32)
+  return k <= 8 ? w32q(8 - k) : k <= 16 ? w32q(k - 8) : k <= 24 ? -w32q(24 - k) : -w32q(k - 24);
+}
+template <int R>
+__host__ __device__ constexpr int brev(int k) {
+  int r = 0;
+  for (int b = 1; b < R; b <<= 1) { r = (r << 1) | (k & 1); k >>= 1; }
+  return r;
+}
+
+// in-register radix-2 DIF DFT of R points (R <= 32); result in bit-reversed order: X[k] = v[brev<R>(k)]
+template <int R, bool INV>
+__device__ __forceinline__ void dft_reg(double2 (&v)[R]) {
+#pragma unroll
+  for (int half = R / 2; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int blk = 0; blk < R; blk += 2 * half) {
+#pragma unroll
+      for (int t = 0; t < half; t++) {
+        const int i0 = blk + t, i1 = i0 + half;
+        const double2 a = v[i0], b = v[i1];
+        v[i0] = make_double2(a.x + b.x, a.y + b.y);
+        const double dx = a.x - b.x, dy = a.y - b.y;
+        const int e = t * (16 / half);  // twiddle exp(-/+ 2 pi i e / 32)
+        if (e == 0) v[i1] = make_double2(dx, dy);
+        else if (e == 8) v[i1] = INV ? make_double2(-dy, dx) : make_double2(dy, -dx);
+        else {
+          const double c = w32c(e), s = w32s(e);
+          v[i1] = INV ? make_double2(dx * c - dy * s, dy * c + dx * s) : make_double2(dx * c + dy * s, dy * c - dx * s);
+        }
+      }
+    }
+  }
+}
+
+template <int R1, int R2, int LANES, bool XDIR>
+struct RfftCfg {
+  static constexpr int H = R1 * R2, N = 2 * H, NT = LANES * R2;
+  static constexpr int SMEM = XDIR ? LANES * (H + 1) * 16 : LANES * H * 16;
+};
+
+template <int R1, int R2, int LANES, bool XDIR, bool INV>
+__global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restrict__ tw, const double *__restrict__ in, LineDesc di,
+                                                         double *__restrict__ out, LineDesc dd, double fac) {
+  constexpr int H = R1 * R2, N = 2 * H, NT = LANES * R2;
+  constexpr int NK1 = R1 / R2;            // pass-2 DFTs per thread
+  constexpr int NPAIR = (H / 2) / R2 + 1;  // split/merge pairs per thread (k = j, j+R2, ... <= H/2)
+  static_assert(R1 % R2 == 0, "R1 must be a multiple of R2");
+  extern __shared__ double2 buf[];
+  double *rbuf = reinterpret_cast<double *>(buf);
+  const int lane = threadIdx.x, j = threadIdx.y, tid = j * LANES + lane;
+  const int b0 = blockIdx.x * LANES;
+  const int nb = min(LANES, di.nb1 - b0);
+  const bool act = lane < nb;
+  const long long ibase = (long long)blockIdx.y * di.s2 + (long long)b0 * di.s1;
+  const long long obase = (long long)blockIdx.y * dd.s2 + (long long)b0 * dd.s1;
+#define SA(p) (XDIR ? (lane * (H + 1) + (p)) : ((p)*LANES + lane))
+#define RS(r) (lane * 2 * (H + 1) + (r))  /* real slot r of this lane's line in the x staging tile */
+
+  double2 v[R1];
+  if (!INV) {
+    if (XDIR) {
+      for (int idx = tid; idx < nb * H; idx += NT) {
+        const int b = idx / H, m = idx - b * H;
+        const double *q = in + ibase + b * di.s1 + 2 * m;
+        buf[b * (H + 1) + m] = make_double2(q[0], q[1]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < R1; q++) v[q] = buf[SA(j + R2 * q)];
+      __syncthreads();
+    } else if (act) {
+      const double *p = in + ibase + lane * di.s1;
+#pragma unroll
+      for (int q = 0; q < R1; q++) {
+        const long long m = j + R2 * q;
+        v[q] = make_double2(p[(2 * m) * di.sp], p[(2 * m + 1) * di.sp]);
+      }
+    }
+  } else {
+    // merge: Z[k] = A + T, Z[h-k] = conj(A - T), A = Xk + conj(Xhk), T = i conj(w^k) (Xk - conj(Xhk))
+    if (XDIR) {
+      for (int idx = tid; idx < nb * H; idx += NT) {
+        const int b = idx / H, m = idx - b * H;
+        const double *q = in + ibase + b * di.s1 + 2 * m;
+        buf[b * (H + 1) + m] = make_double2(q[0], q[1]);
+      }
+      __syncthreads();
+    }
+    double2 zk[NPAIR], zh[NPAIR];
+#pragma unroll
+    for (int t = 0; t < NPAIR; t++) {
+      const int k = j + R2 * t;
+      zk[t] = zh[t] = make_double2(0., 0.);
+      if (k <= H / 2 && act) {
+        double x0, x1, y0, y1;
+        if (k == 0) {
+          if (XDIR) { x0 = rbuf[RS(0)]; y0 = rbuf[RS(N - 1)]; }
+          else { const double *p = in + ibase + lane * di.s1; x0 = p[0]; y0 = p[(long long)(N - 1) * di.sp]; }
+          zk[t] = make_double2(x0 + y0, x0 - y0);
+        } else {
+          if (XDIR) { x0 = rbuf[RS(2 * k - 1)]; x1 = rbuf[RS(2 * k)]; y0 = rbuf[RS(2 * (H - k) - 1)]; y1 = rbuf[RS(2 * (H - k))]; }
+          else {
+            const double *p = in + ibase + lane * di.s1;
+            x0 = p[(long long)(2 * k - 1) * di.sp]; x1 = p[(long long)(2 * k) * di.sp];
+            y0 = p[(long long)(2 * (H - k) - 1) * di.sp]; y1 = p[(long long)(2 * (H - k)) * di.sp];
+          }
+          const double2 A = make_double2(x0 + y0, x1 - y1), Bv = make_double2(x0 - y0, x1 + y1);
+          const double2 w = tw[k];
+          const double2 T = cmul(make_double2(w.y, w.x), Bv);
+          zk[t] = cadd(A, T);
+          zh[t] = cconj(csub(A, T));
+        }
+      }
+    }
+    if (XDIR) __syncthreads();
+#pragma unroll
+    for (int t = 0; t < NPAIR; t++) {
+      const int k = j + R2 * t;
+      if (k <= H / 2) {
+        if (k != 0 && k != H - k) buf[SA(H - k)] = zh[t];
+        buf[SA(k)] = zk[t];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < R1; q++) v[q] = buf[SA(j + R2 * q)];
+    __syncthreads();
+  }
+
+  // ---- pass 1: radix-R1 over q, twiddle W_h^{j k1}, exchange ----
+  dft_reg<R1, INV>(v);
+#pragma unroll
+  for (int k1 = 0; k1 < R1; k1++) {
+    double2 y = v[brev<R1>(k1)];
+    if (k1 != 0) {
+      double2 w = tw[2 * j * k1];  // W_h^{j k1} = exp(-2 pi i 2 j k1 / n);  j*k1 < h so 2 j k1 < n
+      if (INV) w.y = -w.y;
+      y = cmul(y, w);
+    }
+    buf[SA(k1 * R2 + j)] = y;
+  }
+  __syncthreads();
+  // ---- pass 2: radix-R2 over j for k1 = j + R2*t ----
+  double2 u[NK1][R2];
+#pragma unroll
+  for (int t = 0; t < NK1; t++) {
+    const int k1 = j + R2 * t;
+#pragma unroll
+    for (int jj = 0; jj < R2; jj++) u[t][jj] = buf[SA(k1 * R2 + jj)];
+    dft_reg<R2, INV>(u[t]);
+  }
+
+  if (!INV) {
+    __syncthreads();
+    // natural order: Z[k1 + R1 k2]
+#pragma unroll
+    for (int t = 0; t < NK1; t++)
+#pragma unroll
+      for (int k2 = 0; k2 < R2; k2++) buf[SA(j + R2 * t + R1 * k2)] = u[t][brev<R2>(k2)];
+    __syncthreads();
+    // split: X[k] = E + T, X[h-k] = conj(E - T), E = (Zk + conj Zhk)/2, T = -i/2 w^k (Zk - conj Zhk)
+    double2 xk[NPAIR], xh[NPAIR];
+#pragma unroll
+    for (int t = 0; t < NPAIR; t++) {
+      const int k = j + R2 * t;
+      xk[t] = xh[t] = make_double2(0., 0.);
+      if (k <= H / 2) {
+        const double2 Zk = buf[SA(k)];
+        if (k == 0) {
+          xk[t] = make_double2((Zk.x + Zk.y) * fac, (Zk.x - Zk.y) * fac);  // (X0, Xh) both real
+        } else {
+          const double2 Zc = cconj(buf[SA(H - k)]);
+          const double2 E = make_double2(0.5 * (Zk.x + Zc.x), 0.5 * (Zk.y + Zc.y));
+          const double2 D = csub(Zk, Zc);
+          const double2 w = tw[k];
+          const double2 T = cmul(make_double2(0.5 * w.y, -0.5 * w.x), D);
+          const double2 a = cadd(E, T), b = cconj(csub(E, T));
+          xk[t] = make_double2(a.x * fac, a.y * fac);
+          xh[t] = make_double2(b.x * fac, b.y * fac);
+        }
+      }
+    }
+    if (XDIR) {
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < NPAIR; t++) {
+        const int k = j + R2 * t;
+        if (k <= H / 2) {
+          if (k == 0) { rbuf[RS(0)] = xk[t].x; rbuf[RS(N - 1)] = xk[t].y; }
+          else {
+            rbuf[RS(2 * k - 1)] = xk[t].x; rbuf[RS(2 * k)] = xk[t].y;
+            rbuf[RS(2 * (H - k) - 1)] = xh[t].x; rbuf[RS(2 * (H - k))] = xh[t].y;
+          }
+        }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < nb * H; idx += NT) {
+        const int b = idx / H, m = idx - b * H;
+        const double2 z = buf[b * (H + 1) + m];
+        double *q = out + obase + b * dd.s1 + 2 * m;
+        q[0] = z.x; q[1] = z.y;
+      }
+    } else if (act) {
+      double *p = out + obase + lane * dd.s1;
+#pragma unroll
+      for (int t = 0; t < NPAIR; t++) {
+        const int k = j + R2 * t;
+        if (k <= H / 2) {
+          if (k == 0) { p[0] = xk[t].x; p[(long long)(N - 1) * dd.sp] = xk[t].y; }
+          else {
+            p[(long long)(2 * k - 1) * dd.sp] = xk[t].x; p[(long long)(2 * k) * dd.sp] = xk[t].y;
+            p[(long long)(2 * (H - k) - 1) * dd.sp] = xh[t].x; p[(long long)(2 * (H - k)) * dd.sp] = xh[t].y;
+          }
+        }
+      }
+    }
+  } else {
+    // inverse: z[m], m = k1 + R1 k2 -> x[2m] = Re, x[2m+1] = Im, times fac
+    if (XDIR) {
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < NK1; t++)
+#pragma unroll
+        for (int k2 = 0; k2 < R2; k2++) {
+          const double2 z = u[t][brev<R2>(k2)];
+          buf[SA(j + R2 * t + R1 * k2)] = make_double2(z.x * fac, z.y * fac);
+        }
+      __syncthreads();
+      for (int idx = tid; idx < nb * H; idx += NT) {
+        const int b = idx / H, m = idx - b * H;
+        const double2 z = buf[b * (H + 1) + m];
+        double *q = out + obase + b * dd.s1 + 2 * m;
+        q[0] = z.x; q[1] = z.y;
+      }
+    } else if (act) {
+      double *p = out + obase + lane * dd.s1;
+#pragma unroll
+      for (int t = 0; t < NK1; t++)
+#pragma unroll
+        for (int k2 = 0; k2 < R2; k2++) {
+          const long long m = j + R2 * t + R1 * k2;
+          const double2 z = u[t][brev<R2>(k2)];
+          p[(2 * m) * dd.sp] = z.x * fac;
+          p[(2 * m + 1) * dd.sp] = z.y * fac;
+        }
+    }
+  }
+#undef SA
+#undef RS
+}
+
+// ---------------------------------------------------------------------------------------------
+// Thomas factor table.  zt[(k*nyh + jy)*nxh + ix] = 1 / (bb_k - a_k d_{k-1}), d_k = c_k z_k, for the
+// eigenvalue pair lambda = xd[ix] + yd[jy] (distinct eigenvalues: ix = 0..itot/2, jy = 0..jtot/2).
+// Same recurrence and special cases as src/modpois.f90:1120-1155 with bxyzrt of :196-220.
+__global__ void k_zfactor(int nxh, int nyh, int K, const double *__restrict__ xd, const double *__restrict__ yd,
+                          const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ c,
+                          double b_top_D, double *__restrict__ zt) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x, jy = blockIdx.y;
+  if (ix >= nxh) return;
+  const double lam = xd[ix] + yd[jy];
+  const long long sk = (long long)nxh * nyh;
+  long long q = (long long)jy * nxh + ix;
+  double bb = (lam == 0. && K == 1) ? b_top_D : b[0] + lam;
+  double z = 1. / bb, d = c[0] * z;
+  zt[q] = z;
+  for (int k = 1; k < K; k++) {
+    q += sk;
+    bb = (k == K - 1 && lam == 0.) ? b_top_D : b[k] + lam;
+    z = 1. / (bb - a[k] * d);
+    d = c[k] * z;
+    zt[q] = z;
+  }
+}
+
+// One thread per (i,j) column of the halo-free spectral array x(imax,jmax,K); forward then backward
+// sweep in place.  ZU levels are prefetched ahead of the recurrence.
+constexpr int ZU = 8;
+__global__ void __launch_bounds__(128) k_zsolve(Geo g, int nxh, int nyh, double *__restrict__ x, const double *__restrict__ zt,
+                                                const double *__restrict__ a, const double *__restrict__ c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= g.imax) return;
+  const int K = g.ktot;
+  const int ig = g.i0g + i, jg = g.j0g + j;       // global packed slot (0-based) -> distinct-eigenvalue index
+  const int ix = (ig + 1) >> 1, jy = (jg + 1) >> 1;
+  const long long sk = (long long)g.imax * g.jmax, tk = (long long)nxh * nyh;
+  double *xp = x + (long long)i + (long long)g.imax * j;
+  const double *zp = zt + (long long)jy * nxh + ix;
+  double xprev = 0.;
+  int k = 0;
+  for (; k + ZU <= K; k += ZU) {
+    double xv[ZU], zv[ZU];
+#pragma unroll
+    for (int u = 0; u < ZU; u++) { xv[u] = xp[(k + u) * sk]; zv[u] = __ldg(zp + (k + u) * tk); }
+#pragma unroll
+    for (int u = 0; u < ZU; u++) {
+      xprev = (xv[u] - __ldg(a + k + u) * xprev) * zv[u];
+      xp[(k + u) * sk] = xprev;
+    }
+  }
+  for (; k < K; k++) {
+    xprev = (xp[k * sk] - __ldg(a + k) * xprev) * __ldg(zp + k * tk);
+    xp[k * sk] = xprev;
+  }
+  // backward: x_k = x'_k - d_k x_{k+1}, d_k = c_k z_k  (c_{K-1} = 0)
+  double xnext = xprev;
+  k = K - 2;
+  for (; k - ZU + 1 >= 0; k -= ZU) {
+    double xv[ZU], zv[ZU];
+#pragma unroll
+    for (int u = 0; u < ZU; u++) { xv[u] = xp[(k - u) * sk]; zv[u] = __ldg(zp + (k - u) * tk); }
+#pragma unroll
+    for (int u = 0; u < ZU; u++) {
+      xnext = xv[u] - (__ldg(c + k - u) * zv[u]) * xnext;
+      xp[(k - u) * sk] = xnext;
+    }
+  }
+  for (; k >= 0; k--) {
+    xnext = xp[k * sk] - (__ldg(c + k) * __ldg(zp + k * tk)) * xnext;
+    xp[k * sk] = xnext;
+  }
+}
+
+}  // namespace udg

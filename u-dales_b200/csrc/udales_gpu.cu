@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "momtend_tma.cuh"
 #include "poisson_v1.cuh"
+#include "poisson_fast.cuh"
 #include "stencil_v1.cuh"
 
 using namespace udg;
@@ -66,6 +67,9 @@ struct udgpu {
   double *d_xrt = nullptr, *d_yrt = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;
   double b_top_D = 0;
   FftPlan px, py;
+  bool fast_x = false, fast_y = false, fast_z = false;
+  double *d_zt = nullptr, *d_xd = nullptr, *d_yd = nullptr;
+  int nxh = 0, nyh = 0;
   // reductions
   double *d_red = nullptr, *h_red = nullptr;
   // TMA path of the fused momentum kernel
@@ -84,6 +88,7 @@ struct udgpu {
 
 // ------------------------------------------------------------------------------------------
 static int flush_pending(udgpu *h);
+static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt);
 static int dev_alloc(udgpu *h, void **p, size_t bytes) {
   CU(cudaMalloc(p, bytes ? bytes : 8));
   CU(cudaMemsetAsync(*p, 0, bytes ? bytes : 8, h->st));
@@ -370,6 +375,7 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     CU(cudaMemcpyAsync(h->d_b, b.data(), K * sizeof(double), cudaMemcpyHostToDevice, h->st));
     CU(cudaMemcpyAsync(h->d_c, cc.data(), K * sizeof(double), cudaMemcpyHostToDevice, h->st));
     CU(cudaStreamSynchronize(h->st));
+    RET(setup_poisson_fast_fwd(h, xrt, yrt));
   }
   RET(make_plan(h, g.itot, &h->px));
   RET(make_plan(h, g.jtot, &h->py));
@@ -569,6 +575,74 @@ extern "C" int udgpu_subgrid(udgpu_t *h) {
   return UDGPU_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// fast power-of-two FFT dispatch: n -> (R1, R2, LANES)
+template <int R1, int R2, int LANES, bool XDIR>
+static int rfft_fast_launch(udgpu *h, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl) {
+  using C = RfftCfg<R1, R2, LANES, XDIR>;
+  const dim3 grid((di.nb1 + LANES - 1) / LANES, di.nb2), block(LANES, R2);
+  if (inverse) k_rfft_fast<R1, R2, LANES, XDIR, true><<<grid, block, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac);
+  else k_rfft_fast<R1, R2, LANES, XDIR, false><<<grid, block, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac);
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+template <int R1, int R2, int LANES, bool XDIR>
+static int rfft_fast_attr() {
+  using C = RfftCfg<R1, R2, LANES, XDIR>;
+  CU(cudaFuncSetAttribute(k_rfft_fast<R1, R2, LANES, XDIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  CU(cudaFuncSetAttribute(k_rfft_fast<R1, R2, LANES, XDIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  return UDGPU_OK;
+}
+static bool fast_len(int n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024; }
+template <bool XDIR>
+static int rfft_fast(udgpu *h, int n, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl) {
+  switch (n) {
+    case 64: return rfft_fast_launch<8, 4, 32, XDIR>(h, inverse, in, di, out, dd, pl);
+    case 128: return rfft_fast_launch<8, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl);
+    case 256: return rfft_fast_launch<16, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl);
+    case 512: return rfft_fast_launch<16, 16, 16, XDIR>(h, inverse, in, di, out, dd, pl);
+    case 1024: return rfft_fast_launch<32, 16, 8, XDIR>(h, inverse, in, di, out, dd, pl);
+  }
+  return set_err(UDGPU_EINVAL, "no fast FFT for n=%d", n);
+}
+template <bool XDIR>
+static int rfft_fast_setattr(int n) {
+  switch (n) {
+    case 64: return rfft_fast_attr<8, 4, 32, XDIR>();
+    case 128: return rfft_fast_attr<8, 8, 32, XDIR>();
+    case 256: return rfft_fast_attr<16, 8, 32, XDIR>();
+    case 512: return rfft_fast_attr<16, 16, 16, XDIR>();
+    case 1024: return rfft_fast_attr<32, 16, 8, XDIR>();
+  }
+  return UDGPU_OK;
+}
+
+static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt) {
+  const Geo &g = h->g;
+  if (h->cfg.flags & UDGPU_F_V1_KERNELS) return UDGPU_OK;
+  h->fast_x = fast_len(g.itot) && g.imax == g.itot;
+  h->fast_y = fast_len(g.jtot) && g.jmax == g.jtot;
+  if (h->fast_x) RET(rfft_fast_setattr<true>(g.itot));
+  if (h->fast_y) RET(rfft_fast_setattr<false>(g.jtot));
+  // distinct eigenvalues: slot s (0-based) -> index (s+1)/2   (src/modpois.f90:100-107)
+  h->nxh = g.itot / 2 + 1; h->nyh = g.jtot / 2 + 1;
+  std::vector<double> xd(h->nxh), yd(h->nyh);
+  for (int s = 0; s < g.itot; s++) xd[(s + 1) >> 1] = xrt[s];
+  for (int s = 0; s < g.jtot; s++) yd[(s + 1) >> 1] = yrt[s];
+  RET(dev_alloc(h, (void **)&h->d_xd, h->nxh * sizeof(double)));
+  RET(dev_alloc(h, (void **)&h->d_yd, h->nyh * sizeof(double)));
+  RET(dev_alloc(h, (void **)&h->d_zt, (size_t)h->nxh * h->nyh * g.ktot * sizeof(double)));
+  CU(cudaMemcpyAsync(h->d_xd, xd.data(), h->nxh * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_yd, yd.data(), h->nyh * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  k_zfactor<<<dim3((h->nxh + 127) / 128, h->nyh), 128, 0, h->st>>>(h->nxh, h->nyh, g.ktot, h->d_xd, h->d_yd, h->d_a, h->d_b, h->d_c, h->b_top_D, h->d_zt);
+  KCHECK();
+  CU(cudaStreamSynchronize(h->st));
+  h->fast_z = true;
+  return UDGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *out, bool out_halo) {
   const Geo &g = h->g;
@@ -578,12 +652,14 @@ static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *
     di = {1, pr, pp, g.jmax, g.ktot};
     dd = di;
     if (out_halo) { dd.s1 = g.pi; dd.s2 = g.pk; }
+    if (h->fast_x) return rfft_fast<true>(h, g.itot, inverse, in, di, out, dd, h->px);
     const size_t smem = (size_t)h->px.h * FFT_BP * sizeof(double2);
     k_rfft<true><<<dim3((g.jmax + FFT_B - 1) / FFT_B, g.ktot), dim3(FFT_B, FFT_TY), smem, h->st>>>(h->px, inverse, in, di, out, dd);
   } else {
     di = {pr, 1, pp, g.imax, g.ktot};
     dd = di;
     if (out_halo) { dd.sp = g.pi; dd.s2 = g.pk; }
+    if (h->fast_y) return rfft_fast<false>(h, g.jtot, inverse, in, di, out, dd, h->py);
     const size_t smem = (size_t)h->py.h * FFT_BP * sizeof(double2);
     k_rfft<false><<<dim3((g.imax + FFT_B - 1) / FFT_B, g.ktot), dim3(FFT_B, FFT_TY), smem, h->st>>>(h->py, inverse, in, di, out, dd);
   }
@@ -599,7 +675,8 @@ static int poisson_core(udgpu *h, double *work, double *p_halo) {
   ProfScope ps(h, PROF_POIS);
   RET(fft_pass(h, true, 0, work, work, false));
   RET(fft_pass(h, false, 0, work, work, false));
-  k_solmpj<<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, work, h->d_scr, h->d_xrt, h->d_yrt, h->d_a, h->d_b, h->d_c, h->b_top_D);
+  if (h->fast_z) k_zsolve<<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, h->nxh, h->nyh, work, h->d_zt, h->d_a, h->d_c);
+  else k_solmpj<<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, work, h->d_scr, h->d_xrt, h->d_yrt, h->d_a, h->d_b, h->d_c, h->b_top_D);
   KCHECK();
   h->launches++;
   RET(fft_pass(h, false, 1, work, work, false));
