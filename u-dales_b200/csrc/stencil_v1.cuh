@@ -284,6 +284,55 @@ __global__ void k_pres_update(long long n, const double *__restrict__ p, double 
   for (; q < n; q += stride) pres0[q] = pres0[q] + p[q];
 }
 
+
+// tderive + tstep_integrate fused (src/modpois.f90:1046-1056,1096-1102 + src/modtstep.f90:171-340): one pass
+// that reads p (halo'd, after bcp), the tendencies and the m-fields and writes u0,v0,w0 and pres0 on
+// the interior; the projected tendencies themselves are never written back (they are zero after
+// tstep_integrate anyway, src/modtstep.f90:322-324).  STEP3: um = u0 too (:330-338).
+template <bool STEP3>
+__global__ void __launch_bounds__(256) k_tderive_integrate(Geo g, double rk3coef, const double *__restrict__ p,
+                                                           const double *__restrict__ up, const double *__restrict__ vp,
+                                                           const double *__restrict__ wp, double *__restrict__ um,
+                                                           double *__restrict__ vm, double *__restrict__ wm,
+                                                           double *__restrict__ u0, double *__restrict__ v0,
+                                                           double *__restrict__ w0, double *__restrict__ pres0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long c = offF(g, i, j, k), t = offT(g, i, j, k);
+  const double pc = p[c];
+  const double ru = up[t] - (pc - p[c - 1]) * g.dxi;
+  const double rv = vp[t] - (pc - p[c - g.pi]) * g.dyi;
+  double rw = wp[t];
+  if (k >= 2) rw = rw - (pc - p[c - g.pk]) * g.dzhi[k];
+  const double a = um[c] + rk3coef * ru;
+  const double b = vm[c] + rk3coef * rv;
+  const double d = wm[c] + rk3coef * rw;
+  u0[c] = a; v0[c] = b; w0[c] = d;
+  if (STEP3) { um[c] = a; vm[c] = b; wm[c] = d; }
+  pres0[c] = pres0[c] + pc;
+}
+// pres0 += p on the halo shell only (everything that is not an interior cell); the interior is done above.
+__global__ void k_pres_update_shell(Geo g, const double *__restrict__ p, double *__restrict__ pres0) {
+  const int lev = blockIdx.y;  // storage level 0 .. ktot+1
+  const long long base = (long long)lev * g.pk;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lev == 0 || lev == g.ktot + 1) {
+    for (long long q = tid; q < g.pk; q += (long long)gridDim.x * blockDim.x) pres0[base + q] += p[base + q];
+  } else {
+    // ring: rows 0 and pj-1 (pi each), columns 0 and pi-1 of rows 1..pj-2
+    const int nring = 2 * g.pi + 2 * (g.pj - 2);
+    for (int r = tid; r < nring; r += gridDim.x * blockDim.x) {
+      long long q;
+      if (r < g.pi) q = r;
+      else if (r < 2 * g.pi) q = (long long)(g.pj - 1) * g.pi + (r - g.pi);
+      else { const int rr = r - 2 * g.pi; q = (long long)(1 + (rr >> 1)) * g.pi + ((rr & 1) ? g.pi - 1 : 0); }
+      pres0[base + q] += p[base + q];
+    }
+  }
+}
+
 // tstep_integrate: src/modtstep.f90:171-340 for u,v,w.  ZERO: also zero the tendencies (:322-324);
 // STEP3: um = u0 on the interior (halos are refreshed by the following halos call, :330-338).
 template <bool ZERO, bool STEP3>

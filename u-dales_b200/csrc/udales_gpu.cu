@@ -79,8 +79,11 @@ struct udgpu {
   int mt_grid = 0;
   int nsm = 148;
   // state
+  bool tder_pending = false;  // poisson() solved for p; tderive is fused into the next tstep_integrate()
   bool adv_pending = false;   // advection() was called, its work is fused into the next subgrid()
-  bool tend_zero = false;
+  bool tend_zero = false;      // tendencies are (logically) zero: next tendency kernel may overwrite
+  bool tend_pushed = false;    // host wrote a tendency array (its halo cells may be non-zero): zero eagerly once
+  bool tend_lazy_zero = false; // ... and the zeros have not been written to memory yet
   bool prof = false;
   ProfSlot ps[PROF_N];
   long launches = 0;
@@ -88,6 +91,7 @@ struct udgpu {
 
 // ------------------------------------------------------------------------------------------
 static int flush_pending(udgpu *h);
+static int materialize_zero_tend(udgpu *h);
 static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt);
 static int dev_alloc(udgpu *h, void **p, size_t bytes) {
   CU(cudaMalloc(p, bytes ? bytes : 8));
@@ -424,14 +428,17 @@ extern "C" int udgpu_field_count(udgpu_t *h, int field, size_t *count, int dims[
 extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
   RET(check_field(h, field, n4));
   RET(flush_pending(h));
+  const bool is_tend = (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP);
+  if (is_tend) { RET(materialize_zero_tend(h)); h->tend_pushed = true; }
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(h->f[field] + (size_t)n4 * h->cnt[field], host, h->cnt[field] * sizeof(double), cudaMemcpyHostToDevice, h->st));
-  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP) h->tend_zero = false;
+  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP) h->tend_zero = false; h->tend_lazy_zero = false;
   return UDGPU_OK;
 }
 extern "C" int udgpu_pull(udgpu_t *h, int field, int n4, double *host) {
   RET(check_field(h, field, n4));
   RET(flush_pending(h));
+  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP) RET(materialize_zero_tend(h));
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(host, h->f[field] + (size_t)n4 * h->cnt[field], h->cnt[field] * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
@@ -546,12 +553,14 @@ static int launch_momtend(udgpu *h, bool acc) {
 }
 
 // run a deferred advection() on its own (something needs the tendencies before subgrid())
+static int tderive_now(udgpu *h);
 static int flush_pending(udgpu *h) {
+  if (h->tder_pending) { h->tder_pending = false; RET(tderive_now(h)); }
   if (!h->adv_pending) return UDGPU_OK;
   h->adv_pending = false;
   ProfScope ps(h, PROF_MOM);
   RET((launch_momtend<true, false>(h, !h->tend_zero)));
-  h->tend_zero = false;
+  h->tend_zero = false; h->tend_lazy_zero = false;
   return UDGPU_OK;
 }
 
@@ -571,7 +580,7 @@ extern "C" int udgpu_subgrid(udgpu_t *h) {
   ProfScope ps(h, PROF_MOM);
   if (fuse) RET((launch_momtend<true, true>(h, !h->tend_zero)));
   else RET((launch_momtend<false, true>(h, !h->tend_zero)));
-  h->tend_zero = false;
+  h->tend_zero = false; h->tend_lazy_zero = false;
   return UDGPU_OK;
 }
 
@@ -705,6 +714,7 @@ extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
   RET(flush_pending(h));
   const Geo &g = h->g;
+  RET(materialize_zero_tend(h));
   ProfScope ps(h, PROF_FILLPS);
   const double rk3coef = (rk3step == 0) ? 1. : dt / (4. - (double)rk3step);
   const double rk3coefi = 1. / rk3coef;
@@ -718,7 +728,19 @@ extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
 extern "C" int udgpu_tderive(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
   RET(flush_pending(h));
+  return tderive_now(h);
+}
+static int materialize_zero_tend(udgpu *h) {
+  // the fused integrate kernels do not spend bandwidth on up = vp = wp = 0 (src/modtstep.f90:322-324);
+  // the zeros are written only if somebody is about to look at (or accumulate into) the arrays
+  if (!h->tend_lazy_zero) return UDGPU_OK;
+  for (int f : {UDGPU_UP, UDGPU_VP, UDGPU_WP}) CU(cudaMemsetAsync(h->f[f], 0, h->cnt[f] * sizeof(double), h->st));
+  h->tend_lazy_zero = false;
+  return UDGPU_OK;
+}
+static int tderive_now(udgpu *h) {
   const Geo &g = h->g;
+  RET(materialize_zero_tend(h));
   ProfScope ps(h, PROF_INTEG);
   RET(wrap_xy(h, {h->f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
   k_tderive<<<grid3(g, B3), B3, 0, h->st>>>(g, h->f[UDGPU_P], h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP]);
@@ -726,7 +748,7 @@ extern "C" int udgpu_tderive(udgpu_t *h) {
   k_pres_update<<<148 * 8, 256, 0, h->st>>>((long long)h->cnt[UDGPU_PRES0], h->f[UDGPU_P], h->f[UDGPU_PRES0]);
   KCHECK();
   h->launches += 2;
-  h->tend_zero = false;
+  h->tend_zero = false; h->tend_lazy_zero = false;
   return UDGPU_OK;
 }
 
@@ -734,26 +756,48 @@ extern "C" int udgpu_poisson(udgpu_t *h, double dt, int rk3step) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
   RET(udgpu_fillps(h, dt, rk3step));
   RET(poisson_core(h, h->f[UDGPU_RHS], h->f[UDGPU_P]));
-  RET(udgpu_tderive(h));
+  if (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION) return tderive_now(h);
+  h->tder_pending = true;   // fused with tstep_integrate(); flushed on any other access
   return UDGPU_OK;
 }
 
 extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
-  RET(flush_pending(h));
   const Geo &g = h->g;
-  ProfScope ps(h, PROF_INTEG);
   const double rk3coef = dt / (4. - (double)rk3step);
   double **f = h->f;
+  if (h->tder_pending && !h->adv_pending) {
+    h->tder_pending = false;
+    ProfScope ps(h, PROF_INTEG);
+    RET(wrap_xy(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
+    if (rk3step == 3)
+      k_tderive_integrate<true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
+                                                                f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0]);
+    else
+      k_tderive_integrate<false><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
+                                                                 f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0]);
+    KCHECK();
+    k_pres_update_shell<<<dim3(8, g.ktot + 2 * g.kh), 256, 0, h->st>>>(g, f[UDGPU_P], f[UDGPU_PRES0]);
+    KCHECK();
+    h->launches += 2;
+    h->tend_zero = true;
+    h->tend_lazy_zero = true;
+    if (h->tend_pushed) { RET(materialize_zero_tend(h)); h->tend_pushed = false; }
+    return UDGPU_OK;
+  }
+  RET(flush_pending(h));
+  ProfScope ps(h, PROF_INTEG);
   if (rk3step == 3)
-    k_integrate<true, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM],
+    k_integrate<false, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM],
                                                             f[UDGPU_WM], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP]);
   else
-    k_integrate<true, false><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM],
+    k_integrate<false, false><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM],
                                                              f[UDGPU_WM], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP]);
   KCHECK();
   h->launches++;
   h->tend_zero = true;
+  h->tend_lazy_zero = true;
+  if (h->tend_pushed) { RET(materialize_zero_tend(h)); h->tend_pushed = false; }
   return UDGPU_OK;
 }
 
