@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 B_PER_CELL = {  # algorithmic (compulsory) fp64 bytes per cell, SURVEY.md §8d / DESIGN.md
-    "mom_tend": 64.0, "closure": 40.0, "poisson_core": 80.0, "fillps": 56.0, "tderive_integrate": 168.0, "halos": 0.0,
+    "mom_tend": 64.0, "closure": 40.0, "poisson_core": 80.0, "fillps": 56.0, "tderive_integrate": 96.0, "halos": 0.0,
 }
 PROF_NAMES = ["mom_tend", "closure", "poisson_core", "fillps", "tderive_integrate", "halos"]
 

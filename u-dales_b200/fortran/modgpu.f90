@@ -1,0 +1,303 @@
+!> \file modgpu.f90
+!! ISO_C_BINDING shim between the uDALES Fortran host (unchanged namelists, unchanged call
+!! surface of src/program.f90:132-207) and libudales_gpu.so (include/udales_gpu.h).
+!!
+!! This is the reference-side binding a maintainer adds as src/modgpu.f90.  It has not been
+!! compiled in the build container (no Fortran compiler there); every interface below is a 1:1
+!! image of a prototype in include/udales_gpu.h and the Python ctypes binding
+!! (u-dales_b200/__init__.py) exercises exactly the same symbols with the same argument shapes.
+!!
+!! Hook points (see INTEGRATION.md): first executable line of
+!!   tstep_update (modtstep.f90:49), advection (modadvection.f90:36), subgrid (modsubgrid.f90:128),
+!!   poisson (modpois.f90:419), tstep_integrate (modtstep.f90:171), halos (modboundary.f90:67),
+!!   boundary (modboundary.f90:115):
+!!     if (lgpu) then; call gpu_<name>(); return; end if
+!! and `call gpu_init` right after `call initpois` (program.f90:89), `call gpu_exit` in exitmodules.
+!! With -fdefault-real-8 (CMakeLists.txt:46) default real == real(c_double) and default integer ==
+!! integer(c_int); logicals are converted explicitly.
+module modgpu
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private
+  public :: lgpu, gpu_init, gpu_exit, gpu_push_state, gpu_pull_state, gpu_push, gpu_pull, &
+            gpu_tstep_update, gpu_advection, gpu_subgrid, gpu_poisson, gpu_tstep_integrate, &
+            gpu_halos, gpu_boundary, gpu_chkdiv
+
+  logical :: lgpu = .false.            !< namelist RUN switch (the only new option)
+  type(c_ptr) :: handle = c_null_ptr
+
+  ! field ids = enum udgpu_field
+  integer(c_int), parameter :: F_U0 = 0, F_V0 = 1, F_W0 = 2, F_UM = 3, F_VM = 4, F_WM = 5, &
+                               F_UP = 6, F_VP = 7, F_WP = 8, F_PRES0 = 9, F_P = 10, F_EKM = 11, &
+                               F_EKH = 12, F_RHS = 13, F_SV0 = 14, F_SVM = 15, F_SVP = 16
+
+  type, bind(C) :: udgpu_cfg
+    integer(c_int) :: abi_version
+    integer(c_int) :: itot, jtot, ktot
+    integer(c_int) :: imax, jmax, kmax
+    integer(c_int) :: ih, jh, kh
+    integer(c_int) :: ihc, jhc, khc
+    integer(c_int) :: nsv
+    integer(c_int) :: zstart(3)
+    integer(c_int) :: nprocx, nprocy
+    integer(c_int) :: myidx, myidy
+    integer(c_int) :: BCxm, BCym, BCtopm, BCzp
+    integer(c_int) :: ipoiss, iadv_mom, iadv_sv
+    integer(c_int) :: lles, lvreman, lsmagorinsky, loneeqn
+    integer(c_int) :: ltempeq, lmoist
+    real(c_double) :: dx, dy
+    type(c_ptr)    :: dzf, dzh, delta
+    real(c_double) :: numol, prandtlmoli, prandtli
+    real(c_double) :: c_vreman, cs
+    real(c_double) :: Uinf, Vinf
+    real(c_double) :: e12min
+    integer(c_int) :: device
+    integer(c_int) :: flags
+  end type udgpu_cfg
+
+  interface
+    integer(c_int) function udgpu_nccl_unique_id(uid) bind(C, name="udgpu_nccl_unique_id")
+      import :: c_int, c_char
+      character(kind=c_char) :: uid(128)
+    end function
+    integer(c_int) function udgpu_init(cfg, uid, h) bind(C, name="udgpu_init")
+      import :: c_int, c_ptr, udgpu_cfg
+      type(udgpu_cfg), intent(in) :: cfg
+      type(c_ptr), value :: uid
+      type(c_ptr), intent(out) :: h
+    end function
+    integer(c_int) function udgpu_finalize(h) bind(C, name="udgpu_finalize")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    function udgpu_last_error() bind(C, name="udgpu_last_error") result(msg)
+      import :: c_ptr
+      type(c_ptr) :: msg
+    end function
+    ! arrays are passed as assumed-size dummies (sequence association): um, up ... do not have the
+    ! TARGET attribute in modfields (src/modfields.f90:30-32,66-68), so c_loc is not an option.
+    integer(c_int) function udgpu_push(h, field, n4, host) bind(C, name="udgpu_push")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: field, n4
+      real(c_double), intent(in) :: host(*)
+    end function
+    integer(c_int) function udgpu_pull(h, field, n4, host) bind(C, name="udgpu_pull")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: field, n4
+      real(c_double), intent(inout) :: host(*)
+    end function
+    integer(c_int) function udgpu_sync(h) bind(C, name="udgpu_sync")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    integer(c_int) function udgpu_tstep_update(h, dt, courant, diffnr, dtmax, ladaptive, rk3step, courtot, diffnrtot) &
+        bind(C, name="udgpu_tstep_update")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      real(c_double), intent(inout) :: dt
+      real(c_double), value :: courant, diffnr, dtmax
+      integer(c_int), value :: ladaptive
+      integer(c_int), intent(inout) :: rk3step
+      real(c_double), intent(out) :: courtot, diffnrtot
+    end function
+    integer(c_int) function udgpu_advection(h) bind(C, name="udgpu_advection")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    integer(c_int) function udgpu_subgrid(h) bind(C, name="udgpu_subgrid")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    integer(c_int) function udgpu_poisson(h, dt, rk3step) bind(C, name="udgpu_poisson")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      real(c_double), value :: dt
+      integer(c_int), value :: rk3step
+    end function
+    integer(c_int) function udgpu_tstep_integrate(h, dt, rk3step) bind(C, name="udgpu_tstep_integrate")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      real(c_double), value :: dt
+      integer(c_int), value :: rk3step
+    end function
+    integer(c_int) function udgpu_halos(h) bind(C, name="udgpu_halos")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    integer(c_int) function udgpu_boundary(h) bind(C, name="udgpu_boundary")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    integer(c_int) function udgpu_divergence(h, divmax, divtot, divrms) bind(C, name="udgpu_divergence")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      real(c_double), intent(out) :: divmax, divtot, divrms
+    end function
+  end interface
+
+contains
+
+  !> the reference's error convention: message on unit 0, stop 1 (e.g. src/modpois.f90:896-898)
+  subroutine chk(ierr, where)
+    integer(c_int), intent(in) :: ierr
+    character(len=*), intent(in) :: where
+    character(kind=c_char), pointer :: msg(:)
+    integer :: n
+    if (ierr == 0) return
+    call c_f_pointer(udgpu_last_error(), msg, [1024])
+    n = 1
+    do while (n < 1024 .and. msg(n) /= c_null_char)
+      n = n + 1
+    end do
+    write (0, *) 'ERROR: libudales_gpu ', where, ' failed with code ', ierr, ': ', msg(1:n - 1)
+    stop 1
+  end subroutine chk
+
+  integer(c_int) function l2i(l)
+    logical, intent(in) :: l
+    l2i = merge(1_c_int, 0_c_int, l)
+  end function l2i
+
+  !> after initpois (src/program.f90:89): hand the grid, metrics and switches to the device library
+  subroutine gpu_init
+    use modglobal, only: itot, jtot, ktot, imax, jmax, kmax, ih, jh, kh, ihc, jhc, khc, nsv, dx, dy, dzf, dzh, &
+                         delta, BCxm, BCym, BCtopm, BCzp, ipoiss, iadv_mom, iadv_sv, lles, ltempeq, lmoist, &
+                         numol, prandtlmoli, Uinf, Vinf, e12min, ib, kb
+    use modsubgriddata, only: lvreman, lsmagorinsky, loneeqn, prandtli, c_vreman, cs
+    use modmpi, only: nprocx, nprocy, myidx, myidy, myid, comm3d, mpierr
+    use decomp_2d, only: zstart
+    use mpi
+    type(udgpu_cfg) :: c
+    character(kind=c_char), target :: uid(128)
+    real(c_double), allocatable, target, save :: dzf_c(:), dzh_c(:), delta_c(:)
+
+    allocate (dzf_c(ktot + 2*kh), dzh_c(ktot + kh), delta_c(ktot + kh))
+    dzf_c = dzf(kb - kh:kb + ktot - 1 + kh)
+    dzh_c = dzh(kb:kb + ktot - 1 + kh)
+    delta_c = delta(ib, kb:kb + ktot - 1 + kh)
+
+    c%abi_version = 1
+    c%itot = itot; c%jtot = jtot; c%ktot = ktot
+    c%imax = imax; c%jmax = jmax; c%kmax = kmax
+    c%ih = ih; c%jh = jh; c%kh = kh
+    c%ihc = ihc; c%jhc = jhc; c%khc = khc
+    c%nsv = nsv
+    c%zstart = zstart
+    c%nprocx = nprocx; c%nprocy = nprocy; c%myidx = myidx; c%myidy = myidy
+    c%BCxm = BCxm; c%BCym = BCym; c%BCtopm = BCtopm; c%BCzp = BCzp
+    c%ipoiss = ipoiss; c%iadv_mom = iadv_mom
+    c%iadv_sv = 7
+    if (nsv > 0) c%iadv_sv = iadv_sv(1)
+    c%lles = l2i(lles); c%lvreman = l2i(lvreman); c%lsmagorinsky = l2i(lsmagorinsky); c%loneeqn = l2i(loneeqn)
+    c%ltempeq = l2i(ltempeq); c%lmoist = l2i(lmoist)
+    c%dx = dx; c%dy = dy
+    c%dzf = c_loc(dzf_c); c%dzh = c_loc(dzh_c); c%delta = c_loc(delta_c)
+    c%numol = numol; c%prandtlmoli = prandtlmoli; c%prandtli = prandtli
+    c%c_vreman = c_vreman; c%cs = cs; c%Uinf = Uinf; c%Vinf = Vinf; c%e12min = e12min
+    c%device = -1          ! LOCAL_RANK (one rank per GPU)
+    c%flags = 0
+
+    if (nprocx*nprocy > 1) then
+      if (myid == 0) call chk(udgpu_nccl_unique_id(uid), 'nccl_unique_id')
+      call MPI_BCAST(uid, 128, MPI_CHARACTER, 0, comm3d, mpierr)
+      call chk(udgpu_init(c, c_loc(uid), handle), 'init')
+    else
+      call chk(udgpu_init(c, c_null_ptr, handle), 'init')
+    end if
+    call gpu_push_state
+  end subroutine gpu_init
+
+  subroutine gpu_exit
+    if (c_associated(handle)) call chk(udgpu_finalize(handle), 'finalize')
+    handle = c_null_ptr
+  end subroutine gpu_exit
+
+  !> residency control: the prognostic state the hot path reads (after readinitfiles / a host add-on)
+  subroutine gpu_push_state
+    use modfields, only: u0, v0, w0, um, vm, wm, pres0, up, vp, wp
+    call chk(udgpu_push(handle, F_U0, 0_c_int, u0), 'push u0')
+    call chk(udgpu_push(handle, F_V0, 0_c_int, v0), 'push v0')
+    call chk(udgpu_push(handle, F_W0, 0_c_int, w0), 'push w0')
+    call chk(udgpu_push(handle, F_UM, 0_c_int, um), 'push um')
+    call chk(udgpu_push(handle, F_VM, 0_c_int, vm), 'push vm')
+    call chk(udgpu_push(handle, F_WM, 0_c_int, wm), 'push wm')
+    call chk(udgpu_push(handle, F_PRES0, 0_c_int, pres0), 'push pres0')
+    call chk(udgpu_push(handle, F_UP, 0_c_int, up), 'push up')
+    call chk(udgpu_push(handle, F_VP, 0_c_int, vp), 'push vp')
+    call chk(udgpu_push(handle, F_WP, 0_c_int, wp), 'push wp')
+    call chk(udgpu_sync(handle), 'sync')
+  end subroutine gpu_push_state
+
+  !> before writerestartfiles / fielddump / statistics (time-gated in program.f90:201-220)
+  subroutine gpu_pull_state
+    use modfields, only: u0, v0, w0, um, vm, wm, pres0
+    use modsubgriddata, only: ekm, ekh
+    call chk(udgpu_pull(handle, F_U0, 0_c_int, u0), 'pull u0')
+    call chk(udgpu_pull(handle, F_V0, 0_c_int, v0), 'pull v0')
+    call chk(udgpu_pull(handle, F_W0, 0_c_int, w0), 'pull w0')
+    call chk(udgpu_pull(handle, F_UM, 0_c_int, um), 'pull um')
+    call chk(udgpu_pull(handle, F_VM, 0_c_int, vm), 'pull vm')
+    call chk(udgpu_pull(handle, F_WM, 0_c_int, wm), 'pull wm')
+    call chk(udgpu_pull(handle, F_PRES0, 0_c_int, pres0), 'pull pres0')
+    call chk(udgpu_pull(handle, F_EKM, 0_c_int, ekm), 'pull ekm')
+    call chk(udgpu_pull(handle, F_EKH, 0_c_int, ekh), 'pull ekh')
+  end subroutine gpu_pull_state
+
+  !> single-field variants for host add-ons that touch the tendencies between subgrid and poisson
+  !! (program.f90:152-191): call gpu_pull(F_UP, up) ... host routine ... call gpu_push(F_UP, up)
+  subroutine gpu_push(field, a)
+    integer(c_int), intent(in) :: field
+    real(c_double), intent(in) :: a(*)
+    call chk(udgpu_push(handle, field, 0_c_int, a), 'push')
+  end subroutine gpu_push
+  subroutine gpu_pull(field, a)
+    integer(c_int), intent(in) :: field
+    real(c_double), intent(inout) :: a(*)
+    call chk(udgpu_pull(handle, field, 0_c_int, a), 'pull')
+  end subroutine gpu_pull
+
+  subroutine gpu_tstep_update
+    use modglobal, only: dt, courant, diffnr, dtmax, ladaptive, rk3step, timee, timeleft, ntimee, ntrun, dt_lim
+    real(c_double) :: ct, dn
+    integer(c_int) :: rk
+    rk = rk3step
+    call chk(udgpu_tstep_update(handle, dt, courant, diffnr, dtmax, l2i(ladaptive), rk, ct, dn), 'tstep_update')
+    rk3step = rk
+    if (rk3step == 1) then          ! bookkeeping of src/modtstep.f90:136-147 stays on the host
+      timeleft = timeleft - dt
+      dt_lim = timeleft
+      timee = timee + dt
+      ntimee = ntimee + 1
+      ntrun = ntrun + 1
+    end if
+  end subroutine gpu_tstep_update
+
+  subroutine gpu_advection
+    call chk(udgpu_advection(handle), 'advection')
+  end subroutine
+  subroutine gpu_subgrid
+    call chk(udgpu_subgrid(handle), 'subgrid')
+  end subroutine
+  subroutine gpu_poisson
+    use modglobal, only: dt, rk3step
+    call chk(udgpu_poisson(handle, dt, int(rk3step, c_int)), 'poisson')
+  end subroutine
+  subroutine gpu_tstep_integrate
+    use modglobal, only: dt, rk3step
+    call chk(udgpu_tstep_integrate(handle, dt, int(rk3step, c_int)), 'tstep_integrate')
+  end subroutine
+  subroutine gpu_halos
+    call chk(udgpu_halos(handle), 'halos')
+  end subroutine
+  subroutine gpu_boundary
+    call chk(udgpu_boundary(handle), 'boundary')
+  end subroutine
+  !> chkdiv (src/modchecksim.f90:161): divmax, divtot from the resident fields
+  subroutine gpu_chkdiv(divmax, divtot)
+    real(c_double), intent(out) :: divmax, divtot
+    real(c_double) :: divrms
+    call chk(udgpu_divergence(handle, divmax, divtot, divrms), 'divergence')
+  end subroutine
+end module modgpu
