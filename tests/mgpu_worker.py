@@ -1,0 +1,70 @@
+"""Multi-GPU parity worker (run under torchrun, one rank per GPU): x-slab decomposition vs the
+single-pencil CPU oracle on identical global inputs.  Tolerance = the reference's own
+decomposition-invariance tolerance 1e-9 (tests/integration/processor_boundaries)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import udales_b200 as U
+    from oracle.oracle import Oracle, stretched_zf
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(dev)
+    obj = [U.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    uid = obj[0]
+    shapes = [(64, 64, 32), (128, 64, 24)] if len(sys.argv) < 2 else [tuple(int(x) for x in sys.argv[1].split("x"))]
+    worst = 0.0
+    for shape in shapes:
+        I, J, K = shape
+        zf = stretched_zf(K, K * 0.5, 1.03)
+        o = Oracle(I, J, K, zf=zf)
+        o.init_channel()
+        g = U.UdalesGPU(I, J, K, zf=zf, device=dev, nprocx=world, myidx=rank, nccl_uid=uid)
+        for n in ("u0", "v0", "w0", "um", "vm", "wm", "pres0"):
+            g.push(n, U.slab_of(getattr(o, n), world, rank))
+        # Poisson alone
+        rng = np.random.default_rng(3)
+        rhs = rng.standard_normal(shape)
+        imax = I // world
+        p_ref = o.poisson_solve(rhs)
+        p = g.poisson_solve(np.asfortranarray(rhs[rank * imax:(rank + 1) * imax]))
+        e = np.abs(p - p_ref[rank * imax:(rank + 1) * imax]).max() / np.abs(p_ref).max()
+        worst = max(worst, e)
+        assert e < 1e-10, ("poisson", shape, e)
+        # substeps
+        dt = 0.02
+        o.dt = g.dt = dt
+        for s in range(6):
+            o.substep(dt)
+            g.substep(dt)
+            for n in ("u0", "v0", "w0", "um", "vm", "wm"):
+                a, b = g.pull(n), U.slab_of(getattr(o, n), world, rank)
+                e = np.abs(a - b).max()
+                worst = max(worst, e)
+                assert e < 1e-9, (n, s, shape, e)
+            dmax, dtot, drms = g.divergence()
+            omax, otot, orms = o.chkdiv()
+            assert drms < 1e-12 and abs(dmax - omax) < 1e-12, (dmax, omax, drms)
+        # adaptive time step: global maxima through the allreduce
+        d_ref, _, ct_ref, dn_ref = o.tstep_update(0.05, 0, courant=1.1, diffnr=0.25, dtmax=2.0)
+        d, _, ct, dn = g.tstep_update(0.05, 0, courant=1.1, diffnr=0.25, dtmax=2.0)
+        assert abs(ct - ct_ref) < 1e-12 * ct_ref and abs(dn - dn_ref) < 1e-12 * dn_ref and abs(d - d_ref) < 1e-12 * d_ref
+        g.close()
+    dist.barrier()
+    print(f"MGPU OK rank {rank}/{world} worst abs err {worst:.2e}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

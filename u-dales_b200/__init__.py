@@ -133,13 +133,32 @@ def grid_metrics(zf: np.ndarray):
     return dzf, dzh
 
 
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId (rank 0 calls this, the host broadcasts it: MPI_Bcast in Fortran,
+    torch.distributed in the tests/bench)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().udgpu_nccl_unique_id(buf)
+    if rc != 0:
+        raise UdalesGPUError(f"udgpu error {rc}: {lib().udgpu_last_error().decode()}")
+    return buf.raw
+
+
+def slab_of(a_global: np.ndarray, nprocx: int, myidx: int, halo: int = 1) -> np.ndarray:
+    """x-slab (with its halo columns) of a global halo'd Fortran-shaped array: local storage column c is
+    global column myidx*imax + c (decomp_2d zstart arithmetic, 2decomp-fft/src/decomp_2d.f90:1172-1204)."""
+    itot = a_global.shape[0] - 2 * halo
+    imax = itot // nprocx
+    lo = myidx * imax
+    return np.asfortranarray(a_global[lo:lo + imax + 2 * halo])
+
+
 class UdalesGPU:
     """One z-pencil of the uDALES dynamics core resident on one B200."""
 
     def __init__(self, itot, jtot, ktot, xlen=None, ylen=None, zf=None, nsv=0, BCtopm=1,
                  lvreman=True, lsmagorinsky=False, lles=None, iadv_sv=7,
                  numol=1.5e-5, prandtlmol=0.71, prandtl=0.333, c_vreman=0.07, cs=-1.0,
-                 Uinf=0.0, Vinf=0.0, device=-1, flags=0):
+                 Uinf=0.0, Vinf=0.0, device=-1, flags=0, nprocx=1, myidx=0, nccl_uid=None):
         self.L = lib()
         xlen = float(xlen if xlen is not None else itot / 2.0)
         ylen = float(ylen if ylen is not None else jtot / 2.0)
@@ -154,13 +173,14 @@ class UdalesGPU:
         c = Cfg()
         c.abi_version = ABI_VERSION
         c.itot, c.jtot, c.ktot = itot, jtot, ktot
-        c.imax, c.jmax, c.kmax = itot, jtot, ktot
+        c.imax, c.jmax, c.kmax = itot // nprocx, jtot, ktot
         c.ih = c.jh = c.kh = 1
         c.ihc = c.jhc = c.khc = hc
         c.nsv = nsv
-        c.zstart[0] = c.zstart[1] = c.zstart[2] = 1
-        c.nprocx = c.nprocy = 1
-        c.myidx = c.myidy = 0
+        c.zstart[0] = myidx * (itot // nprocx) + 1
+        c.zstart[1] = c.zstart[2] = 1
+        c.nprocx, c.nprocy = nprocx, 1
+        c.myidx, c.myidy = myidx, 0
         c.BCxm = c.BCym = 1
         c.BCtopm = BCtopm
         c.BCzp = 1
@@ -178,8 +198,10 @@ class UdalesGPU:
         c.device, c.flags = device, flags
         self.cfg = c
         self.h = C.c_void_p()
-        self._chk(self.L.udgpu_init(C.byref(c), None, C.byref(self.h)))
+        uid = C.create_string_buffer(nccl_uid, 128) if nccl_uid is not None else None
+        self._chk(self.L.udgpu_init(C.byref(c), uid, C.byref(self.h)))
         self.itot, self.jtot, self.ktot, self.nsv = itot, jtot, ktot, nsv
+        self.imax, self.nprocx, self.myidx = itot // nprocx, nprocx, myidx
         self.dt, self.rk3step = 0.0, 0
 
     def _chk(self, rc):
@@ -243,7 +265,7 @@ class UdalesGPU:
 
     def poisson_solve(self, rhs):
         a = np.array(rhs, dtype=np.float64, order="F", copy=True)
-        assert a.shape == (self.itot, self.jtot, self.ktot)
+        assert a.shape == (self.imax, self.jtot, self.ktot)
         self._chk(self.L.udgpu_poisson_solve(self.h, a.ctypes.data, a.ctypes.data))
         return a
 

@@ -63,15 +63,27 @@ __device__ __forceinline__ void dft_reg(double2 (&v)[R]) {
   }
 }
 
+// Blocked ("wire format") addressing of one side of a transform for the multi-GPU transposes: the
+// points of a line are split into nblk = n/blk consecutive runs, run d living in its own buffer
+// base[d] (the block exchanged with rank d: local send/receive buffer or, with peer access, the
+// receive buffer of GPU d itself).  Inside a block the LineDesc strides apply.  This is the pack /
+// unpack (mem_split_* / mem_merge_*, 2decomp-fft/src/transpose_x_to_y.f90:275-327,385-437) fused into the
+// FFT kernels' own loads and stores.
+struct BlkDesc {
+  double *base[8];
+  int shift, mask;   // blk = 1 << shift points per block, mask = blk - 1
+};
+
 template <int R1, int R2, int LANES, bool XDIR>
 struct RfftCfg {
   static constexpr int H = R1 * R2, N = 2 * H, NT = LANES * R2;
   static constexpr int SMEM = XDIR ? LANES * (H + 1) * 16 : LANES * H * 16;
 };
 
-template <int R1, int R2, int LANES, bool XDIR, bool INV>
+template <int R1, int R2, int LANES, bool XDIR, bool INV, bool IBLK = false, bool OBLK = false>
 __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restrict__ tw, const double *__restrict__ in, LineDesc di,
-                                                         double *__restrict__ out, LineDesc dd, double fac) {
+                                                         double *__restrict__ out, LineDesc dd, double fac,
+                                                         BlkDesc ib = BlkDesc(), BlkDesc ob = BlkDesc()) {
   constexpr int H = R1 * R2, N = 2 * H, NT = LANES * R2;
   constexpr int NK1 = R1 / R2;            // pass-2 DFTs per thread
   constexpr int NPAIR = (H / 2) / R2 + 1;  // split/merge pairs per thread (k = j, j+R2, ... <= H/2)
@@ -84,6 +96,13 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
   const bool act = lane < nb;
   const long long ibase = (long long)blockIdx.y * di.s2 + (long long)b0 * di.s1;
   const long long obase = (long long)blockIdx.y * dd.s2 + (long long)b0 * dd.s1;
+  // element addresses: (line offset within the CTA's batch, point index)
+  auto IN = [&](long long loff, int pt) -> const double * {
+    return IBLK ? ib.base[pt >> ib.shift] + ibase + loff + (long long)(pt & ib.mask) * di.sp : in + ibase + loff + (long long)pt * di.sp;
+  };
+  auto OUT = [&](long long loff, int pt) -> double * {
+    return OBLK ? ob.base[pt >> ob.shift] + obase + loff + (long long)(pt & ob.mask) * dd.sp : out + obase + loff + (long long)pt * dd.sp;
+  };
 #define SA(p) (XDIR ? (lane * (H + 1) + (p)) : ((p)*LANES + lane))
 #define RS(r) (lane * 2 * (H + 1) + (r))  /* real slot r of this lane's line in the x staging tile */
 
@@ -92,7 +111,7 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
     if (XDIR) {
       for (int idx = tid; idx < nb * H; idx += NT) {
         const int b = idx / H, m = idx - b * H;
-        const double *q = in + ibase + b * di.s1 + 2 * m;
+        const double *q = IN((long long)b * di.s1, 2 * m);
         buf[b * (H + 1) + m] = make_double2(q[0], q[1]);
       }
       __syncthreads();
@@ -100,11 +119,11 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
       for (int q = 0; q < R1; q++) v[q] = buf[SA(j + R2 * q)];
       __syncthreads();
     } else if (act) {
-      const double *p = in + ibase + lane * di.s1;
+      const long long lo = (long long)lane * di.s1;
 #pragma unroll
       for (int q = 0; q < R1; q++) {
-        const long long m = j + R2 * q;
-        v[q] = make_double2(p[(2 * m) * di.sp], p[(2 * m + 1) * di.sp]);
+        const int m = j + R2 * q;
+        v[q] = make_double2(*IN(lo, 2 * m), *IN(lo, 2 * m + 1));
       }
     }
   } else {
@@ -112,7 +131,7 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
     if (XDIR) {
       for (int idx = tid; idx < nb * H; idx += NT) {
         const int b = idx / H, m = idx - b * H;
-        const double *q = in + ibase + b * di.s1 + 2 * m;
+        const double *q = IN((long long)b * di.s1, 2 * m);
         buf[b * (H + 1) + m] = make_double2(q[0], q[1]);
       }
       __syncthreads();
@@ -126,14 +145,14 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
         double x0, x1, y0, y1;
         if (k == 0) {
           if (XDIR) { x0 = rbuf[RS(0)]; y0 = rbuf[RS(N - 1)]; }
-          else { const double *p = in + ibase + lane * di.s1; x0 = p[0]; y0 = p[(long long)(N - 1) * di.sp]; }
+          else { const long long lo = (long long)lane * di.s1; x0 = *IN(lo, 0); y0 = *IN(lo, N - 1); }
           zk[t] = make_double2(x0 + y0, x0 - y0);
         } else {
           if (XDIR) { x0 = rbuf[RS(2 * k - 1)]; x1 = rbuf[RS(2 * k)]; y0 = rbuf[RS(2 * (H - k) - 1)]; y1 = rbuf[RS(2 * (H - k))]; }
           else {
-            const double *p = in + ibase + lane * di.s1;
-            x0 = p[(long long)(2 * k - 1) * di.sp]; x1 = p[(long long)(2 * k) * di.sp];
-            y0 = p[(long long)(2 * (H - k) - 1) * di.sp]; y1 = p[(long long)(2 * (H - k)) * di.sp];
+            const long long lo = (long long)lane * di.s1;
+            x0 = *IN(lo, 2 * k - 1); x1 = *IN(lo, 2 * k);
+            y0 = *IN(lo, 2 * (H - k) - 1); y1 = *IN(lo, 2 * (H - k));
           }
           const double2 A = make_double2(x0 + y0, x1 - y1), Bv = make_double2(x0 - y0, x1 + y1);
           const double2 w = tw[k];
@@ -228,19 +247,19 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
       for (int idx = tid; idx < nb * H; idx += NT) {
         const int b = idx / H, m = idx - b * H;
         const double2 z = buf[b * (H + 1) + m];
-        double *q = out + obase + b * dd.s1 + 2 * m;
+        double *q = OUT((long long)b * dd.s1, 2 * m);
         q[0] = z.x; q[1] = z.y;
       }
     } else if (act) {
-      double *p = out + obase + lane * dd.s1;
+      const long long lo = (long long)lane * dd.s1;
 #pragma unroll
       for (int t = 0; t < NPAIR; t++) {
         const int k = j + R2 * t;
         if (k <= H / 2) {
-          if (k == 0) { p[0] = xk[t].x; p[(long long)(N - 1) * dd.sp] = xk[t].y; }
+          if (k == 0) { *OUT(lo, 0) = xk[t].x; *OUT(lo, N - 1) = xk[t].y; }
           else {
-            p[(long long)(2 * k - 1) * dd.sp] = xk[t].x; p[(long long)(2 * k) * dd.sp] = xk[t].y;
-            p[(long long)(2 * (H - k) - 1) * dd.sp] = xh[t].x; p[(long long)(2 * (H - k)) * dd.sp] = xh[t].y;
+            *OUT(lo, 2 * k - 1) = xk[t].x; *OUT(lo, 2 * k) = xk[t].y;
+            *OUT(lo, 2 * (H - k) - 1) = xh[t].x; *OUT(lo, 2 * (H - k)) = xh[t].y;
           }
         }
       }
@@ -260,19 +279,19 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
       for (int idx = tid; idx < nb * H; idx += NT) {
         const int b = idx / H, m = idx - b * H;
         const double2 z = buf[b * (H + 1) + m];
-        double *q = out + obase + b * dd.s1 + 2 * m;
+        double *q = OUT((long long)b * dd.s1, 2 * m);
         q[0] = z.x; q[1] = z.y;
       }
     } else if (act) {
-      double *p = out + obase + lane * dd.s1;
+      const long long lo = (long long)lane * dd.s1;
 #pragma unroll
       for (int t = 0; t < NK1; t++)
 #pragma unroll
         for (int k2 = 0; k2 < R2; k2++) {
-          const long long m = j + R2 * t + R1 * k2;
+          const int m = j + R2 * t + R1 * k2;
           const double2 z = u[t][brev<R2>(k2)];
-          p[(2 * m) * dd.sp] = z.x * fac;
-          p[(2 * m + 1) * dd.sp] = z.y * fac;
+          *OUT(lo, 2 * m) = z.x * fac;
+          *OUT(lo, 2 * m + 1) = z.y * fac;
         }
     }
   }

@@ -140,6 +140,27 @@ __global__ void k_wrap_y(PtrPack a, int pi, int pj, int nlev, int jmax, int h) {
   }
 }
 
+// x-halo exchange between slabs (replaces exchange_halo_z's E/W phase, 2decomp-fft/src/halo_comm_z.f90:73-110):
+// gather the first / last interior column of every (j,k) row incl. halo rows into contiguous send
+// buffers, and scatter received columns into the halo columns.  One thread per row.
+struct HaloPack { double *f[8]; int nlev[8]; long long off[8]; int n; };
+__global__ void k_halo_pack_x(HaloPack a, int pi, int pj, int imax, double *__restrict__ sendL, double *__restrict__ sendR) {
+  const int f = blockIdx.y;
+  const long long jk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (jk >= (long long)pj * a.nlev[f]) return;
+  const double *q = a.f[f] + jk * pi;
+  sendL[a.off[f] + jk] = q[1];
+  sendR[a.off[f] + jk] = q[imax];
+}
+__global__ void k_halo_unpack_x(HaloPack a, int pi, int pj, int imax, const double *__restrict__ recvL, const double *__restrict__ recvR) {
+  const int f = blockIdx.y;
+  const long long jk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (jk >= (long long)pj * a.nlev[f]) return;
+  double *q = a.f[f] + jk * pi;
+  q[0] = recvL[a.off[f] + jk];
+  q[imax + 1] = recvR[a.off[f] + jk];
+}
+
 // ---------------------------------------------------------------------------------------------
 // momentum tendencies, direct form.  advecu/v/w_2nd src/modadvection.f90:158-314 and
 // diffu/v/w src/modsubgrid.f90:672-997.  ACC: add to the existing tendency (drop-in semantics)

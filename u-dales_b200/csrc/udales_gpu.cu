@@ -3,6 +3,7 @@
 #include "../../include/udales_gpu.h"
 
 #include <cuda_runtime.h>
+#include <nccl.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -36,6 +37,12 @@ static int set_err(int code, const char *fmt, ...) {
       return set_err(UDGPU_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
   } while (0)
 #define KCHECK() CU(cudaGetLastError())
+#define NC(x)                                                                                          \
+  do {                                                                                                 \
+    ncclResult_t e_ = (x);                                                                             \
+    if (e_ != ncclSuccess)                                                                             \
+      return set_err(UDGPU_ENCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #x, ncclGetErrorString(e_));  \
+  } while (0)
 #define RET(x)                \
   do {                        \
     int r_ = (x);             \
@@ -72,6 +79,14 @@ struct udgpu {
   int nxh = 0, nyh = 0;
   // reductions
   double *d_red = nullptr, *h_red = nullptr;
+  // multi-GPU x-slabs (nprocx = P, nprocy = 1)
+  int P = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  double *sendL = nullptr, *sendR = nullptr, *recvL = nullptr, *recvR = nullptr;  // halo columns
+  size_t halo_cap = 0;
+  double *sbuf = nullptr, *rbuf = nullptr, *workB = nullptr;  // transposes: wire-format send / receive, x-pencil work
+  int IB = 0, JB = 0;         // local i extent of the slab, local j extent of the x-pencil
+  Geo gB;                     // geometry of the x-pencil (itot, JB, ktot) for the z solve
   // TMA path of the fused momentum kernel
   bool use_tma = false;
   CUtensorMap tm[5];
@@ -218,8 +233,10 @@ extern "C" const char *udgpu_last_error(void) { return g_err; }
 extern "C" int udgpu_abi_version(void) { return UDGPU_ABI_VERSION; }
 
 extern "C" int udgpu_nccl_unique_id(void *uid128) {
-  (void)uid128;
-  return set_err(UDGPU_ENCCL, "multi-GPU support not compiled in yet");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (!uid128) return set_err(UDGPU_EINVAL, "null uid buffer");
+  NC(ncclGetUniqueId((ncclUniqueId *)uid128));
+  return UDGPU_OK;
 }
 
 extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **out) {
@@ -239,13 +256,19 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
   if (c->BCzp != 1) return set_err(UDGPU_EINVAL, "BCzp=%d: only the tridiagonal z solve (1) is in scope", c->BCzp);
   if (c->ltempeq || c->lmoist || c->loneeqn) return set_err(UDGPU_EINVAL, "ltempeq/lmoist/loneeqn are out of scope (neutral configs)");
   if (c->ih != 1 || c->jh != 1 || c->kh != 1) return set_err(UDGPU_EINVAL, "momentum halo must be 1 (cd2, src/modglobal.f90:592-599)");
-  if (c->nprocx * c->nprocy != 1) return set_err(UDGPU_EINVAL, "multi-GPU pencils not available in this build");
-  if (c->imax != c->itot || c->jmax != c->jtot || c->kmax != c->ktot) return set_err(UDGPU_EINVAL, "single pencil requires imax=itot, jmax=jtot, kmax=ktot");
+  if (c->nprocy != 1) return set_err(UDGPU_EINVAL, "only x-slab decompositions (nprocy = 1) are supported (nprocx x nprocy pencils: next)");
+  if (c->nprocx < 1 || c->nprocx > 8) return set_err(UDGPU_EINVAL, "nprocx must be 1..8 (one NVSwitch box)");
+  if (c->itot % c->nprocx || c->jtot % c->nprocx) return set_err(UDGPU_EINVAL, "itot and jtot must be divisible by nprocx (src/modstartup.f90:730-760)");
+  if (c->imax != c->itot / c->nprocx || c->jmax != c->jtot || c->kmax != c->ktot) return set_err(UDGPU_EINVAL, "local extents do not match an x-slab: imax=itot/nprocx, jmax=jtot, kmax=ktot");
+  if (c->nprocx > 1 && !nccl_uid) return set_err(UDGPU_EINVAL, "nprocx > 1 needs the broadcast ncclUniqueId");
+  if (c->nprocx > 1 && (c->myidx < 0 || c->myidx >= c->nprocx || c->zstart[0] != c->myidx * c->imax + 1)) return set_err(UDGPU_EINVAL, "myidx / zstart inconsistent with the slab");
   if (c->nsv != 0) return set_err(UDGPU_EINVAL, "nsv > 0 not available in this build");
   if (!c->dzf || !c->dzh) return set_err(UDGPU_EINVAL, "dzf/dzh missing");
 
   udgpu *h = new udgpu();
   h->cfg = *c;
+  h->P = c->nprocx;
+  h->rank = c->nprocx > 1 ? c->myidx : 0;
   h->dev = c->device;
   if (h->dev < 0) {
     const char *lr = getenv("LOCAL_RANK");
@@ -260,6 +283,7 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     return set_err(UDGPU_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", dv, prop.major, prop.minor);
   }
   CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  if (h->P > 1) NC(ncclCommInitRank(&h->comm, h->P, *(const ncclUniqueId *)nccl_uid, h->rank));
 
   Geo &g = h->g;
   memset(&g, 0, sizeof(g));
@@ -337,6 +361,14 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     if (n) RET(dev_alloc(h, (void **)&h->f[f], n * sl * sizeof(double)));
   }
   RET(dev_alloc(h, (void **)&h->d_scr, nR * sizeof(double)));
+  if (h->P > 1) {
+    h->IB = g.imax; h->JB = g.jtot / h->P;
+    h->halo_cap = (size_t)8 * g.pj * (K + 2 * g.kh);
+    for (double **b : {&h->sendL, &h->sendR, &h->recvL, &h->recvR}) RET(dev_alloc(h, (void **)b, h->halo_cap * sizeof(double)));
+    for (double **b : {&h->sbuf, &h->rbuf, &h->workB}) RET(dev_alloc(h, (void **)b, nR * sizeof(double)));
+    h->gB = g;
+    h->gB.imax = g.itot; h->gB.jmax = h->JB; h->gB.i0g = 0; h->gB.j0g = h->rank * h->JB;
+  }
   RET(dev_alloc(h, (void **)&h->d_red, 16 * sizeof(double)));
   CU(cudaMallocHost((void **)&h->h_red, 16 * sizeof(double)));
 
@@ -402,6 +434,7 @@ extern "C" int udgpu_finalize(udgpu_t *h) {
   cudaStreamSynchronize(h->st);
   for (void *p : h->allocs) cudaFree(p);
   if (h->h_red) cudaFreeHost(h->h_red);
+  if (h->comm) ncclCommDestroy(h->comm);
   for (int w = 0; w < PROF_N; w++)
     for (auto &e : h->ps[w].pend) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   cudaStreamDestroy(h->st);
@@ -472,16 +505,47 @@ extern "C" int udgpu_stream(udgpu_t *h, void **s) {
 static dim3 grid3(const Geo &g, dim3 b) { return dim3((g.imax + b.x - 1) / b.x, (g.jmax + b.y - 1) / b.y, g.ktot); }
 static const dim3 B3(64, 4, 1);
 
+// x-halo exchange between neighbouring slabs over NCCL (periodic ring), width 1.
+// Send order right-then-left / receive order left-then-right so that with P = 2 (both neighbours are
+// the same peer) the first send meets the first receive.
+static int halo_x_exchange(udgpu *h, std::initializer_list<double *> fields, int nlev) {
+  const Geo &g = h->g;
+  HaloPack hp; hp.n = 0;
+  long long off = 0;
+  for (double *p : fields) { hp.f[hp.n] = p; hp.nlev[hp.n] = nlev; hp.off[hp.n] = off; off += (long long)g.pj * nlev; hp.n++; }
+  if ((size_t)off > h->halo_cap) return set_err(UDGPU_EINVAL, "halo buffer too small");
+  const long long rows = (long long)g.pj * nlev;
+  const dim3 gr((unsigned)((rows + 127) / 128), hp.n);
+  k_halo_pack_x<<<gr, 128, 0, h->st>>>(hp, g.pi, g.pj, g.imax, h->sendL, h->sendR);
+  KCHECK();
+  const int left = (h->rank + h->P - 1) % h->P, right = (h->rank + 1) % h->P;
+  NC(ncclGroupStart());
+  NC(ncclSend(h->sendR, off, ncclDouble, right, h->comm, h->st));
+  NC(ncclSend(h->sendL, off, ncclDouble, left, h->comm, h->st));
+  NC(ncclRecv(h->recvL, off, ncclDouble, left, h->comm, h->st));
+  NC(ncclRecv(h->recvR, off, ncclDouble, right, h->comm, h->st));
+  NC(ncclGroupEnd());
+  k_halo_unpack_x<<<gr, 128, 0, h->st>>>(hp, g.pi, g.pj, g.imax, h->recvL, h->recvR);
+  KCHECK();
+  h->launches += 2;
+  return UDGPU_OK;
+}
+
+// lateral halos of momentum-halo arrays: x by local periodic wrap (unsplit) or slab exchange, then y wrap
 static int wrap_xy(udgpu *h, std::initializer_list<double *> fields, int nlev) {
   const Geo &g = h->g;
   PtrPack pp; pp.n = 0;
   for (double *p : fields) pp.p[pp.n++] = p;
   const long long rows = (long long)g.pj * nlev;
-  k_wrap_x<<<(unsigned)((rows + 127) / 128), 128, 0, h->st>>>(pp, g.pi, g.pj, nlev, g.imax, g.ih);
-  KCHECK();
+  if (h->P > 1) RET(halo_x_exchange(h, fields, nlev));
+  else {
+    k_wrap_x<<<(unsigned)((rows + 127) / 128), 128, 0, h->st>>>(pp, g.pi, g.pj, nlev, g.imax, g.ih);
+    KCHECK();
+    h->launches++;
+  }
   k_wrap_y<<<dim3((g.pi + 127) / 128, nlev), 128, 0, h->st>>>(pp, g.pi, g.pj, nlev, g.jmax, g.jh);
   KCHECK();
-  h->launches += 2;
+  h->launches++;
   return UDGPU_OK;
 }
 
@@ -588,11 +652,15 @@ extern "C" int udgpu_subgrid(udgpu_t *h) {
 // ------------------------------------------------------------------------------------------
 // fast power-of-two FFT dispatch: n -> (R1, R2, LANES)
 template <int R1, int R2, int LANES, bool XDIR>
-static int rfft_fast_launch(udgpu *h, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl) {
+static int rfft_fast_launch(udgpu *h, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl,
+                            const BlkDesc *ib, const BlkDesc *ob) {
   using C = RfftCfg<R1, R2, LANES, XDIR>;
   const dim3 grid((di.nb1 + LANES - 1) / LANES, di.nb2), block(LANES, R2);
-  if (inverse) k_rfft_fast<R1, R2, LANES, XDIR, true><<<grid, block, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac);
-  else k_rfft_fast<R1, R2, LANES, XDIR, false><<<grid, block, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac);
+  const BlkDesc z = BlkDesc();
+#define GO(INV, IB_, OB_) k_rfft_fast<R1, R2, LANES, XDIR, INV, IB_, OB_><<<grid, block, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac, ib ? *ib : z, ob ? *ob : z)
+  if (inverse) { if (ib) GO(true, true, false); else if (ob) GO(true, false, true); else GO(true, false, false); }
+  else { if (ib) GO(false, true, false); else if (ob) GO(false, false, true); else GO(false, false, false); }
+#undef GO
   KCHECK();
   h->launches++;
   return UDGPU_OK;
@@ -600,19 +668,21 @@ static int rfft_fast_launch(udgpu *h, int inverse, const double *in, LineDesc di
 template <int R1, int R2, int LANES, bool XDIR>
 static int rfft_fast_attr() {
   using C = RfftCfg<R1, R2, LANES, XDIR>;
-  CU(cudaFuncSetAttribute(k_rfft_fast<R1, R2, LANES, XDIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-  CU(cudaFuncSetAttribute(k_rfft_fast<R1, R2, LANES, XDIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+#define SA_(INV, IB_, OB_) CU(cudaFuncSetAttribute(k_rfft_fast<R1, R2, LANES, XDIR, INV, IB_, OB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM))
+  SA_(true, false, false); SA_(false, false, false); SA_(true, true, false); SA_(false, true, false); SA_(true, false, true); SA_(false, false, true);
+#undef SA_
   return UDGPU_OK;
 }
 static bool fast_len(int n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024; }
 template <bool XDIR>
-static int rfft_fast(udgpu *h, int n, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl) {
+static int rfft_fast(udgpu *h, int n, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl,
+                     const BlkDesc *ib = nullptr, const BlkDesc *ob = nullptr) {
   switch (n) {
-    case 64: return rfft_fast_launch<8, 4, 32, XDIR>(h, inverse, in, di, out, dd, pl);
-    case 128: return rfft_fast_launch<8, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl);
-    case 256: return rfft_fast_launch<16, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl);
-    case 512: return rfft_fast_launch<16, 16, 16, XDIR>(h, inverse, in, di, out, dd, pl);
-    case 1024: return rfft_fast_launch<32, 16, 8, XDIR>(h, inverse, in, di, out, dd, pl);
+    case 64: return rfft_fast_launch<8, 4, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
+    case 128: return rfft_fast_launch<8, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
+    case 256: return rfft_fast_launch<16, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
+    case 512: return rfft_fast_launch<16, 16, 16, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
+    case 1024: return rfft_fast_launch<32, 16, 8, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
   }
   return set_err(UDGPU_EINVAL, "no fast FFT for n=%d", n);
 }
@@ -630,9 +700,11 @@ static int rfft_fast_setattr(int n) {
 
 static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt) {
   const Geo &g = h->g;
-  if (h->cfg.flags & UDGPU_F_V1_KERNELS) return UDGPU_OK;
-  h->fast_x = fast_len(g.itot) && g.imax == g.itot;
-  h->fast_y = fast_len(g.jtot) && g.jmax == g.jtot;
+  if ((h->cfg.flags & UDGPU_F_V1_KERNELS) && h->P == 1) return UDGPU_OK;
+  h->fast_x = fast_len(g.itot);
+  h->fast_y = fast_len(g.jtot);
+  if (h->P > 1 && !(h->fast_x && h->fast_y))
+    return set_err(UDGPU_EINVAL, "multi-GPU slabs need itot, jtot in {64,128,256,512,1024} (fused-transpose FFT kernels)");
   if (h->fast_x) RET(rfft_fast_setattr<true>(g.itot));
   if (h->fast_y) RET(rfft_fast_setattr<false>(g.jtot));
   // distinct eigenvalues: slot s (0-based) -> index (s+1)/2   (src/modpois.f90:100-107)
@@ -679,8 +751,58 @@ static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *
 
 // rhs (halo-free work array) -> solution.  Final pass writes either in place or into the interior of
 // the halo'd p array.  Order x, y, z, y^-1, x^-1 as in src/modpois.f90:478-679.
+// all-to-all of the wire-format blocks (block d of sbuf -> rank d, block s of rbuf <- rank s): the
+// MPI_ALLTOALLV of the reference's transposes (2decomp-fft/src/transpose_x_to_y.f90:121-123)
+static int a2a_blocks(udgpu *h) {
+  const size_t blk = (size_t)h->IB * h->JB * h->g.ktot;
+  NC(ncclGroupStart());
+  for (int d = 0; d < h->P; d++) {
+    if (d == h->rank) continue;
+    NC(ncclSend(h->sbuf + d * blk, blk, ncclDouble, d, h->comm, h->st));
+    NC(ncclRecv(h->rbuf + d * blk, blk, ncclDouble, d, h->comm, h->st));
+  }
+  NC(ncclGroupEnd());
+  CU(cudaMemcpyAsync(h->rbuf + h->rank * blk, h->sbuf + h->rank * blk, blk * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  return UDGPU_OK;
+}
+static int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
+
+// slab-decomposed solve: y-FFT in the slab, all-to-all, x-FFT + z-solve + inverse x-FFT in the x-pencil,
+// all-to-all, inverse y-FFT.  2 exchanges per solve (the reference needs 4 at this decomposition); pack and
+// unpack are fused into the FFT kernels through the blocked descriptors.
+static int poisson_core_slab(udgpu *h, double *work, double *p_halo) {
+  const Geo &g = h->g;
+  ProfScope ps(h, PROF_POIS);
+  const int IB = h->IB, JB = h->JB, K = g.ktot, P = h->P;
+  const size_t blk = (size_t)IB * JB * K;
+  BlkDesc bs, br;
+  for (int d = 0; d < 8; d++) { bs.base[d] = d < P ? h->sbuf + d * blk : nullptr; br.base[d] = d < P ? h->rbuf + d * blk : nullptr; }
+  const LineDesc yA = {(long long)IB, 1, (long long)IB * g.jtot, IB, K};        // y lines in the slab
+  const LineDesc yW = {(long long)IB, 1, (long long)JB * IB, IB, K};            // ... in wire format (per block)
+  const LineDesc xW = {1, (long long)IB, (long long)JB * IB, JB, K};            // x lines in wire format (per block)
+  const LineDesc xB = {1, (long long)g.itot, (long long)g.itot * JB, JB, K};    // x lines in the x-pencil
+  bs.shift = br.shift = ilog2(JB); bs.mask = br.mask = JB - 1;
+  RET(rfft_fast<false>(h, g.jtot, 0, work, yA, nullptr, yW, h->py, nullptr, &bs));
+  RET(a2a_blocks(h));
+  br.shift = ilog2(IB); br.mask = IB - 1;
+  RET(rfft_fast<true>(h, g.itot, 0, nullptr, xW, h->workB, xB, h->px, &br, nullptr));
+  k_zsolve<<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
+  KCHECK();
+  h->launches++;
+  bs.shift = ilog2(IB); bs.mask = IB - 1;
+  RET(rfft_fast<true>(h, g.itot, 1, h->workB, xB, nullptr, xW, h->px, nullptr, &bs));
+  RET(a2a_blocks(h));
+  br.shift = ilog2(JB); br.mask = JB - 1;
+  LineDesc yOut = yA;
+  double *outp = work;
+  if (p_halo) { yOut.sp = g.pi; yOut.s2 = g.pk; outp = p_halo + offF(g, 1, 1, 1); }
+  RET(rfft_fast<false>(h, g.jtot, 1, nullptr, yW, outp, yOut, h->py, &br, nullptr));
+  return UDGPU_OK;
+}
+
 static int poisson_core(udgpu *h, double *work, double *p_halo) {
   const Geo &g = h->g;
+  if (h->P > 1) return poisson_core_slab(h, work, p_halo);
   ProfScope ps(h, PROF_POIS);
   RET(fft_pass(h, true, 0, work, work, false));
   RET(fft_pass(h, false, 0, work, work, false));
@@ -718,6 +840,12 @@ extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
   ProfScope ps(h, PROF_FILLPS);
   const double rk3coef = (rk3step == 0) ? 1. : dt / (4. - (double)rk3step);
   const double rk3coefi = 1. / rk3coef;
+  if (h->P > 1) {
+    // bcpup's exchange_halo_z(pup) (src/modboundary.f90:1219): only up(ie+1) is missing, um's halo is valid
+    RET(halo_x_exchange(h, {h->f[UDGPU_UP]}, g.ktot + g.kh));
+    k_fillps<false, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
+                                                          h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS]);
+  } else
   k_fillps<true, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
                                                        h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS]);
   KCHECK();
@@ -835,6 +963,7 @@ extern "C" int udgpu_tstep_update(udgpu_t *h, double *dt, double courant, double
     k_cfl<<<grid3(g, B3), B3, 0, h->st>>>(g, f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_EKM], f[UDGPU_EKH], *dt, h->d_red);
     KCHECK();
     h->launches++;
+    if (h->P > 1) NC(ncclAllReduce(h->d_red, h->d_red, 2, ncclDouble, ncclMax, h->comm, h->st));  // MPI_ALLREDUCE(MAX), src/modtstep.f90:131-132
     CU(cudaMemcpyAsync(h->h_red, h->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
     const double ct = h->h_red[0], dn = fmax(1e-5, h->h_red[1]);  // src/modtstep.f90:114-115
@@ -856,6 +985,10 @@ extern "C" int udgpu_divergence(udgpu_t *h, double *divmax, double *divtot, doub
   k_div<<<grid3(g, B3), B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], h->d_red + 4);
   KCHECK();
   h->launches++;
+  if (h->P > 1) {  // MPI_ALLREDUCE MAX / SUM, src/modchecksim.f90:192-195
+    NC(ncclAllReduce(h->d_red + 4, h->d_red + 4, 1, ncclDouble, ncclMax, h->comm, h->st));
+    NC(ncclAllReduce(h->d_red + 5, h->d_red + 5, 2, ncclDouble, ncclSum, h->comm, h->st));
+  }
   CU(cudaMemcpyAsync(h->h_red + 4, h->d_red + 4, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   if (divmax) *divmax = h->h_red[4];
