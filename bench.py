@@ -84,14 +84,22 @@ class ClockSampler:
         return out
 
 
-def channel_state(n_i, n_j, n_k, seed=0):
-    """synthetic periodic channel of SURVEY.md §8d: u = 1 + noise, v, w noise, halo-consistent."""
-    rng = np.random.default_rng(seed)
-    shp = (n_i + 2, n_j + 2, n_k + 2)
+def grid_for(n_gpus, base):
+    """weak scaling: 256^3 cells per GPU.  1: 256^3 (BASELINE config 2), 2: 512x256x256, 4: 512x512x256, 8: 512^3."""
+    b = base
+    return {1: (b, b, b), 2: (2 * b, b, b), 4: (2 * b, 2 * b, b), 8: (2 * b, 2 * b, 2 * b)}[n_gpus]
+
+
+def channel_slab(I, J, K, i_lo, imax, seed=0):
+    """synthetic periodic channel of SURVEY.md §8d on the x-slab [i_lo, i_lo+imax): u = 1 + noise, v, w noise.
+    Seeded per global i-plane, so the field does not depend on the decomposition."""
+    shp = (imax + 2, J + 2, K + 2)
     u = np.zeros(shp, order="F"); v = np.zeros(shp, order="F"); w = np.zeros(shp, order="F")
-    u[1:-1, 1:-1, 1:-1] = 1.0 + 0.05 * (rng.random((n_i, n_j, n_k)) - 0.5)
-    v[1:-1, 1:-1, 1:-1] = 0.05 * (rng.random((n_i, n_j, n_k)) - 0.5)
-    w[1:-1, 1:-1, 2:-1] = 0.05 * (rng.random((n_i, n_j, n_k - 1)) - 0.5)
+    for il in range(imax):
+        rng = np.random.default_rng([seed, i_lo + il])
+        u[il + 1, 1:-1, 1:-1] = 1.0 + 0.05 * (rng.random((J, K)) - 0.5)
+        v[il + 1, 1:-1, 1:-1] = 0.05 * (rng.random((J, K)) - 0.5)
+        w[il + 1, 1:-1, 2:-1] = 0.05 * (rng.random((J, K - 1)) - 0.5)
     return u, v, w
 
 
@@ -103,8 +111,9 @@ def run_reference(args, rank, world):
         return
     from oracle.oracle import Oracle
     n = args.size
+    I, J, K = grid_for(world, args.size)
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ["OMP_NUM_THREADS"] = str(cores)     # torchrun sets it to 1
     o = Oracle(n, n, n)
     o.init_channel()
     dt = 0.25 * o.dx / 1.1
@@ -120,11 +129,14 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "cell-updates/s", "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"neutral periodic channel {n}^3, stencil+Poisson only, no IBM/scalars (BASELINE config 2)",
-                   "grid": [n, n, n], "substeps_per_step": 1},
+        "config": {"workload": f"neutral periodic channel {I}x{J}x{K}, stencil+Poisson only, no IBM/scalars "
+                               + ("(BASELINE config 2)" if world == 1 else f"(config 2 weak-scaled: {args.size}^3 cells per GPU, x-slabs)"),
+                   "grid": [I, J, K], "substeps_per_step": 1,
+                   "sample_grid": [n, n, n]},
         "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} RK3 substeps of the full {n}^3 workload, C/OpenMP restatement of the reference loops "
-                                   "(not the Fortran/MPI binary; in-tree radix-2 FFT instead of FFTW)"},
+                         "sample": f"{args.steps} RK3 substeps on a {n}^3 block of the workload (the whole workload at N=1; cell-updates/s "
+                                   "is intensive), C/OpenMP restatement of the reference loops on all host cores "
+                                   "(not the Fortran/MPI binary: no Fortran/MPI/FFTW in the image; in-tree radix-2 FFT instead of FFTW)"},
         "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -135,13 +147,21 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world):
     import torch
     import udales_b200 as U
-    if world > 1:
-        raise SystemExit("multi-GPU slabs are not wired into bench.py yet")
-    n = args.size
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
-    g = U.UdalesGPU(n, n, n, device=dev)
-    u, v, w = channel_state(n, n, n)
+    uid = None
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+        obj = [U.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        uid = obj[0]
+    I, J, K = grid_for(world, args.size)
+    imax = I // world
+    g = U.UdalesGPU(I, J, K, xlen=I / 2.0, ylen=J / 2.0, zf=(np.arange(K) + 0.5) * 0.5, device=dev,
+                    nprocx=world, myidx=rank, nccl_uid=uid)
+    u, v, w = channel_slab(I, J, K, rank * imax, imax)
     for nm, f in (("u0", u), ("v0", v), ("w0", w)):
         g.push(nm, f)
     g.halos(); g.boundary()
@@ -150,22 +170,34 @@ def run_ours(args, rank, world):
     dt = 0.25 * 0.5 / 1.1
     g.dt = dt
     st = torch.cuda.ExternalStream(g.stream(), device=dev)
-    ncell = n ** 3
+    ncell = I * J * K            # whole job
+    ncell_loc = imax * J * K
+
+    def barrier():
+        g.sync(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- device-resident throughput ("value") ----
     for _ in range(max(args.warmup, 3)):
         g.substep(dt)
-    g.sync()
+    barrier()
     sampler = ClockSampler(dev); sampler.start()
     l0 = g.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     e0.record(st)
     for _ in range(args.steps):
         g.substep(dt)
     e1.record(st)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))      # device time, max over ranks
     launches = g.launch_count() - l0
     clocks = sampler.stop()
     value = ncell * args.steps / (ms * 1e-3)
@@ -185,7 +217,7 @@ def run_ours(args, rank, world):
     roof_all = {}
     for nm, t in fam.items():
         if t > 0 and B_PER_CELL[nm] > 0:
-            ach = B_PER_CELL[nm] * ncell / (t * 1e-3) / 1e9
+            ach = B_PER_CELL[nm] * ncell_loc / (t * 1e-3) / 1e9
             roof_all[nm] = {"ms": t, "achieved_gbs": ach, "frac": ach / hbm}
     dom = max(roof_all, key=lambda k: roof_all[k]["ms"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": roof_all[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
@@ -195,7 +227,8 @@ def run_ours(args, rank, world):
     # ---- end to end through the C-ABI with HOST buffers (state lives on the host, literal drop-in) ----
     names_in = ("u0", "v0", "w0", "um", "vm", "wm", "pres0")
     names_out = ("u0", "v0", "w0", "pres0")
-    host = {nm: torch.empty((n + 2) ** 3, dtype=torch.float64).pin_memory() for nm in names_in}
+    nloc = (imax + 2) * (J + 2) * (K + 2)
+    host = {nm: torch.empty(nloc, dtype=torch.float64).pin_memory() for nm in names_in}
     for nm in names_in:
         g.pull_raw(nm, host[nm].data_ptr())
     g.sync()
@@ -203,21 +236,24 @@ def run_ours(args, rank, world):
     rk = g.rk3step
     for it in range(2 + ne2e):
         if it == 2:
-            torch.cuda.synchronize(); t0 = time.perf_counter()
+            barrier(); t0 = time.perf_counter()
         for nm in names_in:
             g.push_raw(nm, host[nm].data_ptr())
         g.substep(dt)
         for nm in names_out:
             g.pull_raw(nm, host[nm].data_ptr())
         g.sync()
-    t_e2e = (time.perf_counter() - t0) / ne2e
-    bi = len(names_in) * (n + 2) ** 3 * 8
-    bo = len(names_out) * (n + 2) ** 3 * 8
+    barrier()
+    t_e2e = max_over_ranks((time.perf_counter() - t0) / ne2e)
+    bi = len(names_in) * nloc * 8 * world
+    bo = len(names_out) * nloc * 8 * world
 
     # ---- CPU baseline beside it (oracle port, bounded sample) ----
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         from oracle.oracle import Oracle
+        n = args.size
         cores = os.cpu_count() or 1
         o = Oracle(n, n, n)
         o.init_channel()
@@ -236,9 +272,10 @@ def run_ours(args, rank, world):
         "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"neutral periodic channel {n}^3, stencil+Poisson only, no IBM/scalars (BASELINE config 2)",
-                   "grid": [n, n, n], "substeps_per_step": 1, "l2": "working set (13 fields x 134 MB) >> 126 MB L2, no flush needed",
-                   "sgs": "vreman", "poisson": "FFT2D x,y + tridiagonal z"},
+        "config": {"workload": f"neutral periodic channel {I}x{J}x{K}, stencil+Poisson only, no IBM/scalars "
+                               + ("(BASELINE config 2)" if world == 1 else f"(config 2 weak-scaled: {args.size}^3 cells per GPU, x-slabs)"),
+                   "grid": [I, J, K], "substeps_per_step": 1, "l2": "per-GPU working set (13 fields x 134 MB) >> 126 MB L2, no flush needed",
+                   "sgs": "vreman", "poisson": "FFT2D x,y + tridiagonal z", "decomposition": f"nprocx={world}, nprocy=1"},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": ncell / t_e2e, "unit": "cell-updates/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
                 "ms_per_step": 1e3 * t_e2e, "note": "state pushed from / pulled to pinned host arrays every substep"},
@@ -246,7 +283,12 @@ def run_ours(args, rank, world):
         "poisson_solves_per_s": (1e3 / fam["poisson_core"]) if fam.get("poisson_core") else None,
         "divergence_rms": drms,
     }
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    g.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
