@@ -145,6 +145,9 @@ def run_reference(args, rank, world):
 
 # --------------------------------------------------------------------------------------------
 def run_ours(args, rank, world):
+    # NCCL prints its version banner on stdout: keep stdout clean for the ONE JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import udales_b200 as U
     dev = int(os.environ.get("LOCAL_RANK", "0"))
@@ -283,9 +286,11 @@ def run_ours(args, rank, world):
         "poisson_solves_per_s": (1e3 / fam["poisson_core"]) if fam.get("poisson_core") else None,
         "divergence_rms": drms,
     }
+    g.close()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
-    g.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -93,7 +93,7 @@ typedef struct udgpu_cfg {
 
 #define UDGPU_F_NO_LAZY_FUSION 1  /* run every call eagerly as its own kernel(s) (debug / parity bisecting) */
 #define UDGPU_F_NO_GRAPH 2        /* do not capture the substep into a CUDA graph                          */
-#define UDGPU_F_P2P_TRANSPOSE 4   /* multi-GPU: peer-store pack+transfer kernels instead of ncclSend/Recv  */
+#define UDGPU_F_NCCL_TRANSPOSE 4  /* multi-GPU: ncclSend/Recv all-to-all instead of the peer-store (NVLink P2P) fused transposes */
 #define UDGPU_F_V1_KERNELS 8      /* use the direct one-thread-per-cell kernels instead of the TMA-staged ones (cross-check) */
 
 typedef struct udgpu udgpu_t;     /* opaque */

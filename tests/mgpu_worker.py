@@ -27,14 +27,15 @@ def main():
         dist.broadcast_object_list(obj, src=0)
         return obj[0]
 
+    flags_list = [0, 4]      # 0: peer-store (NVLink P2P) fused transposes, 4: UDGPU_F_NCCL_TRANSPOSE
     shapes = [(64, 64, 32), (128, 64, 24)] if len(sys.argv) < 2 else [tuple(int(x) for x in sys.argv[1].split("x"))]
     worst = 0.0
-    for shape in shapes:
+    for shape, flags in [(s_, f_) for s_ in shapes for f_ in flags_list]:
         I, J, K = shape
         zf = stretched_zf(K, K * 0.5, 1.03)
         o = Oracle(I, J, K, zf=zf)
         o.init_channel()
-        g = U.UdalesGPU(I, J, K, zf=zf, device=dev, nprocx=world, myidx=rank, nccl_uid=fresh_uid())
+        g = U.UdalesGPU(I, J, K, zf=zf, device=dev, nprocx=world, myidx=rank, nccl_uid=fresh_uid(), flags=flags)
         for n in ("u0", "v0", "w0", "um", "vm", "wm", "pres0"):
             g.push(n, U.slab_of(getattr(o, n), world, rank))
         # Poisson alone
@@ -65,7 +66,7 @@ def main():
         d, _, ct, dn = g.tstep_update(0.05, 0, courant=1.1, diffnr=0.25, dtmax=2.0)
         assert abs(ct - ct_ref) < 1e-12 * ct_ref and abs(dn - dn_ref) < 1e-12 * dn_ref and abs(d - d_ref) < 1e-12 * d_ref
         g.close()
-        print(f"rank {rank}: shape {shape} ok, worst so far {worst:.2e}", flush=True)
+        print(f"rank {rank}: shape {shape} flags {flags} ok, worst so far {worst:.2e}", flush=True)
     dist.barrier()
     print(f"MGPU OK rank {rank}/{world} worst abs err {worst:.2e}", flush=True)
     dist.destroy_process_group()

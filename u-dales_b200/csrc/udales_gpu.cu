@@ -57,6 +57,27 @@ struct ProfSlot {
   long n = 0;
 };
 
+// ---- peer-to-peer (NVLink) transposes --------------------------------------------------------
+// Every rank exposes one allocation [recvA | recvB | flags] through CUDA IPC.  The FFT kernels store
+// their output blocks straight into the peers' receive buffers (pack + transfer fused into the
+// producing kernel, no send buffer, no NCCL in the data path); k_p2p_barrier is the cross-GPU
+// "all blocks have landed" synchronisation: a system-scope flag exchange over the same mappings.
+struct P2PPtrs { unsigned long long *flags[8]; };
+__global__ void k_p2p_barrier(P2PPtrs f, int P, int rank, unsigned long long epoch, int *status) {
+  const int d = threadIdx.x;
+  if (d < P) {
+    __threadfence_system();
+    volatile unsigned long long *remote = f.flags[d] + rank;   // my slot in peer d's flag array
+    *remote = epoch;
+    __threadfence_system();
+    volatile unsigned long long *mine = f.flags[rank] + d;
+    const long long t0 = clock64();
+    while (*mine < epoch) {
+      if (clock64() - t0 > 20000000000LL) { *status = 1; break; }  // ~10 s: a peer died; do not hang the GPU
+    }
+  }
+}
+
 struct udgpu {
   udgpu_cfg cfg;
   Geo g;
@@ -84,6 +105,13 @@ struct udgpu {
   ncclComm_t comm = nullptr;
   double *sendL = nullptr, *sendR = nullptr, *recvL = nullptr, *recvR = nullptr;  // halo columns
   size_t halo_cap = 0;
+  bool p2p = false;           // peer-store transposes (default when CUDA IPC + peer access work)
+  void *ipc_mine = nullptr;   // [recvA | recvB | flags]
+  void *ipc_peer[8] = {};
+  double *rA[8] = {}, *rB[8] = {};
+  P2PPtrs pflags;
+  unsigned long long epoch = 0;
+  int *d_status = nullptr;
   double *sbuf = nullptr, *rbuf = nullptr, *workB = nullptr;  // transposes: wire-format send / receive, x-pencil work
   int IB = 0, JB = 0;         // local i extent of the slab, local j extent of the x-pencil
   Geo gB;                     // geometry of the x-pencil (itot, JB, ktot) for the z solve
@@ -106,6 +134,7 @@ struct udgpu {
 
 // ------------------------------------------------------------------------------------------
 static int flush_pending(udgpu *h);
+static int setup_p2p(udgpu *h, size_t nR);
 static int materialize_zero_tend(udgpu *h);
 static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt);
 static int dev_alloc(udgpu *h, void **p, size_t bytes) {
@@ -368,6 +397,7 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     for (double **b : {&h->sbuf, &h->rbuf, &h->workB}) RET(dev_alloc(h, (void **)b, nR * sizeof(double)));
     h->gB = g;
     h->gB.imax = g.itot; h->gB.jmax = h->JB; h->gB.i0g = 0; h->gB.j0g = h->rank * h->JB;
+    RET(setup_p2p(h, nR));
   }
   RET(dev_alloc(h, (void **)&h->d_red, 16 * sizeof(double)));
   CU(cudaMallocHost((void **)&h->h_red, 16 * sizeof(double)));
@@ -434,6 +464,8 @@ extern "C" int udgpu_finalize(udgpu_t *h) {
   cudaStreamSynchronize(h->st);
   for (void *p : h->allocs) cudaFree(p);
   if (h->h_red) cudaFreeHost(h->h_red);
+  for (int d = 0; d < 8; d++)
+    if (h->ipc_peer[d] && h->ipc_peer[d] != h->ipc_mine) cudaIpcCloseMemHandle(h->ipc_peer[d]);
   if (h->comm) ncclCommDestroy(h->comm);
   for (int w = 0; w < PROF_N; w++)
     for (auto &e : h->ps[w].pend) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -485,6 +517,11 @@ extern "C" int udgpu_device_ptr(udgpu_t *h, int field, int n4, void **dptr) {
 extern "C" int udgpu_sync(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
   CU(cudaStreamSynchronize(h->st));
+  if (h->p2p) {
+    int st = 0;
+    CU(cudaMemcpy(&st, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) return set_err(UDGPU_ESTATE, "peer-to-peer barrier timed out: a peer rank is gone");
+  }
   return UDGPU_OK;
 }
 extern "C" int udgpu_host_register(void *ptr, size_t bytes) {
@@ -751,6 +788,64 @@ static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *
 
 // rhs (halo-free work array) -> solution.  Final pass writes either in place or into the interior of
 // the halo'd p array.  Order x, y, z, y^-1, x^-1 as in src/modpois.f90:478-679.
+
+// exchange CUDA IPC handles of the receive windows through NCCL and map every peer's window
+static int setup_p2p(udgpu *h, size_t nR) {
+  h->p2p = false;
+  if (h->cfg.flags & UDGPU_F_NCCL_TRANSPOSE) return UDGPU_OK;
+  const int P = h->P;
+  const size_t bytes = 2 * nR * sizeof(double) + 4096;
+  if (cudaMalloc(&h->ipc_mine, bytes) != cudaSuccess) { cudaGetLastError(); return UDGPU_OK; }
+  h->allocs.push_back(h->ipc_mine);
+  CU(cudaMemsetAsync(h->ipc_mine, 0, bytes, h->st));
+  RET(dev_alloc(h, (void **)&h->d_status, sizeof(int)));
+  cudaIpcMemHandle_t mine;
+  unsigned char ok = cudaIpcGetMemHandle(&mine, h->ipc_mine) == cudaSuccess ? 1 : 0;
+  if (!ok) cudaGetLastError();
+  // allgather {handle, ok} (80 bytes per rank) on the device through the communicator we already have
+  struct Rec { cudaIpcMemHandle_t hd; unsigned char ok; unsigned char pad[15]; };
+  static_assert(sizeof(Rec) == 80, "ipc record");
+  Rec rec; memset(&rec, 0, sizeof(rec)); rec.hd = mine; rec.ok = ok;
+  unsigned char *d_all;
+  RET(dev_alloc(h, (void **)&d_all, sizeof(Rec) * P));
+  CU(cudaMemcpyAsync(d_all + sizeof(Rec) * h->rank, &rec, sizeof(Rec), cudaMemcpyHostToDevice, h->st));
+  NC(ncclAllGather(d_all + sizeof(Rec) * h->rank, d_all, sizeof(Rec), ncclUint8, h->comm, h->st));
+  std::vector<Rec> all(P);
+  CU(cudaMemcpyAsync(all.data(), d_all, sizeof(Rec) * P, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  bool good = true;
+  for (int d = 0; d < P; d++) good = good && all[d].ok;
+  for (int d = 0; d < P && good; d++) {
+    if (d == h->rank) { h->ipc_peer[d] = h->ipc_mine; continue; }
+    if (cudaIpcOpenMemHandle(&h->ipc_peer[d], all[d].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; }
+  }
+  // every rank must take the same decision: allreduce(min) of the local verdict
+  int *d_flag;
+  RET(dev_alloc(h, (void **)&d_flag, sizeof(int)));
+  int v = good ? 1 : 0;
+  CU(cudaMemcpyAsync(d_flag, &v, sizeof(int), cudaMemcpyHostToDevice, h->st));
+  NC(ncclAllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, h->comm, h->st));
+  CU(cudaMemcpyAsync(&v, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  if (!v) return UDGPU_OK;   // stay on the NCCL send/recv path
+  for (int d = 0; d < P; d++) {
+    h->rA[d] = (double *)h->ipc_peer[d];
+    h->rB[d] = h->rA[d] + nR;
+    h->pflags.flags[d] = (unsigned long long *)(h->rB[d] + nR);
+  }
+  for (int d = P; d < 8; d++) h->pflags.flags[d] = nullptr;
+  h->p2p = true;
+  return UDGPU_OK;
+}
+
+static int p2p_barrier(udgpu *h) {
+  h->epoch++;
+  k_p2p_barrier<<<1, 32, 0, h->st>>>(h->pflags, h->P, h->rank, h->epoch, h->d_status);
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+
 // all-to-all of the wire-format blocks (block d of sbuf -> rank d, block s of rbuf <- rank s): the
 // MPI_ALLTOALLV of the reference's transposes (2decomp-fft/src/transpose_x_to_y.f90:121-123)
 static int a2a_blocks(udgpu *h) {
@@ -781,17 +876,23 @@ static int poisson_core_slab(udgpu *h, double *work, double *p_halo) {
   const LineDesc yW = {(long long)IB, 1, (long long)JB * IB, IB, K};            // ... in wire format (per block)
   const LineDesc xW = {1, (long long)IB, (long long)JB * IB, JB, K};            // x lines in wire format (per block)
   const LineDesc xB = {1, (long long)g.itot, (long long)g.itot * JB, JB, K};    // x lines in the x-pencil
+  if (h->p2p) {
+    // block for rank d is stored directly at slot `rank` of d's receive window A (return path: window B)
+    for (int d = 0; d < P; d++) { bs.base[d] = h->rA[d] + h->rank * blk; br.base[d] = h->rA[h->rank] + d * blk; }
+  }
   bs.shift = br.shift = ilog2(JB); bs.mask = br.mask = JB - 1;
   RET(rfft_fast<false>(h, g.jtot, 0, work, yA, nullptr, yW, h->py, nullptr, &bs));
-  RET(a2a_blocks(h));
+  if (h->p2p) RET(p2p_barrier(h)); else RET(a2a_blocks(h));
   br.shift = ilog2(IB); br.mask = IB - 1;
   RET(rfft_fast<true>(h, g.itot, 0, nullptr, xW, h->workB, xB, h->px, &br, nullptr));
   k_zsolve<<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
   KCHECK();
   h->launches++;
+  if (h->p2p)
+    for (int d = 0; d < P; d++) { bs.base[d] = h->rB[d] + h->rank * blk; br.base[d] = h->rB[h->rank] + d * blk; }
   bs.shift = ilog2(IB); bs.mask = IB - 1;
   RET(rfft_fast<true>(h, g.itot, 1, h->workB, xB, nullptr, xW, h->px, nullptr, &bs));
-  RET(a2a_blocks(h));
+  if (h->p2p) RET(p2p_barrier(h)); else RET(a2a_blocks(h));
   br.shift = ilog2(JB); br.mask = JB - 1;
   LineDesc yOut = yA;
   double *outp = work;
