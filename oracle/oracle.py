@@ -178,8 +178,9 @@ class Oracle:
         self.randomize("w0", ampl, ir + 2)
         self.w0[:, :, 1] = 0.0
         for n in range(self.nsv):
+            hc = self.ihc
             self.sv0[..., n] = 0.0
-            self.sv0[2:-2, 2:-2, 2:-2, n] = 1.0
+            self.sv0[hc:-hc, hc:-hc, hc:-hc, n] = 1.0
             self.randomize("sv0", 0.1, ir + 10 + n, n)
         self.halos()
         self.boundary()

@@ -25,6 +25,9 @@ def make_pair(itot, jtot, ktot, stretched=True, seed_ir=43, gpu_flags=0, **kw):
 def push_state(o, g, names=STATE):
     for n in names:
         g.push(n, getattr(o, n))
+    for n4 in range(o.nsv):
+        g.push("sv0", o.sv0[..., n4], n4)
+        g.push("svm", o.svm[..., n4], n4)
 
 
 def interior(a):
@@ -34,6 +37,14 @@ def interior(a):
 def tend_interior(a):
     """(ib:ie, jb:je, kb:ke) of a tendency-shaped array (k starts at kb, one ghost level on top)."""
     return a[1:-1, 1:-1, :-1]
+
+
+def sv_interior(a, hc):
+    return a[hc:-hc, hc:-hc, hc:-hc]
+
+
+def svp_interior(a, hc):
+    return a[hc:-hc, hc:-hc, :-hc]
 
 
 def relerr(a, b):

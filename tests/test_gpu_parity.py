@@ -6,7 +6,7 @@ rel-L_inf <= 1e-10, post-projection divergence RMS far below north_star's 1e-6.
 import numpy as np
 import pytest
 
-from helpers import interior, make_pair, push_state, relerr, tend_interior
+from helpers import interior, make_pair, push_state, relerr, sv_interior, svp_interior, tend_interior
 
 pytestmark = pytest.mark.gpu
 
@@ -164,3 +164,32 @@ def test_full_size_properties_256():
         dmax, dtot, drms = g.divergence()
         assert drms < 1e-12, (s, drms)
     assert np.isfinite(g.pull("u0")).all()
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 24, 20), (48, 40, 33)])
+@pytest.mark.parametrize("kw", [dict(nsv=2), dict(nsv=1, iadv_sv=2), dict(nsv=3, lvreman=False, lsmagorinsky=False),
+                                dict(nsv=1, lvreman=False, lsmagorinsky=True)])
+@pytest.mark.parametrize("flags", [0, F_NO_LAZY])
+def test_scalars(shape, kw, flags):
+    """advecc_kappa / advecc_2nd + diffc, scalar integrate / halos / top BC."""
+    o, g = make_pair(*shape, gpu_flags=flags, **kw)
+    hc = o.ihc
+    o.advection(); g.advection()
+    if flags:   # eager: advection alone is observable
+        for n4 in range(o.nsv):
+            assert relerr(svp_interior(g.pull("svp", n4), hc), svp_interior(o.svp[..., n4], hc)) < TOL_STENCIL
+    o.subgrid(); g.subgrid()
+    for n4 in range(o.nsv):
+        assert relerr(svp_interior(g.pull("svp", n4), hc), svp_interior(o.svp[..., n4], hc)) < TOL_STENCIL
+    dt = 0.02
+    o.dt = g.dt = dt
+    o2, g2 = make_pair(*shape, gpu_flags=flags, **kw)
+    o2.dt = g2.dt = dt
+    for s in range(4):
+        o2.substep(dt); g2.substep(dt)
+        for n4 in range(o2.nsv):
+            for nm in ("sv0", "svm"):
+                a, b = g2.pull(nm, n4), getattr(o2, nm)[..., n4]
+                # whole array except the bottom ghost levels (never written by the path) incl. lateral halos, top ghosts
+                assert relerr(a[:, :, hc:], b[:, :, hc:]) < 1e-11, (s, nm, n4)
+        assert relerr(g2.pull("u0"), o2.u0) < 1e-11

@@ -227,7 +227,7 @@ class UdalesGPU:
 
     def push(self, name, arr, n4=0):
         a = np.asfortranarray(arr, dtype=np.float64)
-        assert a.shape[:3] == self.shape(name), (name, a.shape, self.shape(name))
+        assert a.shape == self.shape(name), (name, a.shape, self.shape(name))
         self._chk(self.L.udgpu_push(self.h, FIELD_IDS[name], n4, a.ctypes.data))
         self._chk(self.L.udgpu_sync(self.h))
 

@@ -1,0 +1,126 @@
+// scalar_v1.cuh — passive scalars (sv): advecc_kappa / advecc_2nd (src/modadvection.f90:316-421,
+// :103-155), diffc (src/modsubgrid.f90:540-623), their part of tstep_integrate
+// (src/modtstep.f90:216-218,327,336) and of boundary (fluxtopscal, src/modboundary.f90:1521-1537).
+// Scalar arrays carry halo ihc (2 with kappa, src/modglobal.f90:602-609); u0,v0,w0,ekh carry halo 1.
+// One thread per cell; every face value of the kappa scheme is evaluated by both cells that share
+// the face (bitwise identical), which keeps the kernel free of temporaries (the reference allocates
+// two full 3-D arrays and makes three whole-array passes per direction, :327-328,355,379,404).
+#pragma once
+#include "common.cuh"
+
+namespace udg {
+
+// rlim: src/modadvection.f90:408-421
+__device__ __forceinline__ double rlim(double d1, double d2) {
+  const double eps1 = 1.e-10;
+  const double ri = (d2 + eps1) / (d1 + eps1);
+  const double phir = fmax(0., fmin(2. * ri, fmin(1. / 3. + 2. / 3. * ri, 2.)));
+  return 0.5 * phir * d1;
+}
+
+// face value cf of the kappa scheme at the lower face of cell index `c` along a direction with
+// element stride st: vel = advecting velocity at that face; hci_m1, hci_0, hci_p1 = inverse centre
+// spacings at c-1, c, c+1; fc = cell size used to scale the limiter (src/modadvection.f90:335-351).
+__device__ __forceinline__ double kappa_face(const double *__restrict__ v, long long c, long long st, double vel,
+                                             double hci_m1, double hci_0, double hci_p1, double fc) {
+  double d1, d2, cf;
+  if (vel > 0) {
+    d1 = (v[c - st] - v[c - 2 * st]) * hci_m1;
+    d2 = (v[c] - v[c - st]) * hci_0;
+    cf = v[c - st];
+  } else {
+    d1 = (v[c] - v[c + st]) * hci_p1;
+    d2 = (v[c - st] - v[c]) * hci_0;
+    cf = v[c];
+  }
+  return cf + fc * rlim(d1, d2);
+}
+
+// SCHEME 7 = kappa, 2 = cd2.  ADV / DIFF select the operators (advection() / subgrid()).
+template <int SCHEME, bool ADV, bool DIFF, bool ACC, bool LES>
+__global__ void __launch_bounds__(256) k_scalar_tend(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
+                                                     const double *__restrict__ w0, const double *__restrict__ ekh,
+                                                     const double *__restrict__ sv, double *__restrict__ svp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long c = offS(g, i, j, k), t = offST(g, i, j, k), m = offF(g, i, j, k);
+  const long long sj = g.pic, sk = g.pkc, mj = g.pi, mk = g.pk;
+  double r = ACC ? svp[t] : 0.0;
+  if (ADV) {
+    if (SCHEME == 7) {
+      const double dxi = g.dxi, dx = g.dx, dyi = g.dyi;
+      // x (uniform: dxhci = dxi, dxfc = dx, dxfci = dxi)
+      const double ul = u0[m], ur = u0[m + 1];
+      const double cl = kappa_face(sv, c, 1, ul, dxi, dxi, dxi, dx);
+      const double cr = kappa_face(sv, c + 1, 1, ur, dxi, dxi, dxi, dx);
+      r = r + (-cr * ur * dxi) + cl * ul * dxi;          // varp + dumu + duml  (:355)
+      // y (no stretching: unit spacings, limiter unscaled)
+      const double vl = v0[m], vr = v0[m + mj];
+      const double cs = kappa_face(sv, c, sj, vl, 1., 1., 1., 1.);
+      const double cn = kappa_face(sv, c + sj, sj, vr, 1., 1., 1., 1.);
+      r = r + (-cn * vr * dyi) + cs * vl * dyi;          // (:379)
+      // z: faces kb+1 .. ke+1 only (:383)
+      const double wt = w0[m + mk];
+      const double ct = kappa_face(sv, c + sk, sk, wt, g.dzhci[k], g.dzhci[k + 1], g.dzhci[k + 2], g.dzfc[k + 1]);
+      double dl = 0.0;
+      if (k >= 2) {
+        const double wb = w0[m];
+        const double cb = kappa_face(sv, c, sk, wb, g.dzhci[k - 1], g.dzhci[k], g.dzhci[k + 1], g.dzfc[k]);
+        dl = cb * wb * g.dzfci[k];
+      }
+      r = r + (-ct * wt * g.dzfci[k]) + dl;              // (:404)
+    } else {
+      const double dzfk = g.dzf[k], dzfkp = g.dzf[k + 1], dzfkm = g.dzf[k - 1];
+      r = r - ((u0[m + 1] * (sv[c + 1] + sv[c]) - u0[m] * (sv[c - 1] + sv[c])) * g.dxi5 +
+               (v0[m + mj] * (sv[c + sj] + sv[c]) - v0[m] * (sv[c - sj] + sv[c])) * g.dyi5);
+      r = r - (w0[m + mk] * (sv[c + sk] * dzfk + sv[c] * dzfkp) * g.dzhi[k + 1] -
+               w0[m] * (sv[c - sk] * dzfk + sv[c] * dzfkm) * g.dzhi[k]) * g.dzfi5[k];
+    }
+  }
+  if (DIFF) {
+    if (LES) {
+      const double dzfk = g.dzf[k], dzfkp = g.dzf[k + 1], dzfkm = g.dzf[k - 1];
+      r = r + 0.5 * (((ekh[m + 1] + ekh[m]) * (sv[c + 1] - sv[c]) - (ekh[m] + ekh[m - 1]) * (sv[c] - sv[c - 1])) * g.dx2i +
+                     ((ekh[m + mj] + ekh[m]) * (sv[c + sj] - sv[c]) - (ekh[m] + ekh[m - mj]) * (sv[c] - sv[c - sj])) * g.dy2i +
+                     ((dzfkp * ekh[m] + dzfk * ekh[m + mk]) * (sv[c + sk] - sv[c]) * g.dzh2i[k + 1] -
+                      (dzfkm * ekh[m] + dzfk * ekh[m - mk]) * (sv[c] - sv[c - sk]) * g.dzh2i[k]) * g.dzfi[k]);
+    } else {
+      const double cekh = g.numol * g.prandtlmoli;
+      r = r + ((cekh * (sv[c + 1] - sv[c]) - cekh * (sv[c] - sv[c - 1])) * g.dx2i +
+               (cekh * (sv[c + sj] - sv[c]) - cekh * (sv[c] - sv[c - sj])) * g.dy2i +
+               (cekh * (sv[c + sk] - sv[c]) * g.dzhi[k + 1] - cekh * (sv[c] - sv[c - sk]) * g.dzhi[k]) * g.dzfi[k]);
+    }
+  }
+  svp[t] = r;
+}
+
+// sv0 = svm + rk3coef*svp ; (step 3) svm = sv0   — src/modtstep.f90:216-218,336
+template <bool STEP3>
+__global__ void __launch_bounds__(256) k_scalar_integrate(Geo g, double rk3coef, double *__restrict__ sv0, double *__restrict__ svm,
+                                                          const double *__restrict__ svp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long c = offS(g, i, j, k), t = offST(g, i, j, k);
+  const double a = svm[c] + rk3coef * svp[t];
+  sv0[c] = a;
+  if (STEP3) svm[c] = a;
+}
+
+// fluxtopscal with zero flux (src/modboundary.f90:1521-1537): ghost levels ke+1..ke+khc copy level ke on the
+// momentum-halo footprint (ib-ih:ie+ih, jb-jh:je+jh) of the scalar arrays
+__global__ void k_scalar_top(Geo g, double *__restrict__ sv0, double *__restrict__ svm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1 - g.ih;
+  const int j = blockIdx.y + 1 - g.jh;
+  if (i > g.imax + g.ih) return;
+  const long long cK = offS(g, i, j, g.ktot);
+  for (int mm = 1; mm <= g.khc; mm++) {
+    sv0[cK + mm * g.pkc] = sv0[cK];
+    svm[cK + mm * g.pkc] = svm[cK];
+  }
+}
+
+}  // namespace udg

@@ -144,21 +144,26 @@ __global__ void k_wrap_y(PtrPack a, int pi, int pj, int nlev, int jmax, int h) {
 // gather the first / last interior column of every (j,k) row incl. halo rows into contiguous send
 // buffers, and scatter received columns into the halo columns.  One thread per row.
 struct HaloPack { double *f[8]; int nlev[8]; long long off[8]; int n; };
-__global__ void k_halo_pack_x(HaloPack a, int pi, int pj, int imax, double *__restrict__ sendL, double *__restrict__ sendR) {
+// width-h columns: send buffers hold h doubles per row (m = 0..h-1: interior columns h+m / imax+m)
+__global__ void k_halo_pack_x(HaloPack a, int pi, int pj, int imax, int h, double *__restrict__ sendL, double *__restrict__ sendR) {
   const int f = blockIdx.y;
   const long long jk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (jk >= (long long)pj * a.nlev[f]) return;
   const double *q = a.f[f] + jk * pi;
-  sendL[a.off[f] + jk] = q[1];
-  sendR[a.off[f] + jk] = q[imax];
+  for (int m = 0; m < h; m++) {
+    sendL[a.off[f] + jk * h + m] = q[h + m];      // first h interior columns  -> left neighbour's right halo
+    sendR[a.off[f] + jk * h + m] = q[imax + m];   // last h interior columns   -> right neighbour's left halo
+  }
 }
-__global__ void k_halo_unpack_x(HaloPack a, int pi, int pj, int imax, const double *__restrict__ recvL, const double *__restrict__ recvR) {
+__global__ void k_halo_unpack_x(HaloPack a, int pi, int pj, int imax, int h, const double *__restrict__ recvL, const double *__restrict__ recvR) {
   const int f = blockIdx.y;
   const long long jk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (jk >= (long long)pj * a.nlev[f]) return;
   double *q = a.f[f] + jk * pi;
-  q[0] = recvL[a.off[f] + jk];
-  q[imax + 1] = recvR[a.off[f] + jk];
+  for (int m = 0; m < h; m++) {
+    q[m] = recvL[a.off[f] + jk * h + m];
+    q[h + imax + m] = recvR[a.off[f] + jk * h + m];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

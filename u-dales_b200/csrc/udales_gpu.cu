@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -18,6 +19,7 @@
 #include "poisson_v1.cuh"
 #include "poisson_fast.cuh"
 #include "stencil_v1.cuh"
+#include "scalar_v1.cuh"
 
 using namespace udg;
 
@@ -291,7 +293,10 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
   if (c->imax != c->itot / c->nprocx || c->jmax != c->jtot || c->kmax != c->ktot) return set_err(UDGPU_EINVAL, "local extents do not match an x-slab: imax=itot/nprocx, jmax=jtot, kmax=ktot");
   if (c->nprocx > 1 && !nccl_uid) return set_err(UDGPU_EINVAL, "nprocx > 1 needs the broadcast ncclUniqueId");
   if (c->nprocx > 1 && (c->myidx < 0 || c->myidx >= c->nprocx || c->zstart[0] != c->myidx * c->imax + 1)) return set_err(UDGPU_EINVAL, "myidx / zstart inconsistent with the slab");
-  if (c->nsv != 0) return set_err(UDGPU_EINVAL, "nsv > 0 not available in this build");
+  if (c->nsv < 0 || c->nsv > 8) return set_err(UDGPU_EINVAL, "nsv must be 0..8");
+  if (c->nsv > 0 && c->iadv_sv != 7 && c->iadv_sv != 2) return set_err(UDGPU_EINVAL, "iadv_sv=%d: kappa (7) or cd2 (2) only", c->iadv_sv);
+  if (c->nsv > 0 && (c->ihc != c->jhc || c->ihc != c->khc || c->ihc != (c->iadv_sv == 7 ? 2 : 1)))
+    return set_err(UDGPU_EINVAL, "scalar halo must be 2 with kappa, 1 with cd2 (src/modglobal.f90:586-609)");
   if (!c->dzf || !c->dzh) return set_err(UDGPU_EINVAL, "dzf/dzh missing");
 
   udgpu *h = new udgpu();
@@ -380,19 +385,21 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     switch (f) {
       case UDGPU_UP: case UDGPU_VP: case UDGPU_WP: n = nT; d3 = K + g.kh; break;
       case UDGPU_RHS: n = nR; d3 = K; break;
-      case UDGPU_SV0: case UDGPU_SVM: case UDGPU_SVP: n = 0; sl = 0; break;
+      case UDGPU_SV0: case UDGPU_SVM: n = c->nsv ? (size_t)g.pic * g.pjc * (K + 2 * g.khc) : 0; sl = c->nsv; d3 = K + 2 * g.khc; break;
+      case UDGPU_SVP: n = c->nsv ? (size_t)g.pic * g.pjc * (K + g.khc) : 0; sl = c->nsv; d3 = K + g.khc; break;
       default: n = nF; d3 = K + 2 * g.kh; break;
     }
     h->cnt[f] = n; h->nslices[f] = sl;
-    h->dims[f][0] = (f == UDGPU_RHS) ? g.imax : g.pi;
-    h->dims[f][1] = (f == UDGPU_RHS) ? g.jmax : g.pj;
+    const bool scal = (f == UDGPU_SV0 || f == UDGPU_SVM || f == UDGPU_SVP);
+    h->dims[f][0] = (f == UDGPU_RHS) ? g.imax : scal ? g.pic : g.pi;
+    h->dims[f][1] = (f == UDGPU_RHS) ? g.jmax : scal ? g.pjc : g.pj;
     h->dims[f][2] = d3;
     if (n) RET(dev_alloc(h, (void **)&h->f[f], n * sl * sizeof(double)));
   }
   RET(dev_alloc(h, (void **)&h->d_scr, nR * sizeof(double)));
   if (h->P > 1) {
     h->IB = g.imax; h->JB = g.jtot / h->P;
-    h->halo_cap = (size_t)8 * g.pj * (K + 2 * g.kh);
+    h->halo_cap = (size_t)8 * 2 * (g.pjc > g.pj ? g.pjc : g.pj) * (K + 2 * (g.khc > g.kh ? g.khc : g.kh));
     for (double **b : {&h->sendL, &h->sendR, &h->recvL, &h->recvR}) RET(dev_alloc(h, (void **)b, h->halo_cap * sizeof(double)));
     for (double **b : {&h->sbuf, &h->rbuf, &h->workB}) RET(dev_alloc(h, (void **)b, nR * sizeof(double)));
     h->gB = g;
@@ -493,7 +500,7 @@ extern "C" int udgpu_field_count(udgpu_t *h, int field, size_t *count, int dims[
 extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
   RET(check_field(h, field, n4));
   RET(flush_pending(h));
-  const bool is_tend = (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP);
+  const bool is_tend = (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP);
   if (is_tend) { RET(materialize_zero_tend(h)); h->tend_pushed = true; }
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(h->f[field] + (size_t)n4 * h->cnt[field], host, h->cnt[field] * sizeof(double), cudaMemcpyHostToDevice, h->st));
@@ -503,7 +510,7 @@ extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
 extern "C" int udgpu_pull(udgpu_t *h, int field, int n4, double *host) {
   RET(check_field(h, field, n4));
   RET(flush_pending(h));
-  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP) RET(materialize_zero_tend(h));
+  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP) RET(materialize_zero_tend(h));
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(host, h->f[field] + (size_t)n4 * h->cnt[field], h->cnt[field] * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
@@ -542,18 +549,17 @@ extern "C" int udgpu_stream(udgpu_t *h, void **s) {
 static dim3 grid3(const Geo &g, dim3 b) { return dim3((g.imax + b.x - 1) / b.x, (g.jmax + b.y - 1) / b.y, g.ktot); }
 static const dim3 B3(64, 4, 1);
 
-// x-halo exchange between neighbouring slabs over NCCL (periodic ring), width 1.
+// x-halo exchange between neighbouring slabs over NCCL (periodic ring).
 // Send order right-then-left / receive order left-then-right so that with P = 2 (both neighbours are
 // the same peer) the first send meets the first receive.
-static int halo_x_exchange(udgpu *h, std::initializer_list<double *> fields, int nlev) {
-  const Geo &g = h->g;
+static int halo_x_exchange_g(udgpu *h, const std::vector<double *> &fields, int nlev, int pi, int pj, int imax, int hw) {
   HaloPack hp; hp.n = 0;
   long long off = 0;
-  for (double *p : fields) { hp.f[hp.n] = p; hp.nlev[hp.n] = nlev; hp.off[hp.n] = off; off += (long long)g.pj * nlev; hp.n++; }
+  for (double *p : fields) { hp.f[hp.n] = p; hp.nlev[hp.n] = nlev; hp.off[hp.n] = off; off += (long long)pj * nlev * hw; hp.n++; }
   if ((size_t)off > h->halo_cap) return set_err(UDGPU_EINVAL, "halo buffer too small");
-  const long long rows = (long long)g.pj * nlev;
+  const long long rows = (long long)pj * nlev;
   const dim3 gr((unsigned)((rows + 127) / 128), hp.n);
-  k_halo_pack_x<<<gr, 128, 0, h->st>>>(hp, g.pi, g.pj, g.imax, h->sendL, h->sendR);
+  k_halo_pack_x<<<gr, 128, 0, h->st>>>(hp, pi, pj, imax, hw, h->sendL, h->sendR);
   KCHECK();
   const int left = (h->rank + h->P - 1) % h->P, right = (h->rank + 1) % h->P;
   NC(ncclGroupStart());
@@ -562,28 +568,39 @@ static int halo_x_exchange(udgpu *h, std::initializer_list<double *> fields, int
   NC(ncclRecv(h->recvL, off, ncclDouble, left, h->comm, h->st));
   NC(ncclRecv(h->recvR, off, ncclDouble, right, h->comm, h->st));
   NC(ncclGroupEnd());
-  k_halo_unpack_x<<<gr, 128, 0, h->st>>>(hp, g.pi, g.pj, g.imax, h->recvL, h->recvR);
+  k_halo_unpack_x<<<gr, 128, 0, h->st>>>(hp, pi, pj, imax, hw, h->recvL, h->recvR);
   KCHECK();
   h->launches += 2;
   return UDGPU_OK;
 }
-
-// lateral halos of momentum-halo arrays: x by local periodic wrap (unsplit) or slab exchange, then y wrap
-static int wrap_xy(udgpu *h, std::initializer_list<double *> fields, int nlev) {
+static int halo_x_exchange(udgpu *h, std::initializer_list<double *> fields, int nlev) {
   const Geo &g = h->g;
-  PtrPack pp; pp.n = 0;
-  for (double *p : fields) pp.p[pp.n++] = p;
-  const long long rows = (long long)g.pj * nlev;
-  if (h->P > 1) RET(halo_x_exchange(h, fields, nlev));
-  else {
-    k_wrap_x<<<(unsigned)((rows + 127) / 128), 128, 0, h->st>>>(pp, g.pi, g.pj, nlev, g.imax, g.ih);
+  return halo_x_exchange_g(h, std::vector<double *>(fields), nlev, g.pi, g.pj, g.imax, g.ih);
+}
+
+// lateral halos: x by local periodic wrap (unsplit) or slab exchange, then y wrap.  Generic in the halo
+// width / pitches so the scalar arrays (halo ihc) use it too.
+static int wrap_xy_g(udgpu *h, const std::vector<double *> &fields, int nlev, int pi, int pj, int imax, int jmax, int hw) {
+  for (size_t f0 = 0; f0 < fields.size(); f0 += 8) {
+    std::vector<double *> part(fields.begin() + f0, fields.begin() + std::min(fields.size(), f0 + 8));
+    PtrPack pp; pp.n = 0;
+    for (double *p : part) pp.p[pp.n++] = p;
+    const long long rows = (long long)pj * nlev;
+    if (h->P > 1) RET(halo_x_exchange_g(h, part, nlev, pi, pj, imax, hw));
+    else {
+      k_wrap_x<<<(unsigned)((rows + 127) / 128), 128, 0, h->st>>>(pp, pi, pj, nlev, imax, hw);
+      KCHECK();
+      h->launches++;
+    }
+    k_wrap_y<<<dim3((pi + 127) / 128, nlev), 128, 0, h->st>>>(pp, pi, pj, nlev, jmax, hw);
     KCHECK();
     h->launches++;
   }
-  k_wrap_y<<<dim3((g.pi + 127) / 128, nlev), 128, 0, h->st>>>(pp, g.pi, g.pj, nlev, g.jmax, g.jh);
-  KCHECK();
-  h->launches++;
   return UDGPU_OK;
+}
+static int wrap_xy(udgpu *h, std::initializer_list<double *> fields, int nlev) {
+  const Geo &g = h->g;
+  return wrap_xy_g(h, std::vector<double *>(fields), nlev, g.pi, g.pj, g.imax, g.jmax, g.ih);
 }
 
 extern "C" int udgpu_closure(udgpu_t *h) {
@@ -653,6 +670,27 @@ static int launch_momtend(udgpu *h, bool acc) {
   return UDGPU_OK;
 }
 
+// per-scalar tendencies: advecc_kappa / advecc_2nd (+ diffc), src/modadvection.f90:86-99, src/modsubgrid.f90:148-150
+template <bool ADV, bool DIFF>
+static int launch_scalars(udgpu *h, bool acc) {
+  const Geo &g = h->g;
+  const int nsv = h->cfg.nsv;
+  if (!nsv) return UDGPU_OK;
+  const dim3 gr = grid3(g, B3);
+  const bool les = g.lles != 0, kappa = h->cfg.iadv_sv == 7;
+  for (int n = 0; n < nsv; n++) {
+    const double *sv = h->f[UDGPU_SV0] + (size_t)n * h->cnt[UDGPU_SV0];
+    double *svp = h->f[UDGPU_SVP] + (size_t)n * h->cnt[UDGPU_SVP];
+#define GO(S, ACC, LES) k_scalar_tend<S, ADV, DIFF, ACC, LES><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKH], sv, svp)
+    if (kappa) { if (acc) { if (les) GO(7, true, true); else GO(7, true, false); } else { if (les) GO(7, false, true); else GO(7, false, false); } }
+    else { if (acc) { if (les) GO(2, true, true); else GO(2, true, false); } else { if (les) GO(2, false, true); else GO(2, false, false); } }
+#undef GO
+    KCHECK();
+    h->launches++;
+  }
+  return UDGPU_OK;
+}
+
 // run a deferred advection() on its own (something needs the tendencies before subgrid())
 static int tderive_now(udgpu *h);
 static int flush_pending(udgpu *h) {
@@ -661,6 +699,7 @@ static int flush_pending(udgpu *h) {
   h->adv_pending = false;
   ProfScope ps(h, PROF_MOM);
   RET((launch_momtend<true, false>(h, !h->tend_zero)));
+  RET((launch_scalars<true, false>(h, !h->tend_zero)));
   h->tend_zero = false; h->tend_lazy_zero = false;
   return UDGPU_OK;
 }
@@ -679,8 +718,8 @@ extern "C" int udgpu_subgrid(udgpu_t *h) {
   h->adv_pending = false;
   RET(udgpu_closure(h));
   ProfScope ps(h, PROF_MOM);
-  if (fuse) RET((launch_momtend<true, true>(h, !h->tend_zero)));
-  else RET((launch_momtend<false, true>(h, !h->tend_zero)));
+  if (fuse) { RET((launch_momtend<true, true>(h, !h->tend_zero))); RET((launch_scalars<true, true>(h, !h->tend_zero))); }
+  else { RET((launch_momtend<false, true>(h, !h->tend_zero))); RET((launch_scalars<false, true>(h, !h->tend_zero))); }
   h->tend_zero = false; h->tend_lazy_zero = false;
   return UDGPU_OK;
 }
@@ -964,6 +1003,7 @@ static int materialize_zero_tend(udgpu *h) {
   // the zeros are written only if somebody is about to look at (or accumulate into) the arrays
   if (!h->tend_lazy_zero) return UDGPU_OK;
   for (int f : {UDGPU_UP, UDGPU_VP, UDGPU_WP}) CU(cudaMemsetAsync(h->f[f], 0, h->cnt[f] * sizeof(double), h->st));
+  if (h->cfg.nsv) CU(cudaMemsetAsync(h->f[UDGPU_SVP], 0, h->cnt[UDGPU_SVP] * h->cfg.nsv * sizeof(double), h->st));
   h->tend_lazy_zero = false;
   return UDGPU_OK;
 }
@@ -990,6 +1030,19 @@ extern "C" int udgpu_poisson(udgpu_t *h, double dt, int rk3step) {
   return UDGPU_OK;
 }
 
+static int integrate_scalars(udgpu *h, double rk3coef, int rk3step) {
+  const Geo &g = h->g;
+  for (int n = 0; n < h->cfg.nsv; n++) {
+    double *s0 = h->f[UDGPU_SV0] + (size_t)n * h->cnt[UDGPU_SV0], *sm = h->f[UDGPU_SVM] + (size_t)n * h->cnt[UDGPU_SVM];
+    const double *sp = h->f[UDGPU_SVP] + (size_t)n * h->cnt[UDGPU_SVP];
+    if (rk3step == 3) k_scalar_integrate<true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, s0, sm, sp);
+    else k_scalar_integrate<false><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, s0, sm, sp);
+    KCHECK();
+    h->launches++;
+  }
+  return UDGPU_OK;
+}
+
 extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
   const Geo &g = h->g;
@@ -1009,6 +1062,7 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
     k_pres_update_shell<<<dim3(8, g.ktot + 2 * g.kh), 256, 0, h->st>>>(g, f[UDGPU_P], f[UDGPU_PRES0]);
     KCHECK();
     h->launches += 2;
+    RET(integrate_scalars(h, rk3coef, rk3step));
     h->tend_zero = true;
     h->tend_lazy_zero = true;
     if (h->tend_pushed) { RET(materialize_zero_tend(h)); h->tend_pushed = false; }
@@ -1024,6 +1078,7 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
                                                              f[UDGPU_WM], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP]);
   KCHECK();
   h->launches++;
+  RET(integrate_scalars(h, rk3coef, rk3step));
   h->tend_zero = true;
   h->tend_lazy_zero = true;
   if (h->tend_pushed) { RET(materialize_zero_tend(h)); h->tend_pushed = false; }
@@ -1037,6 +1092,14 @@ extern "C" int udgpu_halos(udgpu_t *h) {
   ProfScope ps(h, PROF_HALO);
   double **f = h->f;
   RET(wrap_xy(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
+  if (h->cfg.nsv) {  // xs_periodic / ys_periodic (src/modboundary.f90:568-579,655-669) or exchange at level ihc
+    std::vector<double *> sv;
+    for (int n = 0; n < h->cfg.nsv; n++) {
+      sv.push_back(f[UDGPU_SV0] + (size_t)n * h->cnt[UDGPU_SV0]);
+      sv.push_back(f[UDGPU_SVM] + (size_t)n * h->cnt[UDGPU_SVM]);
+    }
+    RET(wrap_xy_g(h, sv, g.ktot + 2 * g.khc, g.pic, g.pjc, g.imax, g.jmax, g.ihc));
+  }
   return UDGPU_OK;
 }
 
@@ -1049,6 +1112,11 @@ extern "C" int udgpu_boundary(udgpu_t *h) {
   k_boundary_topbot<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]);
   KCHECK();
   h->launches++;
+  for (int n = 0; n < h->cfg.nsv; n++) {
+    k_scalar_top<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, f[UDGPU_SV0] + (size_t)n * h->cnt[UDGPU_SV0], f[UDGPU_SVM] + (size_t)n * h->cnt[UDGPU_SVM]);
+    KCHECK();
+    h->launches++;
+  }
   return UDGPU_OK;
 }
 
