@@ -190,6 +190,12 @@ def test_scalars(shape, kw, flags):
         for n4 in range(o2.nsv):
             for nm in ("sv0", "svm"):
                 a, b = g2.pull(nm, n4), getattr(o2, nm)[..., n4]
-                # whole array except the bottom ghost levels (never written by the path) incl. lateral halos, top ghosts
-                assert relerr(a[:, :, hc:], b[:, :, hc:]) < 1e-11, (s, nm, n4)
+                # interior levels: whole lateral extent incl. the width-hc halos
+                assert relerr(a[:, :, hc:-hc], b[:, :, hc:-hc]) < 1e-11, (s, nm, n4)
+                # top ghost levels: defined on the momentum-halo footprint only (fluxtopscal, src/modboundary.f90:1530-1531);
+                # the bottom ghosts and the outer halo ring of the ghost levels are never written nor read by the path
+                e = hc - 1
+                fa = a[e:a.shape[0] - e, e:a.shape[1] - e, -hc:]
+                fb = b[e:b.shape[0] - e, e:b.shape[1] - e, -hc:]
+                assert relerr(fa, fb) < 1e-11, (s, nm, n4, "top ghosts")
         assert relerr(g2.pull("u0"), o2.u0) < 1e-11
