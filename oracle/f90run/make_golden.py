@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE'S FORTRAN SOURCE TEXT with oracle/f90run/interp.py.
+
+Run in the build container only (needs /root/reference):   python oracle/f90run/make_golden.py
+Nothing from the reference is copied: the .f90 files are read where they lie, interpreted, and only
+seeded inputs + numerical outputs are stored.  Module state that the hot path reads (grid metrics,
+switches) is set up here following src/modglobal.f90:708-870 / namelist defaults; MPI, 2decomp-fft
+and FFTW calls are replaced by single-pencil Python callbacks (halo exchange = no-op on one rank with
+non-periodic communicators, transposes = copies, FFTW r2c/c2r = numpy.fft).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+from interp import FArray, Interp  # noqa: E402
+
+REF = os.environ.get("UDALES_REFERENCE", "/root/reference")
+SRC = os.path.join(REF, "src")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def fa(shape_bounds, fill=0.0, dtype=float):
+    return FArray.alloc(shape_bounds, dtype, fill)
+
+
+def stretched_zf(ktot, zsize, ratio):
+    dz = ratio ** np.arange(ktot)
+    dz *= zsize / dz.sum()
+    zh = np.concatenate([[0.0], np.cumsum(dz)])
+    return 0.5 * (zh[:-1] + zh[1:])
+
+
+class World:
+    """module variables of modglobal / modfields / modsubgriddata / modpois / decomp_2d for one pencil."""
+
+    def __init__(self, itot, jtot, ktot, xlen, ylen, zf, nsv=0, iadv_sv=7, BCtopm=1, lvreman=True, lsmagorinsky=False,
+                 Uinf=0.0, Vinf=0.0, seed=0):
+        g = {}
+        self.g = g
+        ib = jb = kb = 1
+        ie, je, ke = itot, jtot, ktot
+        ih = jh = kh = 1
+        hc = 2 if (nsv > 0 and iadv_sv == 7) else 1
+        g.update(ib=ib, ie=ie, jb=jb, je=je, kb=kb, ke=ke, ih=ih, jh=jh, kh=kh, ihc=hc, jhc=hc, khc=hc,
+                 imax=itot, jmax=jtot, kmax=ktot, itot=itot, jtot=jtot, ktot=ktot, nsv=nsv)
+        K = ktot
+        # ---- metrics: src/modglobal.f90:708-870 -------------------------------------------------
+        dx, dy = xlen / float(itot), ylen / float(jtot)
+        zfA = fa([(kb, ke + kh)]); zhA = fa([(kb, ke + kh)])
+        dzf = fa([(kb - kh, ke + kh)]); dzh = fa([(kb, ke + kh)])
+        for k in range(1, K + 1):
+            zfA.a[k - 1] = zf[k - 1]
+        zhA.a[0] = 0.0
+        for k in range(1, K + 1):
+            zhA.a[k] = zhA.a[k - 1] + 2.0 * (zfA.a[k - 1] - zhA.a[k - 1])
+        zfA.a[K] = zfA.a[K - 1] + 2.0 * (zhA.a[K] - zfA.a[K - 1])
+        for k in range(1, K + 1):
+            dzf.a[k] = zhA.a[k] - zhA.a[k - 1]
+        dzf.a[K + 1] = dzf.a[K]
+        dzf.a[0] = dzf.a[1]
+        dzh.a[0] = 2 * zfA.a[0]
+        for k in range(2, K + 2):
+            dzh.a[k - 1] = zfA.a[k - 1] - zfA.a[k - 2]
+        dxf = fa([(ib - ih, itot + ih)], dx)
+        delta = fa([(ib - ih, itot + ih), (kb, ke + kh)])
+        for k in range(1, K + 2):
+            delta.a[:, k - 1] = (dx * dy * dzf.a[k]) ** (1. / 3.)
+        dzhi = FArray(1. / dzh.a, dzh.lb); dzfi = FArray(1. / dzf.a, dzf.lb)
+        g.update(dx=dx, dy=dy, zf=zfA, zh=zhA, dzf=dzf, dzh=dzh, dxf=dxf, delta=delta,
+                 dzhi=dzhi, dzfi=dzfi, dzf2=FArray(dzf.a * dzf.a, dzf.lb),
+                 dxi=1. / dx, dyi=1. / dy, dx2=dx * dx, dy2=dy * dy,
+                 dzhiq=FArray(0.25 * dzhi.a, dzh.lb), dzfiq=FArray(0.25 * dzfi.a, dzf.lb),
+                 dzh2i=FArray(dzhi.a * dzhi.a, dzh.lb), dzfi5=FArray(0.5 * dzfi.a, dzf.lb))
+        g["dxiq"] = 0.25 * g["dxi"]; g["dyiq"] = 0.25 * g["dyi"]
+        g["dx2i"] = g["dxi"] * g["dxi"]; g["dy2i"] = g["dyi"] * g["dyi"]
+        g["dxi5"] = 0.5 * g["dxi"]; g["dyi5"] = 0.5 * g["dyi"]
+        # kappa grids (:841-870)
+        dzfc = fa([(kb - hc, ke + hc)]); dzhci = fa([(kb - 1, ke + hc)])
+        dxfc = fa([(ib - hc, itot + hc)], dx); dxhci = fa([(ib - 1, itot + hc)], 1. / dx)
+        dzfc.a[hc - kh:hc - kh + K + 2 * kh] = dzf.a
+        dzfc.a[0] = dzfc.a[hc - kh]; dzfc.a[-1] = dzfc.a[-1 - (hc - kh)]
+        dzhci.a[1:1 + K + kh] = dzhi.a
+        dzhci.a[0] = dzhci.a[1]
+        if hc > kh:
+            dzhci.a[-1] = dzhci.a[-2]
+        g.update(dzfc=dzfc, dzfci=FArray(1. / dzfc.a, dzfc.lb), dzhci=dzhci, dxfc=dxfc, dxfci=FArray(1. / dxfc.a, dxfc.lb), dxhci=dxhci)
+        # ---- constants & switches (namelist defaults, src/modglobal.f90, src/modsubgriddata.f90) -----
+        g.update(numol=1.5e-5, prandtlmoli=1. / 0.71, eps1=1.e-10, pi=3.141592653589793116, e12min=5.e-5, grav=9.81,
+                 lles=bool(lvreman or lsmagorinsky), lmoist=False, ltempeq=False, lbuoyancy=False, lchem=False,
+                 iadv_mom=2, iadv_tke=2, iadv_thl=2, iadv_qt=2, iadv_cd2=2, iadv_kappa=7, iadv_upw=1,
+                 iadv_sv=FArray(np.full(100, iadv_sv if nsv else -1, dtype=int), [1]),
+                 bcxm=1, bcym=1, bcxt=1, bcyt=1, bcxq=1, bcyq=1, bcxs=1, bcys=1, bctopm=BCtopm, bctopt=1, bctopq=1, bctops=1, bczp=1,
+                 bcxm_periodic=1, bcxm_profile=2, bcxm_driver=3, bcym_periodic=1, bcym_profile=2,
+                 bcxt_periodic=1, bcxt_profile=2, bcxt_driver=3, bcyt_periodic=1, bcyt_profile=2,
+                 bcxq_periodic=1, bcxq_profile=2, bcxq_driver=3, bcyq_periodic=1, bcyq_profile=2,
+                 bcxs_periodic=1, bcxs_profile=2, bcxs_driver=3, bcxs_custom=4, bcys_periodic=1,
+                 bctopm_freeslip=1, bctopm_noslip=2, bctopm_pressure=3, bctopt_flux=1, bctopt_value=2,
+                 bctopq_flux=1, bctopq_value=2, bctops_flux=1, bctops_value=2,
+                 ibrank=True, ierank=True, jbrank=True, jerank=True, uinf=Uinf, vinf=Vinf,
+                 ipoiss=0, poiss_fft2d=0, poiss_cyc=1, poiss_fft3d=2, poiss_fft2d_2decomp=3,
+                 rk3step=0, dt=0.0, dtmax=1e9, courant=1.0, diffnr=0.25, ladaptive=False, lwarmstart=True,
+                 timee=0.0, timeleft=1e9, ntimee=0, ntrun=0, dt_lim=0.0, ifixuinf=0, iinletgen=0, idriver=0,
+                 luoutflowr=True, luvolflowr=False, lchunkread=False, thlsrc=0.0, dgdt=0.0, myid=0, cmyid="000",
+                 nrank=0, comm3d=0, mpierr=0, my_real=0, mpi_max=1, mpi_sum=2,
+                 lsmagorinsky=lsmagorinsky, lvreman=lvreman, loneeqn=False, lbuoycorr=False, ldelta=False,
+                 c_vreman=0.07, cs=-1.0, prandtli=1. / 0.333, dampmin=1e-10, rigc=0.25,
+                 cm=0.12, cn=0.76, ch1=1., ch2=2., thvs=300.0,
+                 fftw_measure=0, fftw_redft10=5, fftw_redft01=4,
+                 thl_top=0.0, qt_top=0.0, wttop=0.0, wqtop=0.0, ubulk=0.0, vbulk=0.0, uouttot=0.0, vouttot=0.0)
+        cf, alpha_kolm = 2.5, 1.5
+        cm = cf / (2. * g["pi"]) * (1.5 * alpha_kolm) ** (-1.5)
+        ceps = 2. * g["pi"] / cf * (1.5 * alpha_kolm) ** (-1.5)
+        g["csz"] = fa([(ib - ih, ie + ih), (kb, ke + kh)], (cm ** 3 / ceps) ** 0.25)      # src/modsubgrid.f90:72-76
+        g["wsvtop"] = fa([(1, max(nsv, 1))], 0.0); g["sv_top"] = fa([(1, max(nsv, 1))], 0.0)
+        g["zsize"] = FArray(np.array([itot, jtot, ktot]), [1]); g["zstart"] = FArray(np.array([1, 1, 1]), [1])
+        g["xsize"] = g["zsize"]; g["ysize"] = g["zsize"]
+        # ---- fields: src/modfields.f90:440-520 -----------------------------------------------------
+        full = [(ib - ih, ie + ih), (jb - jh, je + jh), (kb - kh, ke + kh)]
+        tend = [(ib - ih, ie + ih), (jb - jh, je + jh), (kb, ke + kh)]
+        for nm in ("u0", "v0", "w0", "um", "vm", "wm", "pres0", "ekm", "ekh", "thl0", "thlm", "qt0", "qtm", "e120", "e12m", "dthvdz"):
+            g[nm] = fa(full)
+        g["thl0c"] = fa([(ib - hc, ie + hc), (jb - hc, je + hc), (kb - hc, ke + hc)])
+        for nm in ("up", "vp", "wp", "thlp", "qtp", "e12p", "zlt"):
+            g[nm] = fa(tend)
+        g["thlpc"] = fa([(ib - hc, ie + hc), (jb - hc, je + hc), (kb, ke + hc)])
+        n4 = max(nsv, 1)
+        g["sv0"] = fa([(ib - hc, ie + hc), (jb - hc, je + hc), (kb - hc, ke + hc), (1, n4)])
+        g["svm"] = fa([(ib - hc, ie + hc), (jb - hc, je + hc), (kb - hc, ke + hc), (1, n4)])
+        g["svp"] = fa([(ib - hc, ie + hc), (jb - hc, je + hc), (kb, ke + hc), (1, n4)])
+        g["damp"] = fa([(ib, ie), (jb, je), (kb, ke)], 1.0)
+        g["rhobf"] = fa([(kb, ke + kh)], 1.0); g["rhobh"] = fa([(kb, ke + kh)], 1.0)   # src/modfields.f90:571-572
+        g["u0av"] = fa([(kb, ke + kh)]); g["v0av"] = fa([(kb, ke + kh)]); g["dpdxl"] = fa([(kb, ke + kh)])
+        # modpois module variables (allocated by initpois)
+        for nm in ("p", "pup", "pvp", "pwp", "rhs", "dpupdx", "dpvpdy", "dpwpdz", "fxy", "fxyz", "xrt", "yrt", "zrt", "xyzrt", "bxyzrt",
+                   "a", "b", "c", "sxr", "sxfr", "syr", "syfr", "szr", "szfr", "sxfc", "syfc", "dpdztop", "pij",
+                   "plan_r2fc_x", "plan_r2fc_y", "plan_fc2r_x", "plan_fc2r_y", "kbc1", "kbc2"):
+            g[nm] = None
+        self.plans = {}
+
+    # -------------------------------------------------------------------------------------------
+    def externals(self):
+        w = self
+
+        def alloc_pencil(it, frame, vals, setters, kw):
+            lev = [0, 0, 0]
+            for k in ("opt_xlevel", "opt_ylevel", "opt_zlevel"):
+                if k in kw:
+                    lev = [int(x) for x in kw[k]]
+            if not kw:
+                g = w.g
+                lev = [g["ih"], g["jh"], g["kh"]]          # decomp_main%zlevel (src/modglobal.f90:638)
+            g = w.g
+            b = [(1 - lev[0], g["itot"] + lev[0]), (1 - lev[1], g["jtot"] + lev[1]), (1 - lev[2], g["ktot"] + lev[2])]
+            setters[0](fa(b, 0.0))
+
+        def transpose(it, frame, vals, setters, kw):
+            vals[1].a[...] = vals[0].a
+
+        def nop(it, frame, vals, setters, kw):
+            pass
+
+        def plan_r2c(it, frame, vals, setters, kw):
+            pid = len(w.plans) + 1
+            w.plans[pid] = ("r2c", vals[1], vals[2], vals[3])
+            setters[0](pid)
+
+        def plan_c2r(it, frame, vals, setters, kw):
+            pid = len(w.plans) + 1
+            w.plans[pid] = ("c2r", vals[1], vals[2], vals[3])
+            setters[0](pid)
+
+        def execute(it, frame, vals, setters, kw):
+            kind, n, a, b = w.plans[vals[0]]
+            if kind == "r2c":
+                b.a[...] = np.fft.rfft(a.a)                       # FFTW r2c: unnormalised, sign -
+            else:
+                b.a[...] = np.fft.irfft(a.a, n) * n               # FFTW c2r: unnormalised
+
+        def allreduce(it, frame, vals, setters, kw):
+            setters[1](vals[0])
+
+        return {"alloc_x": alloc_pencil, "alloc_y": alloc_pencil, "alloc_z": alloc_pencil,
+                "transpose_x_to_y": transpose, "transpose_y_to_x": transpose, "transpose_y_to_z": transpose,
+                "transpose_z_to_y": transpose, "exchange_halo_z": nop, "mpi_bcast": nop, "barrou": nop,
+                "dfftw_plan_dft_r2c_1d": plan_r2c, "dfftw_plan_dft_c2r_1d": plan_c2r, "dfftw_execute": execute,
+                "mpi_allreduce": allreduce}
+
+
+def make_interp(w):
+    it = Interp(w.g, w.externals())
+    it.gtypes = {"sxfc": complex, "syfc": complex}
+    for f in ("modadvection.f90", "modsubgrid.f90", "modpois.f90", "modtstep.f90", "modboundary.f90", "modchecksim.f90"):
+        it.load(os.path.join(SRC, f))
+    return it
+
+
+def seed_fields(w, seed, nsv):
+    g = w.g
+    rng = np.random.default_rng(seed)
+    I, J, K = g["itot"], g["jtot"], g["ktot"]
+    for nm, base, amp in (("u0", 1.0, 0.3), ("v0", 0.2, 0.3), ("w0", 0.0, 0.3), ("pres0", 0.0, 0.5)):
+        g[nm].a[...] = 0.0
+        g[nm].a[1:-1, 1:-1, 1:-1] = base + amp * rng.standard_normal((I, J, K))
+    g["w0"].a[:, :, 1] = 0.0
+    hc = g["ihc"]
+    for n in range(nsv):
+        g["sv0"].a[..., n] = 0.0
+        g["sv0"].a[hc:-hc, hc:-hc, hc:-hc, n] = 1.0 + 0.2 * rng.standard_normal((I, J, K))
+
+
+def snapshot(w, names):
+    return {n: np.array(w.g[n].a, copy=True) for n in names}
+
+
+def case_substeps(tag, nsub=3, **kw):
+    """the in-scope part of src/program.f90:132-207, executed from the reference text."""
+    I, J, K = kw.pop("shape")
+    nsv = kw.get("nsv", 0)
+    zf = stretched_zf(K, 0.5 * K * 1.1, 1.07)
+    w = World(I, J, K, xlen=0.55 * I, ylen=0.45 * J, zf=zf, **kw)
+    it = make_interp(w)
+    g = w.g
+    it.call("initpois")
+    seed_fields(w, 11, nsv)
+    g["ekm"].a[...] = g["numol"]                      # startup state of the reference: molecular values
+    g["ekh"].a[...] = g["numol"] * g["prandtlmoli"]   # (fluxtopscal divides by ekh, src/modboundary.f90:1530)
+    it.call("halos"); it.call("boundary")
+    for a, b in (("um", "u0"), ("vm", "v0"), ("wm", "w0")):
+        g[a].a[...] = g[b].a
+    g["svm"].a[...] = g["sv0"].a
+    out = {"zf": zf, "shape": np.array([I, J, K]), "xlen": 0.55 * I, "ylen": 0.45 * J, "nsv": nsv,
+           "BCtopm": g["bctopm"], "lvreman": int(g["lvreman"]), "lsmagorinsky": int(g["lsmagorinsky"]),
+           "iadv_sv": int(g["iadv_sv"].a[0]), "Uinf": g["uinf"], "Vinf": g["vinf"]}
+    state = ["u0", "v0", "w0", "um", "vm", "wm", "pres0", "sv0", "svm"]
+    for k_, v_ in snapshot(w, state).items():
+        out["in_" + k_] = v_
+    for nm in ("xrt", "yrt", "a", "b", "c", "bxyzrt"):
+        out["pois_" + nm] = np.array(g[nm].a, copy=True)
+    dt = 0.03
+    g["dt"] = dt
+    g["dtmax"] = dt
+    g["ladaptive"] = False
+    for s in range(nsub):
+        it.call("tstep_update")
+        it.call("advection")
+        if s == 0:
+            for k_, v_ in snapshot(w, ["up", "vp", "wp", "svp"]).items():
+                out["adv_" + k_] = v_
+        it.call("subgrid")
+        if s == 0:
+            for k_, v_ in snapshot(w, ["up", "vp", "wp", "svp", "ekm", "ekh"]).items():
+                out["sub_" + k_] = v_
+        it.call("poisson")
+        if s == 0:
+            for k_, v_ in snapshot(w, ["p", "up", "vp", "wp", "pres0", "rhs"]).items():
+                out["pois_" + k_] = v_
+        it.call("tstep_integrate")
+        it.call("halos")
+        it.call("boundary")
+        for k_, v_ in snapshot(w, state).items():
+            out[f"s{s + 1}_" + k_] = v_
+        out[f"s{s + 1}_rk3step"] = g["rk3step"]
+    # chkdiv formula (src/modchecksim.f90:182-188) evaluated by the reference text: capture through allreduce
+    caught = {}
+    ext = it.ext
+
+    def allreduce(it_, frame, vals, setters, kw_):
+        setters[1](vals[0])
+        caught[len(caught)] = vals[0]
+    ext["mpi_allreduce"] = allreduce
+    it.call("chkdiv")
+    out["divtot"], out["divmax"] = caught[0], caught[1]
+    # adaptive time step from the reference text
+    g["ladaptive"] = True; g["rk3step"] = 0; g["dt"] = 0.05; g["dtmax"] = 2.0; g["courant"] = 1.1; g["diffnr"] = 0.25
+    caught.clear()
+    it.call("tstep_update")
+    out["adapt_courtot"], out["adapt_diffnrtot"], out["adapt_dt"] = caught[0], caught[1], g["dt"]
+    for k_, v_ in out.items():
+        if isinstance(v_, np.ndarray) and v_.dtype.kind == "f" and not k_.startswith("in_") and "bxyzrt" not in k_:
+            # interior of every output must be finite
+            assert np.isfinite(v_[tuple(slice(2, -2) for _ in range(min(3, v_.ndim)))]).all(), k_
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, f"ref_{tag}.npz"), **out)
+    print(f"wrote ref_{tag}.npz  ({len(out)} arrays)  final |u0|max {np.abs(g['u0'].a).max():.6f} divmax {out['divmax']:.2e}")
+
+
+if __name__ == "__main__":
+    case_substeps("vreman_freeslip", shape=(10, 8, 6))
+    case_substeps("smag_noslip", shape=(8, 12, 5), lvreman=False, lsmagorinsky=True, BCtopm=2, Uinf=1.2, Vinf=-0.3)
+    case_substeps("dns", shape=(8, 6, 7), lvreman=False, lsmagorinsky=False)
+    case_substeps("kappa2", shape=(8, 8, 6), nsv=2, iadv_sv=7)
+    case_substeps("cd2scalar", shape=(6, 8, 5), nsv=1, iadv_sv=2)

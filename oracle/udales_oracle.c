@@ -4,12 +4,12 @@
  * reference (-fdefault-real-8, CMakeLists.txt:46).  Build with -ffp-contract=off so
  * that, like the reference's generic x86-64 -O3 build, no FMA contraction happens.
  *
- * PINNING STATUS: the reference holds no golden vectors for these routines
- *  and cannot be compiled here (no Fortran compiler).  This file is
- * pinned instead by tests/golden/ (npz files), which are produced by oracle/f90run — a
- * Fortran-subset interpreter that executes the reference's own source text from
- * /root/reference on seeded inputs (see oracle/README.md).  The FFT (FFTW in the
- * reference, absent here) is pinned against numpy.fft (pocketfft).
+ * PINNING STATUS: pinned to the reference's own source text.  tests/golden/ref_*.npz are produced by
+ * oracle/f90run (an interpreter that executes /root/reference/src/*.f90 on seeded inputs; see
+ * oracle/README.md) and tests/test_oracle_golden.py checks every stage of three RK3 substeps of this
+ * file against them (<= 2e-13 for the stencils, 1e-11 through the FFT solve).  The reference itself is
+ * unbuildable here (no Fortran compiler / MPI / FFTW) and ships no golden vectors of its own; FFTW is
+ * represented by numpy.fft in the golden generator.
  */
 #include "udales_oracle.h"
 #include <math.h>
