@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "momtend_tma.cuh"
+#include "closure_tma.cuh"
 #include "poisson_v1.cuh"
 #include "poisson_fast.cuh"
 #include "stencil_v1.cuh"
@@ -120,8 +121,8 @@ struct udgpu {
   // TMA path of the fused momentum kernel
   bool use_tma = false;
   CUtensorMap tm[5];
-  MomTmaParams mtp;
-  int mt_grid = 0;
+  MomTmaParams mtp, clp;
+  int mt_grid = 0, cl_grid = 0, cl_occ = 2;
   int nsm = 148;
   // state
   bool tder_pending = false;  // poisson() solved for p; tderive is fused into the next tstep_integrate()
@@ -255,6 +256,28 @@ static int setup_momtend_tma(udgpu *h) {
   SETATTR(true, false, false, false); SETATTR(true, false, false, true);
   SETATTR(false, true, true, true); SETATTR(false, true, true, false); SETATTR(false, true, false, true); SETATTR(false, true, false, false);
 #undef SETATTR
+  CU(cudaFuncSetAttribute(k_closure_vreman_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
+  CU(cudaFuncSetAttribute(k_closure_vreman_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
+  {
+    // closure: its own chunking of k over occ x #SM concurrent CTAs
+    h->clp = P;
+    const char *eo = getenv("UDGPU_CLOSURE_OCC");
+    h->cl_occ = eo ? atoi(eo) : 2;
+    if (h->cl_occ != 1) h->cl_occ = 2;
+    const int Gc = h->cl_occ * h->nsm;
+    int bestc = 1; double bestec = -1;
+    for (int c = 1; c <= g.ktot && c <= 64; c++) {
+      const double L = (double)g.ktot / c;
+      if (L < 4 && c > 1) break;
+      const long items = (long)ntile * c;
+      const double rounds = ceil((double)items / Gc);
+      const double eff = (double)items / (Gc * rounds) * L / (L + 1.0);
+      if (eff > bestec + 1e-9) { bestec = eff; bestc = c; }
+    }
+    h->clp.nchunk = bestc;
+    h->clp.nitems = ntile * bestc;
+    h->cl_grid = h->clp.nitems < Gc ? h->clp.nitems : Gc;
+  }
   h->use_tma = true;
   return UDGPU_OK;
 }
@@ -611,6 +634,11 @@ extern "C" int udgpu_closure(udgpu_t *h) {
   const dim3 gr = grid3(g, B3);
   // model selection order of the reference: smagorinsky first, then vreman, else DNS (modsubgrid.f90:208,269,401)
   if (h->cfg.lsmagorinsky) k_closure<2><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
+  else if (h->cfg.lvreman && h->use_tma)
+  {
+    if (h->cl_occ == 1) k_closure_vreman_tma<1><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
+    else k_closure_vreman_tma<2><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
+  }
   else if (h->cfg.lvreman) k_closure<1><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
   else k_closure<0><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
   KCHECK();
