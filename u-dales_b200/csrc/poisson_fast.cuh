@@ -325,7 +325,7 @@ __global__ void k_zfactor(int nxh, int nyh, int K, const double *__restrict__ xd
 
 // One thread per (i,j) column of the halo-free spectral array x(imax,jmax,K); forward then backward
 // sweep in place.  ZU levels are prefetched ahead of the recurrence.
-constexpr int ZU = 8;
+template <int ZU>
 __global__ void __launch_bounds__(128) k_zsolve(Geo g, int nxh, int nyh, double *__restrict__ x, const double *__restrict__ zt,
                                                 const double *__restrict__ a, const double *__restrict__ c) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;

@@ -99,6 +99,7 @@ struct udgpu {
   double b_top_D = 0;
   FftPlan px, py;
   bool fast_x = false, fast_y = false, fast_z = false;
+  int zu = 8, fft_lanes = 32;
   double *d_zt = nullptr, *d_xd = nullptr, *d_yd = nullptr;
   int nxh = 0, nyh = 0;
   // reductions
@@ -112,6 +113,8 @@ struct udgpu {
   void *ipc_mine = nullptr;   // [recvA | recvB | flags]
   void *ipc_peer[8] = {};
   double *rA[8] = {}, *rB[8] = {};
+  double *hL[8][2] = {}, *hR[8][2] = {};   // halo receive windows (left / right halo columns), double-buffered
+  unsigned halo_par = 0;
   P2PPtrs pflags;
   unsigned long long epoch = 0;
   int *d_status = nullptr;
@@ -138,6 +141,7 @@ struct udgpu {
 // ------------------------------------------------------------------------------------------
 static int flush_pending(udgpu *h);
 static int setup_p2p(udgpu *h, size_t nR);
+static int p2p_barrier(udgpu *h);
 static int materialize_zero_tend(udgpu *h);
 static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt);
 static int dev_alloc(udgpu *h, void **p, size_t bytes) {
@@ -261,10 +265,10 @@ static int setup_momtend_tma(udgpu *h) {
   {
     // closure: its own chunking of k over occ x #SM concurrent CTAs
     h->clp = P;
-    const char *eo = getenv("UDGPU_CLOSURE_OCC");
-    h->cl_occ = eo ? atoi(eo) : 2;
-    if (h->cl_occ != 1) h->cl_occ = 2;
-    const int Gc = h->cl_occ * h->nsm;
+    const char *eo = getenv("UDGPU_CLOSURE_OCC");   // 1 / 2: TMA closure kernel at that occupancy; default: direct kernel
+    h->cl_occ = eo ? atoi(eo) : 0;
+    if (h->cl_occ < 0 || h->cl_occ > 2) h->cl_occ = 0;
+    const int Gc = (h->cl_occ > 0 ? h->cl_occ : 1) * h->nsm;
     int bestc = 1; double bestec = -1;
     for (int c = 1; c <= g.ktot && c <= 64; c++) {
       const double L = (double)g.ktot / c;
@@ -582,9 +586,22 @@ static int halo_x_exchange_g(udgpu *h, const std::vector<double *> &fields, int 
   if ((size_t)off > h->halo_cap) return set_err(UDGPU_EINVAL, "halo buffer too small");
   const long long rows = (long long)pj * nlev;
   const dim3 gr((unsigned)((rows + 127) / 128), hp.n);
+  const int left = (h->rank + h->P - 1) % h->P, right = (h->rank + 1) % h->P;
+  if (h->p2p) {
+    // peer stores: my first columns land in the left neighbour's right-halo window, my last columns in the right
+    // neighbour's left-halo window; one flag barrier; unpack from my own windows.  Windows alternate (parity) so a
+    // fast neighbour's next exchange cannot overwrite data that has not been unpacked yet.
+    const unsigned par = (h->halo_par++) & 1;
+    k_halo_pack_x<<<gr, 128, 0, h->st>>>(hp, pi, pj, imax, hw, h->hR[left][par], h->hL[right][par]);
+    KCHECK();
+    RET(p2p_barrier(h));
+    k_halo_unpack_x<<<gr, 128, 0, h->st>>>(hp, pi, pj, imax, hw, h->hL[h->rank][par], h->hR[h->rank][par]);
+    KCHECK();
+    h->launches += 2;
+    return UDGPU_OK;
+  }
   k_halo_pack_x<<<gr, 128, 0, h->st>>>(hp, pi, pj, imax, hw, h->sendL, h->sendR);
   KCHECK();
-  const int left = (h->rank + h->P - 1) % h->P, right = (h->rank + 1) % h->P;
   NC(ncclGroupStart());
   NC(ncclSend(h->sendR, off, ncclDouble, right, h->comm, h->st));
   NC(ncclSend(h->sendL, off, ncclDouble, left, h->comm, h->st));
@@ -634,7 +651,7 @@ extern "C" int udgpu_closure(udgpu_t *h) {
   const dim3 gr = grid3(g, B3);
   // model selection order of the reference: smagorinsky first, then vreman, else DNS (modsubgrid.f90:208,269,401)
   if (h->cfg.lsmagorinsky) k_closure<2><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
-  else if (h->cfg.lvreman && h->use_tma)
+  else if (h->cfg.lvreman && h->use_tma && h->cl_occ > 0)
   {
     if (h->cl_occ == 1) k_closure_vreman_tma<1><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
     else k_closure_vreman_tma<2><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
@@ -784,7 +801,8 @@ static int rfft_fast(udgpu *h, int n, int inverse, const double *in, LineDesc di
   switch (n) {
     case 64: return rfft_fast_launch<8, 4, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
     case 128: return rfft_fast_launch<8, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
-    case 256: return rfft_fast_launch<16, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
+    case 256: if (h->fft_lanes == 16) return rfft_fast_launch<16, 8, 16, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
+              return rfft_fast_launch<16, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
     case 512: return rfft_fast_launch<16, 16, 16, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
     case 1024: return rfft_fast_launch<32, 16, 8, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
   }
@@ -795,7 +813,7 @@ static int rfft_fast_setattr(int n) {
   switch (n) {
     case 64: return rfft_fast_attr<8, 4, 32, XDIR>();
     case 128: return rfft_fast_attr<8, 8, 32, XDIR>();
-    case 256: return rfft_fast_attr<16, 8, 32, XDIR>();
+    case 256: RET((rfft_fast_attr<16, 8, 16, XDIR>())); return rfft_fast_attr<16, 8, 32, XDIR>();
     case 512: return rfft_fast_attr<16, 16, 16, XDIR>();
     case 1024: return rfft_fast_attr<32, 16, 8, XDIR>();
   }
@@ -805,6 +823,8 @@ static int rfft_fast_setattr(int n) {
 static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt) {
   const Geo &g = h->g;
   if ((h->cfg.flags & UDGPU_F_V1_KERNELS) && h->P == 1) return UDGPU_OK;
+  { const char *e = getenv("UDGPU_ZU"); if (e && atoi(e) == 16) h->zu = 16; }
+  { const char *e = getenv("UDGPU_FFT_LANES"); if (e && atoi(e) == 16) h->fft_lanes = 16; }
   h->fast_x = fast_len(g.itot);
   h->fast_y = fast_len(g.jtot);
   if (h->P > 1 && !(h->fast_x && h->fast_y))
@@ -861,7 +881,7 @@ static int setup_p2p(udgpu *h, size_t nR) {
   h->p2p = false;
   if (h->cfg.flags & UDGPU_F_NCCL_TRANSPOSE) return UDGPU_OK;
   const int P = h->P;
-  const size_t bytes = 2 * nR * sizeof(double) + 4096;
+  const size_t bytes = (2 * nR + 4 * h->halo_cap) * sizeof(double) + 4096;
   if (cudaMalloc(&h->ipc_mine, bytes) != cudaSuccess) { cudaGetLastError(); return UDGPU_OK; }
   h->allocs.push_back(h->ipc_mine);
   CU(cudaMemsetAsync(h->ipc_mine, 0, bytes, h->st));
@@ -898,7 +918,9 @@ static int setup_p2p(udgpu *h, size_t nR) {
   for (int d = 0; d < P; d++) {
     h->rA[d] = (double *)h->ipc_peer[d];
     h->rB[d] = h->rA[d] + nR;
-    h->pflags.flags[d] = (unsigned long long *)(h->rB[d] + nR);
+    double *hb = h->rB[d] + nR;
+    h->hL[d][0] = hb; h->hL[d][1] = hb + h->halo_cap; h->hR[d][0] = hb + 2 * h->halo_cap; h->hR[d][1] = hb + 3 * h->halo_cap;
+    h->pflags.flags[d] = (unsigned long long *)(hb + 4 * h->halo_cap);
   }
   for (int d = P; d < 8; d++) h->pflags.flags[d] = nullptr;
   h->p2p = true;
@@ -952,7 +974,8 @@ static int poisson_core_slab(udgpu *h, double *work, double *p_halo) {
   if (h->p2p) RET(p2p_barrier(h)); else RET(a2a_blocks(h));
   br.shift = ilog2(IB); br.mask = IB - 1;
   RET(rfft_fast<true>(h, g.itot, 0, nullptr, xW, h->workB, xB, h->px, &br, nullptr));
-  k_zsolve<<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
+  if (h->zu == 16) k_zsolve<16><<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
+  else k_zsolve<8><<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
   KCHECK();
   h->launches++;
   if (h->p2p)
@@ -974,7 +997,8 @@ static int poisson_core(udgpu *h, double *work, double *p_halo) {
   ProfScope ps(h, PROF_POIS);
   RET(fft_pass(h, true, 0, work, work, false));
   RET(fft_pass(h, false, 0, work, work, false));
-  if (h->fast_z) k_zsolve<<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, h->nxh, h->nyh, work, h->d_zt, h->d_a, h->d_c);
+  if (h->fast_z) { if (h->zu == 16) k_zsolve<16><<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, h->nxh, h->nyh, work, h->d_zt, h->d_a, h->d_c);
+    else k_zsolve<8><<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, h->nxh, h->nyh, work, h->d_zt, h->d_a, h->d_c); }
   else k_solmpj<<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, work, h->d_scr, h->d_xrt, h->d_yrt, h->d_a, h->d_b, h->d_c, h->b_top_D);
   KCHECK();
   h->launches++;
