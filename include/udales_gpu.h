@@ -95,6 +95,8 @@ typedef struct udgpu_cfg {
 #define UDGPU_F_NO_GRAPH 2        /* do not capture the substep into a CUDA graph                          */
 #define UDGPU_F_NCCL_TRANSPOSE 4  /* multi-GPU: ncclSend/Recv all-to-all instead of the peer-store (NVLink P2P) fused transposes */
 #define UDGPU_F_V1_KERNELS 8      /* use the direct one-thread-per-cell kernels instead of the TMA-staged ones (cross-check) */
+#define UDGPU_F_NO_HALO_FUSION 16 /* closure / tderive+integrate do not write their own halo and ghost cells: separate wrap,
+                                     closurebc, bcp, halos and boundary kernels run instead (cross-check)                    */
 
 typedef struct udgpu udgpu_t;     /* opaque */
 
@@ -152,6 +154,13 @@ int udgpu_divergence(udgpu_t *h, double *divmax, double *divtot, double *divrms)
  * tstep_update, advection, subgrid, poisson, tstep_integrate, halos, boundary. */
 int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax, int ladaptive,
                   double courant, double diffnr);
+
+/* One full RK3 time step on HOST arrays (the literal drop-in for a host-resident model): pushes u0,v0,w0,pres0
+ * (reference shapes; um=u0 at the start of a time step, src/modtstep.f90:330-338), runs the three substeps of
+ * src/program.f90:132-207 on the device and pulls the same four arrays back.  Pin the arrays once with
+ * udgpu_host_register for full PCIe bandwidth.  dt is in/out as in udgpu_tstep_update. */
+int udgpu_rk3_step_host(udgpu_t *h, double *u0, double *v0, double *w0, double *pres0, double *dt,
+                        double dtmax, int ladaptive, double courant, double diffnr);
 
 /* ---- measurement hooks (used by bench.py; no effect on results) --------------------- */
 /* device time in ms of the most recent launch group of one hot-path kernel family, measured

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 TOL_STENCIL = 1e-12
 TOL_PRES = 1e-10
 
-F_NO_LAZY, F_V1 = 1, 8
+F_NO_LAZY, F_V1, F_NO_HALO = 1, 8, 16
 
 SIZES = [(16, 16, 16), (32, 24, 20), (64, 64, 64), (48, 40, 33), (20, 36, 7)]
 
@@ -94,9 +94,10 @@ def test_poisson_fillps_tderive(shape, rk3step):
 
 @pytest.mark.parametrize("shape", [(32, 24, 20), (64, 64, 64), (20, 36, 7)])
 @pytest.mark.parametrize("kw", [dict(), dict(lvreman=False, lsmagorinsky=True), dict(BCtopm=2, Uinf=1.0)])
-def test_substeps_track_oracle(shape, kw):
+@pytest.mark.parametrize("flags", [0, F_NO_HALO])
+def test_substeps_track_oracle(shape, kw, flags):
     """six RK3 substeps (two full time steps) through the reference call surface."""
-    o, g = make_pair(*shape, **kw)
+    o, g = make_pair(*shape, gpu_flags=flags, **kw)
     dt = 0.02
     o.dt = g.dt = dt
     for s in range(6):
@@ -108,6 +109,32 @@ def test_substeps_track_oracle(shape, kw):
         omax, otot, orms = o.chkdiv()
         assert drms < 1e-12 and dmax < 1e-11
         assert abs(drms - orms) < 1e-13
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 24, 20), (64, 64, 64), (20, 36, 7), (4, 4, 3), (6, 4, 5)])
+@pytest.mark.parametrize("kw", [dict(), dict(lvreman=False, lsmagorinsky=True), dict(BCtopm=2, Uinf=1.0, Vinf=0.3),
+                                dict(lvreman=False, lsmagorinsky=False)])
+def test_halo_ownership_is_bitwise_neutral(shape, kw):
+    """closure and the fused tderive+integrate kernel write their own periodic images and ghost levels
+    (closurebc, bcp, halos, boundary: src/modboundary.f90:434-505, 1344-1408, 67-109, 163-204); with
+    UDGPU_F_NO_HALO_FUSION the separate wrap / ghost kernels run instead.  Both must give identical bits
+    in every cell of every array, halos and ghosts included."""
+    import udales_b200 as U
+    o, ga = make_pair(*shape, **kw)
+    _, gb = make_pair(*shape, gpu_flags=F_NO_HALO, **kw)
+    dt = 0.02
+    ga.dt = gb.dt = dt
+    for s in range(5):
+        ga.substep(dt); gb.substep(dt)
+        for n in ("u0", "v0", "w0", "um", "vm", "wm", "pres0", "ekm", "ekh", "p"):
+            a, b = ga.pull(n), gb.pull(n)
+            assert np.array_equal(a, b), (s, n, np.abs(a - b).max())
+    # the same after the host touched a field mid-run (falls back to the separate kernels until halos+boundary ran)
+    u = ga.pull("u0"); ga.push("u0", u); gb.push("u0", u)
+    for s in range(3):
+        ga.substep(dt); gb.substep(dt)
+        for n in ("u0", "w0", "um", "pres0", "ekm"):
+            assert np.array_equal(ga.pull(n), gb.pull(n)), (s, n)
 
 
 def test_tstep_update_adaptive():

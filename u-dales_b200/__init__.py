@@ -31,6 +31,7 @@ EXPORTS = [
     "udgpu_tstep_update", "udgpu_advection", "udgpu_subgrid", "udgpu_closure", "udgpu_poisson",
     "udgpu_poisson_solve", "udgpu_poisson_solve_resident", "udgpu_fillps", "udgpu_tderive",
     "udgpu_tstep_integrate", "udgpu_halos", "udgpu_boundary", "udgpu_divergence", "udgpu_substep",
+    "udgpu_rk3_step_host",
     "udgpu_profile_enable", "udgpu_profile_get", "udgpu_profile_reset", "udgpu_launch_count", "udgpu_stream",
 ]
 
@@ -102,6 +103,8 @@ def lib():
         L.udgpu_divergence.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3
         L.udgpu_substep.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_double, C.c_int,
                                     C.c_double, C.c_double]
+        L.udgpu_rk3_step_host.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.POINTER(C.c_double), C.c_double, C.c_int,
+                                                                              C.c_double, C.c_double]
         L.udgpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.udgpu_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
         L.udgpu_profile_reset.argtypes = [C.c_void_p]
@@ -278,6 +281,14 @@ class UdalesGPU:
         d, r = C.c_double(self.dt), C.c_int(self.rk3step)
         self._chk(self.L.udgpu_substep(self.h, C.byref(d), C.byref(r), dtmax, int(ladaptive), courant, diffnr))
         self.dt, self.rk3step = d.value, r.value
+
+    def rk3_step_host(self, u0, v0, w0, pres0, dtmax, ladaptive=False, courant=1.0, diffnr=0.25):
+        """one full RK3 time step on host arrays (numpy F-ordered, reference shapes, updated in place) or raw
+        pointers (ints) to pinned memory"""
+        ptrs = [a if isinstance(a, int) else a.ctypes.data for a in (u0, v0, w0, pres0)]
+        d = C.c_double(self.dt)
+        self._chk(self.L.udgpu_rk3_step_host(self.h, *ptrs, C.byref(d), dtmax, int(ladaptive), courant, diffnr))
+        self.dt, self.rk3step = d.value, 3
 
     # measurement ---------------------------------------------------------------
     def profile_enable(self, on=True): self._chk(self.L.udgpu_profile_enable(self.h, int(on)))

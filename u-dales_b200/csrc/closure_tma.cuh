@@ -7,6 +7,7 @@
 // next to the hard `bb < 1e-8` switch (:323).
 #pragma once
 #include "momtend_tma.cuh"
+#include "stencil_v1.cuh"
 
 namespace udg {
 
@@ -20,7 +21,7 @@ template <int MINB>
 __global__ void __launch_bounds__(CL_THREADS, MINB)
     k_closure_vreman_tma(const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                          const __grid_constant__ CUtensorMap mw, const MomTmaParams P, double *__restrict__ ekm,
-                         double *__restrict__ ekh) {
+                         double *__restrict__ ekh, int halo) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + CL_S * CL_STAGE_BYTES);
   const Geo &g = P.g;
@@ -74,7 +75,6 @@ __global__ void __launch_bounds__(CL_THREADS, MINB)
     const int np = k1 - k0 + 2;
     const int ci = it * MT_TX + gx + 1, cj = jt * MT_TY + gy + 1;
     const bool store_ok = ci <= g.imax && cj <= g.jmax;
-    const long long cbase = (long long)ci + (long long)g.pi * cj;   // + pk * k (storage level = k, kh = 1)
 
     mbar_wait(&bars[q % CL_S], (q / CL_S) & 1);
     const double *b0 = reinterpret_cast<const double *>(smem + (q % CL_S) * CL_STAGE_BYTES);
@@ -123,11 +123,7 @@ __global__ void __launch_bounds__(CL_THREADS, MINB)
         const double b23 = dx2 * a12 * a13 + dy2 * a22 * a23 + dzf2 * a32 * a33;
         const double bb = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
         const double e = (bb < 1.e-8) ? 0.0 : g.c_vreman * sqrt(bb / aa);
-        if (store_ok) {
-          const long long c = cbase + (long long)g.pk * k;
-          ekm[c] = e + g.numol;
-          ekh[c] = e * g.prandtli + g.numol * g.prandtlmoli;
-        }
+        if (store_ok) ek_store(g, ci, cj, k, e, ekm, ekh, halo);
       }
       __syncthreads();
       if (tid == 0) {

@@ -25,6 +25,7 @@ struct Geo {
   double numol, prandtlmoli, prandtli, c_vreman, csz;
   double Uinf, Vinf;
   int BCtopm, lles;
+  int wrapx;             // 1: x is unsplit and kernels that own their halos write the periodic x images themselves
 };
 
 // offset of Fortran element (i,j,k) in a momentum-halo array starting at k = 1-kh
@@ -42,6 +43,11 @@ __host__ __device__ __forceinline__ long long offR(const Geo &g, int i, int j, i
 __host__ __device__ __forceinline__ long long offS(const Geo &g, int i, int j, int k) {
   return (long long)(i + g.ihc - 1) + (long long)g.pic * ((j + g.jhc - 1) + (long long)g.pjc * (k + g.khc - 1));
 }
+// Periodic images of interior cell (i,j) in the halo ring (width 1, imax,jmax >= 2): at most one in x
+// (only when x is unsplit), one in y (nprocy = 1 always) and the corner.  -1 = none.
+__device__ __forceinline__ int img_x(const Geo &g, int i) { return g.wrapx ? (i == 1 ? g.imax + 1 : (i == g.imax ? 0 : -1)) : -1; }
+__device__ __forceinline__ int img_y(const Geo &g, int j) { return j == 1 ? g.jmax + 1 : (j == g.jmax ? 0 : -1); }
+
 __host__ __device__ __forceinline__ long long offST(const Geo &g, int i, int j, int k) {
   return (long long)(i + g.ihc - 1) + (long long)g.pic * ((j + g.jhc - 1) + (long long)g.pjc * (k - 1));
 }

@@ -103,17 +103,61 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
   auto OUT = [&](long long loff, int pt) -> double * {
     return OBLK ? ob.base[pt >> ob.shift] + obase + loff + (long long)(pt & ob.mask) * dd.sp : out + obase + loff + (long long)pt * dd.sp;
   };
+  // x lines: global -> padded shared tile.  All of a thread's loads are issued before the first use (R1
+  // independent 16-byte requests in flight per thread); 128-bit accesses when the lines are 16-byte aligned.
+  constexpr int NIT = (LANES * H) / NT;   // = R1
+  const bool al_in = !IBLK ? ((((size_t)(in + ibase)) & 15) == 0 && ((di.s1 | di.s2) & 1) == 0)
+                           : ((((size_t)ib.base[0]) & 15) == 0 && ((di.s1 | di.s2 | ibase) & 1) == 0);
+  const bool al_out = !OBLK ? ((((size_t)(out + obase)) & 15) == 0 && ((dd.s1 | dd.s2) & 1) == 0)
+                            : ((((size_t)ob.base[0]) & 15) == 0 && ((dd.s1 | dd.s2 | obase) & 1) == 0);
+  auto stage_in = [&]() {
+    double2 st[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int idx = tid + it * NT;
+      if (idx < nb * H) {
+        const int b = idx / H, m = idx - b * H;
+        const double *q = IN((long long)b * di.s1, 2 * m);
+        st[it] = al_in ? *reinterpret_cast<const double2 *>(q) : make_double2(q[0], q[1]);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int idx = tid + it * NT;
+      if (idx < nb * H) {
+        const int b = idx / H, m = idx - b * H;
+        buf[b * (H + 1) + m] = st[it];
+      }
+    }
+  };
+  auto stage_out = [&]() {
+    double2 st[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int idx = tid + it * NT;
+      if (idx < nb * H) {
+        const int b = idx / H, m = idx - b * H;
+        st[it] = buf[b * (H + 1) + m];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int idx = tid + it * NT;
+      if (idx < nb * H) {
+        const int b = idx / H, m = idx - b * H;
+        double *q = OUT((long long)b * dd.s1, 2 * m);
+        if (al_out) *reinterpret_cast<double2 *>(q) = st[it];
+        else { q[0] = st[it].x; q[1] = st[it].y; }
+      }
+    }
+  };
 #define SA(p) (XDIR ? (lane * (H + 1) + (p)) : ((p)*LANES + lane))
 #define RS(r) (lane * 2 * (H + 1) + (r))  /* real slot r of this lane's line in the x staging tile */
 
   double2 v[R1];
   if (!INV) {
     if (XDIR) {
-      for (int idx = tid; idx < nb * H; idx += NT) {
-        const int b = idx / H, m = idx - b * H;
-        const double *q = IN((long long)b * di.s1, 2 * m);
-        buf[b * (H + 1) + m] = make_double2(q[0], q[1]);
-      }
+      stage_in();
       __syncthreads();
 #pragma unroll
       for (int q = 0; q < R1; q++) v[q] = buf[SA(j + R2 * q)];
@@ -129,14 +173,27 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
   } else {
     // merge: Z[k] = A + T, Z[h-k] = conj(A - T), A = Xk + conj(Xhk), T = i conj(w^k) (Xk - conj(Xhk))
     if (XDIR) {
-      for (int idx = tid; idx < nb * H; idx += NT) {
-        const int b = idx / H, m = idx - b * H;
-        const double *q = IN((long long)b * di.s1, 2 * m);
-        buf[b * (H + 1) + m] = make_double2(q[0], q[1]);
-      }
+      stage_in();
       __syncthreads();
     }
     double2 zk[NPAIR], zh[NPAIR];
+    // y lines: issue every global load of the thread first (4 NPAIR independent requests in flight), then merge
+    double gx0[NPAIR], gx1[NPAIR], gy0[NPAIR], gy1[NPAIR];
+    if (!XDIR) {
+      const long long lo = (long long)lane * di.s1;
+#pragma unroll
+      for (int t = 0; t < NPAIR; t++) {
+        const int k = j + R2 * t;
+        gx0[t] = gx1[t] = gy0[t] = gy1[t] = 0.;
+        if (k <= H / 2 && act) {
+          if (k == 0) { gx0[t] = *IN(lo, 0); gy0[t] = *IN(lo, N - 1); }
+          else {
+            gx0[t] = *IN(lo, 2 * k - 1); gx1[t] = *IN(lo, 2 * k);
+            gy0[t] = *IN(lo, 2 * (H - k) - 1); gy1[t] = *IN(lo, 2 * (H - k));
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int t = 0; t < NPAIR; t++) {
       const int k = j + R2 * t;
@@ -145,15 +202,11 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
         double x0, x1, y0, y1;
         if (k == 0) {
           if (XDIR) { x0 = rbuf[RS(0)]; y0 = rbuf[RS(N - 1)]; }
-          else { const long long lo = (long long)lane * di.s1; x0 = *IN(lo, 0); y0 = *IN(lo, N - 1); }
+          else { x0 = gx0[t]; y0 = gy0[t]; }
           zk[t] = make_double2(x0 + y0, x0 - y0);
         } else {
           if (XDIR) { x0 = rbuf[RS(2 * k - 1)]; x1 = rbuf[RS(2 * k)]; y0 = rbuf[RS(2 * (H - k) - 1)]; y1 = rbuf[RS(2 * (H - k))]; }
-          else {
-            const long long lo = (long long)lane * di.s1;
-            x0 = *IN(lo, 2 * k - 1); x1 = *IN(lo, 2 * k);
-            y0 = *IN(lo, 2 * (H - k) - 1); y1 = *IN(lo, 2 * (H - k));
-          }
+          else { x0 = gx0[t]; x1 = gx1[t]; y0 = gy0[t]; y1 = gy1[t]; }
           const double2 A = make_double2(x0 + y0, x1 - y1), Bv = make_double2(x0 - y0, x1 + y1);
           const double2 w = tw[k];
           const double2 T = cmul(make_double2(w.y, w.x), Bv);
@@ -244,12 +297,7 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
         }
       }
       __syncthreads();
-      for (int idx = tid; idx < nb * H; idx += NT) {
-        const int b = idx / H, m = idx - b * H;
-        const double2 z = buf[b * (H + 1) + m];
-        double *q = OUT((long long)b * dd.s1, 2 * m);
-        q[0] = z.x; q[1] = z.y;
-      }
+      stage_out();
     } else if (act) {
       const long long lo = (long long)lane * dd.s1;
 #pragma unroll
@@ -276,12 +324,7 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
           buf[SA(j + R2 * t + R1 * k2)] = make_double2(z.x * fac, z.y * fac);
         }
       __syncthreads();
-      for (int idx = tid; idx < nb * H; idx += NT) {
-        const int b = idx / H, m = idx - b * H;
-        const double2 z = buf[b * (H + 1) + m];
-        double *q = OUT((long long)b * dd.s1, 2 * m);
-        q[0] = z.x; q[1] = z.y;
-      }
+      stage_out();
     } else if (act) {
       const long long lo = (long long)lane * dd.s1;
 #pragma unroll
@@ -324,7 +367,8 @@ __global__ void k_zfactor(int nxh, int nyh, int K, const double *__restrict__ xd
 }
 
 // One thread per (i,j) column of the halo-free spectral array x(imax,jmax,K); forward then backward
-// sweep in place.  ZU levels are prefetched ahead of the recurrence.
+// sweep in place.  The recurrence is a dependent FMA chain, so memory latency is hidden by explicit
+// double buffering: while batch A (ZU levels) runs through the chain, the loads of batch B are in flight.
 template <int ZU>
 __global__ void __launch_bounds__(128) k_zsolve(Geo g, int nxh, int nyh, double *__restrict__ x, const double *__restrict__ zt,
                                                 const double *__restrict__ a, const double *__restrict__ c) {
@@ -336,39 +380,46 @@ __global__ void __launch_bounds__(128) k_zsolve(Geo g, int nxh, int nyh, double 
   const long long sk = (long long)g.imax * g.jmax, tk = (long long)nxh * nyh;
   double *xp = x + (long long)i + (long long)g.imax * j;
   const double *zp = zt + (long long)jy * nxh + ix;
+  double xa[ZU], za[ZU], xb[ZU], zb[ZU];
+  const int nb = K / ZU;
+#define ZLOADF(X, Z, k0) _Pragma("unroll") for (int u = 0; u < ZU; u++) { X[u] = xp[((k0) + u) * sk]; Z[u] = __ldg(zp + ((k0) + u) * tk); }
+#define ZRUNF(X, Z, k0) _Pragma("unroll") for (int u = 0; u < ZU; u++) { xprev = (X[u] - __ldg(a + (k0) + u) * xprev) * Z[u]; xp[((k0) + u) * sk] = xprev; }
   double xprev = 0.;
-  int k = 0;
-  for (; k + ZU <= K; k += ZU) {
-    double xv[ZU], zv[ZU];
-#pragma unroll
-    for (int u = 0; u < ZU; u++) { xv[u] = xp[(k + u) * sk]; zv[u] = __ldg(zp + (k + u) * tk); }
-#pragma unroll
-    for (int u = 0; u < ZU; u++) {
-      xprev = (xv[u] - __ldg(a + k + u) * xprev) * zv[u];
-      xp[(k + u) * sk] = xprev;
+  if (nb > 0) ZLOADF(xa, za, 0)
+  for (int b = 0; b < nb; b += 2) {
+    if (b + 1 < nb) ZLOADF(xb, zb, (b + 1) * ZU)
+    ZRUNF(xa, za, b * ZU)
+    if (b + 1 < nb) {
+      if (b + 2 < nb) ZLOADF(xa, za, (b + 2) * ZU)
+      ZRUNF(xb, zb, (b + 1) * ZU)
     }
   }
-  for (; k < K; k++) {
+  for (int k = nb * ZU; k < K; k++) {
     xprev = (xp[k * sk] - __ldg(a + k) * xprev) * __ldg(zp + k * tk);
     xp[k * sk] = xprev;
   }
-  // backward: x_k = x'_k - d_k x_{k+1}, d_k = c_k z_k  (c_{K-1} = 0)
+#undef ZLOADF
+#undef ZRUNF
+  // backward: x_k = x'_k - d_k x_{k+1}, d_k = c_k z_k  (c_{K-1} = 0), levels K-2 .. 0
   double xnext = xprev;
-  k = K - 2;
-  for (; k - ZU + 1 >= 0; k -= ZU) {
-    double xv[ZU], zv[ZU];
-#pragma unroll
-    for (int u = 0; u < ZU; u++) { xv[u] = xp[(k - u) * sk]; zv[u] = __ldg(zp + (k - u) * tk); }
-#pragma unroll
-    for (int u = 0; u < ZU; u++) {
-      xnext = xv[u] - (__ldg(c + k - u) * zv[u]) * xnext;
-      xp[(k - u) * sk] = xnext;
+  const int nbb = (K - 1) / ZU;
+#define ZLOADB(X, Z, k0) _Pragma("unroll") for (int u = 0; u < ZU; u++) { X[u] = xp[((k0) - u) * sk]; Z[u] = __ldg(zp + ((k0) - u) * tk); }
+#define ZRUNB(X, Z, k0) _Pragma("unroll") for (int u = 0; u < ZU; u++) { xnext = X[u] - (__ldg(c + (k0) - u) * Z[u]) * xnext; xp[((k0) - u) * sk] = xnext; }
+  if (nbb > 0) ZLOADB(xa, za, K - 2)
+  for (int b = 0; b < nbb; b += 2) {
+    if (b + 1 < nbb) ZLOADB(xb, zb, K - 2 - (b + 1) * ZU)
+    ZRUNB(xa, za, K - 2 - b * ZU)
+    if (b + 1 < nbb) {
+      if (b + 2 < nbb) ZLOADB(xa, za, K - 2 - (b + 2) * ZU)
+      ZRUNB(xb, zb, K - 2 - (b + 1) * ZU)
     }
   }
-  for (; k >= 0; k--) {
+  for (int k = K - 2 - nbb * ZU; k >= 0; k--) {
     xnext = xp[k * sk] - (__ldg(c + k) * __ldg(zp + k * tk)) * xnext;
     xp[k * sk] = xnext;
   }
+#undef ZLOADB
+#undef ZRUNB
 }
 
 }  // namespace udg

@@ -11,13 +11,41 @@ namespace udg {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double sq_(double x) { return x * x; }
 
+// ekm/ekh of interior cell (i,j,k) from the eddy viscosity e (src/modsubgrid.f90:356-360).  With halo != 0 the
+// thread also writes everything closurebc (src/modboundary.f90:434-505) derives from this cell: its periodic
+// images in y (and in x when unsplit) and, for k = 1 / k = ktot, the bottom / top ghost levels of the cell and
+// of its images — so no separate wrap / ghost kernels run afterwards (x-split: the slab exchange follows).
+__device__ __forceinline__ void ek_store(const Geo &g, int i, int j, int k, double e, double *__restrict__ ekm,
+                                         double *__restrict__ ekh, int halo) {
+  const double m = e + g.numol, hh = e * g.prandtli + g.numol * g.prandtlmoli;
+  if (!halo) {
+    const long long c = offF(g, i, j, k);
+    ekm[c] = m; ekh[c] = hh;
+    return;
+  }
+  const double tm = 2. * g.numol, th = 2. * g.numol * g.prandtlmoli;
+  auto put = [&](int ti, int tj) {
+    const long long c = offF(g, ti, tj, k);
+    ekm[c] = m; ekh[c] = hh;
+    if (k == 1) { ekm[c - g.pk] = tm - m; ekh[c - g.pk] = th - hh; }
+    if (k == g.ktot) {
+      if (g.BCtopm == 2) { ekm[c + g.pk] = tm - m; ekh[c + g.pk] = th - hh; }
+      else { ekm[c + g.pk] = m; ekh[c + g.pk] = hh; }
+    }
+  };
+  const int ix = img_x(g, i), jy = img_y(g, j);
+  put(i, j);
+  if (ix >= 0) put(ix, j);
+  if (jy >= 0) { put(i, jy); if (ix >= 0) put(ix, jy); }
+}
+
 // closure: src/modsubgrid.f90:159-412.  MODEL 0 = DNS (:401-404), 1 = Vreman (:269-360),
 // 2 = Smagorinsky (:208-267).  Writes interior ekm/ekh including "+ numol" (:263-264,359-360).
 // Ghost cells are produced by k_closurebc_*.
 template <int MODEL>
 __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
                                                  const double *__restrict__ w0, double *__restrict__ ekm,
-                                                 double *__restrict__ ekh) {
+                                                 double *__restrict__ ekh, int halo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   const int k = blockIdx.z + 1;
@@ -83,8 +111,66 @@ __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict
 #undef V
 #undef W
   }
-  ekm[c] = e + g.numol;
-  ekh[c] = e * g.prandtli + g.numol * g.prandtlmoli;
+  ek_store(g, i, j, k, e, ekm, ekh, halo);
+}
+
+// Vreman closure, k-marching form of k_closure<1>: one thread owns an (i,j) column over KC levels and carries
+// everything that is shared between consecutive levels in registers (the level-k and level-(k+1) operands of the
+// vertical derivatives, the w ring), so a level costs 17 loads instead of 30 and almost no address arithmetic.
+// Operand order inside each gradient is the reference's (src/modsubgrid.f90:271-327): differences to k_closure<1>
+// and to the oracle are FMA-contraction rounding only.
+template <int KC>
+__global__ void __launch_bounds__(256) k_closure_vreman_march(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
+                                                              const double *__restrict__ w0, double *__restrict__ ekm,
+                                                              double *__restrict__ ekh, int halo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const int k0 = blockIdx.z * KC + 1, k1 = min(k0 + KC, g.ktot + 1);
+  const long long sj = g.pi, sk = g.pk;
+  const long long c0 = offF(g, i, j, k0 - 1);
+  const double *pu = u0 + c0, *pv = v0 + c0, *pw = w0 + c0;
+  const double dxi = g.dxi, dyi = g.dyi, dxiq = g.dxiq, dyiq = g.dyiq, dx2 = g.dx2, dy2 = g.dy2;
+  double su_km = __ldg(pu + 1) + __ldg(pu), sv_km = __ldg(pv + sj) + __ldg(pv);   // level k0-1
+  pu += sk; pv += sk; pw += sk;                                                   // level k0
+  double u_c = __ldg(pu), u_ip = __ldg(pu + 1), v_c = __ldg(pv), v_jp = __ldg(pv + sj);
+  double w_c = __ldg(pw), w_ip = __ldg(pw + 1), w_im = __ldg(pw - 1), w_jp = __ldg(pw + sj), w_jm = __ldg(pw - sj);
+  for (int k = k0; k < k1; k++) {
+    const int K = k + 1;
+    const double u_ipjp = __ldg(pu + sj + 1), u_jp = __ldg(pu + sj), u_ipjm = __ldg(pu - sj + 1), u_jm = __ldg(pu - sj);
+    const double v_ipjp = __ldg(pv + sj + 1), v_ip = __ldg(pv + 1), v_imjp = __ldg(pv + sj - 1), v_im = __ldg(pv - 1);
+    const double uK_c = __ldg(pu + sk), uK_ip = __ldg(pu + sk + 1), vK_c = __ldg(pv + sk), vK_jp = __ldg(pv + sk + sj);
+    const double wK_c = __ldg(pw + sk), wK_ip = __ldg(pw + sk + 1), wK_im = __ldg(pw + sk - 1);
+    const double wK_jp = __ldg(pw + sk + sj), wK_jm = __ldg(pw + sk - sj);
+    const double dzfk = __ldg(g.dzf + k), dzfK = __ldg(g.dzf + K), dzfkm = __ldg(g.dzf + k - 1);
+    const double dzhik = __ldg(g.dzhi + k), dzhiK = __ldg(g.dzhi + K);
+    const double dzfiqk = __ldg(g.dzfiq + k), dzfik = __ldg(g.dzfi + k), dzf2 = __ldg(g.dzf2 + k);
+    const double su_k = u_ip + u_c, sv_k = v_jp + v_c;
+    const double a11 = (u_ip - u_c) * dxi;
+    const double a12 = (v_ipjp + v_ip - v_imjp - v_im) * dxiq;
+    const double a13 = (wK_ip + w_ip - wK_im - w_im) * dxiq;
+    const double a21 = (u_ipjp + u_jp - u_ipjm - u_jm) * dyiq;
+    const double a22 = (v_jp - v_c) * dyi;
+    const double a23 = (wK_jp + w_jp - wK_jm - w_jm) * dyiq;
+    const double suK = uK_ip + uK_c, svK = vK_jp + vK_c;
+    const double a31 = ((suK * dzfk + su_k * dzfK) * dzhiK - (su_k * dzfkm + su_km * dzfk) * dzhik) * dzfiqk;
+    const double a32 = ((svK * dzfk + sv_k * dzfK) * dzhiK - (sv_k * dzfkm + sv_km * dzfk) * dzhik) * dzfiqk;
+    const double a33 = (wK_c - w_c) * dzfik;
+    const double aa = a11 * a11 + a21 * a21 + a31 * a31 + a12 * a12 + a22 * a22 + a32 * a32 + a13 * a13 + a23 * a23 + a33 * a33;
+    const double b11 = dx2 * a11 * a11 + dy2 * a21 * a21 + dzf2 * a31 * a31;
+    const double b22 = dx2 * a12 * a12 + dy2 * a22 * a22 + dzf2 * a32 * a32;
+    const double b12 = dx2 * a11 * a12 + dy2 * a21 * a22 + dzf2 * a31 * a32;
+    const double b33 = dx2 * a13 * a13 + dy2 * a23 * a23 + dzf2 * a33 * a33;
+    const double b13 = dx2 * a11 * a13 + dy2 * a21 * a23 + dzf2 * a31 * a33;
+    const double b23 = dx2 * a12 * a13 + dy2 * a22 * a23 + dzf2 * a32 * a33;
+    const double bb = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
+    const double e = (bb < 1.e-8) ? 0.0 : g.c_vreman * sqrt(bb / aa);
+    ek_store(g, i, j, k, e, ekm, ekh, halo);
+    su_km = su_k; sv_km = sv_k;
+    u_c = uK_c; u_ip = uK_ip; v_c = vK_c; v_jp = vK_jp;
+    w_c = wK_c; w_ip = wK_ip; w_im = wK_im; w_jp = wK_jp; w_jm = wK_jm;
+    pu += sk; pv += sk; pw += sk;
+  }
 }
 
 // closurebc part 1: src/modboundary.f90:447-465 top/bottom ghost levels on (0..imax+1, 0..jmax+1).
@@ -338,6 +424,51 @@ __global__ void __launch_bounds__(256) k_tderive_integrate(Geo g, double rk3coef
   u0[c] = a; v0[c] = b; w0[c] = d;
   if (STEP3) { um[c] = a; vm[c] = b; wm[c] = d; }
   pres0[c] = pres0[c] + pc;
+}
+// Same pass, additionally owning everything `bcp`, `halos` and `boundary` do for the cells it writes (periodic
+// x,y; src/modboundary.f90:1362-1408, :508-626, :163-204): p(i-1), p(j-1) are read from the periodic image instead
+// of a pre-wrapped halo; every new value is also stored to the cell's periodic images (y always, x when unsplit);
+// cells at k = ktot also set the top ghost level (freeslip copy / noslip mirror, w = 0); pres0 += p reaches the
+// image cells too (:1096-1102).  Only legal when the m-fields / w(k=1) / tendencies at k=1 are in the state the
+// reference's own halos+boundary leave them in (the host tracks that; otherwise the plain kernel + wraps run).
+template <bool STEP3>
+__global__ void __launch_bounds__(256) k_tderive_integrate_halo(Geo g, double rk3coef, const double *__restrict__ p,
+                                                                const double *__restrict__ up, const double *__restrict__ vp,
+                                                                const double *__restrict__ wp, double *__restrict__ um,
+                                                                double *__restrict__ vm, double *__restrict__ wm,
+                                                                double *__restrict__ u0, double *__restrict__ v0,
+                                                                double *__restrict__ w0, double *__restrict__ pres0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long c = offF(g, i, j, k), t = offT(g, i, j, k);
+  const double pc = p[c];
+  const long long cim = (g.wrapx && i == 1) ? c + (g.imax - 1) : c - 1;
+  const long long cjm = (j == 1) ? c + (long long)g.pi * (g.jmax - 1) : c - g.pi;
+  const double ru = up[t] - (pc - p[cim]) * g.dxi;
+  const double rv = vp[t] - (pc - p[cjm]) * g.dyi;
+  double rw = wp[t];
+  if (k >= 2) rw = rw - (pc - p[c - g.pk]) * g.dzhi[k];
+  const double a = um[c] + rk3coef * ru;
+  const double b = vm[c] + rk3coef * rv;
+  const double d = wm[c] + rk3coef * rw;
+  const bool top = (k == g.ktot);
+  const double at = (g.BCtopm == 2) ? 2. * g.Uinf - a : a, bt = (g.BCtopm == 2) ? 2. * g.Vinf - b : b;
+  auto put = [&](long long q) {
+    u0[q] = a; v0[q] = b; w0[q] = d;
+    if (STEP3) { um[q] = a; vm[q] = b; wm[q] = d; }
+    pres0[q] = pres0[q] + pc;
+    if (top) {
+      const long long qt = q + g.pk;
+      u0[qt] = at; v0[qt] = bt; w0[qt] = 0.;
+      if (STEP3) { um[qt] = at; vm[qt] = bt; wm[qt] = 0.; }
+    }
+  };
+  put(c);
+  const int ix = img_x(g, i), jy = img_y(g, j);
+  if (ix >= 0) put(offF(g, ix, j, k));
+  if (jy >= 0) { put(offF(g, i, jy, k)); if (ix >= 0) put(offF(g, ix, jy, k)); }
 }
 // pres0 += p on the halo shell only (everything that is not an interior cell); the interior is done above.
 __global__ void k_pres_update_shell(Geo g, const double *__restrict__ p, double *__restrict__ pres0) {

@@ -126,6 +126,7 @@ struct udgpu {
   CUtensorMap tm[5];
   MomTmaParams mtp, clp;
   int mt_grid = 0, cl_grid = 0, cl_occ = 2;
+  int cl_march = 1;           // Vreman closure: k-marching register-carry kernel (UDGPU_CLOSURE_MARCH=0: one thread per cell)
   int nsm = 148;
   // state
   bool tder_pending = false;  // poisson() solved for p; tderive is fused into the next tstep_integrate()
@@ -133,6 +134,14 @@ struct udgpu {
   bool tend_zero = false;      // tendencies are (logically) zero: next tendency kernel may overwrite
   bool tend_pushed = false;    // host wrote a tendency array (its halo cells may be non-zero): zero eagerly once
   bool tend_lazy_zero = false; // ... and the zeros have not been written to memory yet
+  // kernels that own their halos (closure, fused tderive+integrate): see DESIGN.md "halo ownership"
+  bool fuse_halo = false;      // configuration allows it (imax, jmax >= 2, not disabled by flag)
+  bool halo_dirty = false;     // host wrote a momentum field: lateral halos unknown until a generic halos() ran
+  bool bc_dirty = false;       // ... top/bottom planes unknown until a generic boundary() ran
+  bool halos_done = false;     // the last tstep_integrate already produced what halos() would
+  bool bc_done = false;        // ... and what boundary() would
+  bool halo_x_pending = false; // x-split: the slab exchange of the new fields is still to run (in halos())
+  bool p_halo_valid = true;    // p's lateral halo is the wrap of its interior (bcp); restored lazily on pull
   bool prof = false;
   ProfSlot ps[PROF_N];
   long launches = 0;
@@ -140,6 +149,7 @@ struct udgpu {
 
 // ------------------------------------------------------------------------------------------
 static int flush_pending(udgpu *h);
+static int settle_for_access(udgpu *h, int field);
 static int setup_p2p(udgpu *h, size_t nR);
 static int p2p_barrier(udgpu *h);
 static int materialize_zero_tend(udgpu *h);
@@ -346,6 +356,8 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
   CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   if (h->P > 1) NC(ncclCommInitRank(&h->comm, h->P, *(const ncclUniqueId *)nccl_uid, h->rank));
 
+  { const char *e = getenv("UDGPU_CLOSURE_MARCH"); if (e) h->cl_march = atoi(e); }
+  if (c->flags & UDGPU_F_V1_KERNELS) h->cl_march = 0;
   Geo &g = h->g;
   memset(&g, 0, sizeof(g));
   g.imax = c->imax; g.jmax = c->jmax; g.ktot = c->ktot; g.itot = c->itot; g.jtot = c->jtot;
@@ -370,6 +382,8 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     g.csz = (c->cs == -1.) ? pow(cm * cm * cm / ceps, 0.25) : c->cs;
   }
   g.Uinf = c->Uinf; g.Vinf = c->Vinf; g.BCtopm = c->BCtopm; g.lles = c->lles;
+  h->fuse_halo = g.imax >= 2 && g.jmax >= 2 && !(c->flags & UDGPU_F_NO_HALO_FUSION);
+  g.wrapx = (h->fuse_halo && h->P == 1) ? 1 : 0;
 
   // ---- metric tables: index k in [-1, ktot+2], 13 tables ----
   const int K = g.ktot, NM = K + 4, OFF = 1;
@@ -529,6 +543,8 @@ extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
   RET(flush_pending(h));
   const bool is_tend = (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP);
   if (is_tend) { RET(materialize_zero_tend(h)); h->tend_pushed = true; }
+  if (field <= UDGPU_WP) { h->halo_dirty = h->bc_dirty = true; h->halos_done = h->bc_done = h->halo_x_pending = false; }
+  if (field == UDGPU_P) h->p_halo_valid = true;   // the host's array is taken as is
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(h->f[field] + (size_t)n4 * h->cnt[field], host, h->cnt[field] * sizeof(double), cudaMemcpyHostToDevice, h->st));
   if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP) h->tend_zero = false; h->tend_lazy_zero = false;
@@ -538,6 +554,7 @@ extern "C" int udgpu_pull(udgpu_t *h, int field, int n4, double *host) {
   RET(check_field(h, field, n4));
   RET(flush_pending(h));
   if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP) RET(materialize_zero_tend(h));
+  RET(settle_for_access(h, field));
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(host, h->f[field] + (size_t)n4 * h->cnt[field], h->cnt[field] * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
@@ -545,6 +562,14 @@ extern "C" int udgpu_pull(udgpu_t *h, int field, int n4, double *host) {
 }
 extern "C" int udgpu_device_ptr(udgpu_t *h, int field, int n4, void **dptr) {
   RET(check_field(h, field, n4));
+  RET(flush_pending(h));
+  RET(settle_for_access(h, field));
+  // the caller may write through the pointer: treat it like a push
+  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP) {
+    RET(materialize_zero_tend(h));
+    h->tend_pushed = true; h->tend_zero = false;
+  }
+  if (field <= UDGPU_WP) { h->halo_dirty = h->bc_dirty = true; h->halos_done = h->bc_done = h->halo_x_pending = false; }
   *dptr = h->f[field] + (size_t)n4 * h->cnt[field];
   return UDGPU_OK;
 }
@@ -649,24 +674,37 @@ extern "C" int udgpu_closure(udgpu_t *h) {
   const Geo &g = h->g;
   ProfScope ps(h, PROF_CLOSURE);
   const dim3 gr = grid3(g, B3);
+  const int halo = h->fuse_halo ? 1 : 0;
+  double **f = h->f;
   // model selection order of the reference: smagorinsky first, then vreman, else DNS (modsubgrid.f90:208,269,401)
-  if (h->cfg.lsmagorinsky) k_closure<2><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
-  else if (h->cfg.lvreman && h->use_tma && h->cl_occ > 0)
-  {
-    if (h->cl_occ == 1) k_closure_vreman_tma<1><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
-    else k_closure_vreman_tma<2><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
+  if (h->cfg.lsmagorinsky) k_closure<2><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
+  else if (h->cfg.lvreman && h->use_tma && h->cl_occ > 0) {
+    if (h->cl_occ == 1) k_closure_vreman_tma<1><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, f[UDGPU_EKM], f[UDGPU_EKH], halo);
+    else k_closure_vreman_tma<2><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, f[UDGPU_EKM], f[UDGPU_EKH], halo);
   }
-  else if (h->cfg.lvreman) k_closure<1><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
-  else k_closure<0><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
+  else if (h->cfg.lvreman && h->cl_march > 0) {
+    constexpr int KC = 16;
+    const dim3 gm(gr.x, gr.y, (g.ktot + KC - 1) / KC);
+    k_closure_vreman_march<KC><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
+  }
+  else if (h->cfg.lvreman) k_closure<1><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
+  else k_closure<0><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
   KCHECK();
   h->launches++;
-  // closurebc: lateral wraps on all levels, then top/bottom ghost levels over the full halo'd plane
-  RET(wrap_xy(h, {h->f[UDGPU_EKM], h->f[UDGPU_EKH]}, g.ktot + 2 * g.kh));
-  k_closurebc_topbot<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, h->f[UDGPU_EKM], h->f[UDGPU_EKH]);
-  KCHECK();
-  h->launches++;
-  if (g.BCtopm == 1) {  // reassure_fluxtop_boundary
-    k_fluxtop_uv<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_UM], h->f[UDGPU_VM]);
+  if (halo) {
+    // closurebc's wraps and ghost levels were written by the closure kernel itself; only a split x needs the exchange
+    if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_EKM], f[UDGPU_EKH]}, g.ktot + 2 * g.kh));
+  } else {
+    // closurebc: lateral wraps on all levels, then top/bottom ghost levels over the full halo'd plane
+    RET(wrap_xy(h, {f[UDGPU_EKM], f[UDGPU_EKH]}, g.ktot + 2 * g.kh));
+    k_closurebc_topbot<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, f[UDGPU_EKM], f[UDGPU_EKH]);
+    KCHECK();
+    h->launches++;
+  }
+  // reassure_fluxtop_boundary (src/modboundary.f90:392-431): a no-op when the top ghost already is what
+  // boundary() left there and nobody wrote the fields since
+  if (g.BCtopm == 1 && (h->bc_dirty || !h->fuse_halo)) {
+    k_fluxtop_uv<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_UM], f[UDGPU_VM]);
     KCHECK();
     h->launches++;
   }
@@ -746,6 +784,15 @@ static int flush_pending(udgpu *h) {
   RET((launch_momtend<true, false>(h, !h->tend_zero)));
   RET((launch_scalars<true, false>(h, !h->tend_zero)));
   h->tend_zero = false; h->tend_lazy_zero = false;
+  return UDGPU_OK;
+}
+
+// bring lazily maintained halo state up to what the reference would show before a field is handed out
+static int settle_for_access(udgpu *h, int field) {
+  if (field == UDGPU_P && !h->p_halo_valid) {
+    RET(wrap_xy(h, {h->f[UDGPU_P]}, h->g.ktot + 2 * h->g.kh));   // bcp, src/modboundary.f90:1344-1408
+    h->p_halo_valid = true;
+  }
   return UDGPU_OK;
 }
 
@@ -1064,6 +1111,7 @@ static int tderive_now(udgpu *h) {
   RET(materialize_zero_tend(h));
   ProfScope ps(h, PROF_INTEG);
   RET(wrap_xy(h, {h->f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
+  h->p_halo_valid = true;
   k_tderive<<<grid3(g, B3), B3, 0, h->st>>>(g, h->f[UDGPU_P], h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP]);
   KCHECK();
   k_pres_update<<<148 * 8, 256, 0, h->st>>>((long long)h->cnt[UDGPU_PRES0], h->f[UDGPU_P], h->f[UDGPU_PRES0]);
@@ -1077,6 +1125,7 @@ extern "C" int udgpu_poisson(udgpu_t *h, double dt, int rk3step) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
   RET(udgpu_fillps(h, dt, rk3step));
   RET(poisson_core(h, h->f[UDGPU_RHS], h->f[UDGPU_P]));
+  h->p_halo_valid = false;
   if (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION) return tderive_now(h);
   h->tder_pending = true;   // fused with tstep_integrate(); flushed on any other access
   return UDGPU_OK;
@@ -1103,17 +1152,35 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
   if (h->tder_pending && !h->adv_pending) {
     h->tder_pending = false;
     ProfScope ps(h, PROF_INTEG);
-    RET(wrap_xy(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
-    if (rk3step == 3)
-      k_tderive_integrate<true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
-                                                                f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0]);
-    else
-      k_tderive_integrate<false><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
-                                                                 f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0]);
-    KCHECK();
-    k_pres_update_shell<<<dim3(8, g.ktot + 2 * g.kh), 256, 0, h->st>>>(g, f[UDGPU_P], f[UDGPU_PRES0]);
-    KCHECK();
-    h->launches += 2;
+    const bool own = h->fuse_halo && !h->halo_dirty && !h->bc_dirty;
+    if (own) {
+      // one pass: bcp (periodic index / slab exchange of p), tderive, integrate, pres0 += p, halos, boundary
+      if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));
+      if (rk3step == 3)
+        k_tderive_integrate_halo<true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
+                                                                       f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0]);
+      else
+        k_tderive_integrate_halo<false><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
+                                                                        f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0]);
+      KCHECK();
+      h->launches++;
+      h->halos_done = h->bc_done = true;
+      h->halo_x_pending = h->P > 1;
+    } else {
+      RET(wrap_xy(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
+      h->p_halo_valid = true;
+      if (rk3step == 3)
+        k_tderive_integrate<true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
+                                                                  f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0]);
+      else
+        k_tderive_integrate<false><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
+                                                                   f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0]);
+      KCHECK();
+      k_pres_update_shell<<<dim3(8, g.ktot + 2 * g.kh), 256, 0, h->st>>>(g, f[UDGPU_P], f[UDGPU_PRES0]);
+      KCHECK();
+      h->launches += 2;
+      h->halos_done = h->bc_done = h->halo_x_pending = false;
+    }
     RET(integrate_scalars(h, rk3coef, rk3step));
     h->tend_zero = true;
     h->tend_lazy_zero = true;
@@ -1130,6 +1197,7 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
                                                              f[UDGPU_WM], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP]);
   KCHECK();
   h->launches++;
+  h->halos_done = h->bc_done = h->halo_x_pending = false;
   RET(integrate_scalars(h, rk3coef, rk3step));
   h->tend_zero = true;
   h->tend_lazy_zero = true;
@@ -1143,7 +1211,16 @@ extern "C" int udgpu_halos(udgpu_t *h) {
   const Geo &g = h->g;
   ProfScope ps(h, PROF_HALO);
   double **f = h->f;
-  RET(wrap_xy(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
+  if (h->halos_done && !h->halo_dirty) {
+    // the fused tderive+integrate kernel wrote the periodic images itself; a split x still needs its exchange
+    if (h->halo_x_pending) {
+      RET(halo_x_exchange(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
+      h->halo_x_pending = false;
+    }
+  } else {
+    RET(wrap_xy(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
+    h->halo_dirty = false;
+  }
   if (h->cfg.nsv) {  // xs_periodic / ys_periodic (src/modboundary.f90:568-579,655-669) or exchange at level ihc
     std::vector<double *> sv;
     for (int n = 0; n < h->cfg.nsv; n++) {
@@ -1161,9 +1238,12 @@ extern "C" int udgpu_boundary(udgpu_t *h) {
   const Geo &g = h->g;
   ProfScope ps(h, PROF_HALO);
   double **f = h->f;
-  k_boundary_topbot<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]);
-  KCHECK();
-  h->launches++;
+  if (!(h->bc_done && !h->bc_dirty)) {
+    k_boundary_topbot<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]);
+    KCHECK();
+    h->launches++;
+    if (!h->halo_dirty) h->bc_dirty = false;   // planes are final only once the lateral halos under them are
+  }
   for (int n = 0; n < h->cfg.nsv; n++) {
     k_scalar_top<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, f[UDGPU_SV0] + (size_t)n * h->cnt[UDGPU_SV0], f[UDGPU_SVM] + (size_t)n * h->cnt[UDGPU_SVM]);
     KCHECK();
@@ -1226,6 +1306,25 @@ extern "C" int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax,
   RET(udgpu_tstep_integrate(h, *dt, *rk3step));
   RET(udgpu_halos(h));
   RET(udgpu_boundary(h));
+  return UDGPU_OK;
+}
+
+// One full RK3 time step (three passes of src/program.f90:132-207) on HOST arrays: at the start of a time step
+// um = u0 (src/modtstep.f90:330-338), so u0,v0,w0,pres0 in and the same four out is the complete prognostic state.
+extern "C" int udgpu_rk3_step_host(udgpu_t *h, double *u0, double *v0, double *w0, double *pres0, double *dt,
+                                   double dtmax, int ladaptive, double courant, double diffnr) {
+  if (!h || !u0 || !v0 || !w0 || !pres0 || !dt) return set_err(UDGPU_ESTATE, "null argument");
+  double *host[4] = {u0, v0, w0, pres0};
+  const int ids[4] = {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_PRES0};
+  for (int q = 0; q < 4; q++) RET(udgpu_push(h, ids[q], 0, host[q]));
+  for (int q = 0; q < 3; q++)
+    CU(cudaMemcpyAsync(h->f[UDGPU_UM + q], h->f[UDGPU_U0 + q], h->cnt[UDGPU_U0 + q] * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  int rk3step = 0;
+  for (int s = 0; s < 3; s++) RET(udgpu_substep(h, dt, &rk3step, dtmax, ladaptive, courant, diffnr));
+  RET(flush_pending(h));
+  for (int q = 0; q < 4; q++)
+    CU(cudaMemcpyAsync(host[q], h->f[ids[q]], h->cnt[ids[q]] * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
   return UDGPU_OK;
 }
 

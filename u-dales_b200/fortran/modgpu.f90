@@ -21,7 +21,7 @@ module modgpu
   private
   public :: lgpu, gpu_init, gpu_exit, gpu_push_state, gpu_pull_state, gpu_push, gpu_pull, &
             gpu_tstep_update, gpu_advection, gpu_subgrid, gpu_poisson, gpu_tstep_integrate, &
-            gpu_halos, gpu_boundary, gpu_chkdiv
+            gpu_halos, gpu_boundary, gpu_chkdiv, gpu_rk3_step_host
 
   logical :: lgpu = .false.            !< namelist RUN switch (the only new option)
   type(c_ptr) :: handle = c_null_ptr
@@ -134,6 +134,15 @@ module modgpu
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: h
       real(c_double), intent(out) :: divmax, divtot, divrms
+    end function
+    integer(c_int) function udgpu_rk3_step_host(h, u0, v0, w0, pres0, dt, dtmax, ladaptive, courant, diffnr) &
+        bind(C, name="udgpu_rk3_step_host")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      real(c_double), intent(inout) :: u0(*), v0(*), w0(*), pres0(*)
+      real(c_double), intent(inout) :: dt
+      real(c_double), value :: dtmax, courant, diffnr
+      integer(c_int), value :: ladaptive
     end function
   end interface
 
@@ -299,5 +308,14 @@ contains
     real(c_double), intent(out) :: divmax, divtot
     real(c_double) :: divrms
     call chk(udgpu_divergence(handle, divmax, divtot, divrms), 'divergence')
+  end subroutine
+  !> one whole RK3 time step (three passes of program.f90:132-207) on the host-resident module arrays:
+  !! the drop-in for a model whose other physics stay on the CPU and touch the fields once per time step
+  subroutine gpu_rk3_step_host
+    use modglobal, only: dt, dtmax, ladaptive, courant, diffnr
+    use modfields, only: u0, v0, w0, pres0
+    integer(c_int) :: lad
+    lad = 0; if (ladaptive) lad = 1
+    call chk(udgpu_rk3_step_host(handle, u0, v0, w0, pres0, dt, dtmax, lad, courant, diffnr), 'rk3_step_host')
   end subroutine
 end module modgpu
