@@ -71,6 +71,26 @@ def test_poisson_solve(shape, flags):
     assert relerr(p, p_ref) < TOL_PRES
 
 
+@pytest.mark.parametrize("shape", [(64, 64, 64), (256, 64, 40), (128, 32, 33), (512, 16, 70), (1024, 8, 9), (64, 48, 1),
+                                   (128, 20, 32), (256, 12, 31)])
+@pytest.mark.parametrize("minb", ["1", "2"])
+def test_poisson_one_pass_x_vs_separate_passes(shape, minb, monkeypatch):
+    """y, [x-FFT + z-solve + x-FFT^-1 in one kernel], y^-1 (poisson_xz.cuh) against the five separate passes
+    x, y, z, y^-1, x^-1 of src/modpois.f90:478-679 and against the oracle."""
+    import udales_b200 as U
+    rng = np.random.default_rng(11)
+    rhs = rng.standard_normal(shape)
+    o, g1 = make_pair(*shape)
+    assert g1.L is not None
+    monkeypatch.setenv("UDGPU_XZ_MINB", minb)
+    _, ga = make_pair(*shape)
+    monkeypatch.setenv("UDGPU_XZ_FUSED", "0")
+    _, gb = make_pair(*shape)
+    pa, pb = ga.poisson_solve(rhs), gb.poisson_solve(rhs)
+    assert relerr(pa, pb) < 1e-12
+    assert relerr(pa, o.poisson_solve(rhs)) < TOL_PRES
+
+
 @pytest.mark.parametrize("shape", SIZES)
 @pytest.mark.parametrize("rk3step", [1, 2, 3])
 def test_poisson_fillps_tderive(shape, rk3step):

@@ -81,7 +81,7 @@ struct RfftCfg {
 };
 
 template <int R1, int R2, int LANES, bool XDIR, bool INV, bool IBLK = false, bool OBLK = false>
-__global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restrict__ tw, const double *__restrict__ in, LineDesc di,
+__global__ void __launch_bounds__(LANES *R2, (R1 <= 16 ? 2 : 1)) k_rfft_fast(const double2 *__restrict__ tw, const double *__restrict__ in, LineDesc di,
                                                          double *__restrict__ out, LineDesc dd, double fac,
                                                          BlkDesc ib = BlkDesc(), BlkDesc ob = BlkDesc()) {
   constexpr int H = R1 * R2, N = 2 * H, NT = LANES * R2;
@@ -110,44 +110,51 @@ __global__ void __launch_bounds__(LANES *R2) k_rfft_fast(const double2 *__restri
                            : ((((size_t)ib.base[0]) & 15) == 0 && ((di.s1 | di.s2 | ibase) & 1) == 0);
   const bool al_out = !OBLK ? ((((size_t)(out + obase)) & 15) == 0 && ((dd.s1 | dd.s2) & 1) == 0)
                             : ((((size_t)ob.base[0]) & 15) == 0 && ((dd.s1 | dd.s2 | obase) & 1) == 0);
+  constexpr int SCH = NIT > 8 ? 8 : NIT;   // requests in flight per thread and staging round
   auto stage_in = [&]() {
-    double2 st[NIT];
 #pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int idx = tid + it * NT;
-      if (idx < nb * H) {
-        const int b = idx / H, m = idx - b * H;
-        const double *q = IN((long long)b * di.s1, 2 * m);
-        st[it] = al_in ? *reinterpret_cast<const double2 *>(q) : make_double2(q[0], q[1]);
+    for (int i0 = 0; i0 < NIT; i0 += SCH) {
+      double2 st[SCH];
+#pragma unroll
+      for (int it = 0; it < SCH; it++) {
+        const int idx = tid + (i0 + it) * NT;
+        if (idx < nb * H) {
+          const int b = idx / H, m = idx - b * H;
+          const double *q = IN((long long)b * di.s1, 2 * m);
+          st[it] = al_in ? *reinterpret_cast<const double2 *>(q) : make_double2(q[0], q[1]);
+        }
       }
-    }
 #pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int idx = tid + it * NT;
-      if (idx < nb * H) {
-        const int b = idx / H, m = idx - b * H;
-        buf[b * (H + 1) + m] = st[it];
+      for (int it = 0; it < SCH; it++) {
+        const int idx = tid + (i0 + it) * NT;
+        if (idx < nb * H) {
+          const int b = idx / H, m = idx - b * H;
+          buf[b * (H + 1) + m] = st[it];
+        }
       }
     }
   };
   auto stage_out = [&]() {
-    double2 st[NIT];
 #pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int idx = tid + it * NT;
-      if (idx < nb * H) {
-        const int b = idx / H, m = idx - b * H;
-        st[it] = buf[b * (H + 1) + m];
+    for (int i0 = 0; i0 < NIT; i0 += SCH) {
+      double2 st[SCH];
+#pragma unroll
+      for (int it = 0; it < SCH; it++) {
+        const int idx = tid + (i0 + it) * NT;
+        if (idx < nb * H) {
+          const int b = idx / H, m = idx - b * H;
+          st[it] = buf[b * (H + 1) + m];
+        }
       }
-    }
 #pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int idx = tid + it * NT;
-      if (idx < nb * H) {
-        const int b = idx / H, m = idx - b * H;
-        double *q = OUT((long long)b * dd.s1, 2 * m);
-        if (al_out) *reinterpret_cast<double2 *>(q) = st[it];
-        else { q[0] = st[it].x; q[1] = st[it].y; }
+      for (int it = 0; it < SCH; it++) {
+        const int idx = tid + (i0 + it) * NT;
+        if (idx < nb * H) {
+          const int b = idx / H, m = idx - b * H;
+          double *q = OUT((long long)b * dd.s1, 2 * m);
+          if (al_out) *reinterpret_cast<double2 *>(q) = st[it];
+          else { q[0] = st[it].x; q[1] = st[it].y; }
+        }
       }
     }
   };

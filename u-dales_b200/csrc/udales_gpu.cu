@@ -19,6 +19,7 @@
 #include "closure_tma.cuh"
 #include "poisson_v1.cuh"
 #include "poisson_fast.cuh"
+#include "poisson_xz.cuh"
 #include "stencil_v1.cuh"
 #include "scalar_v1.cuh"
 
@@ -100,6 +101,8 @@ struct udgpu {
   FftPlan px, py;
   bool fast_x = false, fast_y = false, fast_z = false;
   int zu = 8, fft_lanes = 32;
+  bool xz_fused = false;      // x-FFT + z-solve + inverse x-FFT as one pass (poisson_xz.cuh)
+  int xz_minb = 1;            // ... compiled for 1 or 2 resident CTAs per SM (UDGPU_XZ_MINB)
   double *d_zt = nullptr, *d_xd = nullptr, *d_yd = nullptr;
   int nxh = 0, nyh = 0;
   // reductions
@@ -867,6 +870,45 @@ static int rfft_fast_setattr(int n) {
   return UDGPU_OK;
 }
 
+// fused x-FFT / z-solve / inverse x-FFT (poisson_xz.cuh): n -> (R1, R2, LANES) as for k_rfft_fast
+template <int R1, int R2, int LANES>
+static int xz_launch(udgpu *h, double *work, int nj, int j0g, const Geo &g) {
+  using T = XzT<R1, R2, LANES>;
+  if (h->xz_minb == 2 && R1 <= 16)
+    k_xzsolve<R1, R2, LANES, (R1 <= 16 ? 2 : 1)><<<nj, dim3(LANES, R2), T::SMEM, h->st>>>(h->px.tw, work, (long long)T::N, (long long)T::N * nj, g.ktot, j0g,
+                                                                                          h->nxh, h->nyh, h->d_zt, h->d_a, h->d_c, h->px.fac);
+  else
+    k_xzsolve<R1, R2, LANES, 1><<<nj, dim3(LANES, R2), T::SMEM, h->st>>>(h->px.tw, work, (long long)T::N, (long long)T::N * nj, g.ktot, j0g,
+                                                                          h->nxh, h->nyh, h->d_zt, h->d_a, h->d_c, h->px.fac);
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+static int xz_solve(udgpu *h, double *work, int nj, int j0g, const Geo &g) {
+  switch (g.itot) {
+    case 64: return xz_launch<8, 4, 32>(h, work, nj, j0g, g);
+    case 128: return xz_launch<8, 8, 32>(h, work, nj, j0g, g);
+    case 256: return xz_launch<16, 8, 32>(h, work, nj, j0g, g);
+    case 512: return xz_launch<16, 16, 16>(h, work, nj, j0g, g);
+    case 1024: return xz_launch<32, 16, 8>(h, work, nj, j0g, g);
+  }
+  return set_err(UDGPU_EINVAL, "no fused x-z solve for itot=%d", g.itot);
+}
+static int xz_setattr(int n) {
+#define SA_(R1, R2, L)                                                                                                           \
+  CU(cudaFuncSetAttribute(k_xzsolve<R1, R2, L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, XzT<R1, R2, L>::SMEM)); \
+  CU(cudaFuncSetAttribute(k_xzsolve<R1, R2, L, (R1 <= 16 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, XzT<R1, R2, L>::SMEM))
+  switch (n) {
+    case 64: SA_(8, 4, 32); break;
+    case 128: SA_(8, 8, 32); break;
+    case 256: SA_(16, 8, 32); break;
+    case 512: SA_(16, 16, 16); break;
+    case 1024: SA_(32, 16, 8); break;
+  }
+#undef SA_
+  return UDGPU_OK;
+}
+
 static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt) {
   const Geo &g = h->g;
   if ((h->cfg.flags & UDGPU_F_V1_KERNELS) && h->P == 1) return UDGPU_OK;
@@ -892,6 +934,10 @@ static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, cons
   KCHECK();
   CU(cudaStreamSynchronize(h->st));
   h->fast_z = true;
+  // one-pass x part: needs the whole x line on this GPU and the register FFT for itot
+  { const char *e = getenv("UDGPU_XZ_FUSED"); h->xz_fused = h->fast_x && h->P == 1 && !(e && atoi(e) == 0); }
+  { const char *e = getenv("UDGPU_XZ_MINB"); if (e && atoi(e) == 2) h->xz_minb = 2; }
+  if (h->xz_fused) RET(xz_setattr(g.itot));
   return UDGPU_OK;
 }
 
@@ -1042,6 +1088,14 @@ static int poisson_core(udgpu *h, double *work, double *p_halo) {
   const Geo &g = h->g;
   if (h->P > 1) return poisson_core_slab(h, work, p_halo);
   ProfScope ps(h, PROF_POIS);
+  if (h->xz_fused && h->fast_z) {
+    // y, [x, z, x^-1] in one pass, y^-1: three passes over memory instead of five (transforms commute)
+    RET(fft_pass(h, false, 0, work, work, false));
+    RET(xz_solve(h, work, g.jmax, g.j0g, g));
+    if (p_halo) RET(fft_pass(h, false, 1, work, p_halo + offF(g, 1, 1, 1), true));
+    else RET(fft_pass(h, false, 1, work, work, false));
+    return UDGPU_OK;
+  }
   RET(fft_pass(h, true, 0, work, work, false));
   RET(fft_pass(h, false, 0, work, work, false));
   if (h->fast_z) { if (h->zu == 16) k_zsolve<16><<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, h->nxh, h->nyh, work, h->d_zt, h->d_a, h->d_c);
