@@ -71,7 +71,7 @@ def test_poisson_solve(shape, flags):
     assert relerr(p, p_ref) < TOL_PRES
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 64), (256, 64, 40), (128, 32, 33), (512, 16, 70), (1024, 8, 9), (64, 48, 1),
+@pytest.mark.parametrize("shape", [(64, 64, 64), (256, 64, 40), (128, 32, 33), (512, 16, 70), (1024, 8, 9), (64, 48, 2),
                                    (128, 20, 32), (256, 12, 31)])
 @pytest.mark.parametrize("minb", ["1", "2"])
 def test_poisson_one_pass_x_vs_separate_passes(shape, minb, monkeypatch):
@@ -83,6 +83,7 @@ def test_poisson_one_pass_x_vs_separate_passes(shape, minb, monkeypatch):
     o, g1 = make_pair(*shape)
     assert g1.L is not None
     monkeypatch.setenv("UDGPU_XZ_MINB", minb)
+    monkeypatch.setenv("UDGPU_XZ_FUSED", "1")
     _, ga = make_pair(*shape)
     monkeypatch.setenv("UDGPU_XZ_FUSED", "0")
     _, gb = make_pair(*shape)
