@@ -58,6 +58,11 @@ def main():
                 e = np.abs(a - b).max()
                 worst = max(worst, e)
                 assert e < 1e-9, (n, s, shape, e)
+            # pres0: interior + x-face halo columns + y-face halo rows (what the next advection reads)
+            a, b = g.pull("pres0"), U.slab_of(o.pres0, world, rank)
+            e = max(np.abs(a[:, 1:-1, 1:-1] - b[:, 1:-1, 1:-1]).max(), np.abs(a[1:-1, :, 1:-1] - b[1:-1, :, 1:-1]).max())
+            worst = max(worst, e)
+            assert e < 1e-9, ("pres0", s, shape, e)
             dmax, dtot, drms = g.divergence()
             omax, otot, orms = o.chkdiv()
             assert drms < 1e-12 and abs(dmax - omax) < 1e-12, (dmax, omax, drms)

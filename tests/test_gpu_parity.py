@@ -216,8 +216,8 @@ def test_full_size_properties_256():
 
 @pytest.mark.parametrize("shape", [(16, 16, 16), (32, 24, 20), (48, 40, 33)])
 @pytest.mark.parametrize("kw", [dict(nsv=2), dict(nsv=1, iadv_sv=2), dict(nsv=3, lvreman=False, lsmagorinsky=False),
-                                dict(nsv=1, lvreman=False, lsmagorinsky=True)])
-@pytest.mark.parametrize("flags", [0, F_NO_LAZY])
+                                dict(nsv=1, lvreman=False, lsmagorinsky=True), dict(nsv=4), dict(nsv=5, iadv_sv=2)])
+@pytest.mark.parametrize("flags", [0, F_NO_LAZY, F_V1])
 def test_scalars(shape, kw, flags):
     """advecc_kappa / advecc_2nd + diffc, scalar integrate / halos / top BC."""
     o, g = make_pair(*shape, gpu_flags=flags, **kw)

@@ -96,6 +96,74 @@ __global__ void __launch_bounds__(256) k_scalar_tend(Geo g, const double *__rest
   svp[t] = r;
 }
 
+// K3: the same operators for NS scalar fields in ONE pass (config 5 "fused multi-field stencil"): the advecting
+// velocities (u, v, w at the six faces) and the seven ekh values are loaded once per cell and reused by all
+// fields, so n fields cost (4 + 2n) * 8 B/cell instead of 6n * 8 B/cell.  Field n lives at sv + n * ssl
+// (svp + n * tsl).  Arithmetic per field is exactly k_scalar_tend's.
+template <int SCHEME, bool ADV, bool DIFF, bool ACC, bool LES, int NS>
+__global__ void __launch_bounds__(256) k_scalar_tend_multi(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
+                                                           const double *__restrict__ w0, const double *__restrict__ ekh,
+                                                           const double *__restrict__ sv, long long ssl, double *__restrict__ svp,
+                                                           long long tsl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long c = offS(g, i, j, k), t = offST(g, i, j, k), m = offF(g, i, j, k);
+  const long long sj = g.pic, sk = g.pkc, mj = g.pi, mk = g.pk;
+  double ul = 0, ur = 0, vl = 0, vr = 0, wb = 0, wt = 0;
+  if (ADV) { ul = u0[m]; ur = u0[m + 1]; vl = v0[m]; vr = v0[m + mj]; wb = w0[m]; wt = w0[m + mk]; }
+  double e0 = 0, exm = 0, exp_ = 0, eym = 0, eyp = 0, ezm = 0, ezp = 0;
+  if (DIFF && LES) {
+    e0 = ekh[m]; exm = ekh[m - 1]; exp_ = ekh[m + 1]; eym = ekh[m - mj]; eyp = ekh[m + mj]; ezm = ekh[m - mk]; ezp = ekh[m + mk];
+  }
+  const double dzfk = g.dzf[k], dzfkp = g.dzf[k + 1], dzfkm = g.dzf[k - 1];
+  const double hc_m1 = g.dzhci[k - 1], hc_0 = g.dzhci[k], hc_p1 = g.dzhci[k + 1], hc_p2 = g.dzhci[k + 2];
+  const double fc_0 = g.dzfc[k], fc_p1 = g.dzfc[k + 1], dzfci = g.dzfci[k];
+#pragma unroll
+  for (int n = 0; n < NS; n++) {
+    const double *__restrict__ s = sv + n * ssl;
+    double r = ACC ? svp[t + n * tsl] : 0.0;
+    if (ADV) {
+      if (SCHEME == 7) {
+        const double dxi = g.dxi, dx = g.dx, dyi = g.dyi;
+        const double cl = kappa_face(s, c, 1, ul, dxi, dxi, dxi, dx);
+        const double cr = kappa_face(s, c + 1, 1, ur, dxi, dxi, dxi, dx);
+        r = r + (-cr * ur * dxi) + cl * ul * dxi;
+        const double cs = kappa_face(s, c, sj, vl, 1., 1., 1., 1.);
+        const double cn = kappa_face(s, c + sj, sj, vr, 1., 1., 1., 1.);
+        r = r + (-cn * vr * dyi) + cs * vl * dyi;
+        const double ct = kappa_face(s, c + sk, sk, wt, hc_0, hc_p1, hc_p2, fc_p1);
+        double dl = 0.0;
+        if (k >= 2) {
+          const double cb = kappa_face(s, c, sk, wb, hc_m1, hc_0, hc_p1, fc_0);
+          dl = cb * wb * dzfci;
+        }
+        r = r + (-ct * wt * dzfci) + dl;
+      } else {
+        r = r - ((ur * (s[c + 1] + s[c]) - ul * (s[c - 1] + s[c])) * g.dxi5 +
+                 (vr * (s[c + sj] + s[c]) - vl * (s[c - sj] + s[c])) * g.dyi5);
+        r = r - (wt * (s[c + sk] * dzfk + s[c] * dzfkp) * g.dzhi[k + 1] -
+                 wb * (s[c - sk] * dzfk + s[c] * dzfkm) * g.dzhi[k]) * g.dzfi5[k];
+      }
+    }
+    if (DIFF) {
+      if (LES) {
+        r = r + 0.5 * (((exp_ + e0) * (s[c + 1] - s[c]) - (e0 + exm) * (s[c] - s[c - 1])) * g.dx2i +
+                       ((eyp + e0) * (s[c + sj] - s[c]) - (e0 + eym) * (s[c] - s[c - sj])) * g.dy2i +
+                       ((dzfkp * e0 + dzfk * ezp) * (s[c + sk] - s[c]) * g.dzh2i[k + 1] -
+                        (dzfkm * e0 + dzfk * ezm) * (s[c] - s[c - sk]) * g.dzh2i[k]) * g.dzfi[k]);
+      } else {
+        const double cekh = g.numol * g.prandtlmoli;
+        r = r + ((cekh * (s[c + 1] - s[c]) - cekh * (s[c] - s[c - 1])) * g.dx2i +
+                 (cekh * (s[c + sj] - s[c]) - cekh * (s[c] - s[c - sj])) * g.dy2i +
+                 (cekh * (s[c + sk] - s[c]) * g.dzhi[k + 1] - cekh * (s[c] - s[c - sk]) * g.dzhi[k]) * g.dzfi[k]);
+      }
+    }
+    svp[t + n * tsl] = r;
+  }
+}
+
 // sv0 = svm + rk3coef*svp ; (step 3) svm = sv0   — src/modtstep.f90:216-218,336
 template <bool STEP3>
 __global__ void __launch_bounds__(256) k_scalar_integrate(Geo g, double rk3coef, double *__restrict__ sv0, double *__restrict__ svm,

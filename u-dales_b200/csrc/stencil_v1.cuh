@@ -469,6 +469,19 @@ __global__ void __launch_bounds__(256) k_tderive_integrate_halo(Geo g, double rk
   const int ix = img_x(g, i), jy = img_y(g, j);
   if (ix >= 0) put(offF(g, ix, j, k));
   if (jy >= 0) { put(offF(g, i, jy, k)); if (ix >= 0) put(offF(g, ix, jy, k)); }
+  if (!g.wrapx) {
+    // x is split over GPUs: the halo columns of p came from the neighbours (slab exchange before this kernel) and
+    // pres0 += p has to reach the halo columns of pres0 too (src/modpois.f90:1096-1102); the velocity halos follow
+    // with the slab exchange in halos()
+    auto ph = [&](int hi) {
+      const long long q = offF(g, hi, j, k);
+      const double pv = p[q];
+      pres0[q] = pres0[q] + pv;
+      if (jy >= 0) { const long long q2 = offF(g, hi, jy, k); pres0[q2] = pres0[q2] + pv; }
+    };
+    if (i == 1) ph(0);
+    if (i == g.imax) ph(g.imax + 1);
+  }
 }
 // pres0 += p on the halo shell only (everything that is not an interior cell); the interior is done above.
 __global__ void k_pres_update_shell(Geo g, const double *__restrict__ p, double *__restrict__ pres0) {

@@ -764,13 +764,33 @@ static int launch_scalars(udgpu *h, bool acc) {
   if (!nsv) return UDGPU_OK;
   const dim3 gr = grid3(g, B3);
   const bool les = g.lles != 0, kappa = h->cfg.iadv_sv == 7;
-  for (int n = 0; n < nsv; n++) {
-    const double *sv = h->f[UDGPU_SV0] + (size_t)n * h->cnt[UDGPU_SV0];
-    double *svp = h->f[UDGPU_SVP] + (size_t)n * h->cnt[UDGPU_SVP];
-#define GO(S, ACC, LES) k_scalar_tend<S, ADV, DIFF, ACC, LES><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKH], sv, svp)
-    if (kappa) { if (acc) { if (les) GO(7, true, true); else GO(7, true, false); } else { if (les) GO(7, false, true); else GO(7, false, false); } }
-    else { if (acc) { if (les) GO(2, true, true); else GO(2, true, false); } else { if (les) GO(2, false, true); else GO(2, false, false); } }
+  const long long ssl = (long long)h->cnt[UDGPU_SV0], tsl = (long long)h->cnt[UDGPU_SVP];
+  // all fields in one pass, four at a time (the velocity / ekh loads are shared between the fields)
+  for (int n0 = 0; n0 < nsv; n0 += 4) {
+    const int ns = nsv - n0 < 4 ? nsv - n0 : 4;
+    const double *sv = h->f[UDGPU_SV0] + (size_t)n0 * ssl;
+    double *svp = h->f[UDGPU_SVP] + (size_t)n0 * tsl;
+#define GO4(S, ACC, LES, NS) k_scalar_tend_multi<S, ADV, DIFF, ACC, LES, NS><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKH], sv, ssl, svp, tsl)
+#define GO3(S, ACC, LES) do { if (ns == 1) GO4(S, ACC, LES, 1); else if (ns == 2) GO4(S, ACC, LES, 2); else if (ns == 3) GO4(S, ACC, LES, 3); else GO4(S, ACC, LES, 4); } while (0)
+#define GO2(S, ACC) do { if (les) GO3(S, ACC, true); else GO3(S, ACC, false); } while (0)
+    if (h->cfg.flags & UDGPU_F_V1_KERNELS) {
+      for (int n = n0; n < n0 + ns; n++) {
+        const double *s1 = h->f[UDGPU_SV0] + (size_t)n * ssl;
+        double *p1 = h->f[UDGPU_SVP] + (size_t)n * tsl;
+#define GO(S, ACC, LES) k_scalar_tend<S, ADV, DIFF, ACC, LES><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKH], s1, p1)
+        if (kappa) { if (acc) { if (les) GO(7, true, true); else GO(7, true, false); } else { if (les) GO(7, false, true); else GO(7, false, false); } }
+        else { if (acc) { if (les) GO(2, true, true); else GO(2, true, false); } else { if (les) GO(2, false, true); else GO(2, false, false); } }
 #undef GO
+        KCHECK();
+        h->launches++;
+      }
+      continue;
+    }
+    if (kappa) { if (acc) GO2(7, true); else GO2(7, false); }
+    else { if (acc) GO2(2, true); else GO2(2, false); }
+#undef GO2
+#undef GO3
+#undef GO4
     KCHECK();
     h->launches++;
   }
