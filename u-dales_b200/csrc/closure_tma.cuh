@@ -21,7 +21,7 @@ template <int MINB>
 __global__ void __launch_bounds__(CL_THREADS, MINB)
     k_closure_vreman_tma(const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                          const __grid_constant__ CUtensorMap mw, const MomTmaParams P, double *__restrict__ ekm,
-                         double *__restrict__ ekh, int halo) {
+                         double *__restrict__ ekh, int halo, PeerCols pc) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + CL_S * CL_STAGE_BYTES);
   const Geo &g = P.g;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(CL_THREADS, MINB)
         const double b23 = dx2 * a12 * a13 + dy2 * a22 * a23 + dzf2 * a32 * a33;
         const double bb = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
         const double e = (bb < 1.e-8) ? 0.0 : g.c_vreman * sqrt(bb / aa);
-        if (store_ok) ek_store(g, ci, cj, k, e, ekm, ekh, halo);
+        if (store_ok) ek_store(g, ci, cj, k, e, ekm, ekh, halo, pc);
       }
       __syncthreads();
       if (tid == 0) {

@@ -164,6 +164,109 @@ __global__ void __launch_bounds__(256) k_scalar_tend_multi(Geo g, const double *
   }
 }
 
+// branch-free form of kappa_face on register operands: the face lies between vm (cell c-1) and v0 (cell c)
+__device__ __forceinline__ double kface(double vmm, double vm, double v0, double vp, double vel, double hci_m1, double hci_0,
+                                        double hci_p1, double fc) {
+  const bool pos = vel > 0;
+  const double d1 = pos ? (vm - vmm) * hci_m1 : (v0 - vp) * hci_p1;
+  const double d2 = pos ? (v0 - vm) * hci_0 : (vm - v0) * hci_0;
+  const double cf = pos ? vm : v0;
+  return cf + fc * rlim(d1, d2);
+}
+
+// K3, k-marching form for the kappa scheme (advecc_kappa + diffc for NS fields in one pass).  A thread owns an (i,j)
+// column over KC levels.  Per field it carries the four levels k-2..k+1 of its column in registers and loads one new
+// value per level; the top-face value of level k is the bottom-face value of level k+1 (identical expression,
+// src/modadvection.f90:383-404), x-neighbours and the right-face value come from the neighbouring lanes by warp
+// shuffle (a warp covers 31 cells + 1 helper lane that only evaluates the face it shares with lane 30).  So a cell
+// costs 4 limiter evaluations and ~6 loads per field instead of 6 evaluations (each with its own divergent branch)
+// and ~21 loads.  Faces, limiter and accumulation order are the reference's: results equal k_scalar_tend's bit for bit.
+constexpr int SC_WX = 31, SC_BY = 8, SC_KC = 32;
+template <bool DIFF, bool ACC, bool LES, int NS>
+__global__ void __launch_bounds__(32 * SC_BY) k_scalar_kappa_march(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
+                                                                   const double *__restrict__ w0, const double *__restrict__ ekh,
+                                                                   const double *__restrict__ sv, long long ssl, double *__restrict__ svp,
+                                                                   long long tsl) {
+  const int lane = threadIdx.x;
+  const int i = blockIdx.x * SC_WX + lane + 1;
+  const int j = blockIdx.y * SC_BY + threadIdx.y + 1;
+  const int k0 = blockIdx.z * SC_KC + 1, k1 = min(k0 + SC_KC, g.ktot + 1);
+  // helper lane / cells right of the slab: still take part in the shuffles, never store.  Clamp the column so
+  // every address stays inside the arrays (halo width 2 gives i <= imax+1 room; j likewise clamped)
+  const bool own = (lane < SC_WX) && (i <= g.imax) && (j <= g.jmax);
+  const int ic = min(i, g.imax + 1), jc = min(j, g.jmax);
+  const long long sj = g.pic, sk = g.pkc, mj = g.pi, mk = g.pk;
+  const double *ps = sv + offS(g, ic, jc, k0);
+  long long m = offF(g, ic, jc, k0);
+  long long t = offST(g, ic, jc, k0);
+  const double dxi = g.dxi, dx = g.dx, dyi = g.dyi;
+  const bool lo0 = lane >= 1, lo1 = lane >= 2, hi0 = lane <= 30;
+  double sm2[NS], sm1[NS], s0[NS], sp1[NS], cz[NS];
+#pragma unroll
+  for (int n = 0; n < NS; n++) {
+    const double *q = ps + n * ssl;
+    sm2[n] = q[-2 * sk]; sm1[n] = q[-sk]; s0[n] = q[0]; sp1[n] = q[sk];
+  }
+  double wb = w0[m];
+  double e0 = 0, ezm = 0;
+  if (DIFF && LES) { e0 = ekh[m]; ezm = ekh[m - mk]; }
+#pragma unroll
+  for (int n = 0; n < NS; n++)
+    cz[n] = (k0 >= 2) ? kface(sm2[n], sm1[n], s0[n], sp1[n], wb, g.dzhci[k0 - 1], g.dzhci[k0], g.dzhci[k0 + 1], g.dzfc[k0]) : 0.0;
+  for (int k = k0; k < k1; k++) {
+    const double ul = u0[m];
+    const double ur = __shfl_down_sync(0xffffffffu, ul, 1);
+    const double vl = v0[m], vr = v0[m + mj];
+    const double wt = w0[m + mk];
+    double exm = 0, exp_ = 0, eym = 0, eyp = 0, ezp = 0;
+    if (DIFF && LES) { exm = ekh[m - 1]; exp_ = ekh[m + 1]; eym = ekh[m - mj]; eyp = ekh[m + mj]; ezp = ekh[m + mk]; }
+    const double dzfk = g.dzf[k], dzfkp = g.dzf[k + 1], dzfkm = g.dzf[k - 1];
+    const double hc_0 = g.dzhci[k], hc_p1 = g.dzhci[k + 1], hc_p2 = g.dzhci[k + 2];
+    const double fc_p1 = g.dzfc[k + 1], dzfci = g.dzfci[k];
+#pragma unroll
+    for (int n = 0; n < NS; n++) {
+      const double *q = ps + n * ssl;
+      const double sp2 = q[2 * sk];
+      // x neighbours of level k: from the neighbouring lanes, edge lanes from memory
+      double xm1 = __shfl_up_sync(0xffffffffu, s0[n], 1), xm2 = __shfl_up_sync(0xffffffffu, s0[n], 2);
+      double xp1 = __shfl_down_sync(0xffffffffu, s0[n], 1);
+      if (!lo0) xm1 = q[-1];
+      if (!lo1) xm2 = q[-2];
+      if (!hi0) xp1 = q[1];
+      const double ym1 = q[-sj], ym2 = q[-2 * sj], yp1 = q[sj], yp2 = q[2 * sj];
+      const double c = s0[n];
+      const double cl = kface(xm2, xm1, c, xp1, ul, dxi, dxi, dxi, dx);
+      const double cr = __shfl_down_sync(0xffffffffu, cl, 1);
+      double r = ACC ? svp[t + n * tsl] : 0.0;
+      r = r + (-cr * ur * dxi) + cl * ul * dxi;
+      const double cs = kface(ym2, ym1, c, yp1, vl, 1., 1., 1., 1.);
+      const double cn = kface(ym1, c, yp1, yp2, vr, 1., 1., 1., 1.);
+      r = r + (-cn * vr * dyi) + cs * vl * dyi;
+      const double ct = kface(sm1[n], c, sp1[n], sp2, wt, hc_0, hc_p1, hc_p2, fc_p1);
+      const double dl = (k >= 2) ? cz[n] * wb * dzfci : 0.0;
+      r = r + (-ct * wt * dzfci) + dl;
+      if (DIFF) {
+        if (LES) {
+          r = r + 0.5 * (((exp_ + e0) * (xp1 - c) - (e0 + exm) * (c - xm1)) * g.dx2i +
+                         ((eyp + e0) * (yp1 - c) - (e0 + eym) * (c - ym1)) * g.dy2i +
+                         ((dzfkp * e0 + dzfk * ezp) * (sp1[n] - c) * g.dzh2i[k + 1] -
+                          (dzfkm * e0 + dzfk * ezm) * (c - sm1[n]) * g.dzh2i[k]) * g.dzfi[k]);
+        } else {
+          const double cekh = g.numol * g.prandtlmoli;
+          r = r + ((cekh * (xp1 - c) - cekh * (c - xm1)) * g.dx2i +
+                   (cekh * (yp1 - c) - cekh * (c - ym1)) * g.dy2i +
+                   (cekh * (sp1[n] - c) * g.dzhi[k + 1] - cekh * (c - sm1[n]) * g.dzhi[k]) * g.dzfi[k]);
+        }
+      }
+      if (own) svp[t + n * tsl] = r;
+      cz[n] = ct;
+      sm2[n] = sm1[n]; sm1[n] = c; s0[n] = sp1[n]; sp1[n] = sp2;
+    }
+    wb = wt; ezm = e0; e0 = ezp;
+    ps += sk; m += mk; t += sk;
+  }
+}
+
 // sv0 = svm + rk3coef*svp ; (step 3) svm = sv0   — src/modtstep.f90:216-218,336
 template <bool STEP3>
 __global__ void __launch_bounds__(256) k_scalar_integrate(Geo g, double rk3coef, double *__restrict__ sv0, double *__restrict__ svm,

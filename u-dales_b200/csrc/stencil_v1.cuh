@@ -16,7 +16,7 @@ __device__ __forceinline__ double sq_(double x) { return x * x; }
 // images in y (and in x when unsplit) and, for k = 1 / k = ktot, the bottom / top ghost levels of the cell and
 // of its images — so no separate wrap / ghost kernels run afterwards (x-split: the slab exchange follows).
 __device__ __forceinline__ void ek_store(const Geo &g, int i, int j, int k, double e, double *__restrict__ ekm,
-                                         double *__restrict__ ekh, int halo) {
+                                         double *__restrict__ ekh, int halo, const PeerCols &pc) {
   const double m = e + g.numol, hh = e * g.prandtli + g.numol * g.prandtlmoli;
   if (!halo) {
     const long long c = offF(g, i, j, k);
@@ -24,19 +24,24 @@ __device__ __forceinline__ void ek_store(const Geo &g, int i, int j, int k, doub
     return;
   }
   const double tm = 2. * g.numol, th = 2. * g.numol * g.prandtlmoli;
-  auto put = [&](int ti, int tj) {
+  auto put1 = [&](double *__restrict__ am, double *__restrict__ ah, int ti, int tj) {
     const long long c = offF(g, ti, tj, k);
-    ekm[c] = m; ekh[c] = hh;
-    if (k == 1) { ekm[c - g.pk] = tm - m; ekh[c - g.pk] = th - hh; }
+    am[c] = m; ah[c] = hh;
+    if (k == 1) { am[c - g.pk] = tm - m; ah[c - g.pk] = th - hh; }
     if (k == g.ktot) {
-      if (g.BCtopm == 2) { ekm[c + g.pk] = tm - m; ekh[c + g.pk] = th - hh; }
-      else { ekm[c + g.pk] = m; ekh[c + g.pk] = hh; }
+      if (g.BCtopm == 2) { am[c + g.pk] = tm - m; ah[c + g.pk] = th - hh; }
+      else { am[c + g.pk] = m; ah[c + g.pk] = hh; }
     }
+  };
+  auto put = [&](int ti, int tj) {
+    put1(ekm, ekh, ti, tj);
+    if (ti == 1 && pc.L[0]) put1(pc.L[0], pc.L[1], g.imax + 1, tj);   // my first column = left neighbour's right halo
+    if (ti == g.imax && pc.R[0]) put1(pc.R[0], pc.R[1], 0, tj);      // my last column = right neighbour's left halo
   };
   const int ix = img_x(g, i), jy = img_y(g, j);
   put(i, j);
-  if (ix >= 0) put(ix, j);
-  if (jy >= 0) { put(i, jy); if (ix >= 0) put(ix, jy); }
+  if (ix >= 0) put1(ekm, ekh, ix, j);
+  if (jy >= 0) { put(i, jy); if (ix >= 0) put1(ekm, ekh, ix, jy); }
 }
 
 // closure: src/modsubgrid.f90:159-412.  MODEL 0 = DNS (:401-404), 1 = Vreman (:269-360),
@@ -45,7 +50,7 @@ __device__ __forceinline__ void ek_store(const Geo &g, int i, int j, int k, doub
 template <int MODEL>
 __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
                                                  const double *__restrict__ w0, double *__restrict__ ekm,
-                                                 double *__restrict__ ekh, int halo) {
+                                                 double *__restrict__ ekh, int halo, PeerCols pc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   const int k = blockIdx.z + 1;
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict
 #undef V
 #undef W
   }
-  ek_store(g, i, j, k, e, ekm, ekh, halo);
+  ek_store(g, i, j, k, e, ekm, ekh, halo, pc);
 }
 
 // Vreman closure, k-marching form of k_closure<1>: one thread owns an (i,j) column over KC levels and carries
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict
 template <int KC>
 __global__ void __launch_bounds__(256) k_closure_vreman_march(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
                                                               const double *__restrict__ w0, double *__restrict__ ekm,
-                                                              double *__restrict__ ekh, int halo) {
+                                                              double *__restrict__ ekh, int halo, PeerCols pc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i > g.imax || j > g.jmax) return;
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(256) k_closure_vreman_march(Geo g, const doubl
     const double b23 = dx2 * a12 * a13 + dy2 * a22 * a23 + dzf2 * a32 * a33;
     const double bb = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
     const double e = (bb < 1.e-8) ? 0.0 : g.c_vreman * sqrt(bb / aa);
-    ek_store(g, i, j, k, e, ekm, ekh, halo);
+    ek_store(g, i, j, k, e, ekm, ekh, halo, pc);
     su_km = su_k; sv_km = sv_k;
     u_c = uK_c; u_ip = uK_ip; v_c = vK_c; v_jp = vK_jp;
     w_c = wK_c; w_ip = wK_ip; w_im = wK_im; w_jp = wK_jp; w_jm = wK_jm;
@@ -437,42 +442,49 @@ __global__ void __launch_bounds__(256) k_tderive_integrate_halo(Geo g, double rk
                                                                 const double *__restrict__ wp, double *__restrict__ um,
                                                                 double *__restrict__ vm, double *__restrict__ wm,
                                                                 double *__restrict__ u0, double *__restrict__ v0,
-                                                                double *__restrict__ w0, double *__restrict__ pres0) {
+                                                                double *__restrict__ w0, double *__restrict__ pres0, PeerCols pc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   const int k = blockIdx.z + 1;
   if (i > g.imax || j > g.jmax) return;
   const long long c = offF(g, i, j, k), t = offT(g, i, j, k);
-  const double pc = p[c];
+  const double pc0 = p[c];
   const long long cim = (g.wrapx && i == 1) ? c + (g.imax - 1) : c - 1;
   const long long cjm = (j == 1) ? c + (long long)g.pi * (g.jmax - 1) : c - g.pi;
-  const double ru = up[t] - (pc - p[cim]) * g.dxi;
-  const double rv = vp[t] - (pc - p[cjm]) * g.dyi;
+  const double ru = up[t] - (pc0 - p[cim]) * g.dxi;
+  const double rv = vp[t] - (pc0 - p[cjm]) * g.dyi;
   double rw = wp[t];
-  if (k >= 2) rw = rw - (pc - p[c - g.pk]) * g.dzhi[k];
+  if (k >= 2) rw = rw - (pc0 - p[c - g.pk]) * g.dzhi[k];
   const double a = um[c] + rk3coef * ru;
   const double b = vm[c] + rk3coef * rv;
   const double d = wm[c] + rk3coef * rw;
   const bool top = (k == g.ktot);
   const double at = (g.BCtopm == 2) ? 2. * g.Uinf - a : a, bt = (g.BCtopm == 2) ? 2. * g.Vinf - b : b;
-  auto put = [&](long long q) {
-    u0[q] = a; v0[q] = b; w0[q] = d;
-    if (STEP3) { um[q] = a; vm[q] = b; wm[q] = d; }
-    pres0[q] = pres0[q] + pc;
+  // velocities (+ top ghost) of one cell image into one set of arrays: local, or a neighbour's halo column
+  auto putv = [&](double *__restrict__ U0, double *__restrict__ V0, double *__restrict__ W0, double *__restrict__ UM,
+                  double *__restrict__ VM, double *__restrict__ WM, long long q) {
+    U0[q] = a; V0[q] = b; W0[q] = d;
+    if (STEP3) { UM[q] = a; VM[q] = b; WM[q] = d; }
     if (top) {
       const long long qt = q + g.pk;
-      u0[qt] = at; v0[qt] = bt; w0[qt] = 0.;
-      if (STEP3) { um[qt] = at; vm[qt] = bt; wm[qt] = 0.; }
+      U0[qt] = at; V0[qt] = bt; W0[qt] = 0.;
+      if (STEP3) { UM[qt] = at; VM[qt] = bt; WM[qt] = 0.; }
     }
   };
-  put(c);
+  auto put = [&](int ti, int tj) {
+    const long long q = offF(g, ti, tj, k);
+    putv(u0, v0, w0, um, vm, wm, q);
+    pres0[q] = pres0[q] + pc0;
+    if (ti == 1 && pc.L[0]) putv(pc.L[0], pc.L[1], pc.L[2], pc.L[3], pc.L[4], pc.L[5], offF(g, g.imax + 1, tj, k));
+    if (ti == g.imax && pc.R[0]) putv(pc.R[0], pc.R[1], pc.R[2], pc.R[3], pc.R[4], pc.R[5], offF(g, 0, tj, k));
+  };
   const int ix = img_x(g, i), jy = img_y(g, j);
-  if (ix >= 0) put(offF(g, ix, j, k));
-  if (jy >= 0) { put(offF(g, i, jy, k)); if (ix >= 0) put(offF(g, ix, jy, k)); }
+  put(i, j);
+  if (ix >= 0) put(ix, j);
+  if (jy >= 0) { put(i, jy); if (ix >= 0) put(ix, jy); }
   if (!g.wrapx) {
-    // x is split over GPUs: the halo columns of p came from the neighbours (slab exchange before this kernel) and
-    // pres0 += p has to reach the halo columns of pres0 too (src/modpois.f90:1096-1102); the velocity halos follow
-    // with the slab exchange in halos()
+    // x is split over GPUs: the halo columns of p came from the neighbours (exchange before this kernel) and
+    // pres0 += p has to reach the halo columns of pres0 too (src/modpois.f90:1096-1102)
     auto ph = [&](int hi) {
       const long long q = offF(g, hi, j, k);
       const double pv = p[q];

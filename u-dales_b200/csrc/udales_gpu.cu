@@ -117,6 +117,14 @@ struct udgpu {
   void *ipc_peer[8] = {};
   double *rA[8] = {}, *rB[8] = {};
   double *hL[8][2] = {}, *hR[8][2] = {};   // halo receive windows (left / right halo columns), double-buffered
+  // direct halo stores: the exchanged fields live inside the IPC window, so a kernel that produces an edge column can
+  // store it straight into the neighbour's halo column over NVLink; only a flag barrier follows (no pack / unpack)
+  bool direct_halo = false;
+  double *wfield[8] = {};                  // start of the field region in every rank's window
+  size_t fwin_off[UDGPU_NFIELDS] = {};     // element offset of a field inside the window (0 = not in the window)
+  size_t win_field_elems = 0;
+  bool up_halo_sent = false;               // the last momentum-tendency kernel already stored up(1) into the left neighbour
+  bool m_changed = true;                   // um, vm, wm changed since their halos were last exchanged
   unsigned halo_par = 0;
   P2PPtrs pflags;
   unsigned long long epoch = 0;
@@ -129,6 +137,8 @@ struct udgpu {
   CUtensorMap tm[5];
   MomTmaParams mtp, clp;
   int mt_grid = 0, cl_grid = 0, cl_occ = 2;
+  int sc_nsmax = 4;           // fields per scalar-tendency launch (UDGPU_SCALAR_NSMAX = 1..4)
+  int sc_march = 1;           // kappa scalars: k-marching shuffle kernel (UDGPU_SCALAR_MARCH=0: one thread per cell)
   int cl_march = 1;           // Vreman closure: k-marching register-carry kernel (UDGPU_CLOSURE_MARCH=0: one thread per cell)
   int nsm = 148;
   // state
@@ -152,6 +162,7 @@ struct udgpu {
 
 // ------------------------------------------------------------------------------------------
 static int flush_pending(udgpu *h);
+static PeerCols peer_cols(udgpu *h, std::initializer_list<int> fields);
 static int settle_for_access(udgpu *h, int field);
 static int setup_p2p(udgpu *h, size_t nR);
 static int p2p_barrier(udgpu *h);
@@ -360,6 +371,8 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
   if (h->P > 1) NC(ncclCommInitRank(&h->comm, h->P, *(const ncclUniqueId *)nccl_uid, h->rank));
 
   { const char *e = getenv("UDGPU_CLOSURE_MARCH"); if (e) h->cl_march = atoi(e); }
+  { const char *e = getenv("UDGPU_SCALAR_MARCH"); if (e) h->sc_march = atoi(e); }
+  { const char *e = getenv("UDGPU_SCALAR_NSMAX"); if (e && atoi(e) >= 1 && atoi(e) <= 4) h->sc_nsmax = atoi(e); }
   if (c->flags & UDGPU_F_V1_KERNELS) h->cl_march = 0;
   Geo &g = h->g;
   memset(&g, 0, sizeof(g));
@@ -423,6 +436,25 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
   // ---- fields ----
   const size_t nF = (size_t)g.pi * g.pj * (K + 2 * g.kh), nT = (size_t)g.pi * g.pj * (K + g.kh);
   const size_t nR = (size_t)g.imax * g.jmax * K;
+  if (h->P > 1) {
+    h->IB = g.imax; h->JB = g.jtot / h->P;
+    h->halo_cap = (size_t)8 * 2 * (g.pjc > g.pj ? g.pjc : g.pj) * (K + 2 * (g.khc > g.kh ? g.khc : g.kh));
+    for (double **b : {&h->sendL, &h->sendR, &h->recvL, &h->recvR}) RET(dev_alloc(h, (void **)b, h->halo_cap * sizeof(double)));
+    for (double **b : {&h->sbuf, &h->rbuf, &h->workB}) RET(dev_alloc(h, (void **)b, nR * sizeof(double)));
+    h->gB = g;
+    h->gB.imax = g.itot; h->gB.jmax = h->JB; h->gB.i0g = 0; h->gB.j0g = h->rank * h->JB;
+    // fields whose edge columns are stored by their producers directly into the neighbours (window-resident)
+    const bool want_direct = h->fuse_halo && !getenv("UDGPU_NO_DIRECT_HALO");
+    size_t off = 0;
+    if (want_direct)
+      for (int f : {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM, UDGPU_UP, UDGPU_EKM, UDGPU_EKH}) {
+        h->fwin_off[f] = off + 32;                      // +32: keeps 0 as "not in the window"; 256-byte aligned slices
+        off += (((f == UDGPU_UP ? nT : nF) + 31) / 32) * 32 + 32;
+      }
+    h->win_field_elems = off;
+    RET(setup_p2p(h, nR));
+    h->direct_halo = h->p2p && want_direct;
+  }
   for (int f = 0; f < UDGPU_NFIELDS; f++) {
     size_t n = 0;
     int d3 = 0, sl = 1;
@@ -438,18 +470,10 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     h->dims[f][0] = (f == UDGPU_RHS) ? g.imax : scal ? g.pic : g.pi;
     h->dims[f][1] = (f == UDGPU_RHS) ? g.jmax : scal ? g.pjc : g.pj;
     h->dims[f][2] = d3;
-    if (n) RET(dev_alloc(h, (void **)&h->f[f], n * sl * sizeof(double)));
+    if (h->direct_halo && h->fwin_off[f]) h->f[f] = h->wfield[h->rank] + h->fwin_off[f];   // zeroed with the window
+    else if (n) RET(dev_alloc(h, (void **)&h->f[f], n * sl * sizeof(double)));
   }
   RET(dev_alloc(h, (void **)&h->d_scr, nR * sizeof(double)));
-  if (h->P > 1) {
-    h->IB = g.imax; h->JB = g.jtot / h->P;
-    h->halo_cap = (size_t)8 * 2 * (g.pjc > g.pj ? g.pjc : g.pj) * (K + 2 * (g.khc > g.kh ? g.khc : g.kh));
-    for (double **b : {&h->sendL, &h->sendR, &h->recvL, &h->recvR}) RET(dev_alloc(h, (void **)b, h->halo_cap * sizeof(double)));
-    for (double **b : {&h->sbuf, &h->rbuf, &h->workB}) RET(dev_alloc(h, (void **)b, nR * sizeof(double)));
-    h->gB = g;
-    h->gB.imax = g.itot; h->gB.jmax = h->JB; h->gB.i0g = 0; h->gB.j0g = h->rank * h->JB;
-    RET(setup_p2p(h, nR));
-  }
   RET(dev_alloc(h, (void **)&h->d_red, 16 * sizeof(double)));
   CU(cudaMallocHost((void **)&h->h_red, 16 * sizeof(double)));
 
@@ -548,6 +572,8 @@ extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
   if (is_tend) { RET(materialize_zero_tend(h)); h->tend_pushed = true; }
   if (field <= UDGPU_WP) { h->halo_dirty = h->bc_dirty = true; h->halos_done = h->bc_done = h->halo_x_pending = false; }
   if (field == UDGPU_P) h->p_halo_valid = true;   // the host's array is taken as is
+  if (field == UDGPU_UP) h->up_halo_sent = false;
+  if (field == UDGPU_UM || field == UDGPU_VM || field == UDGPU_WM) h->m_changed = true;
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(h->f[field] + (size_t)n4 * h->cnt[field], host, h->cnt[field] * sizeof(double), cudaMemcpyHostToDevice, h->st));
   if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP) h->tend_zero = false; h->tend_lazy_zero = false;
@@ -679,24 +705,26 @@ extern "C" int udgpu_closure(udgpu_t *h) {
   const dim3 gr = grid3(g, B3);
   const int halo = h->fuse_halo ? 1 : 0;
   double **f = h->f;
+  const PeerCols pc = halo ? peer_cols(h, {UDGPU_EKM, UDGPU_EKH}) : peer_cols(h, {});
   // model selection order of the reference: smagorinsky first, then vreman, else DNS (modsubgrid.f90:208,269,401)
-  if (h->cfg.lsmagorinsky) k_closure<2><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
+  if (h->cfg.lsmagorinsky) k_closure<2><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
   else if (h->cfg.lvreman && h->use_tma && h->cl_occ > 0) {
-    if (h->cl_occ == 1) k_closure_vreman_tma<1><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, f[UDGPU_EKM], f[UDGPU_EKH], halo);
-    else k_closure_vreman_tma<2><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, f[UDGPU_EKM], f[UDGPU_EKH], halo);
+    if (h->cl_occ == 1) k_closure_vreman_tma<1><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
+    else k_closure_vreman_tma<2><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
   }
   else if (h->cfg.lvreman && h->cl_march > 0) {
     constexpr int KC = 16;
     const dim3 gm(gr.x, gr.y, (g.ktot + KC - 1) / KC);
-    k_closure_vreman_march<KC><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
+    k_closure_vreman_march<KC><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
   }
-  else if (h->cfg.lvreman) k_closure<1><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
-  else k_closure<0><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
+  else if (h->cfg.lvreman) k_closure<1><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
+  else k_closure<0><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
   KCHECK();
   h->launches++;
   if (halo) {
-    // closurebc's wraps and ghost levels were written by the closure kernel itself; only a split x needs the exchange
-    if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_EKM], f[UDGPU_EKH]}, g.ktot + 2 * g.kh));
+    // closurebc's wraps and ghost levels were written by the closure kernel itself.  Split x: the edge columns went
+    // straight into the neighbours' halo columns (flag barrier), or travel through the pack / exchange / unpack path
+    if (h->P > 1) { if (h->direct_halo) RET(p2p_barrier(h)); else RET(halo_x_exchange(h, {f[UDGPU_EKM], f[UDGPU_EKH]}, g.ktot + 2 * g.kh)); }
   } else {
     // closurebc: lateral wraps on all levels, then top/bottom ghost levels over the full halo'd plane
     RET(wrap_xy(h, {f[UDGPU_EKM], f[UDGPU_EKH]}, g.ktot + 2 * g.kh));
@@ -736,7 +764,9 @@ static int launch_momtend(udgpu *h, bool acc) {
   const Geo &g = h->g;
   const bool les = g.lles != 0;
   if (h->use_tma) {
-    const MomTmaParams &P = h->mtp;
+    MomTmaParams &P = h->mtp;
+    P.upL = h->direct_halo ? h->wfield[(h->rank + h->P - 1) % h->P] + h->fwin_off[UDGPU_UP] : nullptr;
+    h->up_halo_sent = P.upL != nullptr;
 #define LAUNCH(ACC, LES) \
   k_momtend_tma<ADV, DIFF, (DIFF && LES), ACC><<<h->mt_grid, MT_THREADS, MT_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->tm[3], h->tm[4], P)
     if (acc) { if (les) LAUNCH(true, true); else LAUNCH(true, false); }
@@ -744,6 +774,7 @@ static int launch_momtend(udgpu *h, bool acc) {
 #undef LAUNCH
   } else {
     const dim3 gr = grid3(g, B3);
+    h->up_halo_sent = false;
     if (ADV && DIFF) {  // the direct kernels are instantiated per operator only
       RET((launch_momtend_v1<true, false>(h, acc)));
       return launch_momtend_v1<false, true>(h, true);
@@ -766,8 +797,9 @@ static int launch_scalars(udgpu *h, bool acc) {
   const bool les = g.lles != 0, kappa = h->cfg.iadv_sv == 7;
   const long long ssl = (long long)h->cnt[UDGPU_SV0], tsl = (long long)h->cnt[UDGPU_SVP];
   // all fields in one pass, four at a time (the velocity / ekh loads are shared between the fields)
-  for (int n0 = 0; n0 < nsv; n0 += 4) {
-    const int ns = nsv - n0 < 4 ? nsv - n0 : 4;
+  const int nsmax = h->sc_nsmax;
+  for (int n0 = 0; n0 < nsv; n0 += nsmax) {
+    const int ns = nsv - n0 < nsmax ? nsv - n0 : nsmax;
     const double *sv = h->f[UDGPU_SV0] + (size_t)n0 * ssl;
     double *svp = h->f[UDGPU_SVP] + (size_t)n0 * tsl;
 #define GO4(S, ACC, LES, NS) k_scalar_tend_multi<S, ADV, DIFF, ACC, LES, NS><<<gr, B3, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKH], sv, ssl, svp, tsl)
@@ -786,7 +818,16 @@ static int launch_scalars(udgpu *h, bool acc) {
       }
       continue;
     }
-    if (kappa) { if (acc) GO2(7, true); else GO2(7, false); }
+    if (kappa && ADV && h->sc_march) {
+      const dim3 gm((g.imax + SC_WX - 1) / SC_WX, (g.jmax + SC_BY - 1) / SC_BY, (g.ktot + SC_KC - 1) / SC_KC), bm(32, SC_BY);
+#define GM4(ACC, LES, NS) k_scalar_kappa_march<DIFF, ACC, LES, NS><<<gm, bm, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKH], sv, ssl, svp, tsl)
+#define GM3(ACC, LES) do { if (ns == 1) GM4(ACC, LES, 1); else if (ns == 2) GM4(ACC, LES, 2); else if (ns == 3) GM4(ACC, LES, 3); else GM4(ACC, LES, 4); } while (0)
+      if (acc) { if (les) GM3(true, true); else GM3(true, false); }
+      else { if (les) GM3(false, true); else GM3(false, false); }
+#undef GM3
+#undef GM4
+    }
+    else if (kappa) { if (acc) GO2(7, true); else GO2(7, false); }
     else { if (acc) GO2(2, true); else GO2(2, false); }
 #undef GO2
 #undef GO3
@@ -808,6 +849,21 @@ static int flush_pending(udgpu *h) {
   RET((launch_scalars<true, false>(h, !h->tend_zero)));
   h->tend_zero = false; h->tend_lazy_zero = false;
   return UDGPU_OK;
+}
+
+// the listed fields on the ring neighbours (direct halo stores); all nullptr when x is unsplit or not mapped
+static PeerCols peer_cols(udgpu *h, std::initializer_list<int> fields) {
+  PeerCols pc;
+  for (int q = 0; q < 6; q++) pc.L[q] = pc.R[q] = nullptr;
+  if (!h->direct_halo) return pc;
+  const int left = (h->rank + h->P - 1) % h->P, right = (h->rank + 1) % h->P;
+  int q = 0;
+  for (int f : fields) {
+    pc.L[q] = h->wfield[left] + h->fwin_off[f];
+    pc.R[q] = h->wfield[right] + h->fwin_off[f];
+    q++;
+  }
+  return pc;
 }
 
 // bring lazily maintained halo state up to what the reference would show before a field is handed out
@@ -996,7 +1052,8 @@ static int setup_p2p(udgpu *h, size_t nR) {
   h->p2p = false;
   if (h->cfg.flags & UDGPU_F_NCCL_TRANSPOSE) return UDGPU_OK;
   const int P = h->P;
-  const size_t bytes = (2 * nR + 4 * h->halo_cap) * sizeof(double) + 4096;
+  const size_t head = (((2 * nR + 4 * h->halo_cap) * sizeof(double) + 4096) + 255) / 256 * 256;   // [recvA | recvB | halo windows | flags]
+  const size_t bytes = head + h->win_field_elems * sizeof(double);                                 // ... | window-resident fields]
   if (cudaMalloc(&h->ipc_mine, bytes) != cudaSuccess) { cudaGetLastError(); return UDGPU_OK; }
   h->allocs.push_back(h->ipc_mine);
   CU(cudaMemsetAsync(h->ipc_mine, 0, bytes, h->st));
@@ -1036,6 +1093,7 @@ static int setup_p2p(udgpu *h, size_t nR) {
     double *hb = h->rB[d] + nR;
     h->hL[d][0] = hb; h->hL[d][1] = hb + h->halo_cap; h->hR[d][0] = hb + 2 * h->halo_cap; h->hR[d][1] = hb + 3 * h->halo_cap;
     h->pflags.flags[d] = (unsigned long long *)(hb + 4 * h->halo_cap);
+    h->wfield[d] = (double *)((char *)h->ipc_peer[d] + head);
   }
   for (int d = P; d < 8; d++) h->pflags.flags[d] = nullptr;
   h->p2p = true;
@@ -1157,7 +1215,8 @@ extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
   const double rk3coefi = 1. / rk3coef;
   if (h->P > 1) {
     // bcpup's exchange_halo_z(pup) (src/modboundary.f90:1219): only up(ie+1) is missing, um's halo is valid
-    RET(halo_x_exchange(h, {h->f[UDGPU_UP]}, g.ktot + g.kh));
+    if (h->up_halo_sent) RET(p2p_barrier(h));   // the tendency kernel stored up(1) into the left neighbour already
+    else RET(halo_x_exchange(h, {h->f[UDGPU_UP]}, g.ktot + g.kh));
     k_fillps<false, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
                                                           h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS]);
   } else
@@ -1232,16 +1291,18 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
     if (own) {
       // one pass: bcp (periodic index / slab exchange of p), tderive, integrate, pres0 += p, halos, boundary
       if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));
+      const PeerCols pc = peer_cols(h, {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM});
       if (rk3step == 3)
         k_tderive_integrate_halo<true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
-                                                                       f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0]);
+                                                                       f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], pc);
       else
         k_tderive_integrate_halo<false><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
-                                                                        f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0]);
+                                                                        f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], pc);
       KCHECK();
       h->launches++;
       h->halos_done = h->bc_done = true;
       h->halo_x_pending = h->P > 1;
+      if (rk3step == 3) h->m_changed = true;
     } else {
       RET(wrap_xy(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
       h->p_halo_valid = true;
@@ -1290,12 +1351,16 @@ extern "C" int udgpu_halos(udgpu_t *h) {
   if (h->halos_done && !h->halo_dirty) {
     // the fused tderive+integrate kernel wrote the periodic images itself; a split x still needs its exchange
     if (h->halo_x_pending) {
-      RET(halo_x_exchange(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
+      if (h->direct_halo) RET(p2p_barrier(h));   // the integrate kernel stored the edge columns into the neighbours
+      else if (h->m_changed) RET(halo_x_exchange(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
+      else RET(halo_x_exchange(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0]}, g.ktot + 2 * g.kh));   // um, vm, wm only change on substep 3
       h->halo_x_pending = false;
+      h->m_changed = false;
     }
   } else {
     RET(wrap_xy(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
     h->halo_dirty = false;
+    h->m_changed = false;
   }
   if (h->cfg.nsv) {  // xs_periodic / ys_periodic (src/modboundary.f90:568-579,655-669) or exchange at level ihc
     std::vector<double *> sv;
