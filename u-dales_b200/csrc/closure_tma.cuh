@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(CL_THREADS, MINB)
         const double b23 = dx2 * a12 * a13 + dy2 * a22 * a23 + dzf2 * a32 * a33;
         const double bb = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
         const double e = (bb < 1.e-8) ? 0.0 : g.c_vreman * sqrt(bb / aa);
-        if (store_ok) ek_store(g, ci, cj, k, e, ekm, ekh, halo, pc);
+        if (store_ok) ek_store<false>(g, ci, cj, k, e, ekm, ekh, halo, pc);
       }
       __syncthreads();
       if (tid == 0) {

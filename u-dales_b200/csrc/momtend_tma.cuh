@@ -41,7 +41,6 @@ struct MomTmaParams {
   int ntx, nty, nchunk;   // tiles in i, j; chunks in k
   int nitems;
   double *up, *vp, *wp;
-  double *upL;            // x split: the left neighbour's up array (its halo column imax+1 receives my up(1)); else nullptr
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -282,7 +281,6 @@ __global__ void __launch_bounds__(MT_THREADS, 1)
           if (ACC) { ru += P.up[t]; rv += P.vp[t]; }
           P.up[t] = ru;
           P.vp[t] = rv;
-          if (ci == 1 && P.upL) P.upL[t + g.imax] = ru;   // bcpup's exchange of pup (src/modboundary.f90:1219), done by the producer
           if (k >= 2) {
             const double dzhik = __ldg(g.dzhi + k);
             double rw = (cxz_bot - cxz_botL) * dxi + (cyz_bot - cyz_botB) * dyi + (Gzz - gzz_prev) * dzhik;

@@ -123,7 +123,6 @@ struct udgpu {
   double *wfield[8] = {};                  // start of the field region in every rank's window
   size_t fwin_off[UDGPU_NFIELDS] = {};     // element offset of a field inside the window (0 = not in the window)
   size_t win_field_elems = 0;
-  bool up_halo_sent = false;               // the last momentum-tendency kernel already stored up(1) into the left neighbour
   bool m_changed = true;                   // um, vm, wm changed since their halos were last exchanged
   unsigned halo_par = 0;
   P2PPtrs pflags;
@@ -447,7 +446,7 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     const bool want_direct = h->fuse_halo && !getenv("UDGPU_NO_DIRECT_HALO");
     size_t off = 0;
     if (want_direct)
-      for (int f : {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM, UDGPU_UP, UDGPU_EKM, UDGPU_EKH}) {
+      for (int f : {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM, UDGPU_UP, UDGPU_EKM, UDGPU_EKH, UDGPU_P}) {
         h->fwin_off[f] = off + 32;                      // +32: keeps 0 as "not in the window"; 256-byte aligned slices
         off += (((f == UDGPU_UP ? nT : nF) + 31) / 32) * 32 + 32;
       }
@@ -572,7 +571,6 @@ extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
   if (is_tend) { RET(materialize_zero_tend(h)); h->tend_pushed = true; }
   if (field <= UDGPU_WP) { h->halo_dirty = h->bc_dirty = true; h->halos_done = h->bc_done = h->halo_x_pending = false; }
   if (field == UDGPU_P) h->p_halo_valid = true;   // the host's array is taken as is
-  if (field == UDGPU_UP) h->up_halo_sent = false;
   if (field == UDGPU_UM || field == UDGPU_VM || field == UDGPU_WM) h->m_changed = true;
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(h->f[field] + (size_t)n4 * h->cnt[field], host, h->cnt[field] * sizeof(double), cudaMemcpyHostToDevice, h->st));
@@ -633,6 +631,7 @@ static const dim3 B3(64, 4, 1);
 // x-halo exchange between neighbouring slabs over NCCL (periodic ring).
 // Send order right-then-left / receive order left-then-right so that with P = 2 (both neighbours are
 // the same peer) the first send meets the first receive.
+static int g_ih(udgpu *h) { return h->g.ih; }
 static int halo_x_exchange_g(udgpu *h, const std::vector<double *> &fields, int nlev, int pi, int pj, int imax, int hw) {
   HaloPack hp; hp.n = 0;
   long long off = 0;
@@ -641,6 +640,25 @@ static int halo_x_exchange_g(udgpu *h, const std::vector<double *> &fields, int 
   const long long rows = (long long)pj * nlev;
   const dim3 gr((unsigned)((rows + 127) / 128), hp.n);
   const int left = (h->rank + h->P - 1) % h->P, right = (h->rank + 1) % h->P;
+  if (h->direct_halo && hw == g_ih(h)) {
+    // window-resident fields: store the edge columns straight into the neighbours' halo columns, one flag barrier
+    PeerPack pk;
+    bool all = true;
+    for (int q = 0; q < hp.n; q++) {
+      int fid = -1;
+      for (int f = 0; f < UDGPU_NFIELDS; f++) if (h->f[f] == hp.f[q] && h->fwin_off[f]) fid = f;
+      if (fid < 0) { all = false; break; }
+      pk.L[q] = h->wfield[left] + h->fwin_off[fid];
+      pk.R[q] = h->wfield[right] + h->fwin_off[fid];
+    }
+    if (all) {
+      k_halo_push_x<<<gr, 128, 0, h->st>>>(hp, pk, pi, pj, imax, hw);
+      KCHECK();
+      RET(p2p_barrier(h));
+      h->launches++;
+      return UDGPU_OK;
+    }
+  }
   if (h->p2p) {
     // peer stores: my first columns land in the left neighbour's right-halo window, my last columns in the right
     // neighbour's left-halo window; one flag barrier; unpack from my own windows.  Windows alternate (parity) so a
@@ -707,7 +725,7 @@ extern "C" int udgpu_closure(udgpu_t *h) {
   double **f = h->f;
   const PeerCols pc = halo ? peer_cols(h, {UDGPU_EKM, UDGPU_EKH}) : peer_cols(h, {});
   // model selection order of the reference: smagorinsky first, then vreman, else DNS (modsubgrid.f90:208,269,401)
-  if (h->cfg.lsmagorinsky) k_closure<2><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
+  if (h->cfg.lsmagorinsky) { if (pc.L[0]) k_closure<2, true><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); else k_closure<2, false><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); }
   else if (h->cfg.lvreman && h->use_tma && h->cl_occ > 0) {
     if (h->cl_occ == 1) k_closure_vreman_tma<1><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
     else k_closure_vreman_tma<2><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
@@ -715,10 +733,11 @@ extern "C" int udgpu_closure(udgpu_t *h) {
   else if (h->cfg.lvreman && h->cl_march > 0) {
     constexpr int KC = 16;
     const dim3 gm(gr.x, gr.y, (g.ktot + KC - 1) / KC);
-    k_closure_vreman_march<KC><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
+    if (pc.L[0]) k_closure_vreman_march<KC, true><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
+    else k_closure_vreman_march<KC, false><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
   }
-  else if (h->cfg.lvreman) k_closure<1><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
-  else k_closure<0><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
+  else if (h->cfg.lvreman) { if (pc.L[0]) k_closure<1, true><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); else k_closure<1, false><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); }
+  else { if (pc.L[0]) k_closure<0, true><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); else k_closure<0, false><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); }
   KCHECK();
   h->launches++;
   if (halo) {
@@ -764,9 +783,7 @@ static int launch_momtend(udgpu *h, bool acc) {
   const Geo &g = h->g;
   const bool les = g.lles != 0;
   if (h->use_tma) {
-    MomTmaParams &P = h->mtp;
-    P.upL = h->direct_halo ? h->wfield[(h->rank + h->P - 1) % h->P] + h->fwin_off[UDGPU_UP] : nullptr;
-    h->up_halo_sent = P.upL != nullptr;
+    const MomTmaParams &P = h->mtp;
 #define LAUNCH(ACC, LES) \
   k_momtend_tma<ADV, DIFF, (DIFF && LES), ACC><<<h->mt_grid, MT_THREADS, MT_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->tm[3], h->tm[4], P)
     if (acc) { if (les) LAUNCH(true, true); else LAUNCH(true, false); }
@@ -774,7 +791,6 @@ static int launch_momtend(udgpu *h, bool acc) {
 #undef LAUNCH
   } else {
     const dim3 gr = grid3(g, B3);
-    h->up_halo_sent = false;
     if (ADV && DIFF) {  // the direct kernels are instantiated per operator only
       RET((launch_momtend_v1<true, false>(h, acc)));
       return launch_momtend_v1<false, true>(h, true);
@@ -1215,8 +1231,7 @@ extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
   const double rk3coefi = 1. / rk3coef;
   if (h->P > 1) {
     // bcpup's exchange_halo_z(pup) (src/modboundary.f90:1219): only up(ie+1) is missing, um's halo is valid
-    if (h->up_halo_sent) RET(p2p_barrier(h));   // the tendency kernel stored up(1) into the left neighbour already
-    else RET(halo_x_exchange(h, {h->f[UDGPU_UP]}, g.ktot + g.kh));
+    RET(halo_x_exchange(h, {h->f[UDGPU_UP]}, g.ktot + g.kh));
     k_fillps<false, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
                                                           h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS]);
   } else
@@ -1292,12 +1307,11 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
       // one pass: bcp (periodic index / slab exchange of p), tderive, integrate, pres0 += p, halos, boundary
       if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));
       const PeerCols pc = peer_cols(h, {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM});
-      if (rk3step == 3)
-        k_tderive_integrate_halo<true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
-                                                                       f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], pc);
-      else
-        k_tderive_integrate_halo<false><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM],
-                                                                        f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], pc);
+#define TI_(S3, PEER) k_tderive_integrate_halo<S3, PEER><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM], \
+                                                                       f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], pc)
+      if (rk3step == 3) { if (pc.L[0]) TI_(true, true); else TI_(true, false); }
+      else { if (pc.L[0]) TI_(false, true); else TI_(false, false); }
+#undef TI_
       KCHECK();
       h->launches++;
       h->halos_done = h->bc_done = true;
