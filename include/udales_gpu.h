@@ -155,6 +155,23 @@ int udgpu_divergence(udgpu_t *h, double *divmax, double *divtot, double *divrms)
 int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax, int ladaptive,
                   double courant, double diffnr);
 
+/* ---- immersed-boundary masking (next tier; src/modibm.f90) ------------------------------- */
+/* point lists of modibm: kind 0-3 = solid_info_{u,v,w,c}%solpts_loc, 4-7 = bound_info_{u,v,w,c}%bndpts_loc; n points,
+ * local 1-based (i,j,k).  layout 0: point-major triples [i0,j0,k0,i1,...]; layout 1: the Fortran array (n,3) as it
+ * lies in memory (all i, then all j, then all k). */
+enum udgpu_ibm_kind { UDGPU_IBM_SOLID_U = 0, UDGPU_IBM_SOLID_V, UDGPU_IBM_SOLID_W, UDGPU_IBM_SOLID_C,
+                      UDGPU_IBM_BOUND_U, UDGPU_IBM_BOUND_V, UDGPU_IBM_BOUND_W, UDGPU_IBM_BOUND_C };
+int udgpu_ibm_set_points(udgpu_t *h, int kind, int n, const int *ijk, int layout);
+/* builds mask_u, mask_v, mask_w, mask_c on the device as initibm does (src/modibm.f90:153-192: 1, ground level 0,
+ * solid points 0, halo exchange) and switches the IBM calls of udgpu_substep on.  m = 0..3 can be pulled for checking. */
+int udgpu_ibm_commit(udgpu_t *h);
+int udgpu_ibm_pull_mask(udgpu_t *h, int m, double *host);
+/* src/modibm.f90:697 ibmnorm (momentum + scalars) */
+int udgpu_ibmnorm(udgpu_t *h);
+/* src/modibm.f90:1211-1213,1240-1242: diffu_corr, diffv_corr, diffw_corr, diffc_corr (the part of ibmwallfun on the
+ * resident path; the wall-function stresses themselves stay with the host) */
+int udgpu_ibm_diffcorr(udgpu_t *h);
+
 /* One full RK3 time step on HOST arrays (the literal drop-in for a host-resident model): pushes u0,v0,w0,pres0
  * (reference shapes; um=u0 at the start of a time step, src/modtstep.f90:330-338), runs the three substeps of
  * src/program.f90:132-207 on the device and pulls the same four arrays back.  Pin the arrays once with

@@ -106,7 +106,17 @@ def tokenize(s):
             out.append(("str", t[1:-1]))
         else:
             out.append(("op", t))
-    return out
+    # derived-type component reference a%b -> one name token "a%b" (resolved through a dict, see Interp.lookup)
+    merged = []
+    i = 0
+    while i < len(out):
+        if (out[i][0] == "name" and i + 2 < len(out) and out[i + 1] == ("op", "%") and out[i + 2][0] == "name"):
+            merged.append(("name", out[i][1] + "%" + out[i + 2][1]))
+            i += 3
+        else:
+            merged.append(out[i])
+            i += 1
+    return merged
 
 
 class Parser:
@@ -702,6 +712,9 @@ class Interp:
 
     def lookup(self, name, frame):
         loc = frame["loc"]
+        if "%" in name:
+            base, comp = name.split("%", 1)
+            return self.lookup(base, frame)[comp]
         if name in loc:
             return loc[name]
         if name in self.g:
@@ -710,6 +723,10 @@ class Interp:
 
     def store(self, name, val, frame):
         loc = frame["loc"]
+        if "%" in name:
+            base, comp = name.split("%", 1)
+            self.lookup(base, frame)[comp] = val
+            return
         if name in loc or name not in self.g:
             if name not in loc and name not in self.g:
                 raise NameError(f"assignment to undeclared {name!r} in {frame['proc'].name}")
@@ -925,6 +942,10 @@ class Interp:
                 return a > b
             if op == ">=":
                 return a >= b
+            if op == ".eqv.":
+                return bool(a) == bool(b)
+            if op == ".neqv.":
+                return bool(a) != bool(b)
             raise NotImplementedError(op)
         if k == "call":
             name = n[1]
@@ -949,6 +970,8 @@ class Interp:
                 return int(arr.a.size)
             if name == "allocated":
                 return self.lookup(n[2][0][1], frame) is not None
+            if name == "present":      # optional dummy: passed iff bound to a value in the callee's frame
+                return frame["loc"].get(n[2][0][1]) is not None
             raise NameError(f"unknown function/array {name!r} in {frame['proc'].name}")
         if k == "arrcon":
             return np.array([self.eval(x, frame) for x in n[1]])

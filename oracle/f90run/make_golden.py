@@ -290,9 +290,114 @@ def case_substeps(tag, nsub=3, **kw):
     print(f"wrote ref_{tag}.npz  ({len(out)} arrays)  final |u0|max {np.abs(g['u0'].a).max():.6f} divmax {out['divmax']:.2e}")
 
 
+def ibm_geometry(I, J, K, boxes):
+    """Synthetic building blocks -> the eight point lists of src/modibm.f90 (local 1-based i,j,k).
+    solid_c: cell centres inside a box; solid_u / v / w: staggered points touching a solid cell;
+    fluid-boundary lists: interior fluid points with at least one masked neighbour in the directions the
+    corresponding diff*_corr routine looks at (incl. the ground level kb-1 and, for w, level kb)."""
+    sc = np.zeros((I + 2, J + 2, K + 2), dtype=bool)
+    for (i0, i1, j0, j1, k1) in boxes:
+        sc[i0:i1 + 1, j0:j1 + 1, 1:k1 + 1] = True
+    su = sc | np.roll(sc, 1, axis=0)            # u(i) sits between cells i-1 and i
+    sv = sc | np.roll(sc, 1, axis=1)
+    sw = sc.copy(); sw[:, :, 1:] |= sc[:, :, :-1]
+    lists, masks = {}, {}
+    for nm, sol in (("u", su), ("v", sv), ("w", sw), ("c", sc)):
+        pts = np.argwhere(sol[1:I + 1, 1:J + 1, 1:K + 1]) + 1
+        lists["solid_" + nm] = pts.astype(np.int32)
+        m = np.ones((I + 2, J + 2, K + 2)); m[:, :, 0] = 0.0
+        if nm == "w":
+            m[:, :, 1] = 0.0
+        m[1:I + 1, 1:J + 1, 1:K + 1][sol[1:I + 1, 1:J + 1, 1:K + 1]] = 0.0
+        m[0] = m[I]; m[I + 1] = m[1]; m[:, 0] = m[:, J]; m[:, J + 1] = m[:, 1]
+        masks[nm] = m
+    dirs = {"u": ((0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)), "v": ((1, 0, 0), (-1, 0, 0), (0, 0, 1), (0, 0, -1)),
+            "w": ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0)),
+            "c": ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1))}
+    for nm in "uvwc":
+        m = masks[nm]
+        out = []
+        klo = 2 if nm == "w" else 1
+        for k in range(klo, K + 1):
+            for j in range(1, J + 1):
+                for i in range(1, I + 1):
+                    if m[i, j, k] == 1.0 and any(m[i + a, j + b, k + c] == 0.0 for a, b, c in dirs[nm]):
+                        out.append((i, j, k))
+        lists["bound_" + nm] = np.array(out, dtype=np.int32).reshape(-1, 3)
+    return lists
+
+
+def case_ibm(tag, shape=(12, 10, 8), nsv=1):
+    """solid / ibmnorm / diffu,v,w,c_corr executed from src/modibm.f90."""
+    I, J, K = shape
+    zf = stretched_zf(K, 0.5 * K * 1.1, 1.07)
+    w = World(I, J, K, xlen=0.55 * I, ylen=0.45 * J, zf=zf, nsv=nsv, iadv_sv=7)
+    it = make_interp(w)
+    it.load(os.path.join(SRC, "modibm.f90"), only=["solid", "diffu_corr", "diffv_corr", "diffw_corr", "diffc_corr", "ibmnorm"])
+    g = w.g
+    lists = ibm_geometry(I, J, K, [(4, 6, 3, 5, 3), (9, 10, 7, 8, 2), (1, 2, 9, 10, 4)])
+    full = [(0, I + 1), (0, J + 1), (0, K + 1)]
+    tend = [(0, I + 1), (0, J + 1), (1, K + 1)]
+    for nm in "uvwc":
+        pts = lists["solid_" + nm]
+        g["solid_info_" + nm] = {"nsolptsrank": int(pts.shape[0]), "solpts_loc": FArray(np.asfortranarray(pts.astype(int)), [1, 1])}
+        b = lists["bound_" + nm]
+        g["bound_info_" + nm] = {"nbndptsrank": int(b.shape[0]), "bndpts_loc": FArray(np.asfortranarray(b.astype(int)), [1, 1])}
+    # masks exactly as initibm builds them (src/modibm.f90:153-192), `solid` interpreted from the reference text
+    dummy = fa(tend)
+    for nm in "uvwc":
+        m = fa(full, 1.0)
+        m.a[:, :, 0] = 0.0
+        if nm == "w":
+            m.a[:, :, 1] = 0.0
+        it.call("solid", g["solid_info_" + nm], m, dummy, 0.0, 1, 1, 1)
+        a = m.a
+        a[0] = a[I]; a[I + 1] = a[1]; a[:, 0] = a[:, J]; a[:, J + 1] = a[:, 1]     # exchange_halo_z on one periodic pencil
+        g["mask_" + nm] = m
+    g.update(libm=True, lconservativeibm=False, thl0av=fa([(1, K + 1)]))
+    rng = np.random.default_rng(23)
+    seed_fields(w, 17, nsv)
+    for nm in ("um", "vm", "wm"):
+        g[nm].a[...] = g[nm.replace("m", "0")].a + 0.05 * rng.standard_normal(g[nm].a.shape)
+    g["svm"].a[...] = g["sv0"].a + 0.05 * rng.standard_normal(g["sv0"].a.shape)
+    g["sv0"].a[...] += 0.01 * rng.standard_normal(g["sv0"].a.shape)     # halos included: neighbours of boundary points are read
+    for nm in ("up", "vp", "wp", "svp"):
+        g[nm].a[...] = rng.standard_normal(g[nm].a.shape)
+    g["ekm"].a[...] = 1e-3 * (1.0 + rng.random(g["ekm"].a.shape))
+    g["ekh"].a[...] = 3e-3 * (1.0 + rng.random(g["ekh"].a.shape))
+    out = {"zf": zf, "shape": np.array([I, J, K]), "xlen": 0.55 * I, "ylen": 0.45 * J, "nsv": nsv}
+    for k_, v_ in lists.items():
+        out["pts_" + k_] = v_
+    for nm in "uvwc":
+        out["mask_" + nm] = np.array(g["mask_" + nm].a, copy=True)
+    state = ["u0", "v0", "w0", "um", "vm", "wm", "up", "vp", "wp", "ekm", "ekh", "sv0", "svm", "svp"]
+    for k_, v_ in snapshot(w, state).items():
+        out["in_" + k_] = v_
+    # the in-scope part of ibmwallfun (src/modibm.f90:1211-1213, 1240-1242)
+    it.call("diffu_corr"); it.call("diffv_corr"); it.call("diffw_corr")
+    hc = g["ihc"]
+    for n in range(1, nsv + 1):
+        sv0n = FArray(g["sv0"].a[:, :, :, n - 1], g["sv0"].lb[:3])
+        svpn = FArray(g["svp"].a[:, :, :, n - 1], g["svp"].lb[:3])
+        it.call("diffc_corr", sv0n, svpn, hc, hc, hc)
+    for k_, v_ in snapshot(w, ["up", "vp", "wp", "svp"]).items():
+        out["corr_" + k_] = v_
+    it.call("ibmnorm")
+    for k_, v_ in snapshot(w, ["um", "vm", "wm", "up", "vp", "wp", "svm", "svp"]).items():
+        out["norm_" + k_] = v_
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, f"ref_{tag}.npz"), **out)
+    print(f"wrote ref_{tag}.npz  solid pts u/v/w/c {[lists['solid_' + n].shape[0] for n in 'uvwc']}  "
+          f"boundary pts {[lists['bound_' + n].shape[0] for n in 'uvwc']}")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ibm":
+        case_ibm("ibm")
+        sys.exit(0)
     case_substeps("vreman_freeslip", shape=(10, 8, 6))
     case_substeps("smag_noslip", shape=(8, 12, 5), lvreman=False, lsmagorinsky=True, BCtopm=2, Uinf=1.2, Vinf=-0.3)
     case_substeps("dns", shape=(8, 6, 7), lvreman=False, lsmagorinsky=False)
     case_substeps("kappa2", shape=(8, 8, 6), nsv=2, iadv_sv=7)
     case_substeps("cd2scalar", shape=(6, 8, 5), nsv=1, iadv_sv=2)
+    case_ibm("ibm")

@@ -61,6 +61,12 @@ def lib():
         L.orc_substep.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_double, C.c_int,
                                   C.c_double, C.c_double]
         L.orc_rfft_packed.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+        L.orc_ibm_set_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_ibm_build_masks.argtypes = [C.c_void_p]
+        L.orc_ibm_mask.restype = C.POINTER(C.c_double)
+        L.orc_ibm_mask.argtypes = [C.c_void_p, C.c_int]
+        L.orc_ibmnorm.argtypes = [C.c_void_p]
+        L.orc_ibm_diffcorr.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -166,6 +172,23 @@ class Oracle:
         d, r = C.c_double(self.dt), C.c_int(self.rk3step)
         self.L.orc_substep(self.h, C.byref(d), C.byref(r), dtmax, int(ladaptive), courant, diffnr)
         self.dt, self.rk3step = d.value, r.value
+
+    # immersed boundary masking (src/modibm.f90) ---------------------------------
+    IBM_KINDS = ("solid_u", "solid_v", "solid_w", "solid_c", "bound_u", "bound_v", "bound_w", "bound_c")
+
+    def ibm_set(self, lists):
+        """lists: dict kind -> (n,3) int array of local 1-based (i,j,k); missing kinds = empty.  Builds the masks."""
+        for kind, name in enumerate(self.IBM_KINDS):
+            pts = np.ascontiguousarray(np.asarray(lists.get(name, np.zeros((0, 3))), dtype=np.int32).reshape(-1, 3))
+            self.L.orc_ibm_set_points(self.h, kind, pts.shape[0], pts.ctypes.data)
+        self.L.orc_ibm_build_masks(self.h)
+
+    def ibm_mask(self, m):
+        shape = (self.itot + 2, self.jtot + 2, self.ktot + 2)
+        return np.ctypeslib.as_array(self.L.orc_ibm_mask(self.h, m), shape=(int(np.prod(shape)),)).reshape(shape, order="F")
+
+    def ibmnorm(self): self.L.orc_ibmnorm(self.h)
+    def ibm_diffcorr(self): self.L.orc_ibm_diffcorr(self.h)
 
     # synthetic channel of SURVEY.md §8d --------------------------------------
     def init_channel(self, ubase=1.0, ampl=0.05, ir=43):

@@ -40,6 +40,11 @@ struct orc {
   double *dumu, *duml;        /* advecc_kappa temporaries                                       */
   /* FFT tables */
   double *twx, *twy;
+  /* immersed boundary (src/modibm.f90): local 1-based point lists + real masks (1 fluid, 0 solid) */
+  int ibm_n[8];               /* 0-3 solid_u,v,w,c ; 4-7 fluid-boundary points u,v,w,c */
+  int *ibm_pts[8];            /* 3*n, point-major: (i,j,k) of point n at [3n..3n+2]    */
+  double *mask[4];            /* mask_u, mask_v, mask_w, mask_c  (momentum-halo shape)  */
+  int libm;
 };
 
 #define MOFF 2
@@ -1077,6 +1082,23 @@ void orc_halos(orc_t *o) {
   }
 }
 
+/* periodic wrap of one momentum-halo array (what exchange_halo_z does on a single periodic pencil) */
+static void wrap_mom(orc_t *o, double *a) {
+  const int I = o->itot, J = o->jtot, K = o->ktot;
+  for (int m = 1; m <= o->ih; m++)
+    for (int k = 1 - o->kh; k <= K + o->kh; k++)
+      for (int j = 1 - o->jh; j <= J + o->jh; j++) {
+        F(a, 1 - m, j, k) = F(a, I + 1 - m, j, k);
+        F(a, I + m, j, k) = F(a, m, j, k);
+      }
+  for (int m = 1; m <= o->jh; m++)
+    for (int k = 1 - o->kh; k <= K + o->kh; k++)
+      for (int i = 1 - o->ih; i <= I + o->ih; i++) {
+        F(a, i, 1 - m, k) = F(a, i, J + 1 - m, k);
+        F(a, i, J + m, k) = F(a, i, m, k);
+      }
+}
+
 /* boundary, periodic x/y subset: src/modboundary.f90:163-204 (+ scalars :238-250 with zero top flux) */
 void orc_boundary(orc_t *o) {
   const int I = o->itot, J = o->jtot, K = o->ktot;
@@ -1142,10 +1164,186 @@ void orc_randomize(orc_t *o, const char *name, int n4, double ampl, int ir) {
 }
 
 /* one RK3 substep restricted to the in-scope calls of src/program.f90:132-207 */
+/* ------------------------------------------------------------------------- */
+/* Immersed boundary masking (next tier): solid (src/modibm.f90:748-826), ibmnorm (:697-745,
+ * momentum + kappa scalars), diffu/v/w/c_corr (:990-1164) and the mask construction of initibm (:153-192). */
+void orc_ibm_set_points(orc_t *o, int kind, int n, const int *ijk) {
+  free(o->ibm_pts[kind]);
+  o->ibm_pts[kind] = (int *)malloc(sizeof(int) * 3 * (size_t)(n > 0 ? n : 1));
+  memcpy(o->ibm_pts[kind], ijk, sizeof(int) * 3 * (size_t)n);
+  o->ibm_n[kind] = n;
+}
+static void wrap_mom(orc_t *o, double *f);
+/* initibm :153-192: masks = 1, level kb-kh = 0 (and mask_w(kb) = 0), solid points = 0, then the halo exchange */
+void orc_ibm_build_masks(orc_t *o) {
+  for (int m = 0; m < 4; m++) {
+    if (!o->mask[m]) o->mask[m] = zalloc(nF(o));
+    double *mk = o->mask[m];
+    for (size_t q = 0; q < nF(o); q++) mk[q] = 1.;
+    for (int j = 1 - o->jh; j <= o->jtot + o->jh; j++)
+      for (int i = 1 - o->ih; i <= o->itot + o->ih; i++) {
+        F(mk, i, j, 0) = 0.;
+        if (m == 2) F(mk, i, j, 1) = 0.;
+      }
+    for (int n = 0; n < o->ibm_n[m]; n++) {
+      const int *q = o->ibm_pts[m] + 3 * n;
+      F(mk, q[0], q[1], q[2]) = 0.;
+    }
+    wrap_mom(o, mk);
+  }
+  o->libm = 1;
+}
+double *orc_ibm_mask(orc_t *o, int m) { return o->mask[m]; }
+
+/* solid() without mask: var = val, rhs = 0 at the solid points (:762-770) */
+static void solid_mom(orc_t *o, int kind, double *var, double *rhs) {
+  for (int n = 0; n < o->ibm_n[kind]; n++) {
+    const int *q = o->ibm_pts[kind] + 3 * n;
+    F(var, q[0], q[1], q[2]) = 0.;
+    T(rhs, q[0], q[1], q[2]) = 0.;
+  }
+}
+/* solid() with mask on a scalar-halo array (:772-822): zero-flux attempt = average of the fluid neighbours */
+static void solid_scalar(orc_t *o, double *var, double *rhs, double val) {
+  const double eps1 = 1.e-10;
+  const double *mk = o->mask[3];
+  static const int nb[6][3] = {{0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}, {1, 0, 0}, {-1, 0, 0}};   /* order of :781-815 */
+  for (int n = 0; n < o->ibm_n[3]; n++) {
+    const int *q = o->ibm_pts[3] + 3 * n;
+    const int i = q[0], j = q[1], k = q[2];
+    S(var, i, j, k) = val;
+    ST(rhs, i, j, k) = 0.;
+    double count = 0.;
+    for (int d = 0; d < 6; d++) {
+      const int ii = i + nb[d][0], jj = j + nb[d][1], kk = k + nb[d][2];
+      if (fabs(F(mk, ii, jj, kk) - 1.) < eps1) {
+        count = count + 1.;
+        S(var, i, j, k) = S(var, i, j, k) + S(var, ii, jj, kk);
+        ST(rhs, i, j, k) = ST(rhs, i, j, k) + ST(rhs, ii, jj, kk);
+      }
+    }
+    if (count > 0.) {
+      S(var, i, j, k) = (S(var, i, j, k) - val) / count;
+      ST(rhs, i, j, k) = ST(rhs, i, j, k) / count;
+    }
+  }
+}
+/* ibmnorm :697-745 (neutral: momentum + scalars; kappa scalars need no advecc2nd correction) */
+void orc_ibmnorm(orc_t *o) {
+  if (!o->libm) return;
+  solid_mom(o, 0, o->um, o->up);
+  solid_mom(o, 1, o->vm, o->vp);
+  solid_mom(o, 2, o->wm, o->wp);
+  for (int n = 0; n < o->nsv; n++) solid_scalar(o, o->svm + n * nS(o), o->svp + n * nST(o), 0.);
+}
+/* diffu_corr / diffv_corr / diffw_corr / diffc_corr :990-1164: cancel the subgrid flux through solid neighbours */
+void orc_ibm_diffcorr(orc_t *o) {
+  if (!o->libm) return;
+  const double eps1 = 1.e-10;
+  const double *ekm = o->ekm, *ekh = o->ekh, *u0 = o->u0, *v0 = o->v0, *w0 = o->w0;
+  const double dx2i = o->dx2i, dy2i = o->dy2i;
+  for (int n = 0; n < o->ibm_n[4]; n++) {
+    const int *q = o->ibm_pts[4] + 3 * n;
+    const int i = q[0], j = q[1], k = q[2];
+    const double *mk = o->mask[0];
+    if (fabs(F(mk, i, j + 1, k)) < eps1) {
+      const double empo = 0.25 * ((F(ekm, i, j, k) + F(ekm, i, j + 1, k)) + (F(ekm, i - 1, j, k) + F(ekm, i - 1, j + 1, k)));
+      T(o->up, i, j, k) = T(o->up, i, j, k) - empo * (F(u0, i, j + 1, k) - F(u0, i, j, k)) * dy2i;
+    }
+    if (fabs(F(mk, i, j - 1, k)) < eps1) {
+      const double emmo = 0.25 * ((F(ekm, i, j, k) + F(ekm, i, j - 1, k)) + (F(ekm, i - 1, j - 1, k) + F(ekm, i - 1, j, k)));
+      T(o->up, i, j, k) = T(o->up, i, j, k) + emmo * (F(u0, i, j, k) - F(u0, i, j - 1, k)) * dy2i;
+    }
+    if (fabs(F(mk, i, j, k + 1)) < eps1) {
+      const double emop = (M(dzf, k + 1) * (F(ekm, i, j, k) + F(ekm, i - 1, j, k)) +
+                           M(dzf, k) * (F(ekm, i, j, k + 1) + F(ekm, i - 1, j, k + 1))) * M(dzhiq, k + 1);
+      T(o->up, i, j, k) = T(o->up, i, j, k) - emop * (F(u0, i, j, k + 1) - F(u0, i, j, k)) * M(dzhi, k + 1) * M(dzfi, k);
+    }
+    if (fabs(F(mk, i, j, k - 1)) < eps1) {
+      const double emom = (M(dzf, k - 1) * (F(ekm, i, j, k) + F(ekm, i - 1, j, k)) +
+                           M(dzf, k) * (F(ekm, i, j, k - 1) + F(ekm, i - 1, j, k - 1))) * M(dzhiq, k);
+      T(o->up, i, j, k) = T(o->up, i, j, k) + emom * (F(u0, i, j, k) - F(u0, i, j, k - 1)) * M(dzhi, k) * M(dzfi, k);
+    }
+  }
+  for (int n = 0; n < o->ibm_n[5]; n++) {
+    const int *q = o->ibm_pts[5] + 3 * n;
+    const int i = q[0], j = q[1], k = q[2];
+    const double *mk = o->mask[1];
+    if (fabs(F(mk, i + 1, j, k)) < eps1) {
+      const double epmo = 0.25 * (F(ekm, i, j, k) + F(ekm, i, j - 1, k) + F(ekm, i + 1, j - 1, k) + F(ekm, i + 1, j, k));
+      T(o->vp, i, j, k) = T(o->vp, i, j, k) - epmo * (F(v0, i + 1, j, k) - F(v0, i, j, k)) * dx2i;
+    }
+    if (fabs(F(mk, i - 1, j, k)) < eps1) {
+      const double emmo = 0.25 * (F(ekm, i, j, k) + F(ekm, i, j - 1, k) + F(ekm, i - 1, j - 1, k) + F(ekm, i - 1, j, k));
+      T(o->vp, i, j, k) = T(o->vp, i, j, k) + emmo * (F(v0, i, j, k) - F(v0, i - 1, j, k)) * dx2i;
+    }
+    if (fabs(F(mk, i, j, k + 1)) < eps1) {
+      const double eomp = (M(dzf, k + 1) * (F(ekm, i, j, k) + F(ekm, i, j - 1, k)) +
+                           M(dzf, k) * (F(ekm, i, j, k + 1) + F(ekm, i, j - 1, k + 1))) * M(dzhiq, k + 1);
+      T(o->vp, i, j, k) = T(o->vp, i, j, k) - eomp * (F(v0, i, j, k + 1) - F(v0, i, j, k)) * M(dzhi, k + 1) * M(dzfi, k);
+    }
+    if (fabs(F(mk, i, j, k - 1)) < eps1) {
+      const double eomm = (M(dzf, k - 1) * (F(ekm, i, j, k) + F(ekm, i, j - 1, k)) +
+                           M(dzf, k) * (F(ekm, i, j, k - 1) + F(ekm, i, j - 1, k - 1))) * M(dzhiq, k);
+      T(o->vp, i, j, k) = T(o->vp, i, j, k) + eomm * (F(v0, i, j, k) - F(v0, i, j, k - 1)) * M(dzhi, k) * M(dzfi, k);
+    }
+  }
+  for (int n = 0; n < o->ibm_n[6]; n++) {
+    const int *q = o->ibm_pts[6] + 3 * n;
+    const int i = q[0], j = q[1], k = q[2];
+    const double *mk = o->mask[2];
+    if (fabs(F(mk, i + 1, j, k)) < eps1) {
+      const double epom = (M(dzf, k - 1) * (F(ekm, i, j, k) + F(ekm, i + 1, j, k)) +
+                           M(dzf, k) * (F(ekm, i, j, k - 1) + F(ekm, i + 1, j, k - 1))) * M(dzhiq, k);
+      T(o->wp, i, j, k) = T(o->wp, i, j, k) - epom * (F(w0, i + 1, j, k) - F(w0, i, j, k)) * dx2i;
+    }
+    if (fabs(F(mk, i - 1, j, k)) < eps1) {
+      const double emom = (M(dzf, k - 1) * (F(ekm, i, j, k) + F(ekm, i - 1, j, k)) +
+                           M(dzf, k) * (F(ekm, i, j, k - 1) + F(ekm, i - 1, j, k - 1))) * M(dzhiq, k);
+      T(o->wp, i, j, k) = T(o->wp, i, j, k) + emom * (F(w0, i, j, k) - F(w0, i - 1, j, k)) * dx2i;
+    }
+    if (fabs(F(mk, i, j + 1, k)) < eps1) {
+      const double eopm = (M(dzf, k - 1) * (F(ekm, i, j, k) + F(ekm, i, j + 1, k)) +
+                           M(dzf, k) * (F(ekm, i, j, k - 1) + F(ekm, i, j + 1, k - 1))) * M(dzhiq, k);
+      T(o->wp, i, j, k) = T(o->wp, i, j, k) - eopm * (F(w0, i, j + 1, k) - F(w0, i, j, k)) * dy2i;
+    }
+    if (fabs(F(mk, i, j - 1, k)) < eps1) {
+      const double eomm = (M(dzf, k - 1) * (F(ekm, i, j, k) + F(ekm, i, j - 1, k)) +
+                           M(dzf, k) * (F(ekm, i, j, k - 1) + F(ekm, i, j - 1, k - 1))) * M(dzhiq, k);
+      T(o->wp, i, j, k) = T(o->wp, i, j, k) + eomm * (F(w0, i, j, k) - F(w0, i, j - 1, k)) * dy2i;
+    }
+  }
+  for (int s4 = 0; s4 < o->nsv; s4++) {
+    const double *var = o->sv0 + s4 * nS(o);
+    double *rhs = o->svp + s4 * nST(o);
+    const double *mk = o->mask[3];
+    for (int n = 0; n < o->ibm_n[7]; n++) {
+      const int *q = o->ibm_pts[7] + 3 * n;
+      const int i = q[0], j = q[1], k = q[2];
+      if (fabs(F(mk, i + 1, j, k)) < eps1)
+        ST(rhs, i, j, k) = ST(rhs, i, j, k) - 0.5 * (F(ekh, i + 1, j, k) + F(ekh, i, j, k)) * (S(var, i + 1, j, k) - S(var, i, j, k)) * dx2i;
+      if (fabs(F(mk, i - 1, j, k)) < eps1)
+        ST(rhs, i, j, k) = ST(rhs, i, j, k) + 0.5 * (F(ekh, i, j, k) + F(ekh, i - 1, j, k)) * (S(var, i, j, k) - S(var, i - 1, j, k)) * dx2i;
+      if (fabs(F(mk, i, j + 1, k)) < eps1)
+        ST(rhs, i, j, k) = ST(rhs, i, j, k) - 0.5 * (F(ekh, i, j + 1, k) + F(ekh, i, j, k)) * (S(var, i, j + 1, k) - S(var, i, j, k)) * dy2i;
+      if (fabs(F(mk, i, j - 1, k)) < eps1)
+        ST(rhs, i, j, k) = ST(rhs, i, j, k) + 0.5 * (F(ekh, i, j, k) + F(ekh, i, j - 1, k)) * (S(var, i, j, k) - S(var, i, j - 1, k)) * dy2i;
+      if (fabs(F(mk, i, j, k + 1)) < eps1)
+        ST(rhs, i, j, k) = ST(rhs, i, j, k) - 0.5 * (M(dzf, k + 1) * F(ekh, i, j, k) + M(dzf, k) * F(ekh, i, j, k + 1)) *
+                                                  (S(var, i, j, k + 1) - S(var, i, j, k)) * M(dzh2i, k + 1) * M(dzfi, k);
+      if (fabs(F(mk, i, j, k - 1)) < eps1)
+        ST(rhs, i, j, k) = ST(rhs, i, j, k) + 0.5 * (M(dzf, k - 1) * F(ekh, i, j, k) + M(dzf, k) * F(ekh, i, j, k - 1)) *
+                                                  (S(var, i, j, k) - S(var, i, j, k - 1)) * M(dzh2i, k) * M(dzfi, k);
+    }
+  }
+}
+
 void orc_substep(orc_t *o, double *dt, int *rk3step, double dtmax, int ladaptive, double courant, double diffnr) {
   orc_tstep_update(o, dt, courant, diffnr, dtmax, ladaptive, rk3step, NULL, NULL);
   orc_advection(o);
   orc_subgrid(o);
+  orc_ibm_diffcorr(o);   /* the in-scope part of ibmwallfun, src/program.f90:166 */
+  orc_ibmnorm(o);        /* src/program.f90:171 */
   orc_poisson(o, *dt, *rk3step);
   orc_tstep_integrate(o, *dt, *rk3step);
   orc_halos(o);

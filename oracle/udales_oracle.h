@@ -70,6 +70,14 @@ void orc_substep(orc_t *o, double *dt, int *rk3step, double dtmax, int ladaptive
 /* stand-alone real FFT helpers (FFTW r2c/c2r conventions + the reference's packing) */
 void orc_rfft_packed(int n, double *line, int inverse);  /* modpois.f90:478-490 / 669-679 on one line */
 
+/* immersed boundary masking: kind 0-3 = solid_u,v,w,c ; 4-7 = fluid-boundary points u,v,w,c;
+ * ijk = n local 1-based (i,j,k) triples, point-major */
+void orc_ibm_set_points(orc_t *o, int kind, int n, const int *ijk);
+void orc_ibm_build_masks(orc_t *o);                 /* modibm.f90:153-192 */
+double *orc_ibm_mask(orc_t *o, int m);              /* mask_u, mask_v, mask_w, mask_c */
+void orc_ibmnorm(orc_t *o);                         /* modibm.f90:697 */
+void orc_ibm_diffcorr(orc_t *o);                    /* modibm.f90:990-1164 (called from ibmwallfun :1211-1241) */
+
 #ifdef __cplusplus
 }
 #endif

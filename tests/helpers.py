@@ -50,3 +50,39 @@ def svp_interior(a, hc):
 def relerr(a, b):
     s = max(np.abs(b).max(), 1e-300)
     return np.abs(a - b).max() / s
+
+
+def ibm_lists(I, J, K, boxes):
+    """synthetic building blocks -> the eight point lists of src/modibm.f90 (same construction as
+    oracle/f90run/make_golden.py:ibm_geometry): solid_c = cells inside a box (i0..i1, j0..j1, 1..k1); solid_u/v/w =
+    staggered points touching a solid cell; bound_* = fluid points with a masked neighbour in the directions the
+    diff*_corr routines look at."""
+    sc = np.zeros((I + 2, J + 2, K + 2), dtype=bool)
+    for (i0, i1, j0, j1, k1) in boxes:
+        sc[i0:i1 + 1, j0:j1 + 1, 1:k1 + 1] = True
+    su = sc | np.roll(sc, 1, axis=0)
+    sv = sc | np.roll(sc, 1, axis=1)
+    sw = sc.copy(); sw[:, :, 1:] |= sc[:, :, :-1]
+    lists, masks = {}, {}
+    for nm, sol in (("u", su), ("v", sv), ("w", sw), ("c", sc)):
+        lists["solid_" + nm] = (np.argwhere(sol[1:I + 1, 1:J + 1, 1:K + 1]) + 1).astype(np.int32)
+        m = np.ones((I + 2, J + 2, K + 2)); m[:, :, 0] = 0.0
+        if nm == "w":
+            m[:, :, 1] = 0.0
+        m[1:I + 1, 1:J + 1, 1:K + 1][sol[1:I + 1, 1:J + 1, 1:K + 1]] = 0.0
+        m[0] = m[I]; m[I + 1] = m[1]; m[:, 0] = m[:, J]; m[:, J + 1] = m[:, 1]
+        masks[nm] = m
+    dirs = {"u": ((0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)), "v": ((1, 0, 0), (-1, 0, 0), (0, 0, 1), (0, 0, -1)),
+            "w": ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0)),
+            "c": ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1))}
+    for nm in "uvwc":
+        m = masks[nm]
+        fluid = m[1:I + 1, 1:J + 1, 1:K + 1] == 1.0
+        touch = np.zeros_like(fluid)
+        for a, b, c in dirs[nm]:
+            touch |= m[1 + a:I + 1 + a, 1 + b:J + 1 + b, 1 + c:K + 1 + c] == 0.0
+        pts = np.argwhere(fluid & touch) + 1
+        if nm == "w":
+            pts = pts[pts[:, 2] >= 2]
+        lists["bound_" + nm] = pts.astype(np.int32)
+    return lists

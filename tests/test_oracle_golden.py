@@ -11,7 +11,8 @@ import pytest
 
 from oracle.oracle import Oracle
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith("ref_ibm.npz"))
+GOLD_IBM = os.path.join(os.path.dirname(__file__), "golden", "ref_ibm.npz")
 TOL = 2e-13      # same arithmetic order, no FMA on either side; FFT library and pow() rounding differ
 
 
@@ -89,3 +90,33 @@ def test_oracle_matches_reference_source(path):
     assert ct == pytest.approx(float(d["adapt_courtot"]), rel=1e-11)
     assert dn == pytest.approx(float(d["adapt_diffnrtot"]), rel=1e-11)
     assert dtn == pytest.approx(float(d["adapt_dt"]), rel=1e-11)
+
+
+def build_ibm(d, cls=Oracle, **kw):
+    I, J, K = (int(x) for x in d["shape"])
+    nsv = int(d["nsv"])
+    o = cls(I, J, K, xlen=float(d["xlen"]), ylen=float(d["ylen"]), zf=d["zf"], nsv=nsv, **kw)
+    return o, nsv
+
+
+def test_oracle_ibm_matches_reference_source():
+    """solid / ibmnorm / diffu,v,w,c_corr (src/modibm.f90:748-826, 697-745, 990-1164) and the masks of initibm
+    (:153-192): golden produced by executing the reference text on synthetic building blocks."""
+    d = np.load(GOLD_IBM)
+    o, nsv = build_ibm(d)
+    for n in ("u0", "v0", "w0", "um", "vm", "wm", "up", "vp", "wp", "ekm", "ekh"):
+        getattr(o, n)[...] = d["in_" + n]
+    o.sv0[...] = d["in_sv0"][..., :nsv]; o.svm[...] = d["in_svm"][..., :nsv]; o.svp[...] = d["in_svp"][..., :nsv]
+    o.ibm_set({k[4:]: d[k] for k in d.files if k.startswith("pts_")})
+    for m, nm in enumerate("uvwc"):
+        assert np.array_equal(o.ibm_mask(m), d["mask_" + nm]), nm
+    o.ibm_diffcorr()
+    for n in ("up", "vp", "wp"):
+        assert np.array_equal(getattr(o, n), d["corr_" + n]), n          # same operations in the same order: identical bits
+    assert np.array_equal(o.svp, d["corr_svp"][..., :nsv])
+    o.ibmnorm()
+    for n in ("um", "vm", "wm", "up", "vp", "wp"):
+        assert np.array_equal(getattr(o, n), d["norm_" + n]), n
+    assert np.array_equal(o.svm, d["norm_svm"][..., :nsv]) and np.array_equal(o.svp, d["norm_svp"][..., :nsv])
+    # something actually happened
+    assert np.abs(d["corr_up"] - d["in_up"]).max() > 1e-6 and np.abs(d["norm_um"] - d["in_um"]).max() > 1e-3

@@ -31,7 +31,7 @@ EXPORTS = [
     "udgpu_tstep_update", "udgpu_advection", "udgpu_subgrid", "udgpu_closure", "udgpu_poisson",
     "udgpu_poisson_solve", "udgpu_poisson_solve_resident", "udgpu_fillps", "udgpu_tderive",
     "udgpu_tstep_integrate", "udgpu_halos", "udgpu_boundary", "udgpu_divergence", "udgpu_substep",
-    "udgpu_rk3_step_host",
+    "udgpu_rk3_step_host", "udgpu_ibm_set_points", "udgpu_ibm_commit", "udgpu_ibm_pull_mask", "udgpu_ibmnorm", "udgpu_ibm_diffcorr",
     "udgpu_profile_enable", "udgpu_profile_get", "udgpu_profile_reset", "udgpu_launch_count", "udgpu_stream",
 ]
 
@@ -105,6 +105,11 @@ def lib():
                                     C.c_double, C.c_double]
         L.udgpu_rk3_step_host.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.POINTER(C.c_double), C.c_double, C.c_int,
                                                                               C.c_double, C.c_double]
+        L.udgpu_ibm_set_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.udgpu_ibm_commit.argtypes = [C.c_void_p]
+        L.udgpu_ibm_pull_mask.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.udgpu_ibmnorm.argtypes = [C.c_void_p]
+        L.udgpu_ibm_diffcorr.argtypes = [C.c_void_p]
         L.udgpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.udgpu_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
         L.udgpu_profile_reset.argtypes = [C.c_void_p]
@@ -289,6 +294,25 @@ class UdalesGPU:
         d = C.c_double(self.dt)
         self._chk(self.L.udgpu_rk3_step_host(self.h, *ptrs, C.byref(d), dtmax, int(ladaptive), courant, diffnr))
         self.dt, self.rk3step = d.value, 3
+
+    # immersed boundary masking (src/modibm.f90) ----------------------------------------
+    IBM_KINDS = ("solid_u", "solid_v", "solid_w", "solid_c", "bound_u", "bound_v", "bound_w", "bound_c")
+
+    def ibm_set(self, lists):
+        """lists: dict kind -> (n,3) int array of LOCAL 1-based (i,j,k) (solid_info%solpts_loc / bound_info%bndpts_loc);
+        missing kinds are empty.  Builds the masks on the device and enables the IBM calls of substep()."""
+        for kind, name in enumerate(self.IBM_KINDS):
+            pts = np.ascontiguousarray(np.asarray(lists.get(name, np.zeros((0, 3))), dtype=np.int32).reshape(-1, 3))
+            self._chk(self.L.udgpu_ibm_set_points(self.h, kind, pts.shape[0], pts.ctypes.data, 0))
+        self._chk(self.L.udgpu_ibm_commit(self.h))
+
+    def ibm_mask(self, m):
+        out = np.empty(self.shape("u0"), dtype=np.float64, order="F")
+        self._chk(self.L.udgpu_ibm_pull_mask(self.h, m, out.ctypes.data))
+        return out
+
+    def ibmnorm(self): self._chk(self.L.udgpu_ibmnorm(self.h))
+    def ibm_diffcorr(self): self._chk(self.L.udgpu_ibm_diffcorr(self.h))
 
     # measurement ---------------------------------------------------------------
     def profile_enable(self, on=True): self._chk(self.L.udgpu_profile_enable(self.h, int(on)))

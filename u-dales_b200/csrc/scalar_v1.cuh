@@ -183,7 +183,7 @@ __device__ __forceinline__ double kface(double vmm, double vm, double v0, double
 // and ~21 loads.  Faces, limiter and accumulation order are the reference's: results equal k_scalar_tend's bit for bit.
 constexpr int SC_WX = 31, SC_BY = 8, SC_KC = 32;
 template <bool DIFF, bool ACC, bool LES, int NS>
-__global__ void __launch_bounds__(32 * SC_BY) k_scalar_kappa_march(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
+__global__ void __launch_bounds__(32 * SC_BY, 2) k_scalar_kappa_march(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
                                                                    const double *__restrict__ w0, const double *__restrict__ ekh,
                                                                    const double *__restrict__ sv, long long ssl, double *__restrict__ svp,
                                                                    long long tsl) {

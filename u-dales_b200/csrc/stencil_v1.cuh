@@ -455,8 +455,10 @@ __global__ void __launch_bounds__(256) k_tderive_integrate(Geo g, double rk3coef
 // cells at k = ktot also set the top ghost level (freeslip copy / noslip mirror, w = 0); pres0 += p reaches the
 // image cells too (:1096-1102).  Only legal when the m-fields / w(k=1) / tendencies at k=1 are in the state the
 // reference's own halos+boundary leave them in (the host tracks that; otherwise the plain kernel + wraps run).
-template <bool STEP3, bool PEER = false>
-__global__ void __launch_bounds__(256, PEER ? 5 : 6) k_tderive_integrate_halo(Geo g, double rk3coef, const double *__restrict__ p,
+// XS: 0 = x unsplit (periodic images in x written here), 1 = x split over GPUs (halo columns of pres0 updated from the
+// exchanged p), 2 = split + the edge columns of the velocities stored straight into the neighbours (PeerCols)
+template <bool STEP3, int XS = 0>
+__global__ void __launch_bounds__(256) k_tderive_integrate_halo(Geo g, double rk3coef, const double *__restrict__ p,
                                                                 const double *__restrict__ up, const double *__restrict__ vp,
                                                                 const double *__restrict__ wp, double *__restrict__ um,
                                                                 double *__restrict__ vm, double *__restrict__ wm,
@@ -490,20 +492,26 @@ __global__ void __launch_bounds__(256, PEER ? 5 : 6) k_tderive_integrate_halo(Ge
       if (STEP3) { UM[qt] = at; VM[qt] = bt; WM[qt] = 0.; }
     }
   };
-  auto put = [&](int ti, int tj) {
-    const long long q = offF(g, ti, tj, k);
+  auto put = [&](long long q) {
     putv(u0, v0, w0, um, vm, wm, q);
     pres0[q] = pres0[q] + pc0;
-    if (PEER) {
-      if (ti == 1) putv(pc.L[0], pc.L[1], pc.L[2], pc.L[3], pc.L[4], pc.L[5], offF(g, g.imax + 1, tj, k));
-      if (ti == g.imax) putv(pc.R[0], pc.R[1], pc.R[2], pc.R[3], pc.R[4], pc.R[5], offF(g, 0, tj, k));
-    }
   };
+  put(c);
   const int ix = img_x(g, i), jy = img_y(g, j);
-  put(i, j);
-  if (ix >= 0) put(ix, j);
-  if (jy >= 0) { put(i, jy); if (ix >= 0) put(ix, jy); }
-  if (!g.wrapx) {
+  if (ix >= 0) put(offF(g, ix, j, k));
+  if (jy >= 0) { put(offF(g, i, jy, k)); if (ix >= 0) put(offF(g, ix, jy, k)); }
+  if (XS == 2) {
+    // my first / last interior column (and its y images) = the left / right neighbour's halo column
+    if (i == 1) {
+      putv(pc.L[0], pc.L[1], pc.L[2], pc.L[3], pc.L[4], pc.L[5], offF(g, g.imax + 1, j, k));
+      if (jy >= 0) putv(pc.L[0], pc.L[1], pc.L[2], pc.L[3], pc.L[4], pc.L[5], offF(g, g.imax + 1, jy, k));
+    }
+    if (i == g.imax) {
+      putv(pc.R[0], pc.R[1], pc.R[2], pc.R[3], pc.R[4], pc.R[5], offF(g, 0, j, k));
+      if (jy >= 0) putv(pc.R[0], pc.R[1], pc.R[2], pc.R[3], pc.R[4], pc.R[5], offF(g, 0, jy, k));
+    }
+  }
+  if (XS >= 1) {
     // x is split over GPUs: the halo columns of p came from the neighbours (exchange before this kernel) and
     // pres0 += p has to reach the halo columns of pres0 too (src/modpois.f90:1096-1102)
     auto ph = [&](int hi) {

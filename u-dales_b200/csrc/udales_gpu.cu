@@ -22,6 +22,7 @@
 #include "poisson_xz.cuh"
 #include "stencil_v1.cuh"
 #include "scalar_v1.cuh"
+#include "ibm.cuh"
 
 using namespace udg;
 
@@ -154,6 +155,13 @@ struct udgpu {
   bool bc_done = false;        // ... and what boundary() would
   bool halo_x_pending = false; // x-split: the slab exchange of the new fields is still to run (in halos())
   bool p_halo_valid = true;    // p's lateral halo is the wrap of its interior (bcp); restored lazily on pull
+  // immersed boundary (src/modibm.f90): point lists, masks
+  int ibm_n[8] = {};
+  int *ibm_pts[8] = {};
+  double *ibm_mask[4] = {};
+  bool libm = false;
+  bool m_halo_stale = false;   // ibmnorm wrote um, vm, wm at solid points: their halo images are stale until halos()
+  bool m_bc_stale = false;     // ... and their top ghost level until boundary()
   bool prof = false;
   ProfSlot ps[PROF_N];
   long launches = 0;
@@ -1232,6 +1240,8 @@ extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
   if (h->P > 1) {
     // bcpup's exchange_halo_z(pup) (src/modboundary.f90:1219): only up(ie+1) is missing, um's halo is valid
     RET(halo_x_exchange(h, {h->f[UDGPU_UP]}, g.ktot + g.kh));
+    // ibmnorm zeroed um at solid points after the last halos(): pup(ie+1) needs the neighbour's current um(1) too
+    if (h->m_halo_stale) RET(halo_x_exchange(h, {h->f[UDGPU_UM]}, g.ktot + 2 * g.kh));
     k_fillps<false, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
                                                           h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS]);
   } else
@@ -1307,10 +1317,10 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
       // one pass: bcp (periodic index / slab exchange of p), tderive, integrate, pres0 += p, halos, boundary
       if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));
       const PeerCols pc = peer_cols(h, {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM});
-#define TI_(S3, PEER) k_tderive_integrate_halo<S3, PEER><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM], \
+#define TI_(S3, XS) k_tderive_integrate_halo<S3, XS><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM], \
                                                                        f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], pc)
-      if (rk3step == 3) { if (pc.L[0]) TI_(true, true); else TI_(true, false); }
-      else { if (pc.L[0]) TI_(false, true); else TI_(false, false); }
+      if (rk3step == 3) { if (pc.L[0]) TI_(true, 2); else if (h->P > 1) TI_(true, 1); else TI_(true, 0); }
+      else { if (pc.L[0]) TI_(false, 2); else if (h->P > 1) TI_(false, 1); else TI_(false, 0); }
 #undef TI_
       KCHECK();
       h->launches++;
@@ -1362,6 +1372,11 @@ extern "C" int udgpu_halos(udgpu_t *h) {
   const Geo &g = h->g;
   ProfScope ps(h, PROF_HALO);
   double **f = h->f;
+  if (h->m_halo_stale && h->halos_done && !h->halo_dirty) {
+    // ibmnorm changed um, vm, wm at interior points after their images were written: redo their wraps (all levels)
+    RET(wrap_xy(h, {f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
+  }
+  h->m_halo_stale = false;
   if (h->halos_done && !h->halo_dirty) {
     // the fused tderive+integrate kernel wrote the periodic images itself; a split x still needs its exchange
     if (h->halo_x_pending) {
@@ -1393,7 +1408,8 @@ extern "C" int udgpu_boundary(udgpu_t *h) {
   const Geo &g = h->g;
   ProfScope ps(h, PROF_HALO);
   double **f = h->f;
-  if (!(h->bc_done && !h->bc_dirty)) {
+  if (!(h->bc_done && !h->bc_dirty) || h->m_bc_stale) {
+    h->m_bc_stale = false;
     k_boundary_topbot<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]);
     KCHECK();
     h->launches++;
@@ -1457,10 +1473,109 @@ extern "C" int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax,
   RET(udgpu_tstep_update(h, dt, courant, diffnr, dtmax, ladaptive, rk3step, nullptr, nullptr));
   RET(udgpu_advection(h));
   RET(udgpu_subgrid(h));
+  if (h->libm) {
+    RET(udgpu_ibm_diffcorr(h));   // the resident part of ibmwallfun, src/program.f90:166
+    RET(udgpu_ibmnorm(h));        // src/program.f90:171
+  }
   RET(udgpu_poisson(h, *dt, *rk3step));
   RET(udgpu_tstep_integrate(h, *dt, *rk3step));
   RET(udgpu_halos(h));
   RET(udgpu_boundary(h));
+  return UDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// immersed-boundary masking (src/modibm.f90)
+extern "C" int udgpu_ibm_set_points(udgpu_t *h, int kind, int n, const int *ijk, int layout) {
+  if (!h || kind < 0 || kind > 7 || n < 0 || (n > 0 && !ijk)) return set_err(UDGPU_EINVAL, "bad IBM point list");
+  const Geo &g = h->g;
+  std::vector<int> pts(3 * (size_t)n);
+  for (int p = 0; p < n; p++) {
+    const int i = layout ? ijk[p] : ijk[3 * p], j = layout ? ijk[n + p] : ijk[3 * p + 1], k = layout ? ijk[2 * (size_t)n + p] : ijk[3 * p + 2];
+    if (i < 1 || i > g.imax || j < 1 || j > g.jmax || k < 1 || k > g.ktot)
+      return set_err(UDGPU_EINVAL, "IBM point %d of list %d = (%d,%d,%d) is outside the local pencil", p, kind, i, j, k);
+    pts[3 * p] = i; pts[3 * p + 1] = j; pts[3 * p + 2] = k;
+  }
+  CU(cudaSetDevice(h->dev));
+  h->ibm_n[kind] = n;
+  h->ibm_pts[kind] = nullptr;
+  if (n) {
+    RET(dev_alloc(h, (void **)&h->ibm_pts[kind], pts.size() * sizeof(int)));
+    CU(cudaMemcpyAsync(h->ibm_pts[kind], pts.data(), pts.size() * sizeof(int), cudaMemcpyHostToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
+  }
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_ibm_commit(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const Geo &g = h->g;
+  const long long nF = g.pk * (g.ktot + 2 * g.kh);
+  for (int m = 0; m < 4; m++) {
+    if (!h->ibm_mask[m]) RET(dev_alloc(h, (void **)&h->ibm_mask[m], nF * sizeof(double)));
+    k_ibm_mask_init<<<(unsigned)((nF + 255) / 256), 256, 0, h->st>>>(g, h->ibm_mask[m], m == 2);
+    KCHECK();
+    if (h->ibm_n[m]) {
+      k_ibm_mask_solid<<<(h->ibm_n[m] + 127) / 128, 128, 0, h->st>>>(g, h->ibm_n[m], h->ibm_pts[m], h->ibm_mask[m]);
+      KCHECK();
+    }
+    h->launches += 2;
+  }
+  // exchange_halo_z(mask_*): periodic wrap / slab exchange
+  RET(wrap_xy(h, {h->ibm_mask[0], h->ibm_mask[1], h->ibm_mask[2], h->ibm_mask[3]}, g.ktot + 2 * g.kh));
+  h->libm = true;
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_ibm_pull_mask(udgpu_t *h, int m, double *host) {
+  if (!h || m < 0 || m > 3 || !h->ibm_mask[m]) return set_err(UDGPU_EINVAL, "no such mask (udgpu_ibm_commit first)");
+  const Geo &g = h->g;
+  CU(cudaMemcpyAsync(host, h->ibm_mask[m], g.pk * (g.ktot + 2 * g.kh) * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_ibm_diffcorr(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (!h->libm) return UDGPU_OK;
+  RET(flush_pending(h));
+  RET(materialize_zero_tend(h));
+  const Geo &g = h->g;
+  double **f = h->f;
+  ProfScope ps(h, PROF_MOM);
+  const int *n = h->ibm_n;
+  if (n[4]) { k_ibm_diffcorr_mom<0><<<(n[4] + 127) / 128, 128, 0, h->st>>>(g, n[4], h->ibm_pts[4], h->ibm_mask[0], f[UDGPU_EKM], f[UDGPU_U0], f[UDGPU_UP]); KCHECK(); h->launches++; }
+  if (n[5]) { k_ibm_diffcorr_mom<1><<<(n[5] + 127) / 128, 128, 0, h->st>>>(g, n[5], h->ibm_pts[5], h->ibm_mask[1], f[UDGPU_EKM], f[UDGPU_V0], f[UDGPU_VP]); KCHECK(); h->launches++; }
+  if (n[6]) { k_ibm_diffcorr_mom<2><<<(n[6] + 127) / 128, 128, 0, h->st>>>(g, n[6], h->ibm_pts[6], h->ibm_mask[2], f[UDGPU_EKM], f[UDGPU_W0], f[UDGPU_WP]); KCHECK(); h->launches++; }
+  if (n[7] && h->cfg.nsv) {
+    k_ibm_diffcorr_c<<<dim3((n[7] + 127) / 128, h->cfg.nsv), 128, 0, h->st>>>(g, n[7], h->ibm_pts[7], h->ibm_mask[3], f[UDGPU_EKH], f[UDGPU_SV0],
+                                                                             (long long)h->cnt[UDGPU_SV0], f[UDGPU_SVP], (long long)h->cnt[UDGPU_SVP]);
+    KCHECK(); h->launches++;
+  }
+  h->tend_zero = false;
+  return UDGPU_OK;
+}
+
+extern "C" int udgpu_ibmnorm(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (!h->libm) return UDGPU_OK;
+  RET(flush_pending(h));
+  RET(materialize_zero_tend(h));
+  const Geo &g = h->g;
+  double **f = h->f;
+  ProfScope ps(h, PROF_MOM);
+  const int *n = h->ibm_n;
+  const int vm[3] = {UDGPU_UM, UDGPU_VM, UDGPU_WM}, vp[3] = {UDGPU_UP, UDGPU_VP, UDGPU_WP};
+  for (int c = 0; c < 3; c++)
+    if (n[c]) { k_ibm_solid_mom<<<(n[c] + 127) / 128, 128, 0, h->st>>>(g, n[c], h->ibm_pts[c], f[vm[c]], f[vp[c]]); KCHECK(); h->launches++; }
+  if (n[3] && h->cfg.nsv) {
+    k_ibm_solid_scalar<<<dim3((n[3] + 127) / 128, h->cfg.nsv), 128, 0, h->st>>>(g, n[3], h->ibm_pts[3], h->ibm_mask[3], f[UDGPU_SVM], (long long)h->cnt[UDGPU_SVM],
+                                                                               f[UDGPU_SVP], (long long)h->cnt[UDGPU_SVP], 0.);
+    KCHECK(); h->launches++;
+  }
+  h->tend_zero = false;
+  h->m_halo_stale = h->m_bc_stale = true;   // um, vm, wm changed at interior points: halos() / boundary() re-establish images and ghosts
+  h->m_changed = true;
   return UDGPU_OK;
 }
 
