@@ -103,6 +103,41 @@ def channel_slab(I, J, K, i_lo, imax, seed=0):
     return u, v, w
 
 
+def urban_blocks(I, J, K, i_lo, imax):
+    """BASELINE config 3 in synthetic form: the 64x64 tile of examples/102 (16x16 blocks of height 8 on a regular
+    grid) repeated over the domain.  Returns the eight LOCAL point lists of src/modibm.f90 for the
+    x-slab [i_lo, i_lo+imax): solid_* = masked points, bound_* = fluid points next to a masked point."""
+    sc = np.zeros((I + 2, J + 2, K + 2), dtype=bool)
+    hb = min(8, max(1, K // 4))
+    for ti in range(0, I, 32):
+        for tj in range(0, J, 32):
+            sc[1 + ti + 8:1 + ti + 24, 1 + tj + 8:1 + tj + 24, 1:hb + 1] = True
+    su = sc | np.roll(sc, 1, axis=0); sv = sc | np.roll(sc, 1, axis=1)
+    sw = sc.copy(); sw[:, :, 1:] |= sc[:, :, :-1]
+    dirs = {"u": ((0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)), "v": ((1, 0, 0), (-1, 0, 0), (0, 0, 1), (0, 0, -1)),
+            "w": ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0)),
+            "c": ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1))}
+    lists = {}
+    for nm, sol in (("u", su), ("v", sv), ("w", sw), ("c", sc)):
+        m = np.ones((I + 2, J + 2, K + 2)); m[:, :, 0] = 0.0
+        if nm == "w":
+            m[:, :, 1] = 0.0
+        m[1:I + 1, 1:J + 1, 1:K + 1][sol[1:I + 1, 1:J + 1, 1:K + 1]] = 0.0
+        m[0] = m[I]; m[I + 1] = m[1]; m[:, 0] = m[:, J]; m[:, J + 1] = m[:, 1]
+        fluid = m[1:I + 1, 1:J + 1, 1:K + 1] == 1.0
+        touch = np.zeros_like(fluid)
+        for a, b, c in dirs[nm]:
+            touch |= m[1 + a:I + 1 + a, 1 + b:J + 1 + b, 1 + c:K + 1 + c] == 0.0
+        for kind, sel in (("solid_", sol[1:I + 1, 1:J + 1, 1:K + 1]), ("bound_", fluid & touch)):
+            pts = np.argwhere(sel) + 1
+            if kind == "bound_" and nm == "w":
+                pts = pts[pts[:, 2] >= 2]
+            pts = pts[(pts[:, 0] > i_lo) & (pts[:, 0] <= i_lo + imax)]
+            pts[:, 0] -= i_lo
+            lists[kind + nm] = pts.astype(np.int32)
+    return lists
+
+
 # --------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """CPU arm: the oracle (C/OpenMP restatement of the reference loops — the Fortran/MPI binary
@@ -162,14 +197,24 @@ def run_ours(args, rank, world):
         uid = obj[0]
     I, J, K = grid_for(world, args.size)
     imax = I // world
+    nsv = 4 if args.workload == "scalars" else 0
     g = U.UdalesGPU(I, J, K, xlen=I / 2.0, ylen=J / 2.0, zf=(np.arange(K) + 0.5) * 0.5, device=dev,
-                    nprocx=world, myidx=rank, nccl_uid=uid)
+                    nprocx=world, myidx=rank, nccl_uid=uid, nsv=nsv)
     u, v, w = channel_slab(I, J, K, rank * imax, imax)
     for nm, f in (("u0", u), ("v0", v), ("w0", w)):
         g.push(nm, f)
+    if nsv:
+        rng = np.random.default_rng([7, rank])
+        for n4 in range(nsv):
+            sf = np.asfortranarray(1.0 + 0.1 * rng.random(g.shape("sv0")))
+            g.push("sv0", sf, n4)
     g.halos(); g.boundary()
     for nm in ("u0", "v0", "w0"):
         g.push(nm.replace("0", "m"), g.pull(nm))
+    for n4 in range(nsv):
+        g.push("svm", g.pull("sv0", n4), n4)
+    if args.workload == "ibm":
+        g.ibm_set(urban_blocks(I, J, K, rank * imax, imax))
     dt = 0.25 * 0.5 / 1.1
     g.dt = dt
     st = torch.cuda.ExternalStream(g.stream(), device=dev)
@@ -187,6 +232,40 @@ def run_ours(args, rank, world):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.workload == "poisson":
+        # BASELINE config 4 style: the Poisson solve alone on the resident right-hand side (udgpu_poisson_solve_resident)
+        rng = np.random.default_rng([3, rank])
+        g.push("rhs", np.asfortranarray(rng.standard_normal(g.shape("rhs"))))
+        for _ in range(max(args.warmup, 3)):
+            g.poisson_solve_resident()
+        barrier()
+        sampler = ClockSampler(dev); sampler.start()
+        l0 = g.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(args.steps):
+            g.poisson_solve_resident()
+        e1.record(st)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        hbm, how = peaks()
+        ach = 80.0 * ncell_loc * args.steps / (ms * 1e-3) / 1e9
+        line = {"metric": "poisson-solves/s", "value": args.steps / (ms * 1e-3), "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"Poisson solve only, {I}x{J}x{K} (x-slabs nprocx={world}), rhs resident", "grid": [I, J, K]},
+                "cells_per_s": ncell * args.steps / (ms * 1e-3),
+                "roofline": {"kernel": "poisson_core", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                             "traffic": None, "peak_source": how, "bytes_per_cell": 80.0},
+                "gpu_launches": g.launch_count() - l0, "clocks": sampler.stop()}
+        g.close()
+        sys.stdout.flush(); os.dup2(real_stdout, 1)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
 
     # ---- device-resident throughput ("value") ----
     for _ in range(max(args.warmup, 3)):
@@ -218,14 +297,18 @@ def run_ours(args, rank, world):
     g.profile_enable(False)
     hbm, how = peaks()
     roof_all = {}
+    bpc = dict(B_PER_CELL)
+    if nsv:   # K3: (4 + 2 n) * 8 B/cell for n fields in one pass; scalar integrate: svm, svp -> sv0 = 24 B/cell/field
+        bpc["mom_tend"] += (4 + 2 * nsv) * 8.0
+        bpc["tderive_integrate"] += 24.0 * nsv
     for nm, t in fam.items():
-        if t > 0 and B_PER_CELL[nm] > 0:
-            ach = B_PER_CELL[nm] * ncell_loc / (t * 1e-3) / 1e9
+        if t > 0 and bpc[nm] > 0:
+            ach = bpc[nm] * ncell_loc / (t * 1e-3) / 1e9
             roof_all[nm] = {"ms": t, "achieved_gbs": ach, "frac": ach / hbm}
     dom = max(roof_all, key=lambda k: roof_all[k]["ms"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": roof_all[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
                 "frac": roof_all[dom]["frac"], "traffic": None, "peak_source": how,
-                "bytes_per_cell": B_PER_CELL[dom], "families": roof_all}
+                "bytes_per_cell": bpc[dom], "families": roof_all}
 
     # ---- end to end through the C-ABI with HOST buffers --------------------------------------------------
     # The prognostic state lives in pinned host arrays (a host-resident model).  One call of
@@ -274,8 +357,12 @@ def run_ours(args, rank, world):
         "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"neutral periodic channel {I}x{J}x{K}, stencil+Poisson only, no IBM/scalars "
-                               + ("(BASELINE config 2)" if world == 1 else f"(config 2 weak-scaled: {args.size}^3 cells per GPU, x-slabs)"),
+        "config": {"workload": (f"neutral periodic channel {I}x{J}x{K}, stencil+Poisson only, no IBM/scalars "
+                                if args.workload == "channel" else
+                                f"periodic channel {I}x{J}x{K} + 4 kappa-advected passive scalars " if args.workload == "scalars" else
+                                f"periodic channel {I}x{J}x{K} + urban blocks (16x16x8 per 32x32 tile) masked by the device IBM path ")
+                               + ("(BASELINE config 2)" if world == 1 and args.workload == "channel" else
+                                  f"({args.size}^3 cells per GPU, x-slabs)"),
                    "grid": [I, J, K], "substeps_per_step": 1, "l2": "per-GPU working set (13 fields x 134 MB) >> 126 MB L2, no flush needed",
                    "sgs": "vreman", "poisson": "FFT2D x,y + tridiagonal z", "decomposition": f"nprocx={world}, nprocy=1"},
         "roofline": roofline, "cpu_baseline": cpu,
@@ -305,6 +392,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="channel", choices=["channel", "scalars", "ibm", "poisson"],
+                    help="channel = BASELINE config 2 (the headline); scalars = + 4 kappa scalars (config 5 style); "
+                         "ibm = + urban blocks masked on the device (config 3 style); poisson = the solve alone (config 4 style)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -267,6 +267,56 @@ __global__ void __launch_bounds__(32 * SC_BY, 2) k_scalar_kappa_march(Geo g, con
   }
 }
 
+// Reference quirk kept for parity (src/modadvection.f90:355,379: `varp = varp + dumu + duml` are WHOLE-array adds and the
+// face loops run to ie+1 / je+1): advecc_kappa leaves the one-sided flux of the first / last face in the lateral halo
+// cells of the tendency: varp(ib-1) = -cf(ib) u0(ib) dxfci, varp(ie+1) = +cf(ie+1) u0(ie+1) dxfci, same in y.  Nothing
+// on the fluid path reads those cells, but ibmnorm's solid() averages the tendencies of the fluid neighbours of a
+// solid point and such a neighbour may lie in the halo (src/modibm.f90:781-815).  Only launched when IBM masking is on.
+// One thread per halo cell of the four strips; blockIdx.z = field.
+template <bool ACC>
+__global__ void k_scalar_kappa_halo_flux(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
+                                         const double *__restrict__ sv, long long ssl, double *__restrict__ svp, long long tsl) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x + 1;   // j (x strips) or i (y strips)
+  const int k = blockIdx.y + 1;
+  const double *s = sv + blockIdx.z * ssl;
+  double *sp = svp + blockIdx.z * tsl;
+  const long long sj = g.pic;
+  if (a <= g.jmax) {   // x strips: cells (0, j, k) and (imax+1, j, k)
+    const int j = a;
+    {
+      const long long c = offS(g, 1, j, k);
+      const double ul = u0[offF(g, 1, j, k)];
+      const double cf = kface(s[c - 2], s[c - 1], s[c], s[c + 1], ul, g.dxi, g.dxi, g.dxi, g.dx);
+      const long long t = offST(g, 0, j, k);
+      sp[t] = (ACC ? sp[t] : 0.0) + (-cf * ul * g.dxi);
+    }
+    {
+      const long long c = offS(g, g.imax + 1, j, k);
+      const double ul = u0[offF(g, g.imax + 1, j, k)];
+      const double cf = kface(s[c - 2], s[c - 1], s[c], s[c + 1], ul, g.dxi, g.dxi, g.dxi, g.dx);
+      const long long t = offST(g, g.imax + 1, j, k);
+      sp[t] = (ACC ? sp[t] : 0.0) + cf * ul * g.dxi;
+    }
+  }
+  if (a <= g.imax) {   // y strips: cells (i, 0, k) and (i, jmax+1, k)
+    const int i = a;
+    {
+      const long long c = offS(g, i, 1, k);
+      const double vl = v0[offF(g, i, 1, k)];
+      const double cf = kface(s[c - 2 * sj], s[c - sj], s[c], s[c + sj], vl, 1., 1., 1., 1.);
+      const long long t = offST(g, i, 0, k);
+      sp[t] = (ACC ? sp[t] : 0.0) + (-cf * vl * g.dyi);
+    }
+    {
+      const long long c = offS(g, i, g.jmax + 1, k);
+      const double vl = v0[offF(g, i, g.jmax + 1, k)];
+      const double cf = kface(s[c - 2 * sj], s[c - sj], s[c], s[c + sj], vl, 1., 1., 1., 1.);
+      const long long t = offST(g, i, g.jmax + 1, k);
+      sp[t] = (ACC ? sp[t] : 0.0) + cf * vl * g.dyi;
+    }
+  }
+}
+
 // sv0 = svm + rk3coef*svp ; (step 3) svm = sv0   — src/modtstep.f90:216-218,336
 template <bool STEP3>
 __global__ void __launch_bounds__(256) k_scalar_integrate(Geo g, double rk3coef, double *__restrict__ sv0, double *__restrict__ svm,

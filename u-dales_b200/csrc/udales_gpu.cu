@@ -859,6 +859,15 @@ static int launch_scalars(udgpu *h, bool acc) {
     KCHECK();
     h->launches++;
   }
+  if (ADV && kappa && h->libm) {
+    // the reference's halo-cell residue of advecc_kappa, read by ibmnorm (see k_scalar_kappa_halo_flux)
+    const int na = g.imax > g.jmax ? g.imax : g.jmax;
+    const dim3 gh((na + 127) / 128, g.ktot, nsv);
+    if (acc) k_scalar_kappa_halo_flux<true><<<gh, 128, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_SV0], ssl, h->f[UDGPU_SVP], tsl);
+    else k_scalar_kappa_halo_flux<false><<<gh, 128, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_SV0], ssl, h->f[UDGPU_SVP], tsl);
+    KCHECK();
+    h->launches++;
+  }
   return UDGPU_OK;
 }
 
