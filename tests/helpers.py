@@ -6,13 +6,13 @@ from oracle.oracle import Oracle, stretched_zf
 STATE = ("u0", "v0", "w0", "um", "vm", "wm", "pres0")
 
 
-def make_pair(itot, jtot, ktot, stretched=True, seed_ir=43, gpu_flags=0, **kw):
+def make_pair(itot, jtot, ktot, stretched=True, seed_ir=43, gpu_flags=0, ubase=1.0, **kw):
     import udales_b200 as U
     zsize = ktot * (itot / 2.0) / itot
     zf = stretched_zf(ktot, zsize, 1.04) if stretched else None
     o = Oracle(itot, jtot, ktot, zf=zf, **kw)
     g = U.UdalesGPU(itot, jtot, ktot, zf=o.zf, flags=gpu_flags, **kw)
-    o.init_channel(ir=seed_ir)
+    o.init_channel(ubase=ubase, ir=seed_ir)
     # a non-trivial pressure field with consistent periodic halos
     rng = np.random.default_rng(seed_ir)
     o.pres0[1:-1, 1:-1, 1:-1] = 0.1 * rng.standard_normal((itot, jtot, ktot))

@@ -301,3 +301,23 @@ def test_ibm_substeps_track_oracle(shape, flags):
         assert relerr(g.pull("sv0", 0)[:, :, hc:-hc], o.sv0[:, :, hc:-hc, 0]) < 1e-11, s
         # the projected field is divergence free also next to the blocks (the reference does not mask the pressure)
         assert g.divergence()[2] < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (31, 9, 6), (33, 24, 20), (62, 8, 5), (64, 12, 7)])
+@pytest.mark.parametrize("flags", [0, F_V1])
+def test_scalars_mixed_sign_flow(shape, flags):
+    """kappa scheme with u changing sign cell by cell (upwind direction flips on every face, also on the faces the
+    31-cell warps of the marching kernel share with their helper lane and on the periodic boundary)."""
+    o, g = make_pair(*shape, gpu_flags=flags, ubase=0.0, nsv=2)
+    hc = o.ihc
+    o.advection(); g.advection(); o.subgrid(); g.subgrid()
+    for n4 in range(2):
+        assert relerr(svp_interior(g.pull("svp", n4), hc), svp_interior(o.svp[..., n4], hc)) < TOL_STENCIL
+    dt = 0.02
+    o.dt = g.dt = dt
+    o2, g2 = make_pair(*shape, gpu_flags=flags, ubase=0.0, nsv=2)
+    o2.dt = g2.dt = dt
+    for s in range(3):
+        o2.substep(dt); g2.substep(dt)
+        for n4 in range(2):
+            assert relerr(g2.pull("sv0", n4)[:, :, hc:-hc], o2.sv0[:, :, hc:-hc, n4]) < 1e-11, (s, n4)

@@ -194,9 +194,12 @@ __global__ void __launch_bounds__(32 * SC_BY, 2) k_scalar_kappa_march(Geo g, con
   // helper lane / cells right of the slab: still take part in the shuffles, never store.  Clamp the column so
   // every address stays inside the arrays (halo width 2 gives i <= imax+1 room; j likewise clamped)
   const bool own = (lane < SC_WX) && (i <= g.imax) && (j <= g.jmax);
-  const int ic = min(i, g.imax + 1), jc = min(j, g.jmax);
+  // column clamps: the scalar arrays have halo 2, so the lane right of the helper (i = imax+2) still supplies a valid
+  // neighbour value; the momentum-halo arrays (halo 1) are clamped one column earlier (their values at a clamped lane
+  // are never consumed by an owned cell)
+  const int ic = min(i, g.imax + 1), ics = min(i, g.imax + 2), jc = min(j, g.jmax);
   const long long sj = g.pic, sk = g.pkc, mj = g.pi, mk = g.pk;
-  const double *ps = sv + offS(g, ic, jc, k0);
+  const double *ps = sv + offS(g, ics, jc, k0);
   long long m = offF(g, ic, jc, k0);
   long long t = offST(g, ic, jc, k0);
   const double dxi = g.dxi, dx = g.dx, dyi = g.dyi;
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(32 * SC_BY, 2) k_scalar_kappa_march(Geo g, con
       double xp1 = __shfl_down_sync(0xffffffffu, s0[n], 1);
       if (!lo0) xm1 = q[-1];
       if (!lo1) xm2 = q[-2];
-      if (!hi0) xp1 = q[1];
+      if (!hi0) xp1 = (i <= g.imax + 1) ? q[1] : 0.0;   // lane 31: from memory unless it sits beyond the halo
       const double ym1 = q[-sj], ym2 = q[-2 * sj], yp1 = q[sj], yp2 = q[2 * sj];
       const double c = s0[n];
       const double cl = kface(xm2, xm1, c, xp1, ul, dxi, dxi, dxi, dx);
