@@ -21,7 +21,7 @@ module modgpu
   private
   public :: lgpu, gpu_init, gpu_exit, gpu_push_state, gpu_pull_state, gpu_push, gpu_pull, &
             gpu_tstep_update, gpu_advection, gpu_subgrid, gpu_poisson, gpu_tstep_integrate, &
-            gpu_halos, gpu_boundary, gpu_chkdiv, gpu_rk3_step_host
+            gpu_halos, gpu_boundary, gpu_chkdiv, gpu_rk3_step_host, gpu_ibm_init, gpu_ibmnorm, gpu_ibm_diffcorr
 
   logical :: lgpu = .false.            !< namelist RUN switch (the only new option)
   type(c_ptr) :: handle = c_null_ptr
@@ -134,6 +134,24 @@ module modgpu
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: h
       real(c_double), intent(out) :: divmax, divtot, divrms
+    end function
+    integer(c_int) function udgpu_ibm_set_points(h, kind, n, ijk, layout) bind(C, name="udgpu_ibm_set_points")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+      integer(c_int), value :: kind, n, layout
+      integer(c_int), intent(in) :: ijk(*)
+    end function
+    integer(c_int) function udgpu_ibm_commit(h) bind(C, name="udgpu_ibm_commit")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    integer(c_int) function udgpu_ibmnorm(h) bind(C, name="udgpu_ibmnorm")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    integer(c_int) function udgpu_ibm_diffcorr(h) bind(C, name="udgpu_ibm_diffcorr")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
     end function
     integer(c_int) function udgpu_rk3_step_host(h, u0, v0, w0, pres0, dt, dtmax, ladaptive, courant, diffnr) &
         bind(C, name="udgpu_rk3_step_host")
@@ -308,6 +326,37 @@ contains
     real(c_double), intent(out) :: divmax, divtot
     real(c_double) :: divrms
     call chk(udgpu_divergence(handle, divmax, divtot, divrms), 'divergence')
+  end subroutine
+  !> hand modibm's local point lists to the device (call once after initibm, src/program.f90); the lists are the
+  !! (n,3) integer arrays solid_info_*%solpts_loc / bound_info_*%bndpts_loc exactly as they lie in memory (layout 1)
+  subroutine gpu_ibm_init
+    use modglobal, only: libm, nsv
+    use modibm, only: solid_info_u, solid_info_v, solid_info_w, solid_info_c, &
+                      bound_info_u, bound_info_v, bound_info_w, bound_info_c
+    integer(c_int) :: dummy(3)
+    if (.not. libm) return
+    dummy = 1
+    call chk(udgpu_ibm_set_points(handle, 0_c_int, int(solid_info_u%nsolptsrank, c_int), solid_info_u%solpts_loc, 1_c_int), 'ibm solid_u')
+    call chk(udgpu_ibm_set_points(handle, 1_c_int, int(solid_info_v%nsolptsrank, c_int), solid_info_v%solpts_loc, 1_c_int), 'ibm solid_v')
+    call chk(udgpu_ibm_set_points(handle, 2_c_int, int(solid_info_w%nsolptsrank, c_int), solid_info_w%solpts_loc, 1_c_int), 'ibm solid_w')
+    call chk(udgpu_ibm_set_points(handle, 4_c_int, int(bound_info_u%nbndptsrank, c_int), bound_info_u%bndpts_loc, 1_c_int), 'ibm bound_u')
+    call chk(udgpu_ibm_set_points(handle, 5_c_int, int(bound_info_v%nbndptsrank, c_int), bound_info_v%bndpts_loc, 1_c_int), 'ibm bound_v')
+    call chk(udgpu_ibm_set_points(handle, 6_c_int, int(bound_info_w%nbndptsrank, c_int), bound_info_w%bndpts_loc, 1_c_int), 'ibm bound_w')
+    if (nsv > 0) then
+      call chk(udgpu_ibm_set_points(handle, 3_c_int, int(solid_info_c%nsolptsrank, c_int), solid_info_c%solpts_loc, 1_c_int), 'ibm solid_c')
+      call chk(udgpu_ibm_set_points(handle, 7_c_int, int(bound_info_c%nbndptsrank, c_int), bound_info_c%bndpts_loc, 1_c_int), 'ibm bound_c')
+    else
+      call chk(udgpu_ibm_set_points(handle, 3_c_int, 0_c_int, dummy, 1_c_int), 'ibm solid_c')
+      call chk(udgpu_ibm_set_points(handle, 7_c_int, 0_c_int, dummy, 1_c_int), 'ibm bound_c')
+    end if
+    call chk(udgpu_ibm_commit(handle), 'ibm commit')
+  end subroutine
+  !> ibmnorm (src/modibm.f90:697) and the diff*_corr part of ibmwallfun (:1211-1213,1240-1242) on the resident fields
+  subroutine gpu_ibmnorm
+    call chk(udgpu_ibmnorm(handle), 'ibmnorm')
+  end subroutine
+  subroutine gpu_ibm_diffcorr
+    call chk(udgpu_ibm_diffcorr(handle), 'ibm_diffcorr')
   end subroutine
   !> one whole RK3 time step (three passes of program.f90:132-207) on the host-resident module arrays:
   !! the drop-in for a model whose other physics stay on the CPU and touch the fields once per time step
