@@ -303,7 +303,7 @@ def test_ibm_substeps_track_oracle(shape, flags):
         assert g.divergence()[2] < 1e-12
 
 
-@pytest.mark.parametrize("shape", [(16, 16, 16), (31, 9, 6), (33, 24, 20), (62, 8, 5), (64, 12, 7)])
+@pytest.mark.parametrize("shape", [(16, 16, 16), (30, 10, 6), (36, 24, 20), (66, 8, 5), (64, 12, 7)])
 @pytest.mark.parametrize("flags", [0, F_V1])
 def test_scalars_mixed_sign_flow(shape, flags):
     """kappa scheme with u changing sign cell by cell (upwind direction flips on every face, also on the faces the
