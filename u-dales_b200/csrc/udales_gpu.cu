@@ -68,14 +68,14 @@ struct ProfSlot {
 // producing kernel, no send buffer, no NCCL in the data path); k_p2p_barrier is the cross-GPU
 // "all blocks have landed" synchronisation: a system-scope flag exchange over the same mappings.
 struct P2PPtrs { unsigned long long *flags[8]; };
-__global__ void k_p2p_barrier(P2PPtrs f, int P, int rank, unsigned long long epoch, int *status) {
+__global__ void k_p2p_barrier(P2PPtrs f, int P, int rank, unsigned long long epoch, int *status, int set) {
   const int d = threadIdx.x;
   if (d < P) {
     __threadfence_system();
-    volatile unsigned long long *remote = f.flags[d] + rank;   // my slot in peer d's flag array
+    volatile unsigned long long *remote = f.flags[d] + 16 * set + rank;   // my slot in peer d's flag array (one array per stream)
     *remote = epoch;
     __threadfence_system();
-    volatile unsigned long long *mine = f.flags[rank] + d;
+    volatile unsigned long long *mine = f.flags[rank] + 16 * set + d;
     const long long t0 = clock64();
     while (*mine < epoch) {
       if (clock64() - t0 > 20000000000LL) { *status = 1; break; }  // ~10 s: a peer died; do not hang the GPU
@@ -127,7 +127,12 @@ struct udgpu {
   bool m_changed = true;                   // um, vm, wm changed since their halos were last exchanged
   unsigned halo_par = 0;
   P2PPtrs pflags;
-  unsigned long long epoch = 0;
+  unsigned long long epoch = 0, epoch2 = 0;
+  // the slab Poisson solve in two k-chunks on two streams, so that the NVLink stores of one chunk's transpose overlap
+  // the FFT arithmetic of the other
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_xfB = nullptr, ev_z = nullptr, ev_doneB = nullptr;
+  int pois_chunks = 1;
   int *d_status = nullptr;
   double *sbuf = nullptr, *rbuf = nullptr, *workB = nullptr;  // transposes: wire-format send / receive, x-pencil work
   int IB = 0, JB = 0;         // local i extent of the slab, local j extent of the x-pencil
@@ -172,7 +177,7 @@ static int flush_pending(udgpu *h);
 static PeerCols peer_cols(udgpu *h, std::initializer_list<int> fields);
 static int settle_for_access(udgpu *h, int field);
 static int setup_p2p(udgpu *h, size_t nR);
-static int p2p_barrier(udgpu *h);
+static int p2p_barrier(udgpu *h, int set = 0);
 static int materialize_zero_tend(udgpu *h);
 static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt);
 static int dev_alloc(udgpu *h, void **p, size_t bytes) {
@@ -461,6 +466,11 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     h->win_field_elems = off;
     RET(setup_p2p(h, nR));
     h->direct_halo = h->p2p && want_direct;
+    { const char *e = getenv("UDGPU_POISSON_CHUNKS"); h->pois_chunks = (h->p2p && K >= 8 && !(e && atoi(e) == 1)) ? 2 : 1; }
+    if (h->pois_chunks > 1) {
+      CU(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+      for (cudaEvent_t *ev : {&h->ev_start, &h->ev_xfB, &h->ev_z, &h->ev_doneB}) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    }
   }
   for (int f = 0; f < UDGPU_NFIELDS; f++) {
     size_t n = 0;
@@ -551,6 +561,8 @@ extern "C" int udgpu_finalize(udgpu_t *h) {
   if (h->comm) ncclCommDestroy(h->comm);
   for (int w = 0; w < PROF_N; w++)
     for (auto &e : h->ps[w].pend) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (h->st2) cudaStreamDestroy(h->st2);
+  for (cudaEvent_t ev : {h->ev_start, h->ev_xfB, h->ev_z, h->ev_doneB}) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(h->st);
   delete h;
   return UDGPU_OK;
@@ -1133,9 +1145,9 @@ static int setup_p2p(udgpu *h, size_t nR) {
   return UDGPU_OK;
 }
 
-static int p2p_barrier(udgpu *h) {
-  h->epoch++;
-  k_p2p_barrier<<<1, 32, 0, h->st>>>(h->pflags, h->P, h->rank, h->epoch, h->d_status);
+static int p2p_barrier(udgpu *h, int set) {
+  const unsigned long long e = set ? ++h->epoch2 : ++h->epoch;
+  k_p2p_barrier<<<1, 32, 0, h->st>>>(h->pflags, h->P, h->rank, e, h->d_status, set);
   KCHECK();
   h->launches++;
   return UDGPU_OK;
@@ -1165,35 +1177,76 @@ static int poisson_core_slab(udgpu *h, double *work, double *p_halo) {
   ProfScope ps(h, PROF_POIS);
   const int IB = h->IB, JB = h->JB, K = g.ktot, P = h->P;
   const size_t blk = (size_t)IB * JB * K;
-  BlkDesc bs, br;
-  for (int d = 0; d < 8; d++) { bs.base[d] = d < P ? h->sbuf + d * blk : nullptr; br.base[d] = d < P ? h->rbuf + d * blk : nullptr; }
-  const LineDesc yA = {(long long)IB, 1, (long long)IB * g.jtot, IB, K};        // y lines in the slab
-  const LineDesc yW = {(long long)IB, 1, (long long)JB * IB, IB, K};            // ... in wire format (per block)
-  const LineDesc xW = {1, (long long)IB, (long long)JB * IB, JB, K};            // x lines in wire format (per block)
-  const LineDesc xB = {1, (long long)g.itot, (long long)g.itot * JB, JB, K};    // x lines in the x-pencil
-  if (h->p2p) {
-    // block for rank d is stored directly at slot `rank` of d's receive window A (return path: window B)
-    for (int d = 0; d < P; d++) { bs.base[d] = h->rA[d] + h->rank * blk; br.base[d] = h->rA[h->rank] + d * blk; }
-  }
-  bs.shift = br.shift = ilog2(JB); bs.mask = br.mask = JB - 1;
-  RET(rfft_fast<false>(h, g.jtot, 0, work, yA, nullptr, yW, h->py, nullptr, &bs));
-  if (h->p2p) RET(p2p_barrier(h)); else RET(a2a_blocks(h));
-  br.shift = ilog2(IB); br.mask = IB - 1;
-  RET(rfft_fast<true>(h, g.itot, 0, nullptr, xW, h->workB, xB, h->px, &br, nullptr));
-  if (h->zu == 16) k_zsolve<16><<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
-  else k_zsolve<8><<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
-  KCHECK();
-  h->launches++;
-  if (h->p2p)
-    for (int d = 0; d < P; d++) { bs.base[d] = h->rB[d] + h->rank * blk; br.base[d] = h->rB[h->rank] + d * blk; }
-  bs.shift = ilog2(IB); bs.mask = IB - 1;
-  RET(rfft_fast<true>(h, g.itot, 1, h->workB, xB, nullptr, xW, h->px, nullptr, &bs));
-  if (h->p2p) RET(p2p_barrier(h)); else RET(a2a_blocks(h));
-  br.shift = ilog2(JB); br.mask = JB - 1;
-  LineDesc yOut = yA;
+  const long long wk = (long long)JB * IB;                                        // level stride inside a wire-format block
+  const LineDesc yA0 = {(long long)IB, 1, (long long)IB * g.jtot, IB, K};        // y lines in the slab
+  const LineDesc yW0 = {(long long)IB, 1, wk, IB, K};                            // ... in wire format (per block)
+  const LineDesc xW0 = {1, (long long)IB, wk, JB, K};                            // x lines in wire format (per block)
+  const LineDesc xB0 = {1, (long long)g.itot, (long long)g.itot * JB, JB, K};    // x lines in the x-pencil
+  LineDesc yOut0 = yA0;
   double *outp = work;
-  if (p_halo) { yOut.sp = g.pi; yOut.s2 = g.pk; outp = p_halo + offF(g, 1, 1, 1); }
-  RET(rfft_fast<false>(h, g.jtot, 1, nullptr, yW, outp, yOut, h->py, &br, nullptr));
+  if (p_halo) { yOut0.sp = g.pi; yOut0.s2 = g.pk; outp = p_halo + offF(g, 1, 1, 1); }
+  // send / receive bases of the two exchanges (A: after the forward y transform, B: after the inverse x transform)
+  auto bases = [&](bool second, long long k0, BlkDesc &bs, BlkDesc &br) {
+    for (int d = 0; d < 8; d++) { bs.base[d] = d < P ? h->sbuf + d * blk + k0 * wk : nullptr; br.base[d] = d < P ? h->rbuf + d * blk + k0 * wk : nullptr; }
+    if (h->p2p)   // block for rank d is stored directly at slot `rank` of d's receive window
+      for (int d = 0; d < P; d++) {
+        double *const *win = second ? h->rB : h->rA;
+        bs.base[d] = win[d] + h->rank * blk + k0 * wk;
+        br.base[d] = win[h->rank] + d * blk + k0 * wk;
+      }
+  };
+  auto with_k = [](LineDesc d, int kc) { d.nb2 = kc; return d; };
+  auto fwd = [&](int k0, int kc, int set) -> int {       // forward y, exchange A, forward x for levels k0 .. k0+kc-1
+    BlkDesc bs, br;
+    bases(false, k0, bs, br);
+    bs.shift = ilog2(JB); bs.mask = JB - 1;
+    RET(rfft_fast<false>(h, g.jtot, 0, work + k0 * yA0.s2, with_k(yA0, kc), nullptr, with_k(yW0, kc), h->py, nullptr, &bs));
+    if (h->p2p) RET(p2p_barrier(h, set)); else RET(a2a_blocks(h));
+    br.shift = ilog2(IB); br.mask = IB - 1;
+    return rfft_fast<true>(h, g.itot, 0, nullptr, with_k(xW0, kc), h->workB + k0 * xB0.s2, with_k(xB0, kc), h->px, &br, nullptr);
+  };
+  auto bwd = [&](int k0, int kc, int set) -> int {       // inverse x, exchange B, inverse y
+    BlkDesc bs, br;
+    bases(true, k0, bs, br);
+    bs.shift = ilog2(IB); bs.mask = IB - 1;
+    RET(rfft_fast<true>(h, g.itot, 1, h->workB + k0 * xB0.s2, with_k(xB0, kc), nullptr, with_k(xW0, kc), h->px, nullptr, &bs));
+    if (h->p2p) RET(p2p_barrier(h, set)); else RET(a2a_blocks(h));
+    br.shift = ilog2(JB); br.mask = JB - 1;
+    return rfft_fast<false>(h, g.jtot, 1, nullptr, with_k(yW0, kc), outp + k0 * yOut0.s2, with_k(yOut0, kc), h->py, &br, nullptr);
+  };
+  auto zsolve = [&]() -> int {
+    if (h->zu == 16) k_zsolve<16><<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
+    else k_zsolve<8><<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
+    KCHECK();
+    h->launches++;
+    return UDGPU_OK;
+  };
+  if (h->pois_chunks < 2) {
+    RET(fwd(0, K, 0));
+    RET(zsolve());
+    return bwd(0, K, 0);
+  }
+  // two k-chunks: A on the library stream, B on the second stream (its own barrier flags); the z solve needs both
+  const int kA = K / 2, kB = K - kA;
+  CU(cudaEventRecord(h->ev_start, h->st));
+  CU(cudaStreamWaitEvent(h->st2, h->ev_start, 0));
+  RET(fwd(0, kA, 0));
+  std::swap(h->st, h->st2);
+  int rc = fwd(kA, kB, 1);
+  if (rc == UDGPU_OK && cudaEventRecord(h->ev_xfB, h->st) != cudaSuccess) rc = set_err(UDGPU_ECUDA, "event record failed");
+  std::swap(h->st, h->st2);
+  RET(rc);
+  CU(cudaStreamWaitEvent(h->st, h->ev_xfB, 0));
+  RET(zsolve());
+  CU(cudaEventRecord(h->ev_z, h->st));
+  CU(cudaStreamWaitEvent(h->st2, h->ev_z, 0));
+  std::swap(h->st, h->st2);
+  rc = bwd(kA, kB, 1);
+  if (rc == UDGPU_OK && cudaEventRecord(h->ev_doneB, h->st) != cudaSuccess) rc = set_err(UDGPU_ECUDA, "event record failed");
+  std::swap(h->st, h->st2);
+  RET(rc);
+  RET(bwd(0, kA, 0));
+  CU(cudaStreamWaitEvent(h->st, h->ev_doneB, 0));
   return UDGPU_OK;
 }
 
