@@ -31,6 +31,11 @@ B_PER_CELL = {  # algorithmic (compulsory) fp64 bytes per cell, SURVEY.md §8d /
     "mom_tend": 64.0, "closure": 40.0, "poisson_core": 80.0, "fillps": 56.0, "tderive_integrate": 96.0, "halos": 0.0,
 }
 PROF_NAMES = ["mom_tend", "closure", "poisson_core", "fillps", "tderive_integrate", "halos"]
+# DRAM traffic per launch group (dram__bytes_read.sum + dram__bytes_write.sum, bytes) from the ncu --set full captures of
+# the 256^3 substep committed under profiles/ (r1_substep_kernels_ncu_[ab].txt); only quoted for that grid on one GPU
+NCU_TRAFFIC_256 = {"mom_tend": 708.0e6 + 372.0e6, "closure": 417.3e6 + 242.0e6, "fillps": 810.7e6 + 126.4e6,
+                   "tderive_integrate": 1083.6e6 + 512.7e6,
+                   "poisson_core": (134.2 + 76.3 + 134.3 + 75.3 + 249.6 + 154.0 + 136.3 + 90.1 + 134.3 + 76.0) * 1e6}
 
 
 def peaks():
@@ -307,7 +312,9 @@ def run_ours(args, rank, world):
             roof_all[nm] = {"ms": t, "achieved_gbs": ach, "frac": ach / hbm}
     dom = max(roof_all, key=lambda k: roof_all[k]["ms"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": roof_all[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
-                "frac": roof_all[dom]["frac"], "traffic": None, "peak_source": how,
+                "frac": roof_all[dom]["frac"],
+                "traffic": NCU_TRAFFIC_256.get(dom) if (world == 1 and (I, J, K) == (256, 256, 256) and args.workload == "channel") else None,
+                "peak_source": how,
                 "bytes_per_cell": bpc[dom], "families": roof_all}
 
     # ---- end to end through the C-ABI with HOST buffers --------------------------------------------------

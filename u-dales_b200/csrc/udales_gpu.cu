@@ -1226,26 +1226,50 @@ static int poisson_core_slab(udgpu *h, double *work, double *p_halo) {
     RET(zsolve());
     return bwd(0, K, 0);
   }
-  // two k-chunks: A on the library stream, B on the second stream (its own barrier flags); the z solve needs both
+  // two k-chunks: A on the library stream, B on the second stream (its own barrier flags); the z solve needs both.
+  // The NVLink-bound kernels (forward y / inverse x, which store into the peers) of B start when A's have finished, so
+  // B's transfer runs under A's x (resp. inverse y) transform instead of competing with A's transfer for the link.
   const int kA = K / 2, kB = K - kA;
-  CU(cudaEventRecord(h->ev_start, h->st));
+  auto on2 = [&](auto &&fn) -> int {   // run a launch sequence on the second stream
+    std::swap(h->st, h->st2);
+    const int rc = fn();
+    std::swap(h->st, h->st2);
+    return rc;
+  };
+  {
+    BlkDesc bs, br;
+    bases(false, 0, bs, br);
+    bs.shift = ilog2(JB); bs.mask = JB - 1;
+    RET(rfft_fast<false>(h, g.jtot, 0, work, with_k(yA0, kA), nullptr, with_k(yW0, kA), h->py, nullptr, &bs));
+    CU(cudaEventRecord(h->ev_start, h->st));           // A's forward y transform (and everything before it) is done
+    RET(p2p_barrier(h, 0));
+    br.shift = ilog2(IB); br.mask = IB - 1;
+    RET(rfft_fast<true>(h, g.itot, 0, nullptr, with_k(xW0, kA), h->workB, with_k(xB0, kA), h->px, &br, nullptr));
+  }
   CU(cudaStreamWaitEvent(h->st2, h->ev_start, 0));
-  RET(fwd(0, kA, 0));
-  std::swap(h->st, h->st2);
-  int rc = fwd(kA, kB, 1);
-  if (rc == UDGPU_OK && cudaEventRecord(h->ev_xfB, h->st) != cudaSuccess) rc = set_err(UDGPU_ECUDA, "event record failed");
-  std::swap(h->st, h->st2);
-  RET(rc);
+  RET(on2([&]() -> int {
+    RET(fwd(kA, kB, 1));
+    CU(cudaEventRecord(h->ev_xfB, h->st));
+    return UDGPU_OK;
+  }));
   CU(cudaStreamWaitEvent(h->st, h->ev_xfB, 0));
   RET(zsolve());
-  CU(cudaEventRecord(h->ev_z, h->st));
+  {
+    BlkDesc bs, br;
+    bases(true, 0, bs, br);
+    bs.shift = ilog2(IB); bs.mask = IB - 1;
+    RET(rfft_fast<true>(h, g.itot, 1, h->workB, with_k(xB0, kA), nullptr, with_k(xW0, kA), h->px, nullptr, &bs));
+    CU(cudaEventRecord(h->ev_z, h->st));               // z solve and A's inverse x transform are done
+    RET(p2p_barrier(h, 0));
+    br.shift = ilog2(JB); br.mask = JB - 1;
+    RET(rfft_fast<false>(h, g.jtot, 1, nullptr, with_k(yW0, kA), outp, with_k(yOut0, kA), h->py, &br, nullptr));
+  }
   CU(cudaStreamWaitEvent(h->st2, h->ev_z, 0));
-  std::swap(h->st, h->st2);
-  rc = bwd(kA, kB, 1);
-  if (rc == UDGPU_OK && cudaEventRecord(h->ev_doneB, h->st) != cudaSuccess) rc = set_err(UDGPU_ECUDA, "event record failed");
-  std::swap(h->st, h->st2);
-  RET(rc);
-  RET(bwd(0, kA, 0));
+  RET(on2([&]() -> int {
+    RET(bwd(kA, kB, 1));
+    CU(cudaEventRecord(h->ev_doneB, h->st));
+    return UDGPU_OK;
+  }));
   CU(cudaStreamWaitEvent(h->st, h->ev_doneB, 0));
   return UDGPU_OK;
 }
