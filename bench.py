@@ -201,6 +201,8 @@ def run_ours(args, rank, world):
         dist.broadcast_object_list(obj, src=0)
         uid = obj[0]
     I, J, K = grid_for(world, args.size)
+    if args.grid:
+        I, J, K = (int(x) for x in args.grid.split(","))
     imax = I // world
     nsv = 4 if args.workload == "scalars" else 0
     g = U.UdalesGPU(I, J, K, xlen=I / 2.0, ylen=J / 2.0, zf=(np.arange(K) + 0.5) * 0.5, device=dev,
@@ -399,6 +401,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--grid", default="", help="explicit global grid I,J,K (e.g. 1024,1024,512 = BASELINE config 4) instead of the weak-scaling grid")
     ap.add_argument("--workload", default="channel", choices=["channel", "scalars", "ibm", "poisson"],
                     help="channel = BASELINE config 2 (the headline); scalars = + 4 kappa scalars (config 5 style); "
                          "ibm = + urban blocks masked on the device (config 3 style); poisson = the solve alone (config 4 style)")
