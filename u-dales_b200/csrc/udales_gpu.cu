@@ -456,7 +456,10 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     h->gB = g;
     h->gB.imax = g.itot; h->gB.jmax = h->JB; h->gB.i0g = 0; h->gB.j0g = h->rank * h->JB;
     // fields whose edge columns are stored by their producers directly into the neighbours (window-resident)
-    const bool want_direct = h->fuse_halo && !getenv("UDGPU_NO_DIRECT_HALO");
+    // opt-in (UDGPU_DIRECT_HALO=1): measured neutral at N = 2 but slower at N = 4, 8 (2.11 vs 1.99 ms per substep at N = 8) —
+    // edge-column stores are 8-byte NVLink transactions, the staged path sends the same columns as coalesced lines
+    const char *edh = getenv("UDGPU_DIRECT_HALO");
+    const bool want_direct = h->fuse_halo && edh && atoi(edh) == 1;
     size_t off = 0;
     if (want_direct)
       for (int f : {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM, UDGPU_UP, UDGPU_EKM, UDGPU_EKH, UDGPU_P}) {
@@ -466,7 +469,8 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     h->win_field_elems = off;
     RET(setup_p2p(h, nR));
     h->direct_halo = h->p2p && want_direct;
-    { const char *e = getenv("UDGPU_POISSON_CHUNKS"); h->pois_chunks = (h->p2p && K >= 8 && !(e && atoi(e) == 1)) ? 2 : 1; }
+    // opt-in (UDGPU_POISSON_CHUNKS=2): measured no gain at N = 2 and N = 8 (0.726 vs 0.730 ms per solve at N = 8)
+    { const char *e = getenv("UDGPU_POISSON_CHUNKS"); h->pois_chunks = (h->p2p && K >= 8 && e && atoi(e) == 2) ? 2 : 1; }
     if (h->pois_chunks > 1) {
       CU(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
       for (cudaEvent_t *ev : {&h->ev_start, &h->ev_xfB, &h->ev_z, &h->ev_doneB}) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
