@@ -165,19 +165,12 @@ __global__ void __launch_bounds__(256, 4) k_closure_vreman_march(Geo g, const do
     const double a32 = ((svK * dzfk + sv_k * dzfK) * dzhiK - (sv_k * dzfkm + sv_km * dzfk) * dzhik) * dzfiqk;
     const double a33 = (wK_c - w_c) * dzfik;
     const double aa = a11 * a11 + a21 * a21 + a31 * a31 + a12 * a12 + a22 * a22 + a32 * a32 + a13 * a13 + a23 * a23 + a33 * a33;
-    // beta_ij = sum_m Delta_m^2 a_mi a_mj (src/modsubgrid.f90:305-316) with the grid spacings folded into the gradients
-    // once (s_mi = Delta_m a_mi): 9 multiplies + 18 FMAs instead of 36 multiplies + 12 adds; differs from the reference's
-    // (Delta^2 a) a grouping by rounding only
-    const double dzfk1 = __ldg(g.dzf + k);
-    const double s11 = g.dx * a11, s12 = g.dx * a12, s13 = g.dx * a13;
-    const double s21 = g.dy * a21, s22 = g.dy * a22, s23 = g.dy * a23;
-    const double s31 = dzfk1 * a31, s32 = dzfk1 * a32, s33 = dzfk1 * a33;
-    const double b11 = s11 * s11 + s21 * s21 + s31 * s31;
-    const double b22 = s12 * s12 + s22 * s22 + s32 * s32;
-    const double b12 = s11 * s12 + s21 * s22 + s31 * s32;
-    const double b33 = s13 * s13 + s23 * s23 + s33 * s33;
-    const double b13 = s11 * s13 + s21 * s23 + s31 * s33;
-    const double b23 = s12 * s13 + s22 * s23 + s32 * s33;
+    const double b11 = dx2 * a11 * a11 + dy2 * a21 * a21 + dzf2 * a31 * a31;
+    const double b22 = dx2 * a12 * a12 + dy2 * a22 * a22 + dzf2 * a32 * a32;
+    const double b12 = dx2 * a11 * a12 + dy2 * a21 * a22 + dzf2 * a31 * a32;
+    const double b33 = dx2 * a13 * a13 + dy2 * a23 * a23 + dzf2 * a33 * a33;
+    const double b13 = dx2 * a11 * a13 + dy2 * a21 * a23 + dzf2 * a31 * a33;
+    const double b23 = dx2 * a12 * a13 + dy2 * a22 * a23 + dzf2 * a32 * a33;
     const double bb = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
     const double e = (bb < 1.e-8) ? 0.0 : g.c_vreman * sqrt(bb / aa);
     ek_store<PEER>(g, i, j, k, e, ekm, ekh, halo, pc);
