@@ -321,3 +321,16 @@ def test_scalars_mixed_sign_flow(shape, flags):
         o2.substep(dt); g2.substep(dt)
         for n4 in range(2):
             assert relerr(g2.pull("sv0", n4)[:, :, hc:-hc], o2.sv0[:, :, hc:-hc, n4]) < 1e-11, (s, n4)
+
+
+def test_reference_restart_block_divergence_on_gpu():
+    """udgpu_divergence on a block of the reference binary's own restart output (examples/102): round-off, as the
+    reference's projection left it."""
+    import udales_b200 as U
+    from test_oracle import load_restart_block
+    n, f, dglob = load_restart_block(None)
+    g = U.UdalesGPU(n, n, n, xlen=float(n), ylen=float(n), zf=np.arange(n) + 0.5)
+    for nm, a in f.items():
+        g.push(nm, a)
+    dmax, dtot, drms = g.divergence()
+    assert dmax < 2e-15 and drms < 5e-16

@@ -128,3 +128,29 @@ def test_lcg_is_decomposition_independent_recipe():
     st = (43 + lin) % 134456
     st = (st * 8121 + 28411) % 134456
     assert o.u0[i, j, k] == pytest.approx((st / 134456 - 0.5) * 2.0, abs=0)
+
+
+def load_restart_block(target):
+    """fill u0, v0, w0 of an Oracle / UdalesGPU-shaped (n+2)^3 array set from the reference restart block"""
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_restart102_block.npz"))
+    n = int(d["n"])
+    out = {}
+    for nm in ("u0", "v0", "w0"):
+        a = np.zeros((n + 2, n + 2, n + 2), order="F")
+        a[:, :, 1:] = d[nm]            # stored levels kb .. kb+n; level kb-1 stays 0
+        out[nm] = a
+    return n, out, float(d["divmax_global"])
+
+
+def test_reference_restart_block_is_divergence_free():
+    """The only output of the real reference binary in its repository (examples/102 restart files, written after the
+    projection by src/modsave.f90:85-99): chkdiv (src/modchecksim.f90:182) on a 24^3 block of it, through the oracle."""
+    from oracle.oracle import Oracle
+    n, f, dglob = load_restart_block(None)
+    o = Oracle(n, n, n, xlen=float(n), ylen=float(n), zf=np.arange(n) + 0.5)       # dx = dy = dz = 1 m as in examples/102
+    for nm, a in f.items():
+        getattr(o, nm)[...] = a
+    divmax, divtot, divrms = o.chkdiv()
+    assert np.abs(f["u0"]).max() > 1.0            # a real turbulent field, not zeros
+    assert divmax < 2e-15 and divmax <= dglob * 1.0000001
