@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(LANES *R2, (R1 <= 16 ? 2 : 1)) k_rfft_fast(con
   const int b0 = blockIdx.x * LANES;
   const int nb = min(LANES, di.nb1 - b0);
   const bool act = lane < nb;
-  const long long ibase = (long long)blockIdx.y * di.s2 + (long long)b0 * di.s1;
-  const long long obase = (long long)blockIdx.y * dd.s2 + (long long)b0 * dd.s1;
+  const int kb = di.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const long long ibase = (long long)kb * di.s2 + (long long)b0 * di.s1;
+  const long long obase = (long long)kb * dd.s2 + (long long)b0 * dd.s1;
   // element addresses: (line offset within the CTA's batch, point index)
   auto IN = [&](long long loff, int pt) -> const double * {
     return IBLK ? ib.base[pt >> ib.shift] + ibase + loff + (long long)(pt & ib.mask) * di.sp : in + ibase + loff + (long long)pt * di.sp;

@@ -19,6 +19,9 @@ struct LineDesc {
   long long s1;   // element stride of the inner batch index (mapped to lanes)
   long long s2;   // element stride of the outer batch index (mapped to blockIdx.y)
   int nb1, nb2;   // batch extents
+  int rev;        // 1: walk the outer batch index downwards (blockIdx.y = 0 handles nb2-1).  Consecutive passes over the
+                  // same array alternate direction so that a pass starts on the part its predecessor wrote last and
+                  // that is still in L2 (the array is larger than L2: same-direction streaming would miss everywhere)
 };
 
 struct FftPlan {

@@ -102,6 +102,7 @@ struct udgpu {
   FftPlan px, py;
   bool fast_x = false, fast_y = false, fast_z = false;
   int zu = 8, fft_lanes = 32;
+  int fft_rev = 1;            // alternate the k direction of consecutive FFT passes for L2 reuse (UDGPU_FFT_REV=0: off)
   bool xz_fused = false;      // x-FFT + z-solve + inverse x-FFT as one pass (poisson_xz.cuh)
   int xz_minb = 1;            // ... compiled for 1 or 2 resident CTAs per SM (UDGPU_XZ_MINB)
   double *d_zt = nullptr, *d_xd = nullptr, *d_yd = nullptr;
@@ -1039,6 +1040,7 @@ static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, cons
   if ((h->cfg.flags & UDGPU_F_V1_KERNELS) && h->P == 1) return UDGPU_OK;
   { const char *e = getenv("UDGPU_ZU"); if (e && atoi(e) == 16) h->zu = 16; }
   { const char *e = getenv("UDGPU_FFT_LANES"); if (e && atoi(e) == 16) h->fft_lanes = 16; }
+  { const char *e = getenv("UDGPU_FFT_REV"); if (e) h->fft_rev = atoi(e) != 0; }
   h->fast_x = fast_len(g.itot);
   h->fast_y = fast_len(g.jtot);
   if (h->P > 1 && !(h->fast_x && h->fast_y))
@@ -1073,15 +1075,18 @@ static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *
   const Geo &g = h->g;
   LineDesc di, dd;
   const long long pr = g.imax, pp = (long long)g.imax * g.jmax;
+  // alternate the level direction between consecutive passes (x passes walk k downwards, y passes upwards): fillps and
+  // the previous pass leave their last-written levels in L2, this pass starts there (results are identical bits)
+  const int rev = (h->fft_rev && xdir) ? 1 : 0;
   if (xdir) {
-    di = {1, pr, pp, g.jmax, g.ktot};
+    di = {1, pr, pp, g.jmax, g.ktot, rev};
     dd = di;
     if (out_halo) { dd.s1 = g.pi; dd.s2 = g.pk; }
     if (h->fast_x) return rfft_fast<true>(h, g.itot, inverse, in, di, out, dd, h->px);
     const size_t smem = (size_t)h->px.h * FFT_BP * sizeof(double2);
     k_rfft<true><<<dim3((g.jmax + FFT_B - 1) / FFT_B, g.ktot), dim3(FFT_B, FFT_TY), smem, h->st>>>(h->px, inverse, in, di, out, dd);
   } else {
-    di = {pr, 1, pp, g.imax, g.ktot};
+    di = {pr, 1, pp, g.imax, g.ktot, rev};
     dd = di;
     if (out_halo) { dd.sp = g.pi; dd.s2 = g.pk; }
     if (h->fast_y) return rfft_fast<false>(h, g.jtot, inverse, in, di, out, dd, h->py);
