@@ -130,11 +130,12 @@ __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict
 template <int KC, bool PEER = false>
 __global__ void __launch_bounds__(256, 4) k_closure_vreman_march(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
                                                               const double *__restrict__ w0, double *__restrict__ ekm,
-                                                              double *__restrict__ ekh, int halo, PeerCols pc) {
+                                                              double *__restrict__ ekh, int halo, PeerCols pc, int rev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i > g.imax || j > g.jmax) return;
-  const int k0 = blockIdx.z * KC + 1, k1 = min(k0 + KC, g.ktot + 1);
+  const int cz = rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;   // rev: top chunk first (L2 reuse)
+  const int k0 = cz * KC + 1, k1 = min(k0 + KC, g.ktot + 1);
   const long long sj = g.pi, sk = g.pk;
   const long long c0 = offF(g, i, j, k0 - 1);
   const double *pu = u0 + c0, *pv = v0 + c0, *pw = w0 + c0;
@@ -384,10 +385,10 @@ template <bool XWRAP, bool YWRAP>
 __global__ void __launch_bounds__(256) k_fillps(Geo g, double rk3coefi, const double *__restrict__ up, const double *__restrict__ vp,
                                                 const double *__restrict__ wp, const double *__restrict__ um,
                                                 const double *__restrict__ vm, const double *__restrict__ wm,
-                                                double *__restrict__ rhs) {
+                                                double *__restrict__ rhs, int rev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  const int k = blockIdx.z + 1;
+  const int k = rev ? g.ktot - (int)blockIdx.z : (int)blockIdx.z + 1;   // rev: top level first (L2 reuse, see LineDesc::rev)
   if (i > g.imax || j > g.jmax) return;
   const int ip = (XWRAP && i == g.imax) ? 1 : i + 1;
   const int jp = (YWRAP && j == g.jmax) ? 1 : j + 1;

@@ -102,7 +102,7 @@ struct udgpu {
   FftPlan px, py;
   bool fast_x = false, fast_y = false, fast_z = false;
   int zu = 8, fft_lanes = 32;
-  int fft_rev = 1;            // alternate the k direction of consecutive FFT passes for L2 reuse (UDGPU_FFT_REV=0: off)
+  int fft_rev = 1;            // consecutive kernels alternate their level direction for L2 reuse (UDGPU_FFT_REV=0: all upwards)
   bool xz_fused = false;      // x-FFT + z-solve + inverse x-FFT as one pass (poisson_xz.cuh)
   int xz_minb = 1;            // ... compiled for 1 or 2 resident CTAs per SM (UDGPU_XZ_MINB)
   double *d_zt = nullptr, *d_xd = nullptr, *d_yd = nullptr;
@@ -758,8 +758,8 @@ extern "C" int udgpu_closure(udgpu_t *h) {
   else if (h->cfg.lvreman && h->cl_march > 0) {
     constexpr int KC = 16;
     const dim3 gm(gr.x, gr.y, (g.ktot + KC - 1) / KC);
-    if (pc.L[0]) k_closure_vreman_march<KC, true><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
-    else k_closure_vreman_march<KC, false><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
+    if (pc.L[0]) k_closure_vreman_march<KC, true><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc, h->fft_rev);
+    else k_closure_vreman_march<KC, false><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc, h->fft_rev);
   }
   else if (h->cfg.lvreman) { if (pc.L[0]) k_closure<1, true><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); else k_closure<1, false><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); }
   else { if (pc.L[0]) k_closure<0, true><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); else k_closure<0, false><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); }
@@ -1075,9 +1075,11 @@ static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *
   const Geo &g = h->g;
   LineDesc di, dd;
   const long long pr = g.imax, pp = (long long)g.imax * g.jmax;
-  // alternate the level direction between consecutive passes (x passes walk k downwards, y passes upwards): fillps and
-  // the previous pass leave their last-written levels in L2, this pass starts there (results are identical bits)
-  const int rev = (h->fft_rev && xdir) ? 1 : 0;
+  // Every kernel of the substep starts on the levels its producer wrote last, which are still in L2 (each array is
+  // larger than L2, so same-direction streaming would miss everywhere): integrate walks k upwards, closure downwards,
+  // the momentum kernel upwards, fillps downwards, then x-FFT up, y-FFT down, z-solve (up, down), y-FFT^-1 up,
+  // x-FFT^-1 down, integrate up.  Pure traversal order: results are identical bits.
+  const int rev = (h->fft_rev && (xdir ? inverse != 0 : inverse == 0)) ? 1 : 0;
   if (xdir) {
     di = {1, pr, pp, g.jmax, g.ktot, rev};
     dd = di;
@@ -1338,10 +1340,10 @@ extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
     // ibmnorm zeroed um at solid points after the last halos(): pup(ie+1) needs the neighbour's current um(1) too
     if (h->m_halo_stale) RET(halo_x_exchange(h, {h->f[UDGPU_UM]}, g.ktot + 2 * g.kh));
     k_fillps<false, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
-                                                          h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS]);
+                                                          h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS], 0);
   } else
   k_fillps<true, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
-                                                       h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS]);
+                                                       h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS], h->fft_rev);
   KCHECK();
   h->launches++;
   return UDGPU_OK;
