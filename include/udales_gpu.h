@@ -155,6 +155,14 @@ int udgpu_divergence(udgpu_t *h, double *divmax, double *divtot, double *divrms)
 int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax, int ladaptive,
                   double courant, double diffnr);
 
+/* ---- resident-channel glue (next tier) ------------------------------------------------------ */
+/* src/modforces.f90:46 forces, neutral branch: up -= dpdxl(k), vp -= dpdyl(k), wp(kb) = 0.  udgpu_set_forcing copies the
+ * two profiles (dpdxl(kb:ke+kh), dpdyl(kb:ke+kh): ktot+1 values each, src/modfields.f90) to the device; udgpu_forces is
+ * the call of src/program.f90:158 (applied inside the fused tderive+integrate kernel unless something looks at the
+ * tendencies first).  udgpu_substep calls it after subgrid once a forcing has been set. */
+int udgpu_set_forcing(udgpu_t *h, const double *dpdxl, const double *dpdyl);
+int udgpu_forces(udgpu_t *h);
+
 /* ---- immersed-boundary masking (next tier; src/modibm.f90) ------------------------------- */
 /* point lists of modibm: kind 0-3 = solid_info_{u,v,w,c}%solpts_loc, 4-7 = bound_info_{u,v,w,c}%bndpts_loc; n points,
  * local 1-based (i,j,k).  layout 0: point-major triples [i0,j0,k0,i1,...]; layout 1: the Fortran array (n,3) as it

@@ -391,7 +391,38 @@ def case_ibm(tag, shape=(12, 10, 8), nsv=1):
           f"boundary pts {[lists['bound_' + n].shape[0] for n in 'uvwc']}")
 
 
+def case_forces(tag, shape=(8, 6, 7)):
+    """forces (src/modforces.f90:46-133, neutral branch) executed from the reference text."""
+    I, J, K = shape
+    zf = stretched_zf(K, 0.5 * K * 1.1, 1.07)
+    w = World(I, J, K, xlen=0.55 * I, ylen=0.45 * J, zf=zf)
+    it = make_interp(w)
+    it.load(os.path.join(SRC, "modforces.f90"), only=["forces"])
+    g = w.g
+    rng = np.random.default_rng(5)
+    g["dpdxl"] = FArray(-1e-3 * (1.0 + rng.random(K + 1)), [1])
+    g["dpdyl"] = FArray(2e-4 * rng.standard_normal(K + 1), [1])
+    g["thlpcar"] = fa([(1, K + 1)], 0.0)
+    g["thv0h"] = fa([(0, I + 1), (0, J + 1), (0, K + 1)], 300.0); g["thvh"] = fa([(1, K + 1)], 300.0)
+    g["lbuoyancy"] = False
+    for nm in ("up", "vp", "wp"):
+        g[nm].a[...] = rng.standard_normal(g[nm].a.shape)
+    g["thlp"].a[...] = 0.0
+    out = {"shape": np.array(shape), "zf": zf, "xlen": 0.55 * I, "ylen": 0.45 * J,
+           "dpdxl": np.array(g["dpdxl"].a), "dpdyl": np.array(g["dpdyl"].a)}
+    for k_, v_ in snapshot(w, ["up", "vp", "wp"]).items():
+        out["in_" + k_] = v_
+    it.call("forces")
+    for k_, v_ in snapshot(w, ["up", "vp", "wp"]).items():
+        out["out_" + k_] = v_
+    np.savez_compressed(os.path.join(OUT, f"ref_{tag}.npz"), **out)
+    print(f"wrote ref_{tag}.npz")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "forces":
+        case_forces("forces")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ibm":
         case_ibm("ibm")
         sys.exit(0)
@@ -401,3 +432,4 @@ if __name__ == "__main__":
     case_substeps("kappa2", shape=(8, 8, 6), nsv=2, iadv_sv=7)
     case_substeps("cd2scalar", shape=(6, 8, 5), nsv=1, iadv_sv=2)
     case_ibm("ibm")
+    case_forces("forces")

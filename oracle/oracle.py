@@ -61,6 +61,8 @@ def lib():
         L.orc_substep.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_double, C.c_int,
                                   C.c_double, C.c_double]
         L.orc_rfft_packed.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+        L.orc_set_forcing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_forces.argtypes = [C.c_void_p]
         L.orc_ibm_set_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_ibm_build_masks.argtypes = [C.c_void_p]
         L.orc_ibm_mask.restype = C.POINTER(C.c_double)
@@ -172,6 +174,14 @@ class Oracle:
         d, r = C.c_double(self.dt), C.c_int(self.rk3step)
         self.L.orc_substep(self.h, C.byref(d), C.byref(r), dtmax, int(ladaptive), courant, diffnr)
         self.dt, self.rk3step = d.value, r.value
+
+    # forces (src/modforces.f90:46) -------------------------------------------------
+    def set_forcing(self, dpdxl, dpdyl):
+        a = np.ascontiguousarray(dpdxl, dtype=np.float64); b = np.ascontiguousarray(dpdyl, dtype=np.float64)
+        assert a.size == self.ktot + 1 and b.size == self.ktot + 1
+        self.L.orc_set_forcing(self.h, a.ctypes.data, b.ctypes.data)
+
+    def forces(self): self.L.orc_forces(self.h)
 
     # immersed boundary masking (src/modibm.f90) ---------------------------------
     IBM_KINDS = ("solid_u", "solid_v", "solid_w", "solid_c", "bound_u", "bound_v", "bound_w", "bound_c")

@@ -45,6 +45,9 @@ struct orc {
   int *ibm_pts[8];            /* 3*n, point-major: (i,j,k) of point n at [3n..3n+2]    */
   double *mask[4];            /* mask_u, mask_v, mask_w, mask_c  (momentum-halo shape)  */
   int libm;
+  /* forces (src/modforces.f90:46): large-scale pressure gradient per level, kb:ke+kh */
+  double *dpdxl, *dpdyl;
+  int has_forcing;
 };
 
 #define MOFF 2
@@ -1338,10 +1341,36 @@ void orc_ibm_diffcorr(orc_t *o) {
   }
 }
 
+/* forces, neutral branch: src/modforces.f90:88-125 */
+void orc_set_forcing(orc_t *o, const double *dpdxl, const double *dpdyl) {
+  const int n = o->ktot + o->kh;
+  if (!o->dpdxl) { o->dpdxl = zalloc(n); o->dpdyl = zalloc(n); }
+  memcpy(o->dpdxl, dpdxl, n * sizeof(double));
+  memcpy(o->dpdyl, dpdyl, n * sizeof(double));
+  o->has_forcing = 1;
+}
+void orc_forces(orc_t *o) {
+  if (!o->has_forcing) return;
+  const int I = o->itot, J = o->jtot, K = o->ktot;
+  for (int k = 2; k <= K; k++)
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++) {
+        T(o->up, i, j, k) = T(o->up, i, j, k) - o->dpdxl[k - 1];
+        T(o->vp, i, j, k) = T(o->vp, i, j, k) - o->dpdyl[k - 1];
+      }
+  for (int j = 1; j <= J; j++)
+    for (int i = 1; i <= I; i++) {
+      T(o->up, i, j, 1) = T(o->up, i, j, 1) - o->dpdxl[0];
+      T(o->vp, i, j, 1) = T(o->vp, i, j, 1) - o->dpdyl[0];
+      T(o->wp, i, j, 1) = 0.0;
+    }
+}
+
 void orc_substep(orc_t *o, double *dt, int *rk3step, double dtmax, int ladaptive, double courant, double diffnr) {
   orc_tstep_update(o, dt, courant, diffnr, dtmax, ladaptive, rk3step, NULL, NULL);
   orc_advection(o);
   orc_subgrid(o);
+  orc_forces(o);         /* src/program.f90:158 */
   orc_ibm_diffcorr(o);   /* the in-scope part of ibmwallfun, src/program.f90:166 */
   orc_ibmnorm(o);        /* src/program.f90:171 */
   orc_poisson(o, *dt, *rk3step);

@@ -70,6 +70,10 @@ void orc_substep(orc_t *o, double *dt, int *rk3step, double dtmax, int ladaptive
 /* stand-alone real FFT helpers (FFTW r2c/c2r conventions + the reference's packing) */
 void orc_rfft_packed(int n, double *line, int inverse);  /* modpois.f90:478-490 / 669-679 on one line */
 
+/* forces (src/modforces.f90:46, neutral branch): dpdxl, dpdyl = ktot+1 values (kb:ke+kh) */
+void orc_set_forcing(orc_t *o, const double *dpdxl, const double *dpdyl);
+void orc_forces(orc_t *o);
+
 /* immersed boundary masking: kind 0-3 = solid_u,v,w,c ; 4-7 = fluid-boundary points u,v,w,c;
  * ijk = n local 1-based (i,j,k) triples, point-major */
 void orc_ibm_set_points(orc_t *o, int kind, int n, const int *ijk);

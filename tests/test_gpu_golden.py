@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith(("ref_ibm.npz", "ref_restart102_block.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith(("ref_ibm.npz", "ref_restart102_block.npz", "ref_forces.npz")))
 GOLD_IBM = os.path.join(os.path.dirname(__file__), "golden", "ref_ibm.npz")
 
 
@@ -85,3 +85,17 @@ def test_cuda_ibm_matches_reference_source():
     for n4 in range(nsv):
         assert rel(g.pull("svm", n4), d["norm_svm"][..., n4]) < 1e-13
         assert rel(g.pull("svp", n4), d["norm_svp"][..., n4]) < 1e-13
+
+
+def test_cuda_forces_matches_reference_source():
+    """udgpu_forces against the vectors produced by executing src/modforces.f90 (eager application through a pull)."""
+    import udales_b200 as U
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_forces.npz"))
+    I, J, K = (int(x) for x in d["shape"])
+    g = U.UdalesGPU(I, J, K, xlen=float(d["xlen"]), ylen=float(d["ylen"]), zf=d["zf"])
+    for n in ("up", "vp", "wp"):
+        g.push(n, d["in_" + n])
+    g.set_forcing(d["dpdxl"], d["dpdyl"])
+    g.forces()
+    for n in ("up", "vp", "wp"):
+        assert np.array_equal(g.pull(n), d["out_" + n]), n      # one subtraction per cell: identical bits

@@ -334,3 +334,31 @@ def test_reference_restart_block_divergence_on_gpu():
         g.push(nm, a)
     dmax, dtot, drms = g.divergence()
     assert dmax < 5e-15 and drms < 1e-15
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 24, 20)])
+@pytest.mark.parametrize("flags", [0, F_NO_LAZY, F_NO_HALO])
+@pytest.mark.parametrize("ibm", [False, True])
+def test_forces_in_the_substep(shape, flags, ibm):
+    """forces (src/modforces.f90:46, src/program.f90:158) inside the resident substep: applied lazily inside the fused
+    tderive+integrate kernel (flags 0), eagerly (NO_LAZY / with IBM masking, where ibmnorm must see the forced tendencies)."""
+    o, g = make_pair(*shape, gpu_flags=flags)
+    K = shape[2]
+    rng = np.random.default_rng(2)
+    fx, fy = -2e-3 * (1 + rng.random(K + 1)), 5e-4 * rng.standard_normal(K + 1)
+    o.set_forcing(fx, fy); g.set_forcing(fx, fy)
+    if ibm:
+        lists = ibm_lists(*shape, IBM_BOXES[shape])
+        o.ibm_set(lists); g.ibm_set(lists)
+    dt = 0.02
+    o.dt = g.dt = dt
+    for s in range(4):
+        o.substep(dt); g.substep(dt)
+        for n in ("u0", "v0", "w0", "um"):
+            assert relerr(g.pull(n), getattr(o, n)) < 1e-11, (s, n)
+        assert g.divergence()[2] < 1e-12
+    # observable in between: pull after forces() shows the forced tendencies
+    o.advection(); o.subgrid(); o.forces()
+    g.advection(); g.subgrid(); g.forces()
+    for n in ("up", "vp", "wp"):
+        assert relerr(tend_interior(g.pull(n)), tend_interior(getattr(o, n))) < TOL_STENCIL, n

@@ -11,7 +11,7 @@ import pytest
 
 from oracle.oracle import Oracle
 
-GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith(("ref_ibm.npz", "ref_restart102_block.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith(("ref_ibm.npz", "ref_restart102_block.npz", "ref_forces.npz")))
 GOLD_IBM = os.path.join(os.path.dirname(__file__), "golden", "ref_ibm.npz")
 TOL = 2e-13      # same arithmetic order, no FMA on either side; FFT library and pow() rounding differ
 
@@ -120,3 +120,17 @@ def test_oracle_ibm_matches_reference_source():
     assert np.array_equal(o.svm, d["norm_svm"][..., :nsv]) and np.array_equal(o.svp, d["norm_svp"][..., :nsv])
     # something actually happened
     assert np.abs(d["corr_up"] - d["in_up"]).max() > 1e-6 and np.abs(d["norm_um"] - d["in_um"]).max() > 1e-3
+
+
+def test_oracle_forces_matches_reference_source():
+    """forces, neutral branch (src/modforces.f90:88-125), executed from the reference text."""
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_forces.npz"))
+    I, J, K = (int(x) for x in d["shape"])
+    o = Oracle(I, J, K, xlen=float(d["xlen"]), ylen=float(d["ylen"]), zf=d["zf"])
+    for n in ("up", "vp", "wp"):
+        getattr(o, n)[...] = d["in_" + n]
+    o.set_forcing(d["dpdxl"], d["dpdyl"])
+    o.forces()
+    for n in ("up", "vp", "wp"):
+        assert np.array_equal(getattr(o, n), d["out_" + n]), n
+    assert np.abs(d["out_up"] - d["in_up"]).max() > 1e-4

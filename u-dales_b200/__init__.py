@@ -31,7 +31,7 @@ EXPORTS = [
     "udgpu_tstep_update", "udgpu_advection", "udgpu_subgrid", "udgpu_closure", "udgpu_poisson",
     "udgpu_poisson_solve", "udgpu_poisson_solve_resident", "udgpu_fillps", "udgpu_tderive",
     "udgpu_tstep_integrate", "udgpu_halos", "udgpu_boundary", "udgpu_divergence", "udgpu_substep",
-    "udgpu_rk3_step_host", "udgpu_ibm_set_points", "udgpu_ibm_commit", "udgpu_ibm_pull_mask", "udgpu_ibmnorm", "udgpu_ibm_diffcorr",
+    "udgpu_rk3_step_host", "udgpu_set_forcing", "udgpu_forces", "udgpu_ibm_set_points", "udgpu_ibm_commit", "udgpu_ibm_pull_mask", "udgpu_ibmnorm", "udgpu_ibm_diffcorr",
     "udgpu_profile_enable", "udgpu_profile_get", "udgpu_profile_reset", "udgpu_launch_count", "udgpu_stream",
 ]
 
@@ -105,6 +105,8 @@ def lib():
                                     C.c_double, C.c_double]
         L.udgpu_rk3_step_host.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.POINTER(C.c_double), C.c_double, C.c_int,
                                                                               C.c_double, C.c_double]
+        L.udgpu_set_forcing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.udgpu_forces.argtypes = [C.c_void_p]
         L.udgpu_ibm_set_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.udgpu_ibm_commit.argtypes = [C.c_void_p]
         L.udgpu_ibm_pull_mask.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -294,6 +296,15 @@ class UdalesGPU:
         d = C.c_double(self.dt)
         self._chk(self.L.udgpu_rk3_step_host(self.h, *ptrs, C.byref(d), dtmax, int(ladaptive), courant, diffnr))
         self.dt, self.rk3step = d.value, 3
+
+    # forces (src/modforces.f90:46) -------------------------------------------------------
+    def set_forcing(self, dpdxl, dpdyl):
+        """large-scale pressure gradient profiles dpdxl(kb:ke+kh), dpdyl(kb:ke+kh): ktot+1 values each"""
+        a = np.ascontiguousarray(dpdxl, dtype=np.float64); b = np.ascontiguousarray(dpdyl, dtype=np.float64)
+        assert a.size == self.ktot + 1 and b.size == self.ktot + 1
+        self._chk(self.L.udgpu_set_forcing(self.h, a.ctypes.data, b.ctypes.data))
+
+    def forces(self): self._chk(self.L.udgpu_forces(self.h))
 
     # immersed boundary masking (src/modibm.f90) ----------------------------------------
     IBM_KINDS = ("solid_u", "solid_v", "solid_w", "solid_c", "bound_u", "bound_v", "bound_w", "bound_c")

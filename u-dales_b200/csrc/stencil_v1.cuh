@@ -401,6 +401,21 @@ __global__ void __launch_bounds__(256) k_fillps(Geo g, double rk3coefi, const do
   rhs[offR(g, i, j, k)] = (pu1 - pu0) * g.dxi + (pv1 - pv0) * g.dyi + (pw1 - pw0) * g.dzfi[k];
 }
 
+// forces, neutral branch (src/modforces.f90:88-125): up -= dpdxl(k), vp -= dpdyl(k), wp(kb) = 0.  Only launched when
+// somebody looks at the tendencies between forces() and tstep_integrate(); otherwise the subtraction is done inside
+// the fused tderive+integrate kernel (fx, fy tables; zero tables when no forcing is pending).
+__global__ void __launch_bounds__(256) k_forces(Geo g, const double *__restrict__ fx, const double *__restrict__ fy,
+                                                double *__restrict__ up, double *__restrict__ vp, double *__restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long t = offT(g, i, j, k);
+  up[t] = up[t] - fx[k];
+  vp[t] = vp[t] - fy[k];
+  if (k == 1) wp[t] = 0.0;
+}
+
 // tderive: src/modpois.f90:1046-1056 (velocity tendencies) on a halo'd p.
 __global__ void __launch_bounds__(256) k_tderive(Geo g, const double *__restrict__ p, double *__restrict__ up,
                                                  double *__restrict__ vp, double *__restrict__ wp) {
@@ -464,7 +479,8 @@ __global__ void __launch_bounds__(256) k_tderive_integrate_halo(Geo g, double rk
                                                                 const double *__restrict__ wp, double *__restrict__ um,
                                                                 double *__restrict__ vm, double *__restrict__ wm,
                                                                 double *__restrict__ u0, double *__restrict__ v0,
-                                                                double *__restrict__ w0, double *__restrict__ pres0, PeerCols pc) {
+                                                                double *__restrict__ w0, double *__restrict__ pres0, PeerCols pc,
+                                                                const double *__restrict__ fx, const double *__restrict__ fy, int fz) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   const int k = blockIdx.z + 1;
@@ -473,9 +489,11 @@ __global__ void __launch_bounds__(256) k_tderive_integrate_halo(Geo g, double rk
   const double pc0 = p[c];
   const long long cim = (g.wrapx && i == 1) ? c + (g.imax - 1) : c - 1;
   const long long cjm = (j == 1) ? c + (long long)g.pi * (g.jmax - 1) : c - g.pi;
-  const double ru = up[t] - (pc0 - p[cim]) * g.dxi;
-  const double rv = vp[t] - (pc0 - p[cjm]) * g.dyi;
-  double rw = wp[t];
+  // a pending forces() (src/modforces.f90:88-125) is applied here: fx, fy = dpdxl, dpdyl (zero tables otherwise, x - 0 = x),
+  // fz = 1: wp(kb) = 0
+  const double ru = (up[t] - __ldg(fx + k)) - (pc0 - p[cim]) * g.dxi;
+  const double rv = (vp[t] - __ldg(fy + k)) - (pc0 - p[cjm]) * g.dyi;
+  double rw = (fz && k == 1) ? 0.0 : wp[t];
   if (k >= 2) rw = rw - (pc0 - p[c - g.pk]) * g.dzhi[k];
   const double a = um[c] + rk3coef * ru;
   const double b = vm[c] + rk3coef * rv;

@@ -161,6 +161,9 @@ struct udgpu {
   bool bc_done = false;        // ... and what boundary() would
   bool halo_x_pending = false; // x-split: the slab exchange of the new fields is still to run (in halos())
   bool p_halo_valid = true;    // p's lateral halo is the wrap of its interior (bcp); restored lazily on pull
+  // forces (src/modforces.f90:46): per-level profiles, index k = 0 .. ktot+1 (k = 0 unused); zero table = no forcing
+  double *d_fx = nullptr, *d_fy = nullptr, *d_fzero = nullptr;
+  bool has_forcing = false, forces_pending = false;
   // immersed boundary (src/modibm.f90): point lists, masks
   int ibm_n[8] = {};
   int *ibm_pts[8] = {};
@@ -174,7 +177,7 @@ struct udgpu {
 };
 
 // ------------------------------------------------------------------------------------------
-static int flush_pending(udgpu *h);
+static int flush_pending(udgpu *h, bool keep_forces = false);
 static PeerCols peer_cols(udgpu *h, std::initializer_list<int> fields);
 static int settle_for_access(udgpu *h, int field);
 static int setup_p2p(udgpu *h, size_t nR);
@@ -497,6 +500,7 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
   }
   RET(dev_alloc(h, (void **)&h->d_scr, nR * sizeof(double)));
   RET(dev_alloc(h, (void **)&h->d_red, 16 * sizeof(double)));
+  for (double **t : {&h->d_fx, &h->d_fy, &h->d_fzero}) RET(dev_alloc(h, (void **)t, (K + 2) * sizeof(double)));
   CU(cudaMallocHost((void **)&h->h_red, 16 * sizeof(double)));
 
   // ---- Poisson coefficients: src/modpois.f90:98-176 (periodic x,y; BCzp = 1; rhobf = rhobh = 1) ----
@@ -890,7 +894,18 @@ static int launch_scalars(udgpu *h, bool acc) {
 
 // run a deferred advection() on its own (something needs the tendencies before subgrid())
 static int tderive_now(udgpu *h);
-static int flush_pending(udgpu *h) {
+static int forces_now(udgpu *h) {
+  h->forces_pending = false;
+  const Geo &g = h->g;
+  RET(materialize_zero_tend(h));
+  k_forces<<<grid3(g, B3), B3, 0, h->st>>>(g, h->d_fx, h->d_fy, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP]);
+  KCHECK();
+  h->launches++;
+  h->tend_zero = false;
+  return UDGPU_OK;
+}
+static int flush_pending(udgpu *h, bool keep_forces) {
+  if (h->forces_pending && !keep_forces) RET(forces_now(h));   // adv_pending cannot be set here: forces() flushed it
   if (h->tder_pending) { h->tder_pending = false; RET(tderive_now(h)); }
   if (!h->adv_pending) return UDGPU_OK;
   h->adv_pending = false;
@@ -1328,7 +1343,9 @@ extern "C" int udgpu_poisson_solve(udgpu_t *h, const double *rhs, double *p) {
 
 extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
-  RET(flush_pending(h));
+  // a pending forces() stays pending: dpdxl(k), dpdyl(k) are uniform in x, y and drop out of the divergence
+  // (src/modpois.f90:968-970), and fillps already takes pwp(kb) = 0 (src/modboundary.f90:1227-1232)
+  RET(flush_pending(h, true));
   const Geo &g = h->g;
   RET(materialize_zero_tend(h));
   ProfScope ps(h, PROF_FILLPS);
@@ -1415,7 +1432,10 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
       if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));
       const PeerCols pc = peer_cols(h, {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM});
 #define TI_(S3, XS) k_tderive_integrate_halo<S3, XS><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM], \
-                                                                       f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], pc)
+                                                                       f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], pc, \
+                                                                       fp ? h->d_fx : h->d_fzero, fp ? h->d_fy : h->d_fzero, fp ? 1 : 0)
+      const bool fp = h->forces_pending;
+      h->forces_pending = false;
       if (rk3step == 3) { if (pc.L[0]) TI_(true, 2); else if (h->P > 1) TI_(true, 1); else TI_(true, 0); }
       else { if (pc.L[0]) TI_(false, 2); else if (h->P > 1) TI_(false, 1); else TI_(false, 0); }
 #undef TI_
@@ -1425,6 +1445,7 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
       h->halo_x_pending = h->P > 1;
       if (rk3step == 3) h->m_changed = true;
     } else {
+      if (h->forces_pending) RET(forces_now(h));
       RET(wrap_xy(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
       h->p_halo_valid = true;
       if (rk3step == 3)
@@ -1570,6 +1591,7 @@ extern "C" int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax,
   RET(udgpu_tstep_update(h, dt, courant, diffnr, dtmax, ladaptive, rk3step, nullptr, nullptr));
   RET(udgpu_advection(h));
   RET(udgpu_subgrid(h));
+  if (h->has_forcing) RET(udgpu_forces(h));   // src/program.f90:158
   if (h->libm) {
     RET(udgpu_ibm_diffcorr(h));   // the resident part of ibmwallfun, src/program.f90:166
     RET(udgpu_ibmnorm(h));        // src/program.f90:171
@@ -1578,6 +1600,30 @@ extern "C" int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax,
   RET(udgpu_tstep_integrate(h, *dt, *rk3step));
   RET(udgpu_halos(h));
   RET(udgpu_boundary(h));
+  return UDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// forces (src/modforces.f90:46-133, neutral branch)
+extern "C" int udgpu_set_forcing(udgpu_t *h, const double *dpdxl, const double *dpdyl) {
+  if (!h || !dpdxl || !dpdyl) return set_err(UDGPU_EINVAL, "null argument");
+  RET(flush_pending(h));
+  const int K = h->g.ktot;
+  CU(cudaSetDevice(h->dev));
+  // table index = Fortran k (1 .. ktot+1); entry 0 unused
+  CU(cudaMemcpyAsync(h->d_fx + 1, dpdxl, (K + 1) * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_fy + 1, dpdyl, (K + 1) * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  h->has_forcing = true;
+  return UDGPU_OK;
+}
+extern "C" int udgpu_forces(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (!h->has_forcing) return UDGPU_OK;
+  RET(flush_pending(h));
+  // with IBM masking the order matters (ibmnorm zeroes the tendencies of solid points after forces, src/program.f90:158,171)
+  if (h->libm || (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION)) return forces_now(h);
+  h->forces_pending = true;
   return UDGPU_OK;
 }
 
