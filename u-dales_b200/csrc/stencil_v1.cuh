@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256) k_tderive_integrate(Geo g, double rk3coef
 // reference's own halos+boundary leave them in (the host tracks that; otherwise the plain kernel + wraps run).
 // XS: 0 = x unsplit (periodic images in x written here), 1 = x split over GPUs (halo columns of pres0 updated from the
 // exchanged p), 2 = split + the edge columns of the velocities stored straight into the neighbours (PeerCols)
-template <bool STEP3, int XS = 0>
+template <bool STEP3, int XS = 0, bool FORCE = false>
 __global__ void __launch_bounds__(256) k_tderive_integrate_halo(Geo g, double rk3coef, const double *__restrict__ p,
                                                                 const double *__restrict__ up, const double *__restrict__ vp,
                                                                 const double *__restrict__ wp, double *__restrict__ um,
@@ -489,11 +489,11 @@ __global__ void __launch_bounds__(256) k_tderive_integrate_halo(Geo g, double rk
   const double pc0 = p[c];
   const long long cim = (g.wrapx && i == 1) ? c + (g.imax - 1) : c - 1;
   const long long cjm = (j == 1) ? c + (long long)g.pi * (g.jmax - 1) : c - g.pi;
-  // a pending forces() (src/modforces.f90:88-125) is applied here: fx, fy = dpdxl, dpdyl (zero tables otherwise, x - 0 = x),
-  // fz = 1: wp(kb) = 0
-  const double ru = (up[t] - __ldg(fx + k)) - (pc0 - p[cim]) * g.dxi;
-  const double rv = (vp[t] - __ldg(fy + k)) - (pc0 - p[cjm]) * g.dyi;
-  double rw = (fz && k == 1) ? 0.0 : wp[t];
+  // FORCE: a pending forces() (src/modforces.f90:88-125) is applied here: up - dpdxl(k), vp - dpdyl(k), wp(kb) = 0.
+  // (A template switch, not zero tables: the two extra per-level loads cost 30 us on this bandwidth-bound kernel.)
+  const double ru = (FORCE ? up[t] - __ldg(fx + k) : up[t]) - (pc0 - p[cim]) * g.dxi;
+  const double rv = (FORCE ? vp[t] - __ldg(fy + k) : vp[t]) - (pc0 - p[cjm]) * g.dyi;
+  double rw = (FORCE && fz && k == 1) ? 0.0 : wp[t];
   if (k >= 2) rw = rw - (pc0 - p[c - g.pk]) * g.dzhi[k];
   const double a = um[c] + rk3coef * ru;
   const double b = vm[c] + rk3coef * rv;

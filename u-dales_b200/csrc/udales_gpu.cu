@@ -1431,13 +1431,15 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
       // one pass: bcp (periodic index / slab exchange of p), tderive, integrate, pres0 += p, halos, boundary
       if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));
       const PeerCols pc = peer_cols(h, {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM});
-#define TI_(S3, XS) k_tderive_integrate_halo<S3, XS><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM], \
+#define TI_(S3, XS, FO) k_tderive_integrate_halo<S3, XS, FO><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM], \
                                                                        f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], pc, \
-                                                                       fp ? h->d_fx : h->d_fzero, fp ? h->d_fy : h->d_fzero, fp ? 1 : 0)
+                                                                       h->d_fx, h->d_fy, 1)
+#define TI2_(S3, XS) do { if (fp) TI_(S3, XS, true); else TI_(S3, XS, false); } while (0)
       const bool fp = h->forces_pending;
       h->forces_pending = false;
-      if (rk3step == 3) { if (pc.L[0]) TI_(true, 2); else if (h->P > 1) TI_(true, 1); else TI_(true, 0); }
-      else { if (pc.L[0]) TI_(false, 2); else if (h->P > 1) TI_(false, 1); else TI_(false, 0); }
+      if (rk3step == 3) { if (pc.L[0]) TI2_(true, 2); else if (h->P > 1) TI2_(true, 1); else TI2_(true, 0); }
+      else { if (pc.L[0]) TI2_(false, 2); else if (h->P > 1) TI2_(false, 1); else TI2_(false, 0); }
+#undef TI2_
 #undef TI_
       KCHECK();
       h->launches++;
