@@ -21,7 +21,7 @@ module modgpu
   private
   public :: lgpu, gpu_init, gpu_exit, gpu_push_state, gpu_pull_state, gpu_push, gpu_pull, &
             gpu_tstep_update, gpu_advection, gpu_subgrid, gpu_poisson, gpu_tstep_integrate, &
-            gpu_halos, gpu_boundary, gpu_chkdiv, gpu_rk3_step_host, gpu_ibm_init, gpu_ibmnorm, gpu_ibm_diffcorr
+            gpu_halos, gpu_boundary, gpu_chkdiv, gpu_rk3_step_host, gpu_ibm_init, gpu_ibmnorm, gpu_ibm_diffcorr, gpu_forces
 
   logical :: lgpu = .false.            !< namelist RUN switch (the only new option)
   type(c_ptr) :: handle = c_null_ptr
@@ -134,6 +134,15 @@ module modgpu
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: h
       real(c_double), intent(out) :: divmax, divtot, divrms
+    end function
+    integer(c_int) function udgpu_set_forcing(h, dpdxl, dpdyl) bind(C, name="udgpu_set_forcing")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      real(c_double), intent(in) :: dpdxl(*), dpdyl(*)
+    end function
+    integer(c_int) function udgpu_forces(h) bind(C, name="udgpu_forces")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
     end function
     integer(c_int) function udgpu_ibm_set_points(h, kind, n, ijk, layout) bind(C, name="udgpu_ibm_set_points")
       import :: c_int, c_ptr
@@ -326,6 +335,18 @@ contains
     real(c_double), intent(out) :: divmax, divtot
     real(c_double) :: divrms
     call chk(udgpu_divergence(handle, divmax, divtot, divrms), 'divergence')
+  end subroutine
+  !> forces (src/modforces.f90:46, neutral branch) on the resident tendencies; dpdxl/dpdyl (kb:ke+kh) are uploaded on
+  !! every call (ktot+1 doubles each: negligible) so that fixuinf / time-dependent forcing on the host is picked up
+  subroutine gpu_forces
+    use modglobal, only: lbuoyancy
+    use modfields, only: dpdxl, dpdyl
+    if (lbuoyancy) then
+      write(0, *) 'gpu_forces: lbuoyancy is outside the GPU path'
+      stop 1
+    end if
+    call chk(udgpu_set_forcing(handle, dpdxl, dpdyl), 'set_forcing')
+    call chk(udgpu_forces(handle), 'forces')
   end subroutine
   !> hand modibm's local point lists to the device (call once after initibm, src/program.f90); the lists are the
   !! (n,3) integer arrays solid_info_*%solpts_loc / bound_info_*%bndpts_loc exactly as they lie in memory (layout 1)
