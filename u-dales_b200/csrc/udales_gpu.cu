@@ -163,6 +163,7 @@ struct udgpu {
   bool p_halo_valid = true;    // p's lateral halo is the wrap of its interior (bcp); restored lazily on pull
   // forces (src/modforces.f90:46): per-level profiles, index k = 0 .. ktot+1 (k = 0 unused); zero table = no forcing
   double *d_fx = nullptr, *d_fy = nullptr, *d_fzero = nullptr;
+  std::vector<double> fx_host, fy_host;   // what the device tables hold (udgpu_set_forcing is a no-op for unchanged profiles)
   bool has_forcing = false, forces_pending = false;
   // immersed boundary (src/modibm.f90): point lists, masks
   int ibm_n[8] = {};
@@ -1609,8 +1610,13 @@ extern "C" int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax,
 // forces (src/modforces.f90:46-133, neutral branch)
 extern "C" int udgpu_set_forcing(udgpu_t *h, const double *dpdxl, const double *dpdyl) {
   if (!h || !dpdxl || !dpdyl) return set_err(UDGPU_EINVAL, "null argument");
-  RET(flush_pending(h));
   const int K = h->g.ktot;
+  if (h->has_forcing && (int)h->fx_host.size() == K + 1 && !memcmp(h->fx_host.data(), dpdxl, (K + 1) * sizeof(double)) &&
+      !memcmp(h->fy_host.data(), dpdyl, (K + 1) * sizeof(double)))
+    return UDGPU_OK;   // unchanged since the last call: nothing to upload, no synchronisation
+  RET(flush_pending(h));
+  h->fx_host.assign(dpdxl, dpdxl + K + 1);
+  h->fy_host.assign(dpdyl, dpdyl + K + 1);
   CU(cudaSetDevice(h->dev));
   // table index = Fortran k (1 .. ktot+1); entry 0 unused
   CU(cudaMemcpyAsync(h->d_fx + 1, dpdxl, (K + 1) * sizeof(double), cudaMemcpyHostToDevice, h->st));
