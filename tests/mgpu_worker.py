@@ -29,17 +29,22 @@ def main():
 
     # 0: peer-store (NVLink P2P) fused transposes, halos packed into the neighbours' windows; 4: UDGPU_F_NCCL_TRANSPOSE
     # (NCCL send/recv for transposes and halos); "direct": producers store edge columns straight into the neighbours'
-    # halo columns (UDGPU_DIRECT_HALO=1); "chunks": the solve in two k-chunks on two streams (UDGPU_POISSON_CHUNKS=2)
+    # halo columns (UDGPU_DIRECT_HALO=1); "chunks": the solve in two k-chunks on two streams (UDGPU_POISSON_CHUNKS=2);
+    # "nbbarrier": halo exchanges rendezvous with the two ring neighbours only (UDGPU_HALO_NB_BARRIER=1)
     flags_list = [0, 4, "direct", "chunks"]
+    if os.environ.get("UDGPU_TEST_EXPERIMENTAL") == "1":      # written at the end of round 1, not yet run on a GPU box
+        flags_list.append("nbbarrier")
     shapes = [(64, 64, 32), (128, 64, 24)] if len(sys.argv) < 2 else [tuple(int(x) for x in sys.argv[1].split("x"))]
     worst = 0.0
     for shape, flags in [(s_, f_) for s_ in shapes for f_ in flags_list]:
         I, J, K = shape
-        os.environ.pop("UDGPU_DIRECT_HALO", None); os.environ.pop("UDGPU_POISSON_CHUNKS", None)
+        os.environ.pop("UDGPU_DIRECT_HALO", None); os.environ.pop("UDGPU_POISSON_CHUNKS", None); os.environ.pop("UDGPU_HALO_NB_BARRIER", None)
         if flags == "direct":
             os.environ["UDGPU_DIRECT_HALO"] = "1"; flags = 0
         elif flags == "chunks":
             os.environ["UDGPU_POISSON_CHUNKS"] = "2"; flags = 0
+        elif flags == "nbbarrier":
+            os.environ["UDGPU_HALO_NB_BARRIER"] = "1"; flags = 0
         zf = stretched_zf(K, K * 0.5, 1.03)
         o = Oracle(I, J, K, zf=zf)
         o.init_channel()

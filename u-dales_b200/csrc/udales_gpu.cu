@@ -68,9 +68,9 @@ struct ProfSlot {
 // producing kernel, no send buffer, no NCCL in the data path); k_p2p_barrier is the cross-GPU
 // "all blocks have landed" synchronisation: a system-scope flag exchange over the same mappings.
 struct P2PPtrs { unsigned long long *flags[8]; };
-__global__ void k_p2p_barrier(P2PPtrs f, int P, int rank, unsigned long long epoch, int *status, int set) {
+__global__ void k_p2p_barrier(P2PPtrs f, int P, int rank, unsigned long long epoch, int *status, int set, unsigned peers) {
   const int d = threadIdx.x;
-  if (d < P) {
+  if (d < P && ((peers >> d) & 1u)) {   // peers: bit d = rendezvous with rank d (all ranks, or the two ring neighbours)
     __threadfence_system();
     volatile unsigned long long *remote = f.flags[d] + 16 * set + rank;   // my slot in peer d's flag array (one array per stream)
     *remote = epoch;
@@ -128,7 +128,8 @@ struct udgpu {
   bool m_changed = true;                   // um, vm, wm changed since their halos were last exchanged
   unsigned halo_par = 0;
   P2PPtrs pflags;
-  unsigned long long epoch = 0, epoch2 = 0;
+  unsigned long long epoch = 0, epoch2 = 0, epoch3 = 0;
+  int halo_set = 0;           // 2: halo exchanges rendezvous with the two ring neighbours only (UDGPU_HALO_NB_BARRIER=1, not yet measured)
   // the slab Poisson solve in two k-chunks on two streams, so that the NVLink stores of one chunk's transpose overlap
   // the FFT arithmetic of the other
   cudaStream_t st2 = nullptr;
@@ -475,6 +476,7 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     RET(setup_p2p(h, nR));
     h->direct_halo = h->p2p && want_direct;
     // opt-in (UDGPU_POISSON_CHUNKS=2): measured no gain at N = 2 and N = 8 (0.726 vs 0.730 ms per solve at N = 8)
+    { const char *e = getenv("UDGPU_HALO_NB_BARRIER"); h->halo_set = (e && atoi(e) == 1) ? 2 : 0; }
     { const char *e = getenv("UDGPU_POISSON_CHUNKS"); h->pois_chunks = (h->p2p && K >= 8 && e && atoi(e) == 2) ? 2 : 1; }
     if (h->pois_chunks > 1) {
       CU(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
@@ -696,7 +698,9 @@ static int halo_x_exchange_g(udgpu *h, const std::vector<double *> &fields, int 
     const unsigned par = (h->halo_par++) & 1;
     k_halo_pack_x<<<gr, 128, 0, h->st>>>(hp, pi, pj, imax, hw, h->hR[left][par], h->hL[right][par]);
     KCHECK();
-    RET(p2p_barrier(h));
+    // neighbour-only rendezvous is enough here: a window is rewritten two exchanges later, and by then the writer has
+    // seen the owner's flag of the exchange in between, which the owner raised after unpacking this one
+    RET(p2p_barrier(h, h->halo_set));
     k_halo_unpack_x<<<gr, 128, 0, h->st>>>(hp, pi, pj, imax, hw, h->hL[h->rank][par], h->hR[h->rank][par]);
     KCHECK();
     h->launches += 2;
@@ -1173,8 +1177,10 @@ static int setup_p2p(udgpu *h, size_t nR) {
 }
 
 static int p2p_barrier(udgpu *h, int set) {
-  const unsigned long long e = set ? ++h->epoch2 : ++h->epoch;
-  k_p2p_barrier<<<1, 32, 0, h->st>>>(h->pflags, h->P, h->rank, e, h->d_status, set);
+  const unsigned long long e = set == 2 ? ++h->epoch3 : set ? ++h->epoch2 : ++h->epoch;
+  unsigned peers = 0xffu;
+  if (set == 2) peers = (1u << ((h->rank + h->P - 1) % h->P)) | (1u << ((h->rank + 1) % h->P));   // halo exchanges: ring neighbours only
+  k_p2p_barrier<<<1, 32, 0, h->st>>>(h->pflags, h->P, h->rank, e, h->d_status, set, peers);
   KCHECK();
   h->launches++;
   return UDGPU_OK;
