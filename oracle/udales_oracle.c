@@ -5,7 +5,7 @@
  * that, like the reference's generic x86-64 -O3 build, no FMA contraction happens.
  *
  * PINNING STATUS: pinned to the reference's own source text.  tests/golden/ref_*.npz are produced by
- * oracle/f90run (an interpreter that executes /root/reference/src/*.f90 on seeded inputs; see
+ * oracle/f90run (an interpreter that executes the .f90 files under /root/reference/src on seeded inputs; see
  * oracle/README.md) and tests/test_oracle_golden.py checks every stage of three RK3 substeps of this
  * file against them (<= 2e-13 for the stencils, 1e-11 through the FFT solve).  The reference itself is
  * unbuildable here (no Fortran compiler / MPI / FFTW) and ships no golden vectors of its own; FFTW is
