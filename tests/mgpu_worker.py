@@ -1,10 +1,10 @@
 """Multi-GPU parity worker (run under torchrun, one rank per GPU): x-slab decomposition vs the
-single-pencil CPU oracle on identical global inputs.  Tolerance = the reference's own
-decomposition-invariance tolerance 1e-9 (tests/integration/processor_boundaries)."""
+single-pencil CPU oracle on identical global inputs, for every transport variant of the library.
+Tolerance = the reference's own decomposition-invariance tolerance 1e-9
+(tests/integration/processor_boundaries).  Cases live in tests/slab_parity.py."""
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -12,10 +12,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+ENV_KEYS = ("UDGPU_XMODE", "UDGPU_XCHUNKS", "UDGPU_HALO_NB_BARRIER")
+# name -> (cfg.flags, environment).  default = copy-engine pipelined transposes in k-chunks + neighbour-only halo rendezvous
+VARIANTS = {
+    "default": (0, {}),
+    "chunks3": (0, {"UDGPU_XCHUNKS": "3"}),                    # uneven k-chunks
+    "chunks1": (0, {"UDGPU_XCHUNKS": "1"}),
+    "store": (0, {"UDGPU_XMODE": "store"}),                    # FFT kernels store straight into the peers' windows
+    "nccl": (4, {}),                                           # UDGPU_F_NCCL_TRANSPOSE: ncclSend/Recv for transposes and halos
+    "allbarrier": (0, {"UDGPU_HALO_NB_BARRIER": "0"}),         # halo exchanges rendezvous with all ranks
+    "nolazy": (1, {}),                                         # UDGPU_F_NO_LAZY_FUSION: every call eager (no pipelining with integrate)
+}
+
 
 def main():
     import udales_b200 as U
     from oracle.oracle import Oracle, stretched_zf
+    from slab_parity import run_case
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = int(os.environ.get("LOCAL_RANK", rank))
@@ -27,64 +40,23 @@ def main():
         dist.broadcast_object_list(obj, src=0)
         return obj[0]
 
-    # 0: peer-store (NVLink P2P) fused transposes, halos packed into the neighbours' windows; 4: UDGPU_F_NCCL_TRANSPOSE
-    # (NCCL send/recv for transposes and halos); "direct": producers store edge columns straight into the neighbours'
-    # halo columns (UDGPU_DIRECT_HALO=1); "chunks": the solve in two k-chunks on two streams (UDGPU_POISSON_CHUNKS=2);
-    # "nbbarrier": halo exchanges rendezvous with the two ring neighbours only (UDGPU_HALO_NB_BARRIER=1)
-    flags_list = [0, 4, "direct", "chunks"]
-    if os.environ.get("UDGPU_TEST_EXPERIMENTAL") == "1":      # written at the end of round 1, not yet run on a GPU box
-        flags_list.append("nbbarrier")
-    shapes = [(64, 64, 32), (128, 64, 24)] if len(sys.argv) < 2 else [tuple(int(x) for x in sys.argv[1].split("x"))]
+    quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    shapes = [(64, 64, 32), (128, 64, 24)]
     worst = 0.0
-    for shape, flags in [(s_, f_) for s_ in shapes for f_ in flags_list]:
-        I, J, K = shape
-        os.environ.pop("UDGPU_DIRECT_HALO", None); os.environ.pop("UDGPU_POISSON_CHUNKS", None); os.environ.pop("UDGPU_HALO_NB_BARRIER", None)
-        if flags == "direct":
-            os.environ["UDGPU_DIRECT_HALO"] = "1"; flags = 0
-        elif flags == "chunks":
-            os.environ["UDGPU_POISSON_CHUNKS"] = "2"; flags = 0
-        elif flags == "nbbarrier":
-            os.environ["UDGPU_HALO_NB_BARRIER"] = "1"; flags = 0
-        zf = stretched_zf(K, K * 0.5, 1.03)
-        o = Oracle(I, J, K, zf=zf)
-        o.init_channel()
-        g = U.UdalesGPU(I, J, K, zf=zf, device=dev, nprocx=world, myidx=rank, nccl_uid=fresh_uid(), flags=flags)
-        for n in ("u0", "v0", "w0", "um", "vm", "wm", "pres0"):
-            g.push(n, U.slab_of(getattr(o, n), world, rank))
-        # Poisson alone
-        rng = np.random.default_rng(3)
-        rhs = rng.standard_normal(shape)
-        imax = I // world
-        p_ref = o.poisson_solve(rhs)
-        p = g.poisson_solve(np.asfortranarray(rhs[rank * imax:(rank + 1) * imax]))
-        e = np.abs(p - p_ref[rank * imax:(rank + 1) * imax]).max() / np.abs(p_ref).max()
-        worst = max(worst, e)
-        assert e < 1e-10, ("poisson", shape, e)
-        # substeps
-        dt = 0.02
-        o.dt = g.dt = dt
-        for s in range(6):
-            o.substep(dt)
-            g.substep(dt)
-            for n in ("u0", "v0", "w0", "um", "vm", "wm"):
-                a, b = g.pull(n), U.slab_of(getattr(o, n), world, rank)
-                e = np.abs(a - b).max()
-                worst = max(worst, e)
-                assert e < 1e-9, (n, s, shape, e)
-            # pres0: interior + x-face halo columns + y-face halo rows (what the next advection reads)
-            a, b = g.pull("pres0"), U.slab_of(o.pres0, world, rank)
-            e = max(np.abs(a[:, 1:-1, 1:-1] - b[:, 1:-1, 1:-1]).max(), np.abs(a[1:-1, :, 1:-1] - b[1:-1, :, 1:-1]).max())
+    for name, (flags, env) in VARIANTS.items():
+        if quick and name not in ("default", "nccl"):
+            continue
+        for k in ENV_KEYS:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        cases = [("channel", s) for s in shapes] + [("scalars", (64, 64, 16)), ("ibm", (64, 64, 16))]
+        if name not in ("default", "store", "nccl"):
+            cases = cases[:1] + cases[2:3]
+        for kind, shape in cases:
+            e = run_case(U, Oracle, kind, shape, world, rank, dev, fresh_uid(), flags=flags, nsub=6 if kind == "channel" else 3,
+                         stretched_zf=stretched_zf)
             worst = max(worst, e)
-            assert e < 1e-9, ("pres0", s, shape, e)
-            dmax, dtot, drms = g.divergence()
-            omax, otot, orms = o.chkdiv()
-            assert drms < 1e-12 and abs(dmax - omax) < 1e-12, (dmax, omax, drms)
-        # adaptive time step: global maxima through the allreduce
-        d_ref, _, ct_ref, dn_ref = o.tstep_update(0.05, 0, courant=1.1, diffnr=0.25, dtmax=2.0)
-        d, _, ct, dn = g.tstep_update(0.05, 0, courant=1.1, diffnr=0.25, dtmax=2.0)
-        assert abs(ct - ct_ref) < 1e-12 * ct_ref and abs(dn - dn_ref) < 1e-12 * dn_ref and abs(d - d_ref) < 1e-12 * d_ref
-        g.close()
-        print(f"rank {rank}: shape {shape} flags {flags} ok, worst so far {worst:.2e}", flush=True)
+            print(f"rank {rank}: {name} {kind} {shape} ok, worst so far {worst:.2e}", flush=True)
     dist.barrier()
     print(f"MGPU OK rank {rank}/{world} worst abs err {worst:.2e}", flush=True)
     dist.destroy_process_group()

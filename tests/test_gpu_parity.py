@@ -71,27 +71,6 @@ def test_poisson_solve(shape, flags):
     assert relerr(p, p_ref) < TOL_PRES
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 64), (256, 64, 40), (128, 32, 33), (512, 16, 70), (1024, 8, 9), (64, 48, 2),
-                                   (128, 20, 32), (256, 12, 31)])
-@pytest.mark.parametrize("minb", ["1", "2"])
-def test_poisson_one_pass_x_vs_separate_passes(shape, minb, monkeypatch):
-    """y, [x-FFT + z-solve + x-FFT^-1 in one kernel], y^-1 (poisson_xz.cuh) against the five separate passes
-    x, y, z, y^-1, x^-1 of src/modpois.f90:478-679 and against the oracle."""
-    import udales_b200 as U
-    rng = np.random.default_rng(11)
-    rhs = rng.standard_normal(shape)
-    o, g1 = make_pair(*shape)
-    assert g1.L is not None
-    monkeypatch.setenv("UDGPU_XZ_MINB", minb)
-    monkeypatch.setenv("UDGPU_XZ_FUSED", "1")
-    _, ga = make_pair(*shape)
-    monkeypatch.setenv("UDGPU_XZ_FUSED", "0")
-    _, gb = make_pair(*shape)
-    pa, pb = ga.poisson_solve(rhs), gb.poisson_solve(rhs)
-    assert relerr(pa, pb) < 1e-12
-    assert relerr(pa, o.poisson_solve(rhs)) < TOL_PRES
-
-
 @pytest.mark.parametrize("shape", SIZES)
 @pytest.mark.parametrize("rk3step", [1, 2, 3])
 def test_poisson_fillps_tderive(shape, rk3step):
@@ -362,3 +341,109 @@ def test_forces_in_the_substep(shape, flags, ibm):
     g.advection(); g.subgrid(); g.forces()
     for n in ("up", "vp", "wp"):
         assert relerr(tend_interior(g.pull(n)), tend_interior(getattr(o, n))) < TOL_STENCIL, n
+
+
+# ---- round 2: entry points the bench's end-to-end number goes through, and lazy-state bookkeeping ------------------
+def test_push_of_a_non_tendency_keeps_the_pending_zero_fill():
+    """tstep_integrate leaves up = vp = wp = 0 (src/modtstep.f90:322-324); the library writes those zeros lazily.
+    Pushing a field that is NOT a tendency must not cancel the pending fill (round-1 bug at udgpu_push)."""
+    o, g = make_pair(16, 16, 16, nsv=1)
+    g.dt = 0.02
+    g.substep(0.02)
+    g.push("u0", g.pull("u0"))                  # non-tendency push while the zero-fill is pending
+    g.push("ekm", g.pull("ekm"))
+    for n in ("up", "vp", "wp"):
+        assert np.abs(g.pull(n)).max() == 0.0, n
+    assert np.abs(g.pull("svp", 0)).max() == 0.0
+    # and a pushed tendency is kept (not zeroed) and accumulated into by the next operator, like the reference would
+    g.substep(0.02)
+    t = np.asfortranarray(np.full(g.shape("svp"), 0.25))
+    g.push("svp", t, 0)
+    assert np.array_equal(g.pull("svp", 0), t)
+    u = np.asfortranarray(np.full(g.shape("up"), 0.5))
+    g.push("up", u)
+    assert np.array_equal(g.pull("up"), u)
+
+
+@pytest.mark.parametrize("shape", [(32, 24, 20), (64, 64, 32)])
+@pytest.mark.parametrize("ladaptive", [False, True])
+def test_rk3_step_host_equals_three_substeps_and_the_oracle(shape, ladaptive):
+    """udgpu_rk3_step_host (the entry point of bench.py's end-to-end number): u0,v0,w0,pres0 on HOST arrays in, one RK3
+    time step, the same four out == three resident substeps == the oracle."""
+    o, ga = make_pair(*shape)
+    _, gb = make_pair(*shape)
+    dt0, dtmax = 0.02, (0.05 if ladaptive else 0.02)
+    o.dt = ga.dt = gb.dt = dt0
+    host = {n: np.array(getattr(o, n), order="F", copy=True) for n in ("u0", "v0", "w0", "pres0")}
+    for step in range(2):
+        for s in range(3):
+            o.substep(dtmax, ladaptive=ladaptive, courant=1.1, diffnr=0.25)
+            gb.substep(dtmax, ladaptive=ladaptive, courant=1.1, diffnr=0.25)
+        ga.rk3_step_host(host["u0"], host["v0"], host["w0"], host["pres0"], dtmax=dtmax, ladaptive=ladaptive, courant=1.1, diffnr=0.25)
+        assert ga.dt == pytest.approx(o.dt, rel=1e-12) and gb.dt == pytest.approx(o.dt, rel=1e-12)
+        for n in ("u0", "v0", "w0"):
+            assert np.array_equal(host[n], gb.pull(n)), (step, n)          # same kernels, same bits
+            assert relerr(host[n], getattr(o, n)) < 1e-11, (step, n)       # whole array incl. halos and ghost levels
+        pr = host["pres0"]
+        assert np.array_equal(pr, gb.pull("pres0"))
+        assert relerr(pr[:, 1:-1, 1:-1], o.pres0[:, 1:-1, 1:-1]) < TOL_PRES
+        assert relerr(pr[1:-1, :, 1:-1], o.pres0[1:-1, :, 1:-1]) < TOL_PRES
+
+
+@pytest.mark.parametrize("shape", [(32, 24, 20), (128, 64, 24), (96, 40, 12)])
+def test_poisson_solve_resident_and_device_ptr(shape):
+    """udgpu_poisson_solve_resident on the resident rhs buffer == udgpu_poisson_solve with host buffers == the oracle;
+    udgpu_device_ptr hands out the very buffer (written through a raw device pointer with torch)."""
+    import ctypes as C
+    import torch
+    o, g = make_pair(*shape)
+    rng = np.random.default_rng(9)
+    rhs = np.asfortranarray(rng.standard_normal(shape))
+    p_ref = o.poisson_solve(rhs)
+    p_host = g.poisson_solve(rhs)
+    g.push("rhs", rhs)
+    g.poisson_solve_resident()
+    p_res = g.pull("rhs")
+    assert np.array_equal(p_res, p_host)
+    assert relerr(p_res, p_ref) < TOL_PRES
+    # device pointer: fill the rhs buffer from the device side, solve, read it back through the pointer
+    dptr = C.c_void_p()
+    g._chk(g.L.udgpu_device_ptr(g.h, 13, 0, C.byref(dptr)))     # UDGPU_RHS
+    n = rhs.size
+    src = torch.from_numpy(np.ascontiguousarray(rhs.ravel(order="F"))).cuda()
+    g.sync()
+    rt = C.CDLL("libcudart.so.12")          # the runtime the library itself is linked against (already loaded)
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    rc = rt.cudaMemcpy(dptr.value, src.data_ptr(), n * 8, 3)   # cudaMemcpyDeviceToDevice
+    assert int(rc) == 0
+    torch.cuda.synchronize()
+    g.poisson_solve_resident()
+    g.sync()
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    rc = rt.cudaMemcpy(out.data_ptr(), dptr.value, n * 8, 3)
+    assert int(rc) == 0
+    assert np.array_equal(out.cpu().numpy().reshape(shape, order="F"), p_host)
+    # a tendency handed out by pointer counts as written by the host: no lazy zero-fill over it
+    g.dt = 0.02
+    g.substep(0.02)
+    g._chk(g.L.udgpu_device_ptr(g.h, 6, 0, C.byref(dptr)))      # UDGPU_UP (materialises the zeros first)
+    assert np.abs(g.pull("up")).max() == 0.0
+
+
+def test_full_size_256_against_the_oracle_directly():
+    """BASELINE config 2 at its full size, compared with the oracle cell by cell: closure, the fused tendencies, the
+    Poisson solve inside a substep and the integrated state after one RK3 substep of 256^3."""
+    n = 256
+    o, g = make_pair(n, n, n, stretched=False)
+    dt = 0.05
+    o.dt = g.dt = dt
+    o.substep(dt); g.substep(dt)
+    for nm in ("u0", "v0", "w0"):
+        assert relerr(g.pull(nm), getattr(o, nm)) < 1e-11, nm
+    assert relerr(g.pull("ekm"), o.ekm) < TOL_STENCIL
+    assert relerr(interior(g.pull("p")), interior(o.p)) < TOL_PRES
+    pr = g.pull("pres0")
+    assert relerr(pr[:, 1:-1, 1:-1], o.pres0[:, 1:-1, 1:-1]) < TOL_PRES
+    dmax, dtot, drms = g.divergence()
+    omax, otot, orms = o.chkdiv()
+    assert drms < 1e-12 and abs(dmax - omax) < 1e-11

@@ -43,11 +43,6 @@ __host__ __device__ __forceinline__ long long offR(const Geo &g, int i, int j, i
 __host__ __device__ __forceinline__ long long offS(const Geo &g, int i, int j, int k) {
   return (long long)(i + g.ihc - 1) + (long long)g.pic * ((j + g.jhc - 1) + (long long)g.pjc * (k + g.khc - 1));
 }
-// x split over GPUs: the same arrays on the left / right ring neighbour (mapped through CUDA IPC, reached over NVLink).
-// A kernel that produces the first / last interior column stores it into the neighbour's halo column as well
-// (left neighbour: its column imax+1, right neighbour: its column 0).  nullptr = x unsplit or no peer mapping.
-struct PeerCols { double *L[6]; double *R[6]; };
-
 // Periodic images of interior cell (i,j) in the halo ring (width 1, imax,jmax >= 2): at most one in x
 // (only when x is unsplit), one in y (nprocy = 1 always) and the corner.  -1 = none.
 __device__ __forceinline__ int img_x(const Geo &g, int i) { return g.wrapx ? (i == 1 ? g.imax + 1 : (i == g.imax ? 0 : -1)) : -1; }

@@ -15,9 +15,8 @@ __device__ __forceinline__ double sq_(double x) { return x * x; }
 // thread also writes everything closurebc (src/modboundary.f90:434-505) derives from this cell: its periodic
 // images in y (and in x when unsplit) and, for k = 1 / k = ktot, the bottom / top ghost levels of the cell and
 // of its images — so no separate wrap / ghost kernels run afterwards (x-split: the slab exchange follows).
-template <bool PEER>
 __device__ __forceinline__ void ek_store(const Geo &g, int i, int j, int k, double e, double *__restrict__ ekm,
-                                         double *__restrict__ ekh, int halo, const PeerCols &pc) {
+                                         double *__restrict__ ekh, int halo) {
   const double m = e + g.numol, hh = e * g.prandtli + g.numol * g.prandtlmoli;
   if (!halo) {
     const long long c = offF(g, i, j, k);
@@ -34,13 +33,7 @@ __device__ __forceinline__ void ek_store(const Geo &g, int i, int j, int k, doub
       else { am[c + g.pk] = m; ah[c + g.pk] = hh; }
     }
   };
-  auto put = [&](int ti, int tj) {
-    put1(ekm, ekh, ti, tj);
-    if (PEER) {
-      if (ti == 1) put1(pc.L[0], pc.L[1], g.imax + 1, tj);      // my first column = left neighbour's right halo
-      if (ti == g.imax) put1(pc.R[0], pc.R[1], 0, tj);          // my last column = right neighbour's left halo
-    }
-  };
+  auto put = [&](int ti, int tj) { put1(ekm, ekh, ti, tj); };
   const int ix = img_x(g, i), jy = img_y(g, j);
   put(i, j);
   if (ix >= 0) put1(ekm, ekh, ix, j);
@@ -50,10 +43,10 @@ __device__ __forceinline__ void ek_store(const Geo &g, int i, int j, int k, doub
 // closure: src/modsubgrid.f90:159-412.  MODEL 0 = DNS (:401-404), 1 = Vreman (:269-360),
 // 2 = Smagorinsky (:208-267).  Writes interior ekm/ekh including "+ numol" (:263-264,359-360).
 // Ghost cells are produced by k_closurebc_*.
-template <int MODEL, bool PEER = false>
+template <int MODEL>
 __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
                                                  const double *__restrict__ w0, double *__restrict__ ekm,
-                                                 double *__restrict__ ekh, int halo, PeerCols pc) {
+                                                 double *__restrict__ ekh, int halo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   const int k = blockIdx.z + 1;
@@ -119,7 +112,7 @@ __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict
 #undef V
 #undef W
   }
-  ek_store<PEER>(g, i, j, k, e, ekm, ekh, halo, pc);
+  ek_store(g, i, j, k, e, ekm, ekh, halo);
 }
 
 // Vreman closure, k-marching form of k_closure<1>: one thread owns an (i,j) column over KC levels and carries
@@ -127,10 +120,10 @@ __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict
 // vertical derivatives, the w ring), so a level costs 17 loads instead of 30 and almost no address arithmetic.
 // Operand order inside each gradient is the reference's (src/modsubgrid.f90:271-327): differences to k_closure<1>
 // and to the oracle are FMA-contraction rounding only.
-template <int KC, bool PEER = false>
+template <int KC>
 __global__ void __launch_bounds__(256, 4) k_closure_vreman_march(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
                                                               const double *__restrict__ w0, double *__restrict__ ekm,
-                                                              double *__restrict__ ekh, int halo, PeerCols pc, int rev) {
+                                                              double *__restrict__ ekh, int halo, int rev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i > g.imax || j > g.jmax) return;
@@ -174,7 +167,7 @@ __global__ void __launch_bounds__(256, 4) k_closure_vreman_march(Geo g, const do
     const double b23 = dx2 * a12 * a13 + dy2 * a22 * a23 + dzf2 * a32 * a33;
     const double bb = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
     const double e = (bb < 1.e-8) ? 0.0 : g.c_vreman * sqrt(bb / aa);
-    ek_store<PEER>(g, i, j, k, e, ekm, ekh, halo, pc);
+    ek_store(g, i, j, k, e, ekm, ekh, halo);
     su_km = su_k; sv_km = sv_k;
     u_c = uK_c; u_ip = uK_ip; v_c = vK_c; v_jp = vK_jp;
     w_c = wK_c; w_ip = wK_ip; w_im = wK_im; w_jp = wK_jp; w_jm = wK_jm;
@@ -258,22 +251,6 @@ __global__ void k_halo_unpack_x(HaloPack a, int pi, int pj, int imax, int h, con
   for (int m = 0; m < h; m++) {
     q[m] = recvL[a.off[f] + jk * h + m];
     q[h + imax + m] = recvR[a.off[f] + jk * h + m];
-  }
-}
-
-// Same exchange without staging: the fields live in the CUDA-IPC window, so the edge columns are stored straight
-// into the neighbours' halo columns over NVLink (left neighbour: columns imax+h.., right neighbour: columns 0..);
-// a flag barrier follows, nothing to unpack.
-struct PeerPack { double *L[8]; double *R[8]; };
-__global__ void k_halo_push_x(HaloPack a, PeerPack pp, int pi, int pj, int imax, int h) {
-  const int f = blockIdx.y;
-  const long long jk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (jk >= (long long)pj * a.nlev[f]) return;
-  const double *q = a.f[f] + jk * pi;
-  double *l = pp.L[f] + jk * pi, *r = pp.R[f] + jk * pi;
-  for (int m = 0; m < h; m++) {
-    l[h + imax + m] = q[h + m];
-    r[m] = q[imax + m];
   }
 }
 
@@ -385,10 +362,11 @@ template <bool XWRAP, bool YWRAP>
 __global__ void __launch_bounds__(256) k_fillps(Geo g, double rk3coefi, const double *__restrict__ up, const double *__restrict__ vp,
                                                 const double *__restrict__ wp, const double *__restrict__ um,
                                                 const double *__restrict__ vm, const double *__restrict__ wm,
-                                                double *__restrict__ rhs, int rev) {
+                                                double *__restrict__ rhs, int rev, int koff) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  const int k = rev ? g.ktot - (int)blockIdx.z : (int)blockIdx.z + 1;   // rev: top level first (L2 reuse, see LineDesc::rev)
+  // levels koff+1 .. koff+gridDim.z; rev: top level first (L2 reuse, see LineDesc::rev)
+  const int k = koff + (rev ? (int)(gridDim.z - blockIdx.z) : (int)blockIdx.z + 1);
   if (i > g.imax || j > g.jmax) return;
   const int ip = (XWRAP && i == g.imax) ? 1 : i + 1;
   const int jp = (YWRAP && j == g.jmax) ? 1 : j + 1;
@@ -472,18 +450,18 @@ __global__ void __launch_bounds__(256) k_tderive_integrate(Geo g, double rk3coef
 // image cells too (:1096-1102).  Only legal when the m-fields / w(k=1) / tendencies at k=1 are in the state the
 // reference's own halos+boundary leave them in (the host tracks that; otherwise the plain kernel + wraps run).
 // XS: 0 = x unsplit (periodic images in x written here), 1 = x split over GPUs (halo columns of pres0 updated from the
-// exchanged p), 2 = split + the edge columns of the velocities stored straight into the neighbours (PeerCols)
+// exchanged p)
 template <bool STEP3, int XS = 0, bool FORCE = false>
 __global__ void __launch_bounds__(256) k_tderive_integrate_halo(Geo g, double rk3coef, const double *__restrict__ p,
                                                                 const double *__restrict__ up, const double *__restrict__ vp,
                                                                 const double *__restrict__ wp, double *__restrict__ um,
                                                                 double *__restrict__ vm, double *__restrict__ wm,
                                                                 double *__restrict__ u0, double *__restrict__ v0,
-                                                                double *__restrict__ w0, double *__restrict__ pres0, PeerCols pc,
-                                                                const double *__restrict__ fx, const double *__restrict__ fy, int fz) {
+                                                                double *__restrict__ w0, double *__restrict__ pres0,
+                                                                const double *__restrict__ fx, const double *__restrict__ fy, int fz, int koff) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  const int k = blockIdx.z + 1;
+  const int k = koff + blockIdx.z + 1;   // levels koff+1 .. koff+gridDim.z
   if (i > g.imax || j > g.jmax) return;
   const long long c = offF(g, i, j, k), t = offT(g, i, j, k);
   const double pc0 = p[c];
@@ -519,17 +497,6 @@ __global__ void __launch_bounds__(256) k_tderive_integrate_halo(Geo g, double rk
   const int ix = img_x(g, i), jy = img_y(g, j);
   if (ix >= 0) put(offF(g, ix, j, k));
   if (jy >= 0) { put(offF(g, i, jy, k)); if (ix >= 0) put(offF(g, ix, jy, k)); }
-  if (XS == 2) {
-    // my first / last interior column (and its y images) = the left / right neighbour's halo column
-    if (i == 1) {
-      putv(pc.L[0], pc.L[1], pc.L[2], pc.L[3], pc.L[4], pc.L[5], offF(g, g.imax + 1, j, k));
-      if (jy >= 0) putv(pc.L[0], pc.L[1], pc.L[2], pc.L[3], pc.L[4], pc.L[5], offF(g, g.imax + 1, jy, k));
-    }
-    if (i == g.imax) {
-      putv(pc.R[0], pc.R[1], pc.R[2], pc.R[3], pc.R[4], pc.R[5], offF(g, 0, j, k));
-      if (jy >= 0) putv(pc.R[0], pc.R[1], pc.R[2], pc.R[3], pc.R[4], pc.R[5], offF(g, 0, jy, k));
-    }
-  }
   if (XS >= 1) {
     // x is split over GPUs: the halo columns of p came from the neighbours (exchange before this kernel) and
     // pres0 += p has to reach the halo columns of pres0 too (src/modpois.f90:1096-1102)

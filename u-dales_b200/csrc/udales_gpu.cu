@@ -16,10 +16,8 @@
 
 #include "common.cuh"
 #include "momtend_tma.cuh"
-#include "closure_tma.cuh"
 #include "poisson_v1.cuh"
 #include "poisson_fast.cuh"
-#include "poisson_xz.cuh"
 #include "stencil_v1.cuh"
 #include "scalar_v1.cuh"
 #include "ibm.cuh"
@@ -54,7 +52,7 @@ static int set_err(int code, const char *fmt, ...) {
     if (r_ != UDGPU_OK) return r_; \
   } while (0)
 
-enum { PROF_MOM = 0, PROF_CLOSURE, PROF_POIS, PROF_FILLPS, PROF_INTEG, PROF_HALO, PROF_N };
+enum { PROF_MOM = 0, PROF_CLOSURE, PROF_POIS, PROF_FILLPS, PROF_INTEG, PROF_HALO, PROF_BWDPIPE, PROF_N };
 
 struct ProfSlot {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pend;
@@ -68,17 +66,27 @@ struct ProfSlot {
 // producing kernel, no send buffer, no NCCL in the data path); k_p2p_barrier is the cross-GPU
 // "all blocks have landed" synchronisation: a system-scope flag exchange over the same mappings.
 struct P2PPtrs { unsigned long long *flags[8]; };
-__global__ void k_p2p_barrier(P2PPtrs f, int P, int rank, unsigned long long epoch, int *status, int set, unsigned peers) {
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// status: one int in mapped pinned host memory (the host reads it after every stream synchronisation without a copy).
+// A rendezvous that times out marks the run as failed for good: later barriers return at once and every
+// host-synchronising entry point reports UDGPU_ESTATE, so nothing computed from unwritten windows is handed out.
+__global__ void k_p2p_barrier(P2PPtrs f, int P, int rank, unsigned long long epoch, volatile int *status, int set, unsigned peers,
+                              unsigned long long timeout_ns) {
   const int d = threadIdx.x;
   if (d < P && ((peers >> d) & 1u)) {   // peers: bit d = rendezvous with rank d (all ranks, or the two ring neighbours)
     __threadfence_system();
-    volatile unsigned long long *remote = f.flags[d] + 16 * set + rank;   // my slot in peer d's flag array (one array per stream)
+    volatile unsigned long long *remote = f.flags[d] + 16 * set + rank;   // my slot in peer d's flag array (one array per flag set)
     *remote = epoch;
     __threadfence_system();
+    if (*status) return;
     volatile unsigned long long *mine = f.flags[rank] + 16 * set + d;
-    const long long t0 = clock64();
+    const unsigned long long t0 = globaltimer_ns();
     while (*mine < epoch) {
-      if (clock64() - t0 > 20000000000LL) { *status = 1; break; }  // ~10 s: a peer died; do not hang the GPU
+      if (globaltimer_ns() - t0 > timeout_ns) { *status = 1; __threadfence_system(); break; }  // a peer died; do not hang the GPU
     }
   }
 }
@@ -103,8 +111,6 @@ struct udgpu {
   bool fast_x = false, fast_y = false, fast_z = false;
   int zu = 8, fft_lanes = 32;
   int fft_rev = 1;            // consecutive kernels alternate their level direction for L2 reuse (UDGPU_FFT_REV=0: all upwards)
-  bool xz_fused = false;      // x-FFT + z-solve + inverse x-FFT as one pass (poisson_xz.cuh)
-  int xz_minb = 1;            // ... compiled for 1 or 2 resident CTAs per SM (UDGPU_XZ_MINB)
   double *d_zt = nullptr, *d_xd = nullptr, *d_yd = nullptr;
   int nxh = 0, nyh = 0;
   // reductions
@@ -119,31 +125,34 @@ struct udgpu {
   void *ipc_peer[8] = {};
   double *rA[8] = {}, *rB[8] = {};
   double *hL[8][2] = {}, *hR[8][2] = {};   // halo receive windows (left / right halo columns), double-buffered
-  // direct halo stores: the exchanged fields live inside the IPC window, so a kernel that produces an edge column can
-  // store it straight into the neighbour's halo column over NVLink; only a flag barrier follows (no pack / unpack)
-  bool direct_halo = false;
-  double *wfield[8] = {};                  // start of the field region in every rank's window
-  size_t fwin_off[UDGPU_NFIELDS] = {};     // element offset of a field inside the window (0 = not in the window)
-  size_t win_field_elems = 0;
   bool m_changed = true;                   // um, vm, wm changed since their halos were last exchanged
   unsigned halo_par = 0;
   P2PPtrs pflags;
-  unsigned long long epoch = 0, epoch2 = 0, epoch3 = 0;
-  int halo_set = 0;           // 2: halo exchanges rendezvous with the two ring neighbours only (UDGPU_HALO_NB_BARRIER=1, not yet measured)
-  // the slab Poisson solve in two k-chunks on two streams, so that the NVLink stores of one chunk's transpose overlap
-  // the FFT arithmetic of the other
-  cudaStream_t st2 = nullptr;
-  cudaEvent_t ev_start = nullptr, ev_xfB = nullptr, ev_z = nullptr, ev_doneB = nullptr;
-  int pois_chunks = 1;
-  int *d_status = nullptr;
+  unsigned long long epoch[4] = {0, 0, 0, 0};   // one counter per flag set (0: transposes, 2: neighbour-only halo rendezvous)
+  int halo_set = 2;           // 2: halo exchanges rendezvous with the two ring neighbours only; 0 (UDGPU_HALO_NB_BARRIER=0): with all ranks
+  // transposes of the slab solve (xmode): 0 = ncclSend/Recv, 1 = FFT kernels store straight into the peers' windows,
+  // 2 (default) = FFT kernels write a local wire-format send buffer and the COPY ENGINES move k-chunks of it into the
+  // peers' windows on a side stream, pipelined against the neighbouring compute (measured on 2 x B200, profiles/
+  // r2_p2p_probe.txt: CE peer copies 770 GB/s and the HBM-bound kernel next to them keeps 93 % of its bandwidth;
+  // per-thread peer stores 685 GB/s (440 GB/s in 64-byte runs) and the kernel next to them keeps 67 %)
+  int xmode = 0;
+  int xchunks = 1;            // k-chunks of the pipelined transposes
+  int xk0[17] = {};           // chunk c covers 0-based levels xk0[c] .. xk0[c+1]-1
+  cudaStream_t sc = nullptr;  // copy stream: CE copies + the rendezvous of every chunk
+  cudaEvent_t ev_f[16] = {}, ev_r[16] = {};   // chunk c: local wire data ready (main -> copy) / all blocks have landed (copy -> main)
+  bool bwd_pending = false;   // poisson() ran the forward half and the z solve; the inverse half is pipelined with tstep_integrate()
+  double *bwd_work = nullptr, *bwd_phalo = nullptr;
+  int *d_status = nullptr;   // device view of h_status
+  volatile int *h_status = nullptr;   // mapped pinned host int: 1 = a peer rendezvous timed out (fatal)
+  unsigned long long barrier_timeout_ns = 120ull * 1000000000ull;   // UDGPU_BARRIER_TIMEOUT_S
   double *sbuf = nullptr, *rbuf = nullptr, *workB = nullptr;  // transposes: wire-format send / receive, x-pencil work
   int IB = 0, JB = 0;         // local i extent of the slab, local j extent of the x-pencil
   Geo gB;                     // geometry of the x-pencil (itot, JB, ktot) for the z solve
   // TMA path of the fused momentum kernel
   bool use_tma = false;
   CUtensorMap tm[5];
-  MomTmaParams mtp, clp;
-  int mt_grid = 0, cl_grid = 0, cl_occ = 2;
+  MomTmaParams mtp;
+  int mt_grid = 0;
   int sc_nsmax = 4;           // fields per scalar-tendency launch (UDGPU_SCALAR_NSMAX = 1..4)
   int sc_march = 1;           // kappa scalars: k-marching shuffle kernel (UDGPU_SCALAR_MARCH=0: one thread per cell)
   int cl_march = 1;           // Vreman closure: k-marching register-carry kernel (UDGPU_CLOSURE_MARCH=0: one thread per cell)
@@ -180,11 +189,11 @@ struct udgpu {
 
 // ------------------------------------------------------------------------------------------
 static int flush_pending(udgpu *h, bool keep_forces = false);
-static PeerCols peer_cols(udgpu *h, std::initializer_list<int> fields);
 static int settle_for_access(udgpu *h, int field);
 static int setup_p2p(udgpu *h, size_t nR);
-static int p2p_barrier(udgpu *h, int set = 0);
+static int p2p_barrier(udgpu *h, int set = 0, cudaStream_t on = nullptr);
 static int materialize_zero_tend(udgpu *h);
+static int sync_check(udgpu *h);
 static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt);
 static int dev_alloc(udgpu *h, void **p, size_t bytes) {
   CU(cudaMalloc(p, bytes ? bytes : 8));
@@ -302,28 +311,6 @@ static int setup_momtend_tma(udgpu *h) {
   SETATTR(true, false, false, false); SETATTR(true, false, false, true);
   SETATTR(false, true, true, true); SETATTR(false, true, true, false); SETATTR(false, true, false, true); SETATTR(false, true, false, false);
 #undef SETATTR
-  CU(cudaFuncSetAttribute(k_closure_vreman_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
-  CU(cudaFuncSetAttribute(k_closure_vreman_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
-  {
-    // closure: its own chunking of k over occ x #SM concurrent CTAs
-    h->clp = P;
-    const char *eo = getenv("UDGPU_CLOSURE_OCC");   // 1 / 2: TMA closure kernel at that occupancy; default: direct kernel
-    h->cl_occ = eo ? atoi(eo) : 0;
-    if (h->cl_occ < 0 || h->cl_occ > 2) h->cl_occ = 0;
-    const int Gc = (h->cl_occ > 0 ? h->cl_occ : 1) * h->nsm;
-    int bestc = 1; double bestec = -1;
-    for (int c = 1; c <= g.ktot && c <= 64; c++) {
-      const double L = (double)g.ktot / c;
-      if (L < 4 && c > 1) break;
-      const long items = (long)ntile * c;
-      const double rounds = ceil((double)items / Gc);
-      const double eff = (double)items / (Gc * rounds) * L / (L + 1.0);
-      if (eff > bestec + 1e-9) { bestec = eff; bestc = c; }
-    }
-    h->clp.nchunk = bestc;
-    h->clp.nitems = ntile * bestc;
-    h->cl_grid = h->clp.nitems < Gc ? h->clp.nitems : Gc;
-  }
   h->use_tma = true;
   return UDGPU_OK;
 }
@@ -339,15 +326,9 @@ extern "C" int udgpu_nccl_unique_id(void *uid128) {
   return UDGPU_OK;
 }
 
-extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **out) {
-  (void)nccl_uid;
-  if (!c || !out) return set_err(UDGPU_EINVAL, "null argument");
-  if (c->abi_version != UDGPU_ABI_VERSION) return set_err(UDGPU_EINVAL, "ABI version mismatch: header %d, caller %d", UDGPU_ABI_VERSION, c->abi_version);
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    cudaGetLastError();
-    return set_err(UDGPU_ENODEV, "no CUDA device visible: this library has no CPU fallback");
-  }
+static bool fast_len(int n);
+static int validate_cfg(const udgpu_cfg *c, const void *nccl_uid) {
+  // pure argument checks: nothing is allocated and no collective is entered before all of them have passed
   // supported switch set (everything else is the reference's business)
   if (c->ipoiss != 0) return set_err(UDGPU_EINVAL, "ipoiss=%d: only POISS_FFT2D (0) is supported (src/modglobal.f90:389)", c->ipoiss);
   if (c->iadv_mom != 2) return set_err(UDGPU_EINVAL, "iadv_mom=%d: only cd2 (2) exists in the reference (src/modadvection.f90:47-54)", c->iadv_mom);
@@ -358,6 +339,7 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
   if (c->ih != 1 || c->jh != 1 || c->kh != 1) return set_err(UDGPU_EINVAL, "momentum halo must be 1 (cd2, src/modglobal.f90:592-599)");
   if (c->nprocy != 1) return set_err(UDGPU_EINVAL, "only x-slab decompositions (nprocy = 1) are supported (nprocx x nprocy pencils: next)");
   if (c->nprocx < 1 || c->nprocx > 8) return set_err(UDGPU_EINVAL, "nprocx must be 1..8 (one NVSwitch box)");
+  if (c->itot < 2 || c->jtot < 2 || c->ktot < 1) return set_err(UDGPU_EINVAL, "grid %dx%dx%d too small", c->itot, c->jtot, c->ktot);
   if (c->itot % c->nprocx || c->jtot % c->nprocx) return set_err(UDGPU_EINVAL, "itot and jtot must be divisible by nprocx (src/modstartup.f90:730-760)");
   if (c->imax != c->itot / c->nprocx || c->jmax != c->jtot || c->kmax != c->ktot) return set_err(UDGPU_EINVAL, "local extents do not match an x-slab: imax=itot/nprocx, jmax=jtot, kmax=ktot");
   if (c->nprocx > 1 && !nccl_uid) return set_err(UDGPU_EINVAL, "nprocx > 1 needs the broadcast ncclUniqueId");
@@ -367,8 +349,42 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
   if (c->nsv > 0 && (c->ihc != c->jhc || c->ihc != c->khc || c->ihc != (c->iadv_sv == 7 ? 2 : 1)))
     return set_err(UDGPU_EINVAL, "scalar halo must be 2 with kappa, 1 with cd2 (src/modglobal.f90:586-609)");
   if (!c->dzf || !c->dzh) return set_err(UDGPU_EINVAL, "dzf/dzh missing");
+  for (int n : {c->itot, c->jtot}) {
+    if (n & 1) return set_err(UDGPU_EINVAL, "FFT length %d must be even (reference packing assumes it, src/modpois.f90:482-487)", n);
+    if (n / 2 > 1 && factor_radices(n / 2).empty()) return set_err(UDGPU_EINVAL, "FFT length %d: n/2 has a prime factor > 13 (unsupported)", n);
+    if ((size_t)(n / 2) * FFT_BP * sizeof(double2) > 227 * 1024 && !fast_len(n)) return set_err(UDGPU_EINVAL, "FFT length %d too large for the shared-memory tile", n);
+  }
+  if (c->nprocx > 1 && !(fast_len(c->itot) && fast_len(c->jtot)))
+    return set_err(UDGPU_EINVAL, "multi-GPU slabs need itot, jtot in {64,128,256,512,1024} (fused-transpose FFT kernels)");
+  return UDGPU_OK;
+}
 
+static int init_impl(udgpu *h, const udgpu_cfg *c, const void *nccl_uid, int ndev);
+extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **out) {
+  if (!c || !out) return set_err(UDGPU_EINVAL, "null argument");
+  *out = nullptr;
+  if (c->abi_version != UDGPU_ABI_VERSION) return set_err(UDGPU_EINVAL, "ABI version mismatch: header %d, caller %d", UDGPU_ABI_VERSION, c->abi_version);
+  RET(validate_cfg(c, nccl_uid));
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_err(UDGPU_ENODEV, "no CUDA device visible: this library has no CPU fallback");
+  }
   udgpu *h = new udgpu();
+  const int rc = init_impl(h, c, nccl_uid, ndev);
+  if (rc != UDGPU_OK) {
+    // release whatever was built so far (stream, allocations, IPC mappings, communicator); keep the error text
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep));
+    udgpu_finalize(h);
+    memcpy(g_err, keep, sizeof(keep));
+    return rc;
+  }
+  *out = h;
+  return UDGPU_OK;
+}
+
+static int init_impl(udgpu *h, const udgpu_cfg *c, const void *nccl_uid, int ndev) {
   h->cfg = *c;
   h->P = c->nprocx;
   h->rank = c->nprocx > 1 ? c->myidx : 0;
@@ -380,11 +396,7 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
   CU(cudaSetDevice(h->dev));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, h->dev));
-  if (prop.major < 10) {
-    const int dv = h->dev;
-    delete h;
-    return set_err(UDGPU_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", dv, prop.major, prop.minor);
-  }
+  if (prop.major < 10) return set_err(UDGPU_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", h->dev, prop.major, prop.minor);
   CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   if (h->P > 1) NC(ncclCommInitRank(&h->comm, h->P, *(const ncclUniqueId *)nccl_uid, h->rank));
 
@@ -458,30 +470,12 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     h->IB = g.imax; h->JB = g.jtot / h->P;
     h->halo_cap = (size_t)8 * 2 * (g.pjc > g.pj ? g.pjc : g.pj) * (K + 2 * (g.khc > g.kh ? g.khc : g.kh));
     for (double **b : {&h->sendL, &h->sendR, &h->recvL, &h->recvR}) RET(dev_alloc(h, (void **)b, h->halo_cap * sizeof(double)));
-    for (double **b : {&h->sbuf, &h->rbuf, &h->workB}) RET(dev_alloc(h, (void **)b, nR * sizeof(double)));
+    for (double **b : {&h->sbuf, &h->workB}) RET(dev_alloc(h, (void **)b, nR * sizeof(double)));   // rbuf: NCCL path only (setup_p2p)
     h->gB = g;
     h->gB.imax = g.itot; h->gB.jmax = h->JB; h->gB.i0g = 0; h->gB.j0g = h->rank * h->JB;
-    // fields whose edge columns are stored by their producers directly into the neighbours (window-resident)
-    // opt-in (UDGPU_DIRECT_HALO=1): measured neutral at N = 2 but slower at N = 4, 8 (2.11 vs 1.99 ms per substep at N = 8) —
-    // edge-column stores are 8-byte NVLink transactions, the staged path sends the same columns as coalesced lines
-    const char *edh = getenv("UDGPU_DIRECT_HALO");
-    const bool want_direct = h->fuse_halo && edh && atoi(edh) == 1;
-    size_t off = 0;
-    if (want_direct)
-      for (int f : {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM, UDGPU_UP, UDGPU_EKM, UDGPU_EKH, UDGPU_P}) {
-        h->fwin_off[f] = off + 32;                      // +32: keeps 0 as "not in the window"; 256-byte aligned slices
-        off += (((f == UDGPU_UP ? nT : nF) + 31) / 32) * 32 + 32;
-      }
-    h->win_field_elems = off;
+    // halo exchanges rendezvous with the two ring neighbours only (default); UDGPU_HALO_NB_BARRIER=0: with all ranks
+    { const char *e = getenv("UDGPU_HALO_NB_BARRIER"); h->halo_set = (e && atoi(e) == 0) ? 0 : 2; }
     RET(setup_p2p(h, nR));
-    h->direct_halo = h->p2p && want_direct;
-    // opt-in (UDGPU_POISSON_CHUNKS=2): measured no gain at N = 2 and N = 8 (0.726 vs 0.730 ms per solve at N = 8)
-    { const char *e = getenv("UDGPU_HALO_NB_BARRIER"); h->halo_set = (e && atoi(e) == 1) ? 2 : 0; }
-    { const char *e = getenv("UDGPU_POISSON_CHUNKS"); h->pois_chunks = (h->p2p && K >= 8 && e && atoi(e) == 2) ? 2 : 1; }
-    if (h->pois_chunks > 1) {
-      CU(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
-      for (cudaEvent_t *ev : {&h->ev_start, &h->ev_xfB, &h->ev_z, &h->ev_doneB}) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
-    }
   }
   for (int f = 0; f < UDGPU_NFIELDS; f++) {
     size_t n = 0;
@@ -498,10 +492,8 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     h->dims[f][0] = (f == UDGPU_RHS) ? g.imax : scal ? g.pic : g.pi;
     h->dims[f][1] = (f == UDGPU_RHS) ? g.jmax : scal ? g.pjc : g.pj;
     h->dims[f][2] = d3;
-    if (h->direct_halo && h->fwin_off[f]) h->f[f] = h->wfield[h->rank] + h->fwin_off[f];   // zeroed with the window
-    else if (n) RET(dev_alloc(h, (void **)&h->f[f], n * sl * sizeof(double)));
+    if (n) RET(dev_alloc(h, (void **)&h->f[f], n * sl * sizeof(double)));
   }
-  RET(dev_alloc(h, (void **)&h->d_scr, nR * sizeof(double)));
   RET(dev_alloc(h, (void **)&h->d_red, 16 * sizeof(double)));
   for (double **t : {&h->d_fx, &h->d_fy, &h->d_fzero}) RET(dev_alloc(h, (void **)t, (K + 2) * sizeof(double)));
   CU(cudaMallocHost((void **)&h->h_red, 16 * sizeof(double)));
@@ -558,24 +550,23 @@ extern "C" int udgpu_init(const udgpu_cfg *c, const void *nccl_uid, udgpu_t **ou
     CU(cudaFuncSetAttribute(k_rfft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   CU(cudaStreamSynchronize(h->st));
-  *out = h;
   return UDGPU_OK;
 }
 
 extern "C" int udgpu_finalize(udgpu_t *h) {
   if (!h) return UDGPU_OK;
   cudaSetDevice(h->dev);
-  cudaStreamSynchronize(h->st);
+  if (h->st) cudaStreamSynchronize(h->st);
   for (void *p : h->allocs) cudaFree(p);
   if (h->h_red) cudaFreeHost(h->h_red);
+  if (h->h_status) cudaFreeHost((void *)h->h_status);
   for (int d = 0; d < 8; d++)
     if (h->ipc_peer[d] && h->ipc_peer[d] != h->ipc_mine) cudaIpcCloseMemHandle(h->ipc_peer[d]);
   if (h->comm) ncclCommDestroy(h->comm);
   for (int w = 0; w < PROF_N; w++)
     for (auto &e : h->ps[w].pend) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-  if (h->st2) cudaStreamDestroy(h->st2);
-  for (cudaEvent_t ev : {h->ev_start, h->ev_xfB, h->ev_z, h->ev_doneB}) if (ev) cudaEventDestroy(ev);
-  cudaStreamDestroy(h->st);
+  if (h->st) cudaStreamDestroy(h->st);
+  cudaGetLastError();
   delete h;
   return UDGPU_OK;
 }
@@ -606,7 +597,9 @@ extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
   if (field == UDGPU_UM || field == UDGPU_VM || field == UDGPU_WM) h->m_changed = true;
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(h->f[field] + (size_t)n4 * h->cnt[field], host, h->cnt[field] * sizeof(double), cudaMemcpyHostToDevice, h->st));
-  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP) h->tend_zero = false; h->tend_lazy_zero = false;
+  // only a pushed TENDENCY changes the tendency bookkeeping (its pending lazy zero-fill was materialised above);
+  // pushing u0, ekm, sv0, ... leaves a pending zero-fill pending
+  if (is_tend) { h->tend_zero = false; h->tend_lazy_zero = false; }
   return UDGPU_OK;
 }
 extern "C" int udgpu_pull(udgpu_t *h, int field, int n4, double *host) {
@@ -616,7 +609,7 @@ extern "C" int udgpu_pull(udgpu_t *h, int field, int n4, double *host) {
   RET(settle_for_access(h, field));
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(host, h->f[field] + (size_t)n4 * h->cnt[field], h->cnt[field] * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaStreamSynchronize(h->st));
+  RET(sync_check(h));
   return UDGPU_OK;
 }
 extern "C" int udgpu_device_ptr(udgpu_t *h, int field, int n4, void **dptr) {
@@ -632,15 +625,17 @@ extern "C" int udgpu_device_ptr(udgpu_t *h, int field, int n4, void **dptr) {
   *dptr = h->f[field] + (size_t)n4 * h->cnt[field];
   return UDGPU_OK;
 }
+// cudaStreamSynchronize + the peer-rendezvous verdict: every entry point that hands results to the host goes through here
+static int sync_check(udgpu *h) {
+  CU(cudaStreamSynchronize(h->st));
+  if (h->h_status && *h->h_status)
+    return set_err(UDGPU_ESTATE, "peer-to-peer rendezvous timed out after %.0f s (UDGPU_BARRIER_TIMEOUT_S): a peer rank is gone or lagging; "
+                                 "the device state is undefined from here on", (double)h->barrier_timeout_ns * 1e-9);
+  return UDGPU_OK;
+}
 extern "C" int udgpu_sync(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
-  CU(cudaStreamSynchronize(h->st));
-  if (h->p2p) {
-    int st = 0;
-    CU(cudaMemcpy(&st, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
-    if (st) return set_err(UDGPU_ESTATE, "peer-to-peer barrier timed out: a peer rank is gone");
-  }
-  return UDGPU_OK;
+  return sync_check(h);
 }
 extern "C" int udgpu_host_register(void *ptr, size_t bytes) {
   CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
@@ -663,7 +658,6 @@ static const dim3 B3(64, 4, 1);
 // x-halo exchange between neighbouring slabs over NCCL (periodic ring).
 // Send order right-then-left / receive order left-then-right so that with P = 2 (both neighbours are
 // the same peer) the first send meets the first receive.
-static int g_ih(udgpu *h) { return h->g.ih; }
 static int halo_x_exchange_g(udgpu *h, const std::vector<double *> &fields, int nlev, int pi, int pj, int imax, int hw) {
   HaloPack hp; hp.n = 0;
   long long off = 0;
@@ -672,25 +666,6 @@ static int halo_x_exchange_g(udgpu *h, const std::vector<double *> &fields, int 
   const long long rows = (long long)pj * nlev;
   const dim3 gr((unsigned)((rows + 127) / 128), hp.n);
   const int left = (h->rank + h->P - 1) % h->P, right = (h->rank + 1) % h->P;
-  if (h->direct_halo && hw == g_ih(h)) {
-    // window-resident fields: store the edge columns straight into the neighbours' halo columns, one flag barrier
-    PeerPack pk;
-    bool all = true;
-    for (int q = 0; q < hp.n; q++) {
-      int fid = -1;
-      for (int f = 0; f < UDGPU_NFIELDS; f++) if (h->f[f] == hp.f[q] && h->fwin_off[f]) fid = f;
-      if (fid < 0) { all = false; break; }
-      pk.L[q] = h->wfield[left] + h->fwin_off[fid];
-      pk.R[q] = h->wfield[right] + h->fwin_off[fid];
-    }
-    if (all) {
-      k_halo_push_x<<<gr, 128, 0, h->st>>>(hp, pk, pi, pj, imax, hw);
-      KCHECK();
-      RET(p2p_barrier(h));
-      h->launches++;
-      return UDGPU_OK;
-    }
-  }
   if (h->p2p) {
     // peer stores: my first columns land in the left neighbour's right-halo window, my last columns in the right
     // neighbour's left-halo window; one flag barrier; unpack from my own windows.  Windows alternate (parity) so a
@@ -757,27 +732,20 @@ extern "C" int udgpu_closure(udgpu_t *h) {
   const dim3 gr = grid3(g, B3);
   const int halo = h->fuse_halo ? 1 : 0;
   double **f = h->f;
-  const PeerCols pc = halo ? peer_cols(h, {UDGPU_EKM, UDGPU_EKH}) : peer_cols(h, {});
   // model selection order of the reference: smagorinsky first, then vreman, else DNS (modsubgrid.f90:208,269,401)
-  if (h->cfg.lsmagorinsky) { if (pc.L[0]) k_closure<2, true><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); else k_closure<2, false><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); }
-  else if (h->cfg.lvreman && h->use_tma && h->cl_occ > 0) {
-    if (h->cl_occ == 1) k_closure_vreman_tma<1><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
-    else k_closure_vreman_tma<2><<<h->cl_grid, CL_THREADS, CL_SMEM, h->st>>>(h->tm[0], h->tm[1], h->tm[2], h->clp, f[UDGPU_EKM], f[UDGPU_EKH], halo, pc);
-  }
+  if (h->cfg.lsmagorinsky) k_closure<2><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
   else if (h->cfg.lvreman && h->cl_march > 0) {
     constexpr int KC = 16;
     const dim3 gm(gr.x, gr.y, (g.ktot + KC - 1) / KC);
-    if (pc.L[0]) k_closure_vreman_march<KC, true><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc, h->fft_rev);
-    else k_closure_vreman_march<KC, false><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc, h->fft_rev);
+    k_closure_vreman_march<KC><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, h->fft_rev);
   }
-  else if (h->cfg.lvreman) { if (pc.L[0]) k_closure<1, true><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); else k_closure<1, false><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); }
-  else { if (pc.L[0]) k_closure<0, true><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); else k_closure<0, false><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, pc); }
+  else if (h->cfg.lvreman) k_closure<1><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
+  else k_closure<0><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
   KCHECK();
   h->launches++;
   if (halo) {
-    // closurebc's wraps and ghost levels were written by the closure kernel itself.  Split x: the edge columns went
-    // straight into the neighbours' halo columns (flag barrier), or travel through the pack / exchange / unpack path
-    if (h->P > 1) { if (h->direct_halo) RET(p2p_barrier(h)); else RET(halo_x_exchange(h, {f[UDGPU_EKM], f[UDGPU_EKH]}, g.ktot + 2 * g.kh)); }
+    // closurebc's wraps and ghost levels were written by the closure kernel itself; a split x still needs its slab exchange
+    if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_EKM], f[UDGPU_EKH]}, g.ktot + 2 * g.kh));
   } else {
     // closurebc: lateral wraps on all levels, then top/bottom ghost levels over the full halo'd plane
     RET(wrap_xy(h, {f[UDGPU_EKM], f[UDGPU_EKH]}, g.ktot + 2 * g.kh));
@@ -899,6 +867,7 @@ static int launch_scalars(udgpu *h, bool acc) {
 
 // run a deferred advection() on its own (something needs the tendencies before subgrid())
 static int tderive_now(udgpu *h);
+template <class After> static int slab_backward(udgpu *h, double *work, double *p_halo, After &&after);
 static int forces_now(udgpu *h) {
   h->forces_pending = false;
   const Geo &g = h->g;
@@ -911,6 +880,11 @@ static int forces_now(udgpu *h) {
 }
 static int flush_pending(udgpu *h, bool keep_forces) {
   if (h->forces_pending && !keep_forces) RET(forces_now(h));   // adv_pending cannot be set here: forces() flushed it
+  if (h->bwd_pending) {   // the inverse half of a pipelined slab solve, on its own
+    h->bwd_pending = false;
+    ProfScope ps(h, PROF_POIS);
+    RET(slab_backward(h, h->bwd_work, h->bwd_phalo, [](int, int) -> int { return UDGPU_OK; }));
+  }
   if (h->tder_pending) { h->tder_pending = false; RET(tderive_now(h)); }
   if (!h->adv_pending) return UDGPU_OK;
   h->adv_pending = false;
@@ -919,21 +893,6 @@ static int flush_pending(udgpu *h, bool keep_forces) {
   RET((launch_scalars<true, false>(h, !h->tend_zero)));
   h->tend_zero = false; h->tend_lazy_zero = false;
   return UDGPU_OK;
-}
-
-// the listed fields on the ring neighbours (direct halo stores); all nullptr when x is unsplit or not mapped
-static PeerCols peer_cols(udgpu *h, std::initializer_list<int> fields) {
-  PeerCols pc;
-  for (int q = 0; q < 6; q++) pc.L[q] = pc.R[q] = nullptr;
-  if (!h->direct_halo) return pc;
-  const int left = (h->rank + h->P - 1) % h->P, right = (h->rank + 1) % h->P;
-  int q = 0;
-  for (int f : fields) {
-    pc.L[q] = h->wfield[left] + h->fwin_off[f];
-    pc.R[q] = h->wfield[right] + h->fwin_off[f];
-    q++;
-  }
-  return pc;
 }
 
 // bring lazily maintained halo state up to what the reference would show before a field is handed out
@@ -1016,48 +975,12 @@ static int rfft_fast_setattr(int n) {
   return UDGPU_OK;
 }
 
-// fused x-FFT / z-solve / inverse x-FFT (poisson_xz.cuh): n -> (R1, R2, LANES) as for k_rfft_fast
-template <int R1, int R2, int LANES>
-static int xz_launch(udgpu *h, double *work, int nj, int j0g, const Geo &g) {
-  using T = XzT<R1, R2, LANES>;
-  if (h->xz_minb == 2 && R1 <= 16)
-    k_xzsolve<R1, R2, LANES, (R1 <= 16 ? 2 : 1)><<<nj, dim3(LANES, R2), T::SMEM, h->st>>>(h->px.tw, work, (long long)T::N, (long long)T::N * nj, g.ktot, j0g,
-                                                                                          h->nxh, h->nyh, h->d_zt, h->d_a, h->d_c, h->px.fac);
-  else
-    k_xzsolve<R1, R2, LANES, 1><<<nj, dim3(LANES, R2), T::SMEM, h->st>>>(h->px.tw, work, (long long)T::N, (long long)T::N * nj, g.ktot, j0g,
-                                                                          h->nxh, h->nyh, h->d_zt, h->d_a, h->d_c, h->px.fac);
-  KCHECK();
-  h->launches++;
-  return UDGPU_OK;
-}
-static int xz_solve(udgpu *h, double *work, int nj, int j0g, const Geo &g) {
-  switch (g.itot) {
-    case 64: return xz_launch<8, 4, 32>(h, work, nj, j0g, g);
-    case 128: return xz_launch<8, 8, 32>(h, work, nj, j0g, g);
-    case 256: return xz_launch<16, 8, 32>(h, work, nj, j0g, g);
-    case 512: return xz_launch<16, 16, 16>(h, work, nj, j0g, g);
-    case 1024: return xz_launch<32, 16, 8>(h, work, nj, j0g, g);
-  }
-  return set_err(UDGPU_EINVAL, "no fused x-z solve for itot=%d", g.itot);
-}
-static int xz_setattr(int n) {
-#define SA_(R1, R2, L)                                                                                                           \
-  CU(cudaFuncSetAttribute(k_xzsolve<R1, R2, L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, XzT<R1, R2, L>::SMEM)); \
-  CU(cudaFuncSetAttribute(k_xzsolve<R1, R2, L, (R1 <= 16 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, XzT<R1, R2, L>::SMEM))
-  switch (n) {
-    case 64: SA_(8, 4, 32); break;
-    case 128: SA_(8, 8, 32); break;
-    case 256: SA_(16, 8, 32); break;
-    case 512: SA_(16, 16, 16); break;
-    case 1024: SA_(32, 16, 8); break;
-  }
-#undef SA_
-  return UDGPU_OK;
-}
-
 static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt) {
   const Geo &g = h->g;
-  if ((h->cfg.flags & UDGPU_F_V1_KERNELS) && h->P == 1) return UDGPU_OK;
+  if ((h->cfg.flags & UDGPU_F_V1_KERNELS) && h->P == 1) {
+    // reference recurrence verbatim (k_solmpj): needs the d(imax,jmax,ktot) scratch of src/modpois.f90:1114
+    return dev_alloc(h, (void **)&h->d_scr, (size_t)g.imax * g.jmax * g.ktot * sizeof(double));
+  }
   { const char *e = getenv("UDGPU_ZU"); if (e && atoi(e) == 16) h->zu = 16; }
   { const char *e = getenv("UDGPU_FFT_LANES"); if (e && atoi(e) == 16) h->fft_lanes = 16; }
   { const char *e = getenv("UDGPU_FFT_REV"); if (e) h->fft_rev = atoi(e) != 0; }
@@ -1081,12 +1004,6 @@ static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, cons
   KCHECK();
   CU(cudaStreamSynchronize(h->st));
   h->fast_z = true;
-  // one-pass x part: needs the whole x line on this GPU and the register FFT for itot
-  // (opt-in: measured slower than the separate passes at 256^3 — 0.33 ms vs 0.26 ms — although it moves 2.3x fewer
-  //  bytes: one CTA per plane leaves 8 warps per SM, every phase is latency-exposed)
-  { const char *e = getenv("UDGPU_XZ_FUSED"); h->xz_fused = h->fast_x && h->P == 1 && (e && atoi(e) == 1); }
-  { const char *e = getenv("UDGPU_XZ_MINB"); if (e && atoi(e) == 2) h->xz_minb = 2; }
-  if (h->xz_fused) RET(xz_setattr(g.itot));
   return UDGPU_OK;
 }
 
@@ -1123,24 +1040,46 @@ static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *
 // rhs (halo-free work array) -> solution.  Final pass writes either in place or into the interior of
 // the halo'd p array.  Order x, y, z, y^-1, x^-1 as in src/modpois.f90:478-679.
 
-// exchange CUDA IPC handles of the receive windows through NCCL and map every peer's window
+// exchange CUDA IPC handles of the receive windows through NCCL and map every peer's window.  Every decision that
+// changes the communication pattern is taken collectively: the option mask must be identical on all ranks
+// (UDGPU_EINVAL everywhere otherwise) and the local "peer mapping works" verdict goes through an allreduce(min), so a
+// rank whose allocation or mapping failed takes all ranks to the NCCL path instead of leaving them in a collective.
 static int setup_p2p(udgpu *h, size_t nR) {
   h->p2p = false;
-  if (h->cfg.flags & UDGPU_F_NCCL_TRANSPOSE) return UDGPU_OK;
+  h->xmode = 0; h->xchunks = 1; h->xk0[0] = 0; h->xk0[1] = h->g.ktot;
   const int P = h->P;
+  int want_mode = 2;
+  { const char *e = getenv("UDGPU_XMODE"); if (e) want_mode = !strcmp(e, "nccl") ? 0 : !strcmp(e, "store") ? 1 : 2; }
+  if (h->cfg.flags & UDGPU_F_NCCL_TRANSPOSE) want_mode = 0;
+  int want_chunks = 0;
+  { const char *e = getenv("UDGPU_XCHUNKS"); if (e && atoi(e) >= 1 && atoi(e) <= 16) want_chunks = atoi(e); }
+  const int mask = want_mode | (h->halo_set << 4) | (want_chunks << 8) | ((h->cfg.flags & 0xff) << 16);
+  int *d_flag;
+  RET(dev_alloc(h, (void **)&d_flag, 4 * sizeof(int)));
+  int v[4] = {mask, -mask, 1, 0};
+  bool good = want_mode != 0;
   const size_t head = (((2 * nR + 4 * h->halo_cap) * sizeof(double) + 4096) + 255) / 256 * 256;   // [recvA | recvB | halo windows | flags]
-  const size_t bytes = head + h->win_field_elems * sizeof(double);                                 // ... | window-resident fields]
-  if (cudaMalloc(&h->ipc_mine, bytes) != cudaSuccess) { cudaGetLastError(); return UDGPU_OK; }
-  h->allocs.push_back(h->ipc_mine);
-  CU(cudaMemsetAsync(h->ipc_mine, 0, bytes, h->st));
-  RET(dev_alloc(h, (void **)&h->d_status, sizeof(int)));
+  if (good && cudaMalloc(&h->ipc_mine, head) != cudaSuccess) { cudaGetLastError(); h->ipc_mine = nullptr; good = false; }
+  if (h->ipc_mine) {
+    h->allocs.push_back(h->ipc_mine);
+    CU(cudaMemsetAsync(h->ipc_mine, 0, head, h->st));
+  }
+  {
+    int *hs = nullptr;
+    CU(cudaHostAlloc((void **)&hs, sizeof(int), cudaHostAllocMapped));
+    *hs = 0;
+    h->h_status = hs;
+    CU(cudaHostGetDevicePointer((void **)&h->d_status, hs, 0));
+    const char *e = getenv("UDGPU_BARRIER_TIMEOUT_S");
+    if (e && atof(e) > 0) h->barrier_timeout_ns = (unsigned long long)(atof(e) * 1e9);
+  }
   cudaIpcMemHandle_t mine;
-  unsigned char ok = cudaIpcGetMemHandle(&mine, h->ipc_mine) == cudaSuccess ? 1 : 0;
-  if (!ok) cudaGetLastError();
+  memset(&mine, 0, sizeof(mine));
+  if (good && cudaIpcGetMemHandle(&mine, h->ipc_mine) != cudaSuccess) { cudaGetLastError(); good = false; }
   // allgather {handle, ok} (80 bytes per rank) on the device through the communicator we already have
   struct Rec { cudaIpcMemHandle_t hd; unsigned char ok; unsigned char pad[15]; };
   static_assert(sizeof(Rec) == 80, "ipc record");
-  Rec rec; memset(&rec, 0, sizeof(rec)); rec.hd = mine; rec.ok = ok;
+  Rec rec; memset(&rec, 0, sizeof(rec)); rec.hd = mine; rec.ok = good ? 1 : 0;
   unsigned char *d_all;
   RET(dev_alloc(h, (void **)&d_all, sizeof(Rec) * P));
   CU(cudaMemcpyAsync(d_all + sizeof(Rec) * h->rank, &rec, sizeof(Rec), cudaMemcpyHostToDevice, h->st));
@@ -1148,39 +1087,59 @@ static int setup_p2p(udgpu *h, size_t nR) {
   std::vector<Rec> all(P);
   CU(cudaMemcpyAsync(all.data(), d_all, sizeof(Rec) * P, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
-  bool good = true;
   for (int d = 0; d < P; d++) good = good && all[d].ok;
   for (int d = 0; d < P && good; d++) {
     if (d == h->rank) { h->ipc_peer[d] = h->ipc_mine; continue; }
-    if (cudaIpcOpenMemHandle(&h->ipc_peer[d], all[d].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; }
+    if (cudaIpcOpenMemHandle(&h->ipc_peer[d], all[d].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); h->ipc_peer[d] = nullptr; good = false; }
   }
-  // every rank must take the same decision: allreduce(min) of the local verdict
-  int *d_flag;
-  RET(dev_alloc(h, (void **)&d_flag, sizeof(int)));
-  int v = good ? 1 : 0;
-  CU(cudaMemcpyAsync(d_flag, &v, sizeof(int), cudaMemcpyHostToDevice, h->st));
-  NC(ncclAllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, h->comm, h->st));
-  CU(cudaMemcpyAsync(&v, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  // one allreduce(min) of {mask, -mask, verdict}: min(mask) == max(mask) <=> all ranks run with the same options
+  v[2] = good ? 1 : 0;
+  CU(cudaMemcpyAsync(d_flag, v, sizeof(v), cudaMemcpyHostToDevice, h->st));
+  NC(ncclAllReduce(d_flag, d_flag, 4, ncclInt, ncclMin, h->comm, h->st));
+  CU(cudaMemcpyAsync(v, d_flag, sizeof(v), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
-  if (!v) return UDGPU_OK;   // stay on the NCCL send/recv path
+  if (v[0] != -v[1])
+    return set_err(UDGPU_EINVAL, "ranks disagree on the communication options (cfg.flags, UDGPU_XMODE, UDGPU_XCHUNKS, UDGPU_HALO_NB_BARRIER): "
+                                 "mask here 0x%x, min 0x%x, max 0x%x", mask, v[0], -v[1]);
+  if (!v[2]) {   // stay on the NCCL send/recv path (all ranks)
+    RET(dev_alloc(h, (void **)&h->rbuf, nR * sizeof(double)));
+    return UDGPU_OK;
+  }
   for (int d = 0; d < P; d++) {
     h->rA[d] = (double *)h->ipc_peer[d];
     h->rB[d] = h->rA[d] + nR;
     double *hb = h->rB[d] + nR;
     h->hL[d][0] = hb; h->hL[d][1] = hb + h->halo_cap; h->hR[d][0] = hb + 2 * h->halo_cap; h->hR[d][1] = hb + 3 * h->halo_cap;
     h->pflags.flags[d] = (unsigned long long *)(hb + 4 * h->halo_cap);
-    h->wfield[d] = (double *)((char *)h->ipc_peer[d] + head);
   }
   for (int d = P; d < 8; d++) h->pflags.flags[d] = nullptr;
   h->p2p = true;
+  h->xmode = want_mode;
+  if (h->xmode == 2) {
+    // k-chunks: per-peer copies of >= ~8 MiB keep the copy engines near their large-transfer rate
+    const int K = h->g.ktot;
+    const size_t blk_bytes = (size_t)h->IB * h->JB * K * sizeof(double);
+    int C = want_chunks ? want_chunks : (int)std::min<size_t>(8, std::max<size_t>(1, blk_bytes / ((size_t)8 << 20)));
+    C = std::max(1, std::min(C, std::min(16, K)));
+    h->xchunks = C;
+    for (int c = 0; c <= C; c++) h->xk0[c] = (int)(((long long)K * c) / C);
+    CU(cudaStreamCreateWithFlags(&h->sc, cudaStreamNonBlocking));
+    for (int c = 0; c < C; c++) {
+      CU(cudaEventCreateWithFlags(&h->ev_f[c], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&h->ev_r[c], cudaEventDisableTiming));
+    }
+  } else {
+    h->xchunks = 1; h->xk0[0] = 0; h->xk0[1] = h->g.ktot;
+  }
   return UDGPU_OK;
 }
 
-static int p2p_barrier(udgpu *h, int set) {
-  const unsigned long long e = set == 2 ? ++h->epoch3 : set ? ++h->epoch2 : ++h->epoch;
+static int p2p_barrier(udgpu *h, int set, cudaStream_t on) {
+  const unsigned long long e = ++h->epoch[set];
   unsigned peers = 0xffu;
   if (set == 2) peers = (1u << ((h->rank + h->P - 1) % h->P)) | (1u << ((h->rank + 1) % h->P));   // halo exchanges: ring neighbours only
-  k_p2p_barrier<<<1, 32, 0, h->st>>>(h->pflags, h->P, h->rank, e, h->d_status, set, peers);
+  if (h->h_status && *h->h_status) return set_err(UDGPU_ESTATE, "an earlier peer-to-peer rendezvous timed out: refusing to enqueue dependent work");
+  k_p2p_barrier<<<1, 32, 0, on ? on : h->st>>>(h->pflags, h->P, h->rank, e, h->d_status, set, peers, h->barrier_timeout_ns);
   KCHECK();
   h->launches++;
   return UDGPU_OK;
@@ -1204,121 +1163,147 @@ static int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 
 // slab-decomposed solve: y-FFT in the slab, all-to-all, x-FFT + z-solve + inverse x-FFT in the x-pencil,
 // all-to-all, inverse y-FFT.  2 exchanges per solve (the reference needs 4 at this decomposition); pack and
-// unpack are fused into the FFT kernels through the blocked descriptors.
-static int poisson_core_slab(udgpu *h, double *work, double *p_halo) {
+// unpack are fused into the FFT kernels through the blocked descriptors (wire format = 2decomp's: block d of a line
+// belongs to rank d, 2decomp-fft/src/transpose_x_to_y.f90:315-322).
+//
+// The solve is cut into k-chunks (h->xchunks).  xmode 2: a transform writes chunk c of the local wire-format buffer,
+// the copy stream moves its P-1 blocks into the peers' windows with the copy engines and closes the chunk with a
+// flag rendezvous; the consumer of chunk c waits for that event only.  So the transfer of chunk c runs under whatever
+// the main stream does next: fillps + forward y transform of chunk c+1 on the way in (`fill`), inverse y transform +
+// tderive/integrate of chunk c-1 on the way out (`after`).  xmode 1: the transforms store into the peers' windows
+// themselves (one chunk, rendezvous on the main stream); xmode 0: ncclSend/Recv.
+struct SlabGeo {
+  int IB, JB, K, P;
+  size_t blk;
+  long long wk;
+  LineDesc yA0, yW0, xW0, xB0, yOut0;
+  double *outp;
+};
+static SlabGeo slab_geo(udgpu *h, double *work, double *p_halo) {
   const Geo &g = h->g;
-  ProfScope ps(h, PROF_POIS);
-  const int IB = h->IB, JB = h->JB, K = g.ktot, P = h->P;
-  const size_t blk = (size_t)IB * JB * K;
-  const long long wk = (long long)JB * IB;                                        // level stride inside a wire-format block
-  const LineDesc yA0 = {(long long)IB, 1, (long long)IB * g.jtot, IB, K};        // y lines in the slab
-  const LineDesc yW0 = {(long long)IB, 1, wk, IB, K};                            // ... in wire format (per block)
-  const LineDesc xW0 = {1, (long long)IB, wk, JB, K};                            // x lines in wire format (per block)
-  const LineDesc xB0 = {1, (long long)g.itot, (long long)g.itot * JB, JB, K};    // x lines in the x-pencil
-  LineDesc yOut0 = yA0;
-  double *outp = work;
-  if (p_halo) { yOut0.sp = g.pi; yOut0.s2 = g.pk; outp = p_halo + offF(g, 1, 1, 1); }
-  // send / receive bases of the two exchanges (A: after the forward y transform, B: after the inverse x transform)
-  auto bases = [&](bool second, long long k0, BlkDesc &bs, BlkDesc &br) {
-    for (int d = 0; d < 8; d++) { bs.base[d] = d < P ? h->sbuf + d * blk + k0 * wk : nullptr; br.base[d] = d < P ? h->rbuf + d * blk + k0 * wk : nullptr; }
-    if (h->p2p)   // block for rank d is stored directly at slot `rank` of d's receive window
-      for (int d = 0; d < P; d++) {
-        double *const *win = second ? h->rB : h->rA;
-        bs.base[d] = win[d] + h->rank * blk + k0 * wk;
-        br.base[d] = win[h->rank] + d * blk + k0 * wk;
-      }
-  };
-  auto with_k = [](LineDesc d, int kc) { d.nb2 = kc; return d; };
-  auto fwd = [&](int k0, int kc, int set) -> int {       // forward y, exchange A, forward x for levels k0 .. k0+kc-1
-    BlkDesc bs, br;
-    bases(false, k0, bs, br);
-    bs.shift = ilog2(JB); bs.mask = JB - 1;
-    RET(rfft_fast<false>(h, g.jtot, 0, work + k0 * yA0.s2, with_k(yA0, kc), nullptr, with_k(yW0, kc), h->py, nullptr, &bs));
-    if (h->p2p) RET(p2p_barrier(h, set)); else RET(a2a_blocks(h));
-    br.shift = ilog2(IB); br.mask = IB - 1;
-    return rfft_fast<true>(h, g.itot, 0, nullptr, with_k(xW0, kc), h->workB + k0 * xB0.s2, with_k(xB0, kc), h->px, &br, nullptr);
-  };
-  auto bwd = [&](int k0, int kc, int set) -> int {       // inverse x, exchange B, inverse y
-    BlkDesc bs, br;
-    bases(true, k0, bs, br);
-    bs.shift = ilog2(IB); bs.mask = IB - 1;
-    RET(rfft_fast<true>(h, g.itot, 1, h->workB + k0 * xB0.s2, with_k(xB0, kc), nullptr, with_k(xW0, kc), h->px, nullptr, &bs));
-    if (h->p2p) RET(p2p_barrier(h, set)); else RET(a2a_blocks(h));
-    br.shift = ilog2(JB); br.mask = JB - 1;
-    return rfft_fast<false>(h, g.jtot, 1, nullptr, with_k(yW0, kc), outp + k0 * yOut0.s2, with_k(yOut0, kc), h->py, &br, nullptr);
-  };
-  auto zsolve = [&]() -> int {
-    if (h->zu == 16) k_zsolve<16><<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
-    else k_zsolve<8><<<dim3((g.itot + 127) / 128, JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
-    KCHECK();
-    h->launches++;
-    return UDGPU_OK;
-  };
-  if (h->pois_chunks < 2) {
-    RET(fwd(0, K, 0));
-    RET(zsolve());
-    return bwd(0, K, 0);
+  SlabGeo s;
+  s.IB = h->IB; s.JB = h->JB; s.K = g.ktot; s.P = h->P;
+  s.blk = (size_t)s.IB * s.JB * s.K;
+  s.wk = (long long)s.JB * s.IB;                                                   // level stride inside a wire-format block
+  s.yA0 = {(long long)s.IB, 1, (long long)s.IB * g.jtot, s.IB, s.K, 0};           // y lines in the slab
+  s.yW0 = {(long long)s.IB, 1, s.wk, s.IB, s.K, 0};                               // ... in wire format (per block)
+  s.xW0 = {1, (long long)s.IB, s.wk, s.JB, s.K, 0};                               // x lines in wire format (per block)
+  s.xB0 = {1, (long long)g.itot, (long long)g.itot * s.JB, s.JB, s.K, 0};         // x lines in the x-pencil
+  s.yOut0 = s.yA0;
+  s.outp = work;
+  if (p_halo) { s.yOut0.sp = g.pi; s.yOut0.s2 = g.pk; s.outp = p_halo + offF(g, 1, 1, 1); }
+  return s;
+}
+static LineDesc with_k(LineDesc d, int kc) { d.nb2 = kc; return d; }
+// send / receive bases of the two exchanges (A: after the forward y transform, B: after the inverse x transform)
+static void slab_bases(udgpu *h, const SlabGeo &s, bool second, long long k0, BlkDesc &bs, BlkDesc &br) {
+  const int P = s.P;
+  for (int d = 0; d < 8; d++) {
+    bs.base[d] = d < P ? h->sbuf + d * s.blk + k0 * s.wk : nullptr;
+    br.base[d] = (d < P && h->rbuf) ? h->rbuf + d * s.blk + k0 * s.wk : nullptr;
   }
-  // two k-chunks: A on the library stream, B on the second stream (its own barrier flags); the z solve needs both.
-  // The NVLink-bound kernels (forward y / inverse x, which store into the peers) of B start when A's have finished, so
-  // B's transfer runs under A's x (resp. inverse y) transform instead of competing with A's transfer for the link.
-  const int kA = K / 2, kB = K - kA;
-  auto on2 = [&](auto &&fn) -> int {   // run a launch sequence on the second stream
-    std::swap(h->st, h->st2);
-    const int rc = fn();
-    std::swap(h->st, h->st2);
-    return rc;
-  };
-  {
-    BlkDesc bs, br;
-    bases(false, 0, bs, br);
-    bs.shift = ilog2(JB); bs.mask = JB - 1;
-    RET(rfft_fast<false>(h, g.jtot, 0, work, with_k(yA0, kA), nullptr, with_k(yW0, kA), h->py, nullptr, &bs));
-    CU(cudaEventRecord(h->ev_start, h->st));           // A's forward y transform (and everything before it) is done
-    RET(p2p_barrier(h, 0));
-    br.shift = ilog2(IB); br.mask = IB - 1;
-    RET(rfft_fast<true>(h, g.itot, 0, nullptr, with_k(xW0, kA), h->workB, with_k(xB0, kA), h->px, &br, nullptr));
+  if (!h->p2p) return;
+  double *const *win = second ? h->rB : h->rA;
+  for (int d = 0; d < P; d++) {
+    // xmode 1: the block for rank d is stored directly at slot `rank` of d's receive window
+    if (h->xmode == 1) bs.base[d] = win[d] + h->rank * s.blk + k0 * s.wk;
+    br.base[d] = win[h->rank] + d * s.blk + k0 * s.wk;
   }
-  CU(cudaStreamWaitEvent(h->st2, h->ev_start, 0));
-  RET(on2([&]() -> int {
-    RET(fwd(kA, kB, 1));
-    CU(cudaEventRecord(h->ev_xfB, h->st));
+  if (h->xmode == 2) br.base[h->rank] = h->sbuf + h->rank * s.blk + k0 * s.wk;   // my own block never leaves the send buffer
+}
+// ship chunk c of the wire-format send buffer: main stream -> (event) -> copy stream: P-1 copy-engine transfers into
+// the peers' windows, rendezvous, -> (event) -> whoever consumes chunk c
+static int slab_ship(udgpu *h, const SlabGeo &s, bool second, int c) {
+  const long long k0 = h->xk0[c], kc = h->xk0[c + 1] - h->xk0[c];
+  if (h->xmode == 2) {
+    CU(cudaEventRecord(h->ev_f[c], h->st));
+    CU(cudaStreamWaitEvent(h->sc, h->ev_f[c], 0));
+    double *const *win = second ? h->rB : h->rA;
+    for (int q = 1; q < s.P; q++) {
+      const int d = (h->rank + q) % s.P;   // step q of all ranks together is a permutation: no destination is hit twice
+      CU(cudaMemcpyAsync(win[d] + h->rank * s.blk + k0 * s.wk, h->sbuf + d * s.blk + k0 * s.wk, (size_t)kc * s.wk * sizeof(double),
+                         cudaMemcpyDeviceToDevice, h->sc));
+    }
+    RET(p2p_barrier(h, 0, h->sc));
+    CU(cudaEventRecord(h->ev_r[c], h->sc));
     return UDGPU_OK;
-  }));
-  CU(cudaStreamWaitEvent(h->st, h->ev_xfB, 0));
-  RET(zsolve());
-  {
-    BlkDesc bs, br;
-    bases(true, 0, bs, br);
-    bs.shift = ilog2(IB); bs.mask = IB - 1;
-    RET(rfft_fast<true>(h, g.itot, 1, h->workB, with_k(xB0, kA), nullptr, with_k(xW0, kA), h->px, nullptr, &bs));
-    CU(cudaEventRecord(h->ev_z, h->st));               // z solve and A's inverse x transform are done
-    RET(p2p_barrier(h, 0));
-    br.shift = ilog2(JB); br.mask = JB - 1;
-    RET(rfft_fast<false>(h, g.jtot, 1, nullptr, with_k(yW0, kA), outp, with_k(yOut0, kA), h->py, &br, nullptr));
   }
-  CU(cudaStreamWaitEvent(h->st2, h->ev_z, 0));
-  RET(on2([&]() -> int {
-    RET(bwd(kA, kB, 1));
-    CU(cudaEventRecord(h->ev_doneB, h->st));
-    return UDGPU_OK;
-  }));
-  CU(cudaStreamWaitEvent(h->st, h->ev_doneB, 0));
+  if (h->p2p) return p2p_barrier(h, 0);
+  return a2a_blocks(h);
+}
+static int slab_landed(udgpu *h, int c) {
+  if (h->xmode == 2) CU(cudaStreamWaitEvent(h->st, h->ev_r[c], 0));
   return UDGPU_OK;
+}
+// forward half + z solve.  fill(k0, kc): producer of the right-hand side levels k0 .. k0+kc-1 (fillps), may be empty
+template <class Fill>
+static int slab_forward(udgpu *h, double *work, Fill &&fill) {
+  const Geo &g = h->g;
+  const SlabGeo s = slab_geo(h, work, nullptr);
+  const int C = h->xchunks;
+  for (int c = 0; c < C; c++) {
+    const int k0 = h->xk0[c], kc = h->xk0[c + 1] - k0;
+    RET(fill(k0, kc));
+    BlkDesc bs, br;
+    slab_bases(h, s, false, k0, bs, br);
+    bs.shift = ilog2(s.JB); bs.mask = s.JB - 1;
+    RET(rfft_fast<false>(h, g.jtot, 0, work + k0 * s.yA0.s2, with_k(s.yA0, kc), nullptr, with_k(s.yW0, kc), h->py, nullptr, &bs));
+    RET(slab_ship(h, s, false, c));
+  }
+  for (int c = 0; c < C; c++) {
+    const int k0 = h->xk0[c], kc = h->xk0[c + 1] - k0;
+    RET(slab_landed(h, c));
+    BlkDesc bs, br;
+    slab_bases(h, s, false, k0, bs, br);
+    br.shift = ilog2(s.IB); br.mask = s.IB - 1;
+    RET(rfft_fast<true>(h, g.itot, 0, nullptr, with_k(s.xW0, kc), h->workB + k0 * s.xB0.s2, with_k(s.xB0, kc), h->px, &br, nullptr));
+  }
+  if (h->zu == 16) k_zsolve<16><<<dim3((g.itot + 127) / 128, s.JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
+  else k_zsolve<8><<<dim3((g.itot + 127) / 128, s.JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+// inverse half.  after(k0, kc): consumer of the solution levels k0 .. k0+kc-1 (tderive + integrate), may be empty.
+// Software pipeline: the inverse x transform of chunk c+1 is enqueued before the consumer side of chunk c, so the
+// copy engines always have the next chunk to move while the main stream works on the previous one.
+template <class After>
+static int slab_backward(udgpu *h, double *work, double *p_halo, After &&after) {
+  const Geo &g = h->g;
+  const SlabGeo s = slab_geo(h, work, p_halo);
+  const int C = h->xchunks;
+  auto xinv = [&](int c) -> int {
+    const int k0 = h->xk0[c], kc = h->xk0[c + 1] - k0;
+    BlkDesc bs, br;
+    slab_bases(h, s, true, k0, bs, br);
+    bs.shift = ilog2(s.IB); bs.mask = s.IB - 1;
+    RET(rfft_fast<true>(h, g.itot, 1, h->workB + k0 * s.xB0.s2, with_k(s.xB0, kc), nullptr, with_k(s.xW0, kc), h->px, nullptr, &bs));
+    return slab_ship(h, s, true, c);
+  };
+  RET(xinv(0));
+  for (int c = 0; c < C; c++) {
+    if (c + 1 < C) RET(xinv(c + 1));
+    const int k0 = h->xk0[c], kc = h->xk0[c + 1] - k0;
+    RET(slab_landed(h, c));
+    BlkDesc bs, br;
+    slab_bases(h, s, true, k0, bs, br);
+    br.shift = ilog2(s.JB); br.mask = s.JB - 1;
+    RET(rfft_fast<false>(h, g.jtot, 1, nullptr, with_k(s.yW0, kc), s.outp + k0 * s.yOut0.s2, with_k(s.yOut0, kc), h->py, &br, nullptr));
+    RET(after(k0, kc));
+  }
+  return UDGPU_OK;
+}
+static int poisson_core_slab(udgpu *h, double *work, double *p_halo) {
+  ProfScope ps(h, PROF_POIS);
+  auto nop = [](int, int) -> int { return UDGPU_OK; };
+  RET(slab_forward(h, work, nop));
+  return slab_backward(h, work, p_halo, nop);
 }
 
 static int poisson_core(udgpu *h, double *work, double *p_halo) {
   const Geo &g = h->g;
   if (h->P > 1) return poisson_core_slab(h, work, p_halo);
   ProfScope ps(h, PROF_POIS);
-  if (h->xz_fused && h->fast_z) {
-    // y, [x, z, x^-1] in one pass, y^-1: three passes over memory instead of five (transforms commute)
-    RET(fft_pass(h, false, 0, work, work, false));
-    RET(xz_solve(h, work, g.jmax, g.j0g, g));
-    if (p_halo) RET(fft_pass(h, false, 1, work, p_halo + offF(g, 1, 1, 1), true));
-    else RET(fft_pass(h, false, 1, work, work, false));
-    return UDGPU_OK;
-  }
   RET(fft_pass(h, true, 0, work, work, false));
   RET(fft_pass(h, false, 0, work, work, false));
   if (h->fast_z) { if (h->zu == 16) k_zsolve<16><<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, h->nxh, h->nyh, work, h->d_zt, h->d_a, h->d_c);
@@ -1340,37 +1325,54 @@ extern "C" int udgpu_poisson_solve_resident(udgpu_t *h) {
 
 extern "C" int udgpu_poisson_solve(udgpu_t *h, const double *rhs, double *p) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (!rhs || !p) return set_err(UDGPU_EINVAL, "null argument");
+  RET(flush_pending(h));
   const size_t bytes = h->cnt[UDGPU_RHS] * sizeof(double);
   CU(cudaMemcpyAsync(h->f[UDGPU_RHS], rhs, bytes, cudaMemcpyHostToDevice, h->st));
   RET(poisson_core(h, h->f[UDGPU_RHS], nullptr));
   CU(cudaMemcpyAsync(p, h->f[UDGPU_RHS], bytes, cudaMemcpyDeviceToHost, h->st));
-  CU(cudaStreamSynchronize(h->st));
+  RET(sync_check(h));
   return UDGPU_OK;
 }
 
-extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
-  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+// fillps (+ bcpup), src/modpois.f90:911-973: everything before the sweep (pending operators, the slab exchange of up) ...
+static int fillps_prepare(udgpu *h) {
   // a pending forces() stays pending: dpdxl(k), dpdyl(k) are uniform in x, y and drop out of the divergence
   // (src/modpois.f90:968-970), and fillps already takes pwp(kb) = 0 (src/modboundary.f90:1227-1232)
   RET(flush_pending(h, true));
   const Geo &g = h->g;
   RET(materialize_zero_tend(h));
-  ProfScope ps(h, PROF_FILLPS);
-  const double rk3coef = (rk3step == 0) ? 1. : dt / (4. - (double)rk3step);
-  const double rk3coefi = 1. / rk3coef;
   if (h->P > 1) {
+    ProfScope ps(h, PROF_FILLPS);
     // bcpup's exchange_halo_z(pup) (src/modboundary.f90:1219): only up(ie+1) is missing, um's halo is valid
     RET(halo_x_exchange(h, {h->f[UDGPU_UP]}, g.ktot + g.kh));
     // ibmnorm zeroed um at solid points after the last halos(): pup(ie+1) needs the neighbour's current um(1) too
     if (h->m_halo_stale) RET(halo_x_exchange(h, {h->f[UDGPU_UM]}, g.ktot + 2 * g.kh));
-    k_fillps<false, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
-                                                          h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS], 0);
-  } else
-  k_fillps<true, true><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
-                                                       h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS], h->fft_rev);
+  }
+  return UDGPU_OK;
+}
+// ... and the sweep itself for the 0-based levels k0 .. k0+kc-1
+static int fillps_launch(udgpu *h, double dt, int rk3step, int k0, int kc) {
+  const Geo &g = h->g;
+  const double rk3coef = (rk3step == 0) ? 1. : dt / (4. - (double)rk3step);
+  const double rk3coefi = 1. / rk3coef;
+  dim3 gr = grid3(g, B3);
+  gr.z = kc;
+  if (h->P > 1)
+    k_fillps<false, true><<<gr, B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
+                                                 h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS], 0, k0);
+  else
+    k_fillps<true, true><<<gr, B3, 0, h->st>>>(g, rk3coefi, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP], h->f[UDGPU_UM],
+                                                h->f[UDGPU_VM], h->f[UDGPU_WM], h->f[UDGPU_RHS], h->fft_rev, k0);
   KCHECK();
   h->launches++;
   return UDGPU_OK;
+}
+extern "C" int udgpu_fillps(udgpu_t *h, double dt, int rk3step) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  RET(fillps_prepare(h));
+  ProfScope ps(h, PROF_FILLPS);
+  return fillps_launch(h, dt, rk3step, 0, h->g.ktot);
 }
 
 extern "C" int udgpu_tderive(udgpu_t *h) {
@@ -1404,6 +1406,20 @@ static int tderive_now(udgpu *h) {
 
 extern "C" int udgpu_poisson(udgpu_t *h, double dt, int rk3step) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (h->P > 1 && h->xmode == 2 && !(h->cfg.flags & UDGPU_F_NO_LAZY_FUSION)) {
+    // pipelined slab solve: fillps and the forward y transform run chunk by chunk under the copy-engine transfers of
+    // the previous chunk; the inverse half is left pending so that tstep_integrate() can run it chunk by chunk
+    // together with tderive + integrate (any other access finishes it first, see flush_pending)
+    RET(fillps_prepare(h));
+    {
+      ProfScope ps(h, PROF_POIS);
+      RET(slab_forward(h, h->f[UDGPU_RHS], [&](int k0, int kc) -> int { return fillps_launch(h, dt, rk3step, k0, kc); }));
+    }
+    h->bwd_pending = true; h->bwd_work = h->f[UDGPU_RHS]; h->bwd_phalo = h->f[UDGPU_P];
+    h->p_halo_valid = false;
+    h->tder_pending = true;
+    return UDGPU_OK;
+  }
   RET(udgpu_fillps(h, dt, rk3step));
   RET(poisson_core(h, h->f[UDGPU_RHS], h->f[UDGPU_P]));
   h->p_halo_valid = false;
@@ -1432,24 +1448,43 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
   double **f = h->f;
   if (h->tder_pending && !h->adv_pending) {
     h->tder_pending = false;
-    ProfScope ps(h, PROF_INTEG);
     const bool own = h->fuse_halo && !h->halo_dirty && !h->bc_dirty;
+    if (!own && h->bwd_pending) {
+      h->bwd_pending = false;
+      ProfScope ps(h, PROF_POIS);
+      RET(slab_backward(h, h->bwd_work, h->bwd_phalo, [](int, int) -> int { return UDGPU_OK; }));
+    }
+    ProfScope ps(h, h->bwd_pending ? PROF_BWDPIPE : PROF_INTEG);
     if (own) {
       // one pass: bcp (periodic index / slab exchange of p), tderive, integrate, pres0 += p, halos, boundary
-      if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));
-      const PeerCols pc = peer_cols(h, {UDGPU_U0, UDGPU_V0, UDGPU_W0, UDGPU_UM, UDGPU_VM, UDGPU_WM});
-#define TI_(S3, XS, FO) k_tderive_integrate_halo<S3, XS, FO><<<grid3(g, B3), B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM], \
-                                                                       f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], pc, \
-                                                                       h->d_fx, h->d_fy, 1)
-#define TI2_(S3, XS) do { if (fp) TI_(S3, XS, true); else TI_(S3, XS, false); } while (0)
       const bool fp = h->forces_pending;
       h->forces_pending = false;
-      if (rk3step == 3) { if (pc.L[0]) TI2_(true, 2); else if (h->P > 1) TI2_(true, 1); else TI2_(true, 0); }
-      else { if (pc.L[0]) TI2_(false, 2); else if (h->P > 1) TI2_(false, 1); else TI2_(false, 0); }
+      auto integ = [&](int k0, int kc) -> int {   // 0-based levels k0 .. k0+kc-1
+        dim3 gr = grid3(g, B3);
+        gr.z = kc;
+#define TI_(S3, XS, FO) k_tderive_integrate_halo<S3, XS, FO><<<gr, B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM], \
+                                                                       f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], \
+                                                                       h->d_fx, h->d_fy, 1, k0)
+#define TI2_(S3, XS) do { if (fp) TI_(S3, XS, true); else TI_(S3, XS, false); } while (0)
+        if (rk3step == 3) { if (h->P > 1) TI2_(true, 1); else TI2_(true, 0); }
+        else { if (h->P > 1) TI2_(false, 1); else TI2_(false, 0); }
 #undef TI2_
 #undef TI_
-      KCHECK();
-      h->launches++;
+        KCHECK();
+        h->launches++;
+        return UDGPU_OK;
+      };
+      if (h->bwd_pending) {
+        // inverse x transform / copy-engine transfer / inverse y transform / p halo / tderive+integrate, chunk by chunk
+        h->bwd_pending = false;
+        RET(slab_backward(h, h->bwd_work, h->bwd_phalo, [&](int k0, int kc) -> int {
+          RET(halo_x_exchange(h, {f[UDGPU_P] + (long long)(k0 + g.kh) * g.pk}, kc));
+          return integ(k0, kc);
+        }));
+      } else {
+        if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));
+        RET(integ(0, g.ktot));
+      }
       h->halos_done = h->bc_done = true;
       h->halo_x_pending = h->P > 1;
       if (rk3step == 3) h->m_changed = true;
@@ -1507,8 +1542,7 @@ extern "C" int udgpu_halos(udgpu_t *h) {
   if (h->halos_done && !h->halo_dirty) {
     // the fused tderive+integrate kernel wrote the periodic images itself; a split x still needs its exchange
     if (h->halo_x_pending) {
-      if (h->direct_halo) RET(p2p_barrier(h));   // the integrate kernel stored the edge columns into the neighbours
-      else if (h->m_changed) RET(halo_x_exchange(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
+      if (h->m_changed) RET(halo_x_exchange(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
       else RET(halo_x_exchange(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0]}, g.ktot + 2 * g.kh));   // um, vm, wm only change on substep 3
       h->halo_x_pending = false;
       h->m_changed = false;
@@ -1564,7 +1598,7 @@ extern "C" int udgpu_tstep_update(udgpu_t *h, double *dt, double courant, double
     h->launches++;
     if (h->P > 1) NC(ncclAllReduce(h->d_red, h->d_red, 2, ncclDouble, ncclMax, h->comm, h->st));  // MPI_ALLREDUCE(MAX), src/modtstep.f90:131-132
     CU(cudaMemcpyAsync(h->h_red, h->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));
+    RET(sync_check(h));
     const double ct = h->h_red[0], dn = fmax(1e-5, h->h_red[1]);  // src/modtstep.f90:114-115
     if (courtot) *courtot = ct;
     if (diffnrtot) *diffnrtot = dn;
@@ -1589,7 +1623,7 @@ extern "C" int udgpu_divergence(udgpu_t *h, double *divmax, double *divtot, doub
     NC(ncclAllReduce(h->d_red + 5, h->d_red + 5, 2, ncclDouble, ncclSum, h->comm, h->st));
   }
   CU(cudaMemcpyAsync(h->h_red + 4, h->d_red + 4, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaStreamSynchronize(h->st));
+  RET(sync_check(h));
   if (divmax) *divmax = h->h_red[4];
   if (divtot) *divtot = h->h_red[5];
   if (divrms) *divrms = sqrt(h->h_red[6] / ((double)g.itot * g.jtot * g.ktot));
@@ -1688,7 +1722,7 @@ extern "C" int udgpu_ibm_pull_mask(udgpu_t *h, int m, double *host) {
   if (!h || m < 0 || m > 3 || !h->ibm_mask[m]) return set_err(UDGPU_EINVAL, "no such mask (udgpu_ibm_commit first)");
   const Geo &g = h->g;
   CU(cudaMemcpyAsync(host, h->ibm_mask[m], g.pk * (g.ktot + 2 * g.kh) * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaStreamSynchronize(h->st));
+  RET(sync_check(h));
   return UDGPU_OK;
 }
 
@@ -1751,7 +1785,7 @@ extern "C" int udgpu_rk3_step_host(udgpu_t *h, double *u0, double *v0, double *w
   RET(flush_pending(h));
   for (int q = 0; q < 4; q++)
     CU(cudaMemcpyAsync(host[q], h->f[ids[q]], h->cnt[ids[q]] * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaStreamSynchronize(h->st));
+  RET(sync_check(h));
   return UDGPU_OK;
 }
 
