@@ -30,13 +30,16 @@ import numpy as np  # noqa: E402
 B_PER_CELL = {  # algorithmic (compulsory) fp64 bytes per cell, SURVEY.md §8d / DESIGN.md
     "mom_tend": 64.0, "closure": 40.0, "poisson_core": 80.0, "fillps": 56.0, "tderive_integrate": 96.0, "halos": 0.0,
 }
-PROF_NAMES = ["mom_tend", "closure", "poisson_core", "fillps", "tderive_integrate", "halos"]
-# DRAM traffic per launch group (dram__bytes_read.sum + dram__bytes_write.sum, bytes) from the ncu --set full captures of
-# the 256^3 substep committed under profiles/ (r1_substep_kernels_ncu_[ab].txt); only quoted for that grid on one GPU
-NCU_TRAFFIC_256 = {"mom_tend": 708.0e6 + 372.0e6, "closure": 417.3e6 + 242.0e6, "fillps": 810.7e6 + 126.4e6,
-                   "tderive_integrate": 1083.6e6 + 512.7e6,
-                   "poisson_core": (134.2 + 76.3 + 134.3 + 75.3 + 249.6 + 154.0 + 136.3 + 90.1 + 134.3 + 76.0) * 1e6}
-
+PROF_NAMES = ["mom_tend", "closure", "poisson_core", "fillps", "tderive_integrate", "halos", "poisson_inverse+tderive_integrate (pipelined)"]
+# DRAM traffic per launch group (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch of the family) of the
+# 256^3 substep: regenerated from an `ncu --set full` capture of the current kernels by tools/ncu_traffic.py, which
+# writes profiles/ncu_traffic_256.json together with the commit it was captured at.  Absent file -> traffic is null.
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_256.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -143,40 +146,77 @@ def urban_blocks(I, J, K, i_lo, imax):
     return lists
 
 
+def workload_config(args, world):
+    """the `config` object: identical in both arms (ours / --impl reference) for the same command line"""
+    I, J, K = grid_for(world, args.size)
+    if args.grid:
+        I, J, K = (int(x) for x in args.grid.split(","))
+    what = {"channel": f"neutral periodic channel {I}x{J}x{K}, stencil+Poisson only, no IBM/scalars",
+            "scalars": f"periodic channel {I}x{J}x{K} + 4 kappa-advected passive scalars",
+            "ibm": f"periodic channel {I}x{J}x{K} + urban blocks (16x16x8 per 32x32 tile) masked by the IBM path",
+            "poisson": f"Poisson solve only, {I}x{J}x{K}, rhs resident"}[args.workload]
+    what += " (BASELINE config 2)" if (world == 1 and args.workload == "channel" and (I, J, K) == (256, 256, 256)) else \
+            f" ({I * J * K // world} cells per GPU, x-slabs nprocx={world})"
+    return {"workload": what, "grid": [I, J, K], "substeps_per_step": 1,
+            "l2": "per-GPU working set (13 fields x 134 MB at 256^3) >> 126 MB L2, no flush needed",
+            "sgs": "vreman", "poisson": "FFT2D x,y + tridiagonal z", "decomposition": f"nprocx={world}, nprocy=1",
+            "ladaptive": False}
+
+
+def native_oracle():
+    """the CPU arm's own build of the oracle: -O3 -march=native (FMA contraction allowed), compiled ON THE BOX that
+    runs it (the parity build oracle/liboracle.so stays -ffp-contract=off and generic x86-64)."""
+    out = os.path.join(ROOT, "oracle", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "liboracle_native.so")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    flags = ["-O3", "-march=native", "-fopenmp", "-fPIC", "-std=gnu11", "-Wno-unused-variable"]
+    try:
+        subprocess.check_call([cc] + flags + ["-shared", "-o", so, os.path.join(ROOT, "oracle", "udales_oracle.c"), "-lm"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return so, " ".join(flags)
+    except Exception:
+        return None, "-O3 -ffp-contract=off (parity build; the native build failed)"
+
+
+def cpu_arm(n, nsub, dt):
+    """time `nsub` RK3 substeps of an n^3 block of the channel with the oracle port on all host cores"""
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)     # torchrun sets it to 1
+    so, flags = native_oracle()
+    import oracle.oracle as OM
+    if so:
+        OM.use_library(so)
+    o = OM.Oracle(n, n, n)
+    o.init_channel()
+    o.dt = dt
+    for _ in range(2):
+        o.substep(dt)
+    t0 = time.perf_counter()
+    for _ in range(nsub):
+        o.substep(dt)
+    el = time.perf_counter() - t0
+    return n ** 3 * nsub / el, el, cores, flags
+
+
 # --------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """CPU arm: the oracle (C/OpenMP restatement of the reference loops — the Fortran/MPI binary
     cannot be built here: no Fortran compiler, MPI or FFTW).  Rank 0 only."""
     if rank != 0:
         return
-    from oracle.oracle import Oracle
-    n = args.size
-    I, J, K = grid_for(world, args.size)
-    cores = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(cores)     # torchrun sets it to 1
-    o = Oracle(n, n, n)
-    o.init_channel()
-    dt = 0.25 * o.dx / 1.1
-    o.dt = dt
-    for _ in range(args.warmup):
-        o.substep(dt)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        o.substep(dt)
-    el = time.perf_counter() - t0
-    val = n ** 3 * args.steps / el
+    n = min(args.size, 256)
+    dt = 0.25 * 0.5 / 1.1
+    val, el, cores, flags = cpu_arm(n, args.steps, dt)
     line = {
         "impl": "reference", "metric": "cell-updates/s", "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": 2, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"neutral periodic channel {I}x{J}x{K}, stencil+Poisson only, no IBM/scalars "
-                               + ("(BASELINE config 2)" if world == 1 else f"(config 2 weak-scaled: {args.size}^3 cells per GPU, x-slabs)"),
-                   "grid": [I, J, K], "substeps_per_step": 1,
-                   "sample_grid": [n, n, n]},
-        "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "cflags": flags,
                          "sample": f"{args.steps} RK3 substeps on a {n}^3 block of the workload (the whole workload at N=1; cell-updates/s "
-                                   "is intensive), C/OpenMP restatement of the reference loops on all host cores "
-                                   "(not the Fortran/MPI binary: no Fortran/MPI/FFTW in the image; in-tree radix-2 FFT instead of FFTW)"},
+                                   "is intensive), C/OpenMP restatement of the reference loops on all host cores of ONE box "
+                                   "(not the Fortran/MPI binary: no Fortran/MPI/FFTW in the image; in-tree iterative radix-2 FFT instead of FFTW)"},
         "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -184,6 +224,47 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------------
+def _cudart():
+    import ctypes as C
+    rt = C.CDLL("libcudart.so.12")
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    return rt
+
+
+def init_state_on_device(g, torch, imax, J, K, seed):
+    """the synthetic channel for grids too large to stage through host memory (1024^3: 8.6 GB per field): u = 1 + noise,
+    v, w = noise, generated by torch on the device level block by level block and copied into the library's arrays
+    (udgpu_device_ptr); halos()/boundary() then fill the halo cells and um, vm, wm become copies of u0, v0, w0."""
+    import ctypes as C
+    rt = _cudart()
+    ptr = {}
+    for nm in ("u0", "v0", "w0", "um", "vm", "wm"):
+        d = C.c_void_p()
+        g._chk(g.L.udgpu_device_ptr(g.h, U_FIELD_IDS[nm], 0, C.byref(d)))
+        ptr[nm] = d.value
+    g.sync()
+    pi, pj = imax + 2, J + 2
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed)
+    blk = max(1, min(K, (256 << 20) // (pi * pj * 8)))
+    for nm, base, lo in (("u0", 1.0, 1), ("v0", 0.0, 1), ("w0", 0.0, 2)):
+        for k0 in range(lo, K + 1, blk):       # storage level = Fortran k (kh = 1); w(kb) stays 0
+            nl = min(blk, K + 1 - k0)
+            t = torch.zeros((nl, pj, pi), dtype=torch.float64, device="cuda")
+            t[:, 1:-1, 1:-1] = base + 0.05 * (torch.rand((nl, J, imax), dtype=torch.float64, device="cuda", generator=gen) - 0.5)
+            torch.cuda.synchronize()
+            assert rt.cudaMemcpy(ptr[nm] + k0 * pi * pj * 8, t.data_ptr(), nl * pi * pj * 8, 3) == 0
+            del t
+    g.halos(); g.boundary(); g.sync()
+    n = pi * pj * (K + 2) * 8
+    for a, b in (("um", "u0"), ("vm", "v0"), ("wm", "w0")):
+        assert rt.cudaMemcpy(ptr[a], ptr[b], n, 3) == 0
+    torch.cuda.synchronize()
+
+
+U_FIELD_IDS = {"u0": 0, "v0": 1, "w0": 2, "um": 3, "vm": 4, "wm": 5}
+
+
 def run_ours(args, rank, world):
     # NCCL prints its version banner on stdout: keep stdout clean for the ONE JSON line
     real_stdout = os.dup(1)
@@ -192,80 +273,107 @@ def run_ours(args, rank, world):
     import udales_b200 as U
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
-    uid = None
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+
+    def fresh_uid():
+        if world == 1:
+            return None
         obj = [U.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
-        uid = obj[0]
-    I, J, K = grid_for(world, args.size)
-    if args.grid:
-        I, J, K = (int(x) for x in args.grid.split(","))
+        return obj[0]
+
+    def max_over_ranks(x, op="max"):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.MIN)
+        return float(t.item())
+
+    # ---- parity of this very build and decomposition against the CPU oracle, OUTSIDE every timed region ------------
+    parity = None
+    if not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from slab_parity import bench_parity
+        from oracle.oracle import Oracle
+        parity = bench_parity(U, Oracle, world, rank, dev, fresh_uid)
+        parity["max_abs_err"] = max_over_ranks(parity["max_abs_err"])
+        parity["ok"] = bool(max_over_ranks(1.0 if parity["ok"] else 0.0, "min") > 0.5)
+
+    cfg = workload_config(args, world)
+    I, J, K = cfg["grid"]
     imax = I // world
     nsv = 4 if args.workload == "scalars" else 0
-    g = U.UdalesGPU(I, J, K, xlen=I / 2.0, ylen=J / 2.0, zf=(np.arange(K) + 0.5) * 0.5, device=dev,
-                    nprocx=world, myidx=rank, nccl_uid=uid, nsv=nsv)
-    u, v, w = channel_slab(I, J, K, rank * imax, imax)
-    for nm, f in (("u0", u), ("v0", v), ("w0", w)):
-        g.push(nm, f)
-    if nsv:
-        rng = np.random.default_rng([7, rank])
-        for n4 in range(nsv):
-            sf = np.asfortranarray(1.0 + 0.1 * rng.random(g.shape("sv0")))
-            g.push("sv0", sf, n4)
-    g.halos(); g.boundary()
-    for nm in ("u0", "v0", "w0"):
-        g.push(nm.replace("0", "m"), g.pull(nm))
-    for n4 in range(nsv):
-        g.push("svm", g.pull("sv0", n4), n4)
-    if args.workload == "ibm":
-        g.ibm_set(urban_blocks(I, J, K, rank * imax, imax))
     dt = 0.25 * 0.5 / 1.1
-    g.dt = dt
-    st = torch.cuda.ExternalStream(g.stream(), device=dev)
-    ncell = I * J * K            # whole job
-    ncell_loc = imax * J * K
+    hbm, how = peaks()
 
-    def barrier():
+    def make(I, J, K, nsv=0, on_device=False, workload="channel"):
+        imax = I // world
+        g = U.UdalesGPU(I, J, K, xlen=I / 2.0, ylen=J / 2.0, zf=(np.arange(K) + 0.5) * 0.5, device=dev,
+                        nprocx=world, myidx=rank, nccl_uid=fresh_uid(), nsv=nsv)
+        if on_device:
+            init_state_on_device(g, torch, imax, J, K, 1234 + rank)
+        else:
+            u, v, w = channel_slab(I, J, K, rank * imax, imax)
+            for nm, f in (("u0", u), ("v0", v), ("w0", w)):
+                g.push(nm, f)
+            if nsv:
+                rng = np.random.default_rng([7, rank])
+                for n4 in range(nsv):
+                    sf = np.asfortranarray(1.0 + 0.1 * rng.random(g.shape("sv0")))
+                    g.push("sv0", sf, n4)
+            g.halos(); g.boundary()
+            for nm in ("u0", "v0", "w0"):
+                g.push(nm.replace("0", "m"), g.pull(nm))
+            for n4 in range(nsv):
+                g.push("svm", g.pull("sv0", n4), n4)
+        if workload == "ibm":
+            g.ibm_set(urban_blocks(I, J, K, rank * imax, imax))
+        g.dt = dt
+        return g
+
+    def barrier(g):
         g.sync(); torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
 
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def timed(g, fn, steps, warmup):
+        """W untimed calls, then exactly `steps` timed ones between barriers, CUDA events on the library stream, max over ranks"""
+        st = torch.cuda.ExternalStream(g.stream(), device=dev)
+        for _ in range(warmup):
+            fn()
+        barrier(g)
+        l0 = g.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            fn()
+        e1.record(st)
+        barrier(g)
+        return max_over_ranks(e0.elapsed_time(e1)), g.launch_count() - l0
+
+    big = I * J * K // world > 300 ** 3      # host staging of > 27 M cells per rank is slow: generate on the device
+    g = make(I, J, K, nsv=nsv, on_device=big and not nsv, workload=args.workload)
+    ncell = I * J * K            # whole job
+    ncell_loc = imax * J * K
+    W = max(args.warmup, 3)
 
     if args.workload == "poisson":
         # BASELINE config 4 style: the Poisson solve alone on the resident right-hand side (udgpu_poisson_solve_resident)
         rng = np.random.default_rng([3, rank])
         g.push("rhs", np.asfortranarray(rng.standard_normal(g.shape("rhs"))))
-        for _ in range(max(args.warmup, 3)):
-            g.poisson_solve_resident()
-        barrier()
         sampler = ClockSampler(dev); sampler.start()
-        l0 = g.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(st)
-        for _ in range(args.steps):
-            g.poisson_solve_resident()
-        e1.record(st)
-        barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        hbm, how = peaks()
+        ms, launches = timed(g, g.poisson_solve_resident, args.steps, W)
         ach = 80.0 * ncell_loc * args.steps / (ms * 1e-3) / 1e9
         line = {"metric": "poisson-solves/s", "value": args.steps / (ms * 1e-3), "unit": "solves/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"Poisson solve only, {I}x{J}x{K} (x-slabs nprocx={world}), rhs resident", "grid": [I, J, K]},
+                "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "cells_per_s": ncell * args.steps / (ms * 1e-3),
                 "roofline": {"kernel": "poisson_core", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                              "traffic": None, "peak_source": how, "bytes_per_cell": 80.0},
-                "gpu_launches": g.launch_count() - l0, "clocks": sampler.stop()}
+                "gpu_launches": launches, "clocks": sampler.stop(), "parity": parity}
         g.close()
         sys.stdout.flush(); os.dup2(real_stdout, 1)
         if rank == 0:
@@ -275,19 +383,8 @@ def run_ours(args, rank, world):
         return
 
     # ---- device-resident throughput ("value") ----
-    for _ in range(max(args.warmup, 3)):
-        g.substep(dt)
-    barrier()
     sampler = ClockSampler(dev); sampler.start()
-    l0 = g.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    for _ in range(args.steps):
-        g.substep(dt)
-    e1.record(st)
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))      # device time, max over ranks
-    launches = g.launch_count() - l0
+    ms, launches = timed(g, lambda: g.substep(dt), args.steps, W)
     clocks = sampler.stop()
     value = ncell * args.steps / (ms * 1e-3)
     dmax, dtot, drms = g.divergence()
@@ -302,22 +399,38 @@ def run_ours(args, rank, world):
         t, cnt = g.profile_get(i)
         fam[nm] = t / nprof
     g.profile_enable(False)
-    hbm, how = peaks()
     roof_all = {}
     bpc = dict(B_PER_CELL)
+    if world > 1:
+        # pipelined slab solve: "poisson_core" is the forward half + z solve (3 of the 5 passes), the inverse half runs
+        # chunk by chunk together with tderive+integrate in its own slot
+        bpc["poisson_core"] = 48.0
+        bpc[PROF_NAMES[6]] = 32.0 + 96.0
     if nsv:   # K3: (4 + 2 n) * 8 B/cell for n fields in one pass; scalar integrate: svm, svp -> sv0 = 24 B/cell/field
         bpc["mom_tend"] += (4 + 2 * nsv) * 8.0
         bpc["tderive_integrate"] += 24.0 * nsv
     for nm, t in fam.items():
-        if t > 0 and bpc[nm] > 0:
+        if t > 0 and bpc.get(nm, 0) > 0:
             ach = bpc[nm] * ncell_loc / (t * 1e-3) / 1e9
-            roof_all[nm] = {"ms": t, "achieved_gbs": ach, "frac": ach / hbm}
-    dom = max(roof_all, key=lambda k: roof_all[k]["ms"])
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": roof_all[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
-                "frac": roof_all[dom]["frac"],
-                "traffic": NCU_TRAFFIC_256.get(dom) if (world == 1 and (I, J, K) == (256, 256, 256) and args.workload == "channel") else None,
-                "peak_source": how,
-                "bytes_per_cell": bpc[dom], "families": roof_all}
+            roof_all[nm] = {"ms": t, "achieved_gbs": ach, "frac": ach / hbm, "bytes_per_cell": bpc[nm]}
+        elif t > 0:
+            roof_all[nm] = {"ms": t}
+    cand = {k: v for k, v in roof_all.items() if "frac" in v}
+    dom = max(cand, key=lambda k: cand[k]["ms"])
+    traffic = ncu_traffic() if (world == 1 and (I, J, K) == (256, 256, 256) and args.workload == "channel") else None
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": cand[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": cand[dom]["frac"],
+                "traffic": (traffic or {}).get("families", {}).get(dom), "traffic_source": (traffic or {}).get("source"),
+                "peak_source": how, "bytes_per_cell": bpc[dom], "families": roof_all,
+                "substep": {"bytes_per_cell": sum(B_PER_CELL.values()), "achieved_gbs": sum(B_PER_CELL.values()) * ncell_loc / (ms / args.steps * 1e-3) / 1e9,
+                            "frac": sum(B_PER_CELL.values()) * ncell_loc / (ms / args.steps * 1e-3) / 1e9 / hbm} if not nsv else None}
+
+    # ---- the same with the adaptive time step of examples/001/999 (ladaptive = .true.): k_cfl + allreduce + one host
+    #      synchronisation per RK3 time step inside the timed region (src/modtstep.f90:69-144) ----
+    nad = max(6, min(args.steps, 30) // 3 * 3)
+    ms_ad, _ = timed(g, lambda: g.substep(dt, ladaptive=True, courant=1e9, diffnr=1e9), nad, 3)
+    adaptive = {"ms_per_step": ms_ad / nad, "value": ncell * nad / (ms_ad * 1e-3), "steps": nad,
+                "note": "ladaptive=.true.: maxima kernel + allreduce + host sync once per RK3 time step; dtmax keeps dt fixed so the flow is the same"}
 
     # ---- end to end through the C-ABI with HOST buffers --------------------------------------------------
     # The prognostic state lives in pinned host arrays (a host-resident model).  One call of
@@ -325,65 +438,70 @@ def run_ours(args, rank, world):
     # (um = u0 at the start of a time step, src/modtstep.f90:330-338), 3 substeps, D2H of the same four.
     names_io = ("u0", "v0", "w0", "pres0")
     nloc = (imax + 2) * (J + 2) * (K + 2)
-    host = {nm: torch.empty(nloc, dtype=torch.float64).pin_memory() for nm in names_io}
-    while g.rk3step != 3:   # finish the running time step first so that um == u0
-        g.substep(dt)
-    for nm in names_io:
-        g.pull_raw(nm, host[nm].data_ptr())
-    g.sync()
-    ne2e = max(3, min(args.steps // 3, 10))
-    ptrs = [host[nm].data_ptr() for nm in names_io]
-    for it in range(2 + ne2e):
-        if it == 2:
-            barrier(); t0 = time.perf_counter()
-        g.rk3_step_host(*ptrs, dtmax=dt)
-    barrier()
-    t_e2e = max_over_ranks((time.perf_counter() - t0) / ne2e) / 3.0      # per substep (= per step of this bench)
-    bi = len(names_io) * nloc * 8 * world / 3.0
-    bo = len(names_io) * nloc * 8 * world / 3.0
+    e2e = None
+    if not big:
+        host = {nm: torch.empty(nloc, dtype=torch.float64).pin_memory() for nm in names_io}
+        while g.rk3step != 3:   # finish the running time step first so that um == u0
+            g.substep(dt)
+        for nm in names_io:
+            g.pull_raw(nm, host[nm].data_ptr())
+        g.sync()
+        ne2e = max(3, min(args.steps // 3, 10))
+        ptrs = [host[nm].data_ptr() for nm in names_io]
+        for it in range(2 + ne2e):
+            if it == 2:
+                barrier(g); t0 = time.perf_counter()
+            g.rk3_step_host(*ptrs, dtmax=dt)
+        barrier(g)
+        t_e2e = max_over_ranks((time.perf_counter() - t0) / ne2e) / 3.0      # per substep (= per step of this bench)
+        bi = len(names_io) * nloc * 8 * world / 3.0
+        e2e = {"value": ncell / t_e2e, "unit": "cell-updates/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bi,
+               "ms_per_step": 1e3 * t_e2e, "substeps_per_call": 3,
+               "note": "udgpu_rk3_step_host: u0,v0,w0,pres0 pushed from / pulled to pinned host arrays once per RK3 time step "
+                       "(3 substeps); bytes and ms are per substep"}
+        del host
+    g.close()
+    del g
+    torch.cuda.empty_cache()
+
+    # ---- north_star grid: 1024^3 periodic channel, the SAME global grid at every N (strong scaling) -------------------
+    ns = None
+    if args.workload == "channel" and not args.grid and not args.no_1024:
+        n1 = args.size1024
+        g1 = make(n1, n1, n1, on_device=True)
+        k1 = max(3, min(args.steps // 10, 9) // 3 * 3)
+        ms1, l1 = timed(g1, lambda: g1.substep(dt), k1, 3)
+        g1.profile_enable(True); g1.profile_reset()
+        for _ in range(3):
+            g1.substep(dt)
+        fam1 = {nm: g1.profile_get(i)[0] / 3 for i, nm in enumerate(PROF_NAMES)}
+        d1 = g1.divergence()
+        ns = {"grid": [n1, n1, n1], "scaling": "strong", "value": n1 ** 3 * k1 / (ms1 * 1e-3), "unit": "cell-updates/s",
+              "ms_per_step": ms1 / k1, "steps": k1, "warmup": 3, "gpu_launches": l1, "divergence_rms": d1[2],
+              "families_ms": fam1, "substep_frac_of_hbm": sum(B_PER_CELL.values()) * (n1 ** 3 // world) / (ms1 / k1 * 1e-3) / 1e9 / hbm,
+              "note": "north_star asks >= 6x from 1 to 8 GPUs on this grid: compare this object's value across the N = 1, 2, 4, 8 lines"}
+        g1.close()
+        del g1
 
     # ---- CPU baseline beside it (oracle port, bounded sample) ----
     cpu = None
     if not args.no_cpu and world == 1:
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-        from oracle.oracle import Oracle
-        n = args.size
-        cores = os.cpu_count() or 1
-        o = Oracle(n, n, n)
-        o.init_channel()
-        o.dt = dt
-        o.substep(dt)
+        n = min(args.size, 256)
         nsub = 30          # ~10 s of host work at 256^3 on 16 cores
-        t0 = time.perf_counter()
-        for _ in range(nsub):
-            o.substep(dt)
-        el = time.perf_counter() - t0
-        cpu = {"value": ncell * nsub / el, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+        val, el, cores, flags = cpu_arm(n, nsub, dt)
+        cpu = {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "cflags": flags,
                "sample": f"{nsub} RK3 substeps of the same {n}^3 workload; C/OpenMP restatement of the reference loops, "
-                         "in-tree radix-2 FFT (FFTW absent) — not the Fortran/MPI binary"}
+                         "in-tree iterative radix-2 FFT (FFTW absent) — not the Fortran/MPI binary"}
 
     line = {
         "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (f"neutral periodic channel {I}x{J}x{K}, stencil+Poisson only, no IBM/scalars "
-                                if args.workload == "channel" else
-                                f"periodic channel {I}x{J}x{K} + 4 kappa-advected passive scalars " if args.workload == "scalars" else
-                                f"periodic channel {I}x{J}x{K} + urban blocks (16x16x8 per 32x32 tile) masked by the device IBM path ")
-                               + ("(BASELINE config 2)" if world == 1 and args.workload == "channel" else
-                                  f"({args.size}^3 cells per GPU, x-slabs)"),
-                   "grid": [I, J, K], "substeps_per_step": 1, "l2": "per-GPU working set (13 fields x 134 MB) >> 126 MB L2, no flush needed",
-                   "sgs": "vreman", "poisson": "FFT2D x,y + tridiagonal z", "decomposition": f"nprocx={world}, nprocy=1"},
-        "roofline": roofline, "cpu_baseline": cpu,
-        "e2e": {"value": ncell / t_e2e, "unit": "cell-updates/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
-                "ms_per_step": 1e3 * t_e2e, "substeps_per_call": 3,
-                "note": "udgpu_rk3_step_host: u0,v0,w0,pres0 pushed from / pulled to pinned host arrays once per RK3 time step "
-                        "(3 substeps); bytes and ms are per substep"},
+        "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks,
-        "poisson_solves_per_s": (1e3 / fam["poisson_core"]) if fam.get("poisson_core") else None,
-        "divergence_rms": drms,
+        "poisson_solves_per_s": (1e3 / fam["poisson_core"]) if fam.get("poisson_core") and world == 1 else None,
+        "divergence_rms": drms, "parity": parity, "adaptive": adaptive, "grid1024": ns,
     }
-    g.close()
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     if rank == 0:
@@ -401,6 +519,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the small-grid oracle comparison that precedes the timed region")
+    ap.add_argument("--no-1024", action="store_true", help="skip the north_star 1024^3 strong-scaling measurement")
+    ap.add_argument("--size1024", type=int, default=1024, help=argparse.SUPPRESS)
     ap.add_argument("--grid", default="", help="explicit global grid I,J,K (e.g. 1024,1024,512 = BASELINE config 4) instead of the weak-scaling grid")
     ap.add_argument("--workload", default="channel", choices=["channel", "scalars", "ibm", "poisson"],
                     help="channel = BASELINE config 2 (the headline); scalars = + 4 kappa scalars (config 5 style); "

@@ -196,6 +196,9 @@ int udgpu_profile_get(udgpu_t *h, int which, double *ms_total, long *launches);
 int udgpu_profile_reset(udgpu_t *h);
 long udgpu_launch_count(udgpu_t *h);          /* kernels launched by this library so far */
 int udgpu_stream(udgpu_t *h, void **cuda_stream);
+/* udgpu_profile_enable(h, 2) records a CUDA event at every stage of the substep on the stream it runs on (main, barrier,
+ * copy streams); udgpu_trace_dump waits for the device and writes one line per mark: "t_ms lane chunk label". */
+int udgpu_trace_dump(udgpu_t *h, const char *path);
 
 #ifdef __cplusplus
 }

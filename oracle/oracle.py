@@ -16,6 +16,13 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_LIB_PATH = None   # None = the parity build (liboracle.so, -ffp-contract=off); bench.py's CPU arm points this at its own
+                   # -O3 -march=native build before the first Oracle is created (timing only, never parity)
+
+
+def use_library(path):
+    global _LIB, _LIB_PATH
+    _LIB, _LIB_PATH = None, path
 
 
 class _Cfg(C.Structure):
@@ -39,7 +46,7 @@ def build(force: bool = False) -> str:
 def lib():
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build())
+        L = C.CDLL(_LIB_PATH or build())
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.POINTER(_Cfg)]
         L.orc_destroy.argtypes = [C.c_void_p]

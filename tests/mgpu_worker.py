@@ -12,12 +12,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-ENV_KEYS = ("UDGPU_XMODE", "UDGPU_XCHUNKS", "UDGPU_HALO_NB_BARRIER")
-# name -> (cfg.flags, environment).  default = copy-engine pipelined transposes in k-chunks + neighbour-only halo rendezvous
+ENV_KEYS = ("UDGPU_XMODE", "UDGPU_XCHUNKS", "UDGPU_XSTREAMS", "UDGPU_HALO_NB_BARRIER")
+# name -> (cfg.flags, environment)
 VARIANTS = {
-    "default": (0, {}),
-    "chunks3": (0, {"UDGPU_XCHUNKS": "3"}),                    # uneven k-chunks
-    "chunks1": (0, {"UDGPU_XCHUNKS": "1"}),
+    "default": (0, {}),                                        # transport chosen by block size (peer stores at these sizes)
+    "ce": (0, {"UDGPU_XMODE": "ce", "UDGPU_XCHUNKS": "2"}),    # copy-engine pipeline in k-chunks, p halo carried by the transposes
+    "chunks3": (0, {"UDGPU_XMODE": "ce", "UDGPU_XCHUNKS": "3"}),   # uneven k-chunks
+    "chunks1": (0, {"UDGPU_XMODE": "ce", "UDGPU_XCHUNKS": "1", "UDGPU_XSTREAMS": "1"}),
     "store": (0, {"UDGPU_XMODE": "store"}),                    # FFT kernels store straight into the peers' windows
     "nccl": (4, {}),                                           # UDGPU_F_NCCL_TRANSPOSE: ncclSend/Recv for transposes and halos
     "allbarrier": (0, {"UDGPU_HALO_NB_BARRIER": "0"}),         # halo exchanges rendezvous with all ranks
@@ -44,13 +45,13 @@ def main():
     shapes = [(64, 64, 32), (128, 64, 24)]
     worst = 0.0
     for name, (flags, env) in VARIANTS.items():
-        if quick and name not in ("default", "nccl"):
+        if quick and name not in ("default", "ce", "nccl"):
             continue
         for k in ENV_KEYS:
             os.environ.pop(k, None)
         os.environ.update(env)
         cases = [("channel", s) for s in shapes] + [("scalars", (64, 64, 16)), ("ibm", (64, 64, 16))]
-        if name not in ("default", "store", "nccl"):
+        if name not in ("default", "ce", "nccl"):
             cases = cases[:1] + cases[2:3]
         for kind, shape in cases:
             e = run_case(U, Oracle, kind, shape, world, rank, dev, fresh_uid(), flags=flags, nsub=6 if kind == "channel" else 3,

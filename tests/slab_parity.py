@@ -107,14 +107,24 @@ def bench_parity(U, Oracle, world, rank, dev, fresh_uid):
     (+1 scalar), all on 64x64xK grids split into `world` x-slabs.  Returns the JSON-able verdict."""
     from oracle.oracle import stretched_zf
     cases = [("channel", (64, 64, 32), 6), ("scalars", (64, 64, 16), 3), ("ibm", (64, 64, 16), 3)]
+    import os
+    if world > 1:
+        cases.append(("channel-ce", (64, 64, 32), 3))     # the copy-engine pipeline (default only for large blocks) forced on
     out = {"tol": TOL, "tol_poisson": TOL_POISSON, "max_abs_err": 0.0, "ok": True, "cases": [], "slabs": world,
            "what": "x-slabs vs the single-pencil CPU oracle on the same global input: Poisson solve, then substeps of u0 v0 w0 um vm wm "
                    "pres0 (sv0) on whole slabs incl. halo columns, divergence, adaptive dt"}
     for kind, shape, nsub in cases:
         fails = []
+        if kind == "channel-ce":
+            os.environ["UDGPU_XMODE"] = "ce"; os.environ["UDGPU_XCHUNKS"] = "2"; kind = "channel"
+            ce = True
+        else:
+            ce = False
         e = run_case(U, Oracle, kind, shape, world, rank, dev, fresh_uid() if world > 1 else None, nsub=nsub, stretched_zf=stretched_zf,
                      failures=fails)
-        rec = {"case": kind, "grid": list(shape), "substeps": nsub, "max_abs_err": e}
+        if ce:
+            os.environ.pop("UDGPU_XMODE", None); os.environ.pop("UDGPU_XCHUNKS", None)
+        rec = {"case": kind + ("-ce" if ce else ""), "grid": list(shape), "substeps": nsub, "max_abs_err": e}
         if fails:
             out["ok"] = False
             rec["failed"] = fails[:3]

@@ -32,7 +32,7 @@ EXPORTS = [
     "udgpu_poisson_solve", "udgpu_poisson_solve_resident", "udgpu_fillps", "udgpu_tderive",
     "udgpu_tstep_integrate", "udgpu_halos", "udgpu_boundary", "udgpu_divergence", "udgpu_substep",
     "udgpu_rk3_step_host", "udgpu_set_forcing", "udgpu_forces", "udgpu_ibm_set_points", "udgpu_ibm_commit", "udgpu_ibm_pull_mask", "udgpu_ibmnorm", "udgpu_ibm_diffcorr",
-    "udgpu_profile_enable", "udgpu_profile_get", "udgpu_profile_reset", "udgpu_launch_count", "udgpu_stream",
+    "udgpu_profile_enable", "udgpu_profile_get", "udgpu_profile_reset", "udgpu_launch_count", "udgpu_stream", "udgpu_trace_dump",
 ]
 
 
@@ -117,6 +117,7 @@ def lib():
         L.udgpu_profile_reset.argtypes = [C.c_void_p]
         L.udgpu_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.udgpu_nccl_unique_id.argtypes = [C.c_void_p]
+        L.udgpu_trace_dump.argtypes = [C.c_void_p, C.c_char_p]
         _LIB = L
     return _LIB
 
@@ -335,6 +336,9 @@ class UdalesGPU:
         return ms.value, n.value
 
     def launch_count(self): return int(self.L.udgpu_launch_count(self.h))
+
+    def trace(self, on=True): self._chk(self.L.udgpu_profile_enable(self.h, 2 if on else 0))
+    def trace_dump(self, path): self._chk(self.L.udgpu_trace_dump(self.h, str(path).encode()))
 
     def stream(self):
         s = C.c_void_p()

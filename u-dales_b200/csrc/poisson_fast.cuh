@@ -72,6 +72,12 @@ __device__ __forceinline__ void dft_reg(double2 (&v)[R]) {
 struct BlkDesc {
   double *base[8];
   int shift, mask;   // blk = 1 << shift points per block, mask = blk - 1
+  // Output side only.  halo = 1: every block carries one extra column on each side (block pitch blk + 2 points): point q of
+  // block d lands in column q + 1, and the first / last point of a block is ALSO stored as the last / first column of
+  // the previous / next block (periodic over nblk blocks).  This is how the inverse x transform hands every slab the
+  // two halo columns of p together with its own columns: bcp's exchange_halo_z (src/modboundary.f90:1344-1408) rides
+  // on the transpose instead of being a separate exchange.
+  int halo, nblk;
 };
 
 template <int R1, int R2, int LANES, bool XDIR>
@@ -102,7 +108,14 @@ __global__ void __launch_bounds__(LANES *R2, (R1 <= 16 ? 2 : 1)) k_rfft_fast(con
     return IBLK ? ib.base[pt >> ib.shift] + ibase + loff + (long long)(pt & ib.mask) * di.sp : in + ibase + loff + (long long)pt * di.sp;
   };
   auto OUT = [&](long long loff, int pt) -> double * {
-    return OBLK ? ob.base[pt >> ob.shift] + obase + loff + (long long)(pt & ob.mask) * dd.sp : out + obase + loff + (long long)pt * dd.sp;
+    return OBLK ? ob.base[pt >> ob.shift] + obase + loff + (long long)((pt & ob.mask) + ob.halo) * dd.sp : out + obase + loff + (long long)pt * dd.sp;
+  };
+  // halo-carrying blocks: duplicate an edge point into the neighbouring block's halo column
+  auto OUT_EDGE = [&](long long loff, int pt, double val) {
+    if (!OBLK || !ob.halo) return;
+    const int q = pt & ob.mask, d = pt >> ob.shift;
+    if (q == 0) { const int dl = d == 0 ? ob.nblk - 1 : d - 1; ob.base[dl][obase + loff + (long long)(ob.mask + 2) * dd.sp] = val; }
+    if (q == ob.mask) { const int dr = d == ob.nblk - 1 ? 0 : d + 1; ob.base[dr][obase + loff] = val; }
   };
   // x lines: global -> padded shared tile.  All of a thread's loads are issued before the first use (R1
   // independent 16-byte requests in flight per thread); 128-bit accesses when the lines are 16-byte aligned.
@@ -110,7 +123,7 @@ __global__ void __launch_bounds__(LANES *R2, (R1 <= 16 ? 2 : 1)) k_rfft_fast(con
   const bool al_in = !IBLK ? ((((size_t)(in + ibase)) & 15) == 0 && ((di.s1 | di.s2) & 1) == 0)
                            : ((((size_t)ib.base[0]) & 15) == 0 && ((di.s1 | di.s2 | ibase) & 1) == 0);
   const bool al_out = !OBLK ? ((((size_t)(out + obase)) & 15) == 0 && ((dd.s1 | dd.s2) & 1) == 0)
-                            : ((((size_t)ob.base[0]) & 15) == 0 && ((dd.s1 | dd.s2 | obase) & 1) == 0);
+                            : ((((size_t)ob.base[0]) & 15) == 0 && ((dd.s1 | dd.s2 | obase) & 1) == 0 && !ob.halo);
   constexpr int SCH = NIT > 8 ? 8 : NIT;   // requests in flight per thread and staging round
   auto stage_in = [&]() {
 #pragma unroll
@@ -155,6 +168,8 @@ __global__ void __launch_bounds__(LANES *R2, (R1 <= 16 ? 2 : 1)) k_rfft_fast(con
           double *q = OUT((long long)b * dd.s1, 2 * m);
           if (al_out) *reinterpret_cast<double2 *>(q) = st[it];
           else { q[0] = st[it].x; q[1] = st[it].y; }
+          OUT_EDGE((long long)b * dd.s1, 2 * m, st[it].x);
+          OUT_EDGE((long long)b * dd.s1, 2 * m + 1, st[it].y);
         }
       }
     }

@@ -254,6 +254,64 @@ __global__ void k_halo_unpack_x(HaloPack a, int pi, int pj, int imax, int h, con
   }
 }
 
+// The same two kernels with the neighbour rendezvous built in (peer-memory path): no separate barrier launch.
+//  * pack + signal: every block stores its lines into the neighbours' windows, fences, and counts itself in; the last
+//    block raises this rank's flag (epoch) in both neighbours: "my columns have landed in your window".
+//  * wait + unpack: thread 0 of every block spins on the two flags the neighbours raise in MY flag array, then the
+//    block scatters the window into the halo columns (window reads bypass L1: the lines were written remotely).
+struct HaloSync {
+  unsigned long long *flagL, *flagR;    // my slot in the left / right neighbour's flag array
+  unsigned long long *mineL, *mineR;    // the slots the left / right neighbour raises in my flag array
+  unsigned long long epoch, timeout_ns;
+  unsigned *counter;                    // blocks of the pack kernel that have finished (reset by the last one)
+  volatile int *status;
+};
+__device__ __forceinline__ unsigned long long halo_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void k_halo_pack_signal(HaloPack a, int pi, int pj, int imax, int h, double *__restrict__ sendL, double *__restrict__ sendR, HaloSync hs) {
+  const int f = blockIdx.y;
+  const long long jk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (jk < (long long)pj * a.nlev[f]) {
+    const double *q = a.f[f] + jk * pi;
+    for (int m = 0; m < h; m++) {
+      sendL[a.off[f] + jk * h + m] = q[h + m];
+      sendR[a.off[f] + jk * h + m] = q[imax + m];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned nblocks = gridDim.x * gridDim.y;
+    if (atomicAdd(hs.counter, 1u) + 1u == nblocks) {
+      *hs.counter = 0;
+      __threadfence_system();
+      *(volatile unsigned long long *)hs.flagL = hs.epoch;
+      *(volatile unsigned long long *)hs.flagR = hs.epoch;
+      __threadfence_system();
+    }
+  }
+}
+__global__ void k_halo_wait_unpack(HaloPack a, int pi, int pj, int imax, int h, const double *__restrict__ recvL, const double *__restrict__ recvR, HaloSync hs) {
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = halo_now_ns();
+    while (*(volatile unsigned long long *)hs.mineL < hs.epoch || *(volatile unsigned long long *)hs.mineR < hs.epoch) {
+      if (halo_now_ns() - t0 > hs.timeout_ns) { *hs.status = 1; __threadfence_system(); break; }
+    }
+  }
+  __syncthreads();
+  const int f = blockIdx.y;
+  const long long jk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (jk >= (long long)pj * a.nlev[f]) return;
+  double *q = a.f[f] + jk * pi;
+  for (int m = 0; m < h; m++) {
+    q[m] = __ldcg(recvL + a.off[f] + jk * h + m);
+    q[h + imax + m] = __ldcg(recvR + a.off[f] + jk * h + m);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // momentum tendencies, direct form.  advecu/v/w_2nd src/modadvection.f90:158-314 and
 // diffu/v/w src/modsubgrid.f90:672-997.  ACC: add to the existing tendency (drop-in semantics)

@@ -91,6 +91,8 @@ __global__ void k_p2p_barrier(P2PPtrs f, int P, int rank, unsigned long long epo
   }
 }
 
+struct TraceRec { const char *label; int chunk, lane; cudaEvent_t ev; };
+
 struct udgpu {
   udgpu_cfg cfg;
   Geo g;
@@ -127,9 +129,11 @@ struct udgpu {
   double *hL[8][2] = {}, *hR[8][2] = {};   // halo receive windows (left / right halo columns), double-buffered
   bool m_changed = true;                   // um, vm, wm changed since their halos were last exchanged
   unsigned halo_par = 0;
+  unsigned *d_halo_cnt = nullptr;          // finished blocks of the running pack+signal kernel
   P2PPtrs pflags;
   unsigned long long epoch[4] = {0, 0, 0, 0};   // one counter per flag set (0: transposes, 2: neighbour-only halo rendezvous)
-  int halo_set = 2;           // 2: halo exchanges rendezvous with the two ring neighbours only; 0 (UDGPU_HALO_NB_BARRIER=0): with all ranks
+  int halo_set = 2;           // flag set of the halo exchanges.  2: rendezvous with the two ring neighbours only, folded into the pack /
+                              // unpack kernels; 1 (UDGPU_HALO_NB_BARRIER=0): separate barrier kernel with all ranks (cross-check)
   // transposes of the slab solve (xmode): 0 = ncclSend/Recv, 1 = FFT kernels store straight into the peers' windows,
   // 2 (default) = FFT kernels write a local wire-format send buffer and the COPY ENGINES move k-chunks of it into the
   // peers' windows on a side stream, pipelined against the neighbouring compute (measured on 2 x B200, profiles/
@@ -138,7 +142,10 @@ struct udgpu {
   int xmode = 0;
   int xchunks = 1;            // k-chunks of the pipelined transposes
   int xk0[17] = {};           // chunk c covers 0-based levels xk0[c] .. xk0[c+1]-1
-  cudaStream_t sc = nullptr;  // copy stream: CE copies + the rendezvous of every chunk
+  cudaStream_t sc = nullptr;  // barrier stream: the rendezvous of every chunk (and the copies when xstreams == 1)
+  cudaStream_t scp[8] = {};   // one copy stream per ring distance q (copies of a chunk run on different copy engines)
+  cudaEvent_t ev_c[8] = {};
+  int xstreams = 8;           // UDGPU_XSTREAMS=1: all copies of a chunk on one stream
   cudaEvent_t ev_f[16] = {}, ev_r[16] = {};   // chunk c: local wire data ready (main -> copy) / all blocks have landed (copy -> main)
   bool bwd_pending = false;   // poisson() ran the forward half and the z solve; the inverse half is pipelined with tstep_integrate()
   double *bwd_work = nullptr, *bwd_phalo = nullptr;
@@ -183,6 +190,8 @@ struct udgpu {
   bool m_halo_stale = false;   // ibmnorm wrote um, vm, wm at solid points: their halo images are stale until halos()
   bool m_bc_stale = false;     // ... and their top ghost level until boundary()
   bool prof = false;
+  bool trace = false;          // udgpu_profile_enable(h, 2): event marks at every stage of the substep (udgpu_trace_dump)
+  std::vector<TraceRec> tr;
   ProfSlot ps[PROF_N];
   long launches = 0;
 };
@@ -195,6 +204,14 @@ static int p2p_barrier(udgpu *h, int set = 0, cudaStream_t on = nullptr);
 static int materialize_zero_tend(udgpu *h);
 static int sync_check(udgpu *h);
 static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, const std::vector<double> &yrt);
+// timeline mark: an event on `on` (lane 0 = main stream, 1 = barrier stream, 2.. = copy streams)
+static void trace_mark(udgpu *h, const char *label, int chunk = -1, cudaStream_t on = nullptr, int lane = 0) {
+  if (!h->trace) return;
+  TraceRec r{label, chunk, lane, nullptr};
+  cudaEventCreate(&r.ev);
+  cudaEventRecord(r.ev, on ? on : h->st);
+  h->tr.push_back(r);
+}
 static int dev_alloc(udgpu *h, void **p, size_t bytes) {
   CU(cudaMalloc(p, bytes ? bytes : 8));
   CU(cudaMemsetAsync(*p, 0, bytes ? bytes : 8, h->st));
@@ -470,11 +487,12 @@ static int init_impl(udgpu *h, const udgpu_cfg *c, const void *nccl_uid, int nde
     h->IB = g.imax; h->JB = g.jtot / h->P;
     h->halo_cap = (size_t)8 * 2 * (g.pjc > g.pj ? g.pjc : g.pj) * (K + 2 * (g.khc > g.kh ? g.khc : g.kh));
     for (double **b : {&h->sendL, &h->sendR, &h->recvL, &h->recvR}) RET(dev_alloc(h, (void **)b, h->halo_cap * sizeof(double)));
-    for (double **b : {&h->sbuf, &h->workB}) RET(dev_alloc(h, (void **)b, nR * sizeof(double)));   // rbuf: NCCL path only (setup_p2p)
+    RET(dev_alloc(h, (void **)&h->workB, nR * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->sbuf, (size_t)(h->IB + 2) * g.jtot * K * sizeof(double)));   // rbuf: NCCL path only (setup_p2p)
     h->gB = g;
     h->gB.imax = g.itot; h->gB.jmax = h->JB; h->gB.i0g = 0; h->gB.j0g = h->rank * h->JB;
     // halo exchanges rendezvous with the two ring neighbours only (default); UDGPU_HALO_NB_BARRIER=0: with all ranks
-    { const char *e = getenv("UDGPU_HALO_NB_BARRIER"); h->halo_set = (e && atoi(e) == 0) ? 0 : 2; }
+    { const char *e = getenv("UDGPU_HALO_NB_BARRIER"); h->halo_set = (e && atoi(e) == 0) ? 1 : 2; }
     RET(setup_p2p(h, nR));
   }
   for (int f = 0; f < UDGPU_NFIELDS; f++) {
@@ -565,6 +583,9 @@ extern "C" int udgpu_finalize(udgpu_t *h) {
   if (h->comm) ncclCommDestroy(h->comm);
   for (int w = 0; w < PROF_N; w++)
     for (auto &e : h->ps[w].pend) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  for (int q = 0; q < 8; q++) { if (h->scp[q]) cudaStreamDestroy(h->scp[q]); if (h->ev_c[q]) cudaEventDestroy(h->ev_c[q]); }
+  for (int c = 0; c < 16; c++) { if (h->ev_f[c]) cudaEventDestroy(h->ev_f[c]); if (h->ev_r[c]) cudaEventDestroy(h->ev_r[c]); }
+  if (h->sc) cudaStreamDestroy(h->sc);
   if (h->st) cudaStreamDestroy(h->st);
   cudaGetLastError();
   delete h;
@@ -671,6 +692,22 @@ static int halo_x_exchange_g(udgpu *h, const std::vector<double *> &fields, int 
     // neighbour's left-halo window; one flag barrier; unpack from my own windows.  Windows alternate (parity) so a
     // fast neighbour's next exchange cannot overwrite data that has not been unpacked yet.
     const unsigned par = (h->halo_par++) & 1;
+    if (h->halo_set == 2) {
+      // neighbour-only rendezvous folded into the two kernels (signal after pack, wait before unpack)
+      if (h->h_status && *h->h_status) return set_err(UDGPU_ESTATE, "an earlier peer-to-peer rendezvous timed out: refusing to enqueue dependent work");
+      HaloSync hs;
+      hs.epoch = ++h->epoch[2];
+      hs.timeout_ns = h->barrier_timeout_ns;
+      hs.flagL = h->pflags.flags[left] + 16 * 2 + h->rank; hs.flagR = h->pflags.flags[right] + 16 * 2 + h->rank;
+      hs.mineL = h->pflags.flags[h->rank] + 16 * 2 + left; hs.mineR = h->pflags.flags[h->rank] + 16 * 2 + right;
+      hs.counter = h->d_halo_cnt; hs.status = h->d_status;
+      k_halo_pack_signal<<<gr, 128, 0, h->st>>>(hp, pi, pj, imax, hw, h->hR[left][par], h->hL[right][par], hs);
+      KCHECK();
+      k_halo_wait_unpack<<<gr, 128, 0, h->st>>>(hp, pi, pj, imax, hw, h->hL[h->rank][par], h->hR[h->rank][par], hs);
+      KCHECK();
+      h->launches += 2;
+      return UDGPU_OK;
+    }
     k_halo_pack_x<<<gr, 128, 0, h->st>>>(hp, pi, pj, imax, hw, h->hR[left][par], h->hL[right][par]);
     KCHECK();
     // neighbour-only rendezvous is enough here: a window is rewritten two exchanges later, and by then the writer has
@@ -743,6 +780,7 @@ extern "C" int udgpu_closure(udgpu_t *h) {
   else k_closure<0><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
   KCHECK();
   h->launches++;
+  trace_mark(h, "closure");
   if (halo) {
     // closurebc's wraps and ghost levels were written by the closure kernel itself; a split x still needs its slab exchange
     if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_EKM], f[UDGPU_EKH]}, g.ktot + 2 * g.kh));
@@ -867,7 +905,7 @@ static int launch_scalars(udgpu *h, bool acc) {
 
 // run a deferred advection() on its own (something needs the tendencies before subgrid())
 static int tderive_now(udgpu *h);
-template <class After> static int slab_backward(udgpu *h, double *work, double *p_halo, After &&after);
+template <class After> static int slab_backward(udgpu *h, double *work, double *p_halo, bool carry, After &&after);
 static int forces_now(udgpu *h) {
   h->forces_pending = false;
   const Geo &g = h->g;
@@ -883,7 +921,7 @@ static int flush_pending(udgpu *h, bool keep_forces) {
   if (h->bwd_pending) {   // the inverse half of a pipelined slab solve, on its own
     h->bwd_pending = false;
     ProfScope ps(h, PROF_POIS);
-    RET(slab_backward(h, h->bwd_work, h->bwd_phalo, [](int, int) -> int { return UDGPU_OK; }));
+    RET(slab_backward(h, h->bwd_work, h->bwd_phalo, false, [](int, int) -> int { return UDGPU_OK; }));
   }
   if (h->tder_pending) { h->tder_pending = false; RET(tderive_now(h)); }
   if (!h->adv_pending) return UDGPU_OK;
@@ -917,10 +955,12 @@ extern "C" int udgpu_subgrid(udgpu_t *h) {
   const bool fuse = h->adv_pending;
   h->adv_pending = false;
   RET(udgpu_closure(h));
+  trace_mark(h, "closure+halo");
   ProfScope ps(h, PROF_MOM);
   if (fuse) { RET((launch_momtend<true, true>(h, !h->tend_zero))); RET((launch_scalars<true, true>(h, !h->tend_zero))); }
   else { RET((launch_momtend<false, true>(h, !h->tend_zero))); RET((launch_scalars<false, true>(h, !h->tend_zero))); }
   h->tend_zero = false; h->tend_lazy_zero = false;
+  trace_mark(h, "momtend");
   return UDGPU_OK;
 }
 
@@ -1048,8 +1088,13 @@ static int setup_p2p(udgpu *h, size_t nR) {
   h->p2p = false;
   h->xmode = 0; h->xchunks = 1; h->xk0[0] = 0; h->xk0[1] = h->g.ktot;
   const int P = h->P;
-  int want_mode = 2;
-  { const char *e = getenv("UDGPU_XMODE"); if (e) want_mode = !strcmp(e, "nccl") ? 0 : !strcmp(e, "store") ? 1 : 2; }
+  // default transport by size (measured on 8 x B200, profiles/r2_trace_*: copy-engine transfers carry ~17 us of fixed
+  // cost each and run one after the other, so 8 MB copies reach 290 GB/s in aggregate, 270 MB copies 770 GB/s; the
+  // FFT kernels' own peer stores reach ~640 GB/s at any size but occupy the SMs while they wait for the link):
+  // per-peer blocks >= 64 MiB -> copy-engine pipeline (2), smaller -> peer stores from the transform kernels (1)
+  const size_t blk_bytes = (size_t)h->IB * h->JB * h->g.ktot * sizeof(double);
+  int want_mode = blk_bytes >= ((size_t)64 << 20) ? 2 : 1;
+  { const char *e = getenv("UDGPU_XMODE"); if (e) want_mode = !strcmp(e, "nccl") ? 0 : !strcmp(e, "store") ? 1 : !strcmp(e, "ce") ? 2 : want_mode; }
   if (h->cfg.flags & UDGPU_F_NCCL_TRANSPOSE) want_mode = 0;
   int want_chunks = 0;
   { const char *e = getenv("UDGPU_XCHUNKS"); if (e && atoi(e) >= 1 && atoi(e) <= 16) want_chunks = atoi(e); }
@@ -1058,7 +1103,8 @@ static int setup_p2p(udgpu *h, size_t nR) {
   RET(dev_alloc(h, (void **)&d_flag, 4 * sizeof(int)));
   int v[4] = {mask, -mask, 1, 0};
   bool good = want_mode != 0;
-  const size_t head = (((2 * nR + 4 * h->halo_cap) * sizeof(double) + 4096) + 255) / 256 * 256;   // [recvA | recvB | halo windows | flags]
+  const size_t nRB = (size_t)(h->IB + 2) * h->g.jtot * h->g.ktot;   // exchange B may carry two halo columns per block
+  const size_t head = (((nR + nRB + 4 * h->halo_cap) * sizeof(double) + 4096) + 255) / 256 * 256;   // [recvA | recvB | halo windows | flags]
   if (good && cudaMalloc(&h->ipc_mine, head) != cudaSuccess) { cudaGetLastError(); h->ipc_mine = nullptr; good = false; }
   if (h->ipc_mine) {
     h->allocs.push_back(h->ipc_mine);
@@ -1073,6 +1119,7 @@ static int setup_p2p(udgpu *h, size_t nR) {
     const char *e = getenv("UDGPU_BARRIER_TIMEOUT_S");
     if (e && atof(e) > 0) h->barrier_timeout_ns = (unsigned long long)(atof(e) * 1e9);
   }
+  RET(dev_alloc(h, (void **)&h->d_halo_cnt, 64));
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
   if (good && cudaIpcGetMemHandle(&mine, h->ipc_mine) != cudaSuccess) { cudaGetLastError(); good = false; }
@@ -1108,7 +1155,7 @@ static int setup_p2p(udgpu *h, size_t nR) {
   for (int d = 0; d < P; d++) {
     h->rA[d] = (double *)h->ipc_peer[d];
     h->rB[d] = h->rA[d] + nR;
-    double *hb = h->rB[d] + nR;
+    double *hb = h->rB[d] + nRB;
     h->hL[d][0] = hb; h->hL[d][1] = hb + h->halo_cap; h->hR[d][0] = hb + 2 * h->halo_cap; h->hR[d][1] = hb + 3 * h->halo_cap;
     h->pflags.flags[d] = (unsigned long long *)(hb + 4 * h->halo_cap);
   }
@@ -1118,12 +1165,17 @@ static int setup_p2p(udgpu *h, size_t nR) {
   if (h->xmode == 2) {
     // k-chunks: per-peer copies of >= ~8 MiB keep the copy engines near their large-transfer rate
     const int K = h->g.ktot;
-    const size_t blk_bytes = (size_t)h->IB * h->JB * K * sizeof(double);
-    int C = want_chunks ? want_chunks : (int)std::min<size_t>(8, std::max<size_t>(1, blk_bytes / ((size_t)8 << 20)));
+    // k-chunks of >= 16 MiB per peer, at most 8
+    int C = want_chunks ? want_chunks : (int)std::min<size_t>(8, std::max<size_t>(1, blk_bytes / ((size_t)16 << 20)));
     C = std::max(1, std::min(C, std::min(16, K)));
     h->xchunks = C;
     for (int c = 0; c <= C; c++) h->xk0[c] = (int)(((long long)K * c) / C);
     CU(cudaStreamCreateWithFlags(&h->sc, cudaStreamNonBlocking));
+    { const char *e = getenv("UDGPU_XSTREAMS"); if (e && atoi(e) == 1) h->xstreams = 1; }
+    for (int q = 1; q < P && h->xstreams > 1; q++) {
+      CU(cudaStreamCreateWithFlags(&h->scp[q], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&h->ev_c[q], cudaEventDisableTiming));
+    }
     for (int c = 0; c < C; c++) {
       CU(cudaEventCreateWithFlags(&h->ev_f[c], cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&h->ev_r[c], cudaEventDisableTiming));
@@ -1173,35 +1225,38 @@ static int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 // tderive/integrate of chunk c-1 on the way out (`after`).  xmode 1: the transforms store into the peers' windows
 // themselves (one chunk, rendezvous on the main stream); xmode 0: ncclSend/Recv.
 struct SlabGeo {
-  int IB, JB, K, P;
-  size_t blk;
-  long long wk;
+  int IB, JB, K, P, hc;      // hc = 1: exchange B carries the two halo columns of p (block pitch IB + 2)
+  size_t blk;                // elements per wire-format block of this exchange
+  long long wk;              // level stride inside a block
   LineDesc yA0, yW0, xW0, xB0, yOut0;
   double *outp;
 };
-static SlabGeo slab_geo(udgpu *h, double *work, double *p_halo) {
+static SlabGeo slab_geo(udgpu *h, double *work, double *p_halo, bool carry) {
   const Geo &g = h->g;
   SlabGeo s;
-  s.IB = h->IB; s.JB = h->JB; s.K = g.ktot; s.P = h->P;
-  s.blk = (size_t)s.IB * s.JB * s.K;
-  s.wk = (long long)s.JB * s.IB;                                                   // level stride inside a wire-format block
+  s.IB = h->IB; s.JB = h->JB; s.K = g.ktot; s.P = h->P; s.hc = carry ? 1 : 0;
+  const int IW = s.IB + 2 * s.hc;                                                  // columns per block on the wire
+  s.blk = (size_t)IW * s.JB * s.K;
+  s.wk = (long long)s.JB * IW;
   s.yA0 = {(long long)s.IB, 1, (long long)s.IB * g.jtot, s.IB, s.K, 0};           // y lines in the slab
-  s.yW0 = {(long long)s.IB, 1, s.wk, s.IB, s.K, 0};                               // ... in wire format (per block)
-  s.xW0 = {1, (long long)s.IB, s.wk, s.JB, s.K, 0};                               // x lines in wire format (per block)
+  s.yW0 = {(long long)IW, 1, s.wk, IW, s.K, 0};                                   // ... in wire format (per block)
+  s.xW0 = {1, (long long)IW, s.wk, s.JB, s.K, 0};                                 // x lines in wire format (per block)
   s.xB0 = {1, (long long)g.itot, (long long)g.itot * s.JB, s.JB, s.K, 0};         // x lines in the x-pencil
   s.yOut0 = s.yA0;
   s.outp = work;
-  if (p_halo) { s.yOut0.sp = g.pi; s.yOut0.s2 = g.pk; s.outp = p_halo + offF(g, 1, 1, 1); }
+  if (p_halo) { s.yOut0.sp = g.pi; s.yOut0.s2 = g.pk; s.yOut0.nb1 = IW; s.outp = p_halo + offF(g, 1 - s.hc, 1, 1); }
   return s;
 }
 static LineDesc with_k(LineDesc d, int kc) { d.nb2 = kc; return d; }
 // send / receive bases of the two exchanges (A: after the forward y transform, B: after the inverse x transform)
 static void slab_bases(udgpu *h, const SlabGeo &s, bool second, long long k0, BlkDesc &bs, BlkDesc &br) {
   const int P = s.P;
+  bs = BlkDesc(); br = BlkDesc();
   for (int d = 0; d < 8; d++) {
     bs.base[d] = d < P ? h->sbuf + d * s.blk + k0 * s.wk : nullptr;
     br.base[d] = (d < P && h->rbuf) ? h->rbuf + d * s.blk + k0 * s.wk : nullptr;
   }
+  bs.halo = s.hc; bs.nblk = P;
   if (!h->p2p) return;
   double *const *win = second ? h->rB : h->rA;
   for (int d = 0; d < P; d++) {
@@ -1211,20 +1266,27 @@ static void slab_bases(udgpu *h, const SlabGeo &s, bool second, long long k0, Bl
   }
   if (h->xmode == 2) br.base[h->rank] = h->sbuf + h->rank * s.blk + k0 * s.wk;   // my own block never leaves the send buffer
 }
-// ship chunk c of the wire-format send buffer: main stream -> (event) -> copy stream: P-1 copy-engine transfers into
-// the peers' windows, rendezvous, -> (event) -> whoever consumes chunk c
+// ship chunk c of the wire-format send buffer: main stream -> (event) -> one copy stream per peer: a copy-engine
+// transfer into that peer's window -> (events) -> rendezvous on the barrier stream -> (event) -> whoever consumes chunk c
 static int slab_ship(udgpu *h, const SlabGeo &s, bool second, int c) {
   const long long k0 = h->xk0[c], kc = h->xk0[c + 1] - h->xk0[c];
   if (h->xmode == 2) {
     CU(cudaEventRecord(h->ev_f[c], h->st));
-    CU(cudaStreamWaitEvent(h->sc, h->ev_f[c], 0));
     double *const *win = second ? h->rB : h->rA;
     for (int q = 1; q < s.P; q++) {
       const int d = (h->rank + q) % s.P;   // step q of all ranks together is a permutation: no destination is hit twice
+      cudaStream_t cs = h->xstreams > 1 ? h->scp[q] : h->sc;
+      if (h->xstreams > 1 || q == 1) CU(cudaStreamWaitEvent(cs, h->ev_f[c], 0));
       CU(cudaMemcpyAsync(win[d] + h->rank * s.blk + k0 * s.wk, h->sbuf + d * s.blk + k0 * s.wk, (size_t)kc * s.wk * sizeof(double),
-                         cudaMemcpyDeviceToDevice, h->sc));
+                         cudaMemcpyDeviceToDevice, cs));
+      trace_mark(h, "copy", c, cs, 1 + q);
+      if (h->xstreams > 1) {
+        CU(cudaEventRecord(h->ev_c[q], cs));
+        CU(cudaStreamWaitEvent(h->sc, h->ev_c[q], 0));
+      }
     }
     RET(p2p_barrier(h, 0, h->sc));
+    trace_mark(h, "landed", c, h->sc, 1);
     CU(cudaEventRecord(h->ev_r[c], h->sc));
     return UDGPU_OK;
   }
@@ -1239,15 +1301,17 @@ static int slab_landed(udgpu *h, int c) {
 template <class Fill>
 static int slab_forward(udgpu *h, double *work, Fill &&fill) {
   const Geo &g = h->g;
-  const SlabGeo s = slab_geo(h, work, nullptr);
+  const SlabGeo s = slab_geo(h, work, nullptr, false);
   const int C = h->xchunks;
   for (int c = 0; c < C; c++) {
     const int k0 = h->xk0[c], kc = h->xk0[c + 1] - k0;
     RET(fill(k0, kc));
+    trace_mark(h, "fillps", c);
     BlkDesc bs, br;
     slab_bases(h, s, false, k0, bs, br);
     bs.shift = ilog2(s.JB); bs.mask = s.JB - 1;
     RET(rfft_fast<false>(h, g.jtot, 0, work + k0 * s.yA0.s2, with_k(s.yA0, kc), nullptr, with_k(s.yW0, kc), h->py, nullptr, &bs));
+    trace_mark(h, "yfft", c);
     RET(slab_ship(h, s, false, c));
   }
   for (int c = 0; c < C; c++) {
@@ -1257,20 +1321,24 @@ static int slab_forward(udgpu *h, double *work, Fill &&fill) {
     slab_bases(h, s, false, k0, bs, br);
     br.shift = ilog2(s.IB); br.mask = s.IB - 1;
     RET(rfft_fast<true>(h, g.itot, 0, nullptr, with_k(s.xW0, kc), h->workB + k0 * s.xB0.s2, with_k(s.xB0, kc), h->px, &br, nullptr));
+    trace_mark(h, "xfft", c);
   }
   if (h->zu == 16) k_zsolve<16><<<dim3((g.itot + 127) / 128, s.JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
   else k_zsolve<8><<<dim3((g.itot + 127) / 128, s.JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
   KCHECK();
   h->launches++;
+  trace_mark(h, "zsolve");
   return UDGPU_OK;
 }
 // inverse half.  after(k0, kc): consumer of the solution levels k0 .. k0+kc-1 (tderive + integrate), may be empty.
 // Software pipeline: the inverse x transform of chunk c+1 is enqueued before the consumer side of chunk c, so the
 // copy engines always have the next chunk to move while the main stream works on the previous one.
+// carry: the blocks carry p's halo columns (needs the halo'd output array and the copy-engine path).
 template <class After>
-static int slab_backward(udgpu *h, double *work, double *p_halo, After &&after) {
+static int slab_backward(udgpu *h, double *work, double *p_halo, bool carry, After &&after) {
   const Geo &g = h->g;
-  const SlabGeo s = slab_geo(h, work, p_halo);
+  carry = carry && p_halo && h->xmode == 2;
+  const SlabGeo s = slab_geo(h, work, p_halo, carry);
   const int C = h->xchunks;
   auto xinv = [&](int c) -> int {
     const int k0 = h->xk0[c], kc = h->xk0[c + 1] - k0;
@@ -1278,6 +1346,7 @@ static int slab_backward(udgpu *h, double *work, double *p_halo, After &&after) 
     slab_bases(h, s, true, k0, bs, br);
     bs.shift = ilog2(s.IB); bs.mask = s.IB - 1;
     RET(rfft_fast<true>(h, g.itot, 1, h->workB + k0 * s.xB0.s2, with_k(s.xB0, kc), nullptr, with_k(s.xW0, kc), h->px, nullptr, &bs));
+    trace_mark(h, "xinv", c);
     return slab_ship(h, s, true, c);
   };
   RET(xinv(0));
@@ -1289,7 +1358,9 @@ static int slab_backward(udgpu *h, double *work, double *p_halo, After &&after) 
     slab_bases(h, s, true, k0, bs, br);
     br.shift = ilog2(s.JB); br.mask = s.JB - 1;
     RET(rfft_fast<false>(h, g.jtot, 1, nullptr, with_k(s.yW0, kc), s.outp + k0 * s.yOut0.s2, with_k(s.yOut0, kc), h->py, &br, nullptr));
+    trace_mark(h, "yinv", c);
     RET(after(k0, kc));
+    trace_mark(h, "after", c);
   }
   return UDGPU_OK;
 }
@@ -1297,7 +1368,7 @@ static int poisson_core_slab(udgpu *h, double *work, double *p_halo) {
   ProfScope ps(h, PROF_POIS);
   auto nop = [](int, int) -> int { return UDGPU_OK; };
   RET(slab_forward(h, work, nop));
-  return slab_backward(h, work, p_halo, nop);
+  return slab_backward(h, work, p_halo, false, nop);
 }
 
 static int poisson_core(udgpu *h, double *work, double *p_halo) {
@@ -1348,6 +1419,7 @@ static int fillps_prepare(udgpu *h) {
     RET(halo_x_exchange(h, {h->f[UDGPU_UP]}, g.ktot + g.kh));
     // ibmnorm zeroed um at solid points after the last halos(): pup(ie+1) needs the neighbour's current um(1) too
     if (h->m_halo_stale) RET(halo_x_exchange(h, {h->f[UDGPU_UM]}, g.ktot + 2 * g.kh));
+    trace_mark(h, "up halo");
   }
   return UDGPU_OK;
 }
@@ -1452,7 +1524,7 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
     if (!own && h->bwd_pending) {
       h->bwd_pending = false;
       ProfScope ps(h, PROF_POIS);
-      RET(slab_backward(h, h->bwd_work, h->bwd_phalo, [](int, int) -> int { return UDGPU_OK; }));
+      RET(slab_backward(h, h->bwd_work, h->bwd_phalo, false, [](int, int) -> int { return UDGPU_OK; }));
     }
     ProfScope ps(h, h->bwd_pending ? PROF_BWDPIPE : PROF_INTEG);
     if (own) {
@@ -1477,10 +1549,8 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
       if (h->bwd_pending) {
         // inverse x transform / copy-engine transfer / inverse y transform / p halo / tderive+integrate, chunk by chunk
         h->bwd_pending = false;
-        RET(slab_backward(h, h->bwd_work, h->bwd_phalo, [&](int k0, int kc) -> int {
-          RET(halo_x_exchange(h, {f[UDGPU_P] + (long long)(k0 + g.kh) * g.pk}, kc));
-          return integ(k0, kc);
-        }));
+        // p's halo columns arrive with the blocks of the second exchange: no bcp exchange
+        RET(slab_backward(h, h->bwd_work, h->bwd_phalo, true, [&](int k0, int kc) -> int { return integ(k0, kc); }));
       } else {
         if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));
         RET(integ(0, g.ktot));
@@ -1546,6 +1616,7 @@ extern "C" int udgpu_halos(udgpu_t *h) {
       else RET(halo_x_exchange(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0]}, g.ktot + 2 * g.kh));   // um, vm, wm only change on substep 3
       h->halo_x_pending = false;
       h->m_changed = false;
+      trace_mark(h, "uvw halo");
     }
   } else {
     RET(wrap_xy(h, {f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM]}, g.ktot + 2 * g.kh));
@@ -1792,7 +1863,8 @@ extern "C" int udgpu_rk3_step_host(udgpu_t *h, double *u0, double *v0, double *w
 // ------------------------------------------------------------------------------------------
 extern "C" int udgpu_profile_enable(udgpu_t *h, int on) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
-  h->prof = on != 0;
+  h->prof = on == 1;
+  h->trace = on == 2;
   return UDGPU_OK;
 }
 static void prof_collect(udgpu *h) {
@@ -1821,3 +1893,19 @@ extern "C" int udgpu_profile_reset(udgpu_t *h) {
   return UDGPU_OK;
 }
 extern "C" long udgpu_launch_count(udgpu_t *h) { return h ? h->launches : 0; }
+// writes "t_ms lane chunk label" per mark (t relative to the first mark) and clears the marks
+extern "C" int udgpu_trace_dump(udgpu_t *h, const char *path) {
+  if (!h || !path) return set_err(UDGPU_EINVAL, "null argument");
+  CU(cudaDeviceSynchronize());
+  FILE *fp = fopen(path, "w");
+  if (!fp) return set_err(UDGPU_EINVAL, "cannot open %s", path);
+  for (size_t q = 0; q < h->tr.size(); q++) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->tr[0].ev, h->tr[q].ev);
+    fprintf(fp, "%10.4f %d %2d %s\n", ms, h->tr[q].lane, h->tr[q].chunk, h->tr[q].label);
+  }
+  fclose(fp);
+  for (auto &r : h->tr) cudaEventDestroy(r.ev);
+  h->tr.clear();
+  return UDGPU_OK;
+}
