@@ -56,6 +56,7 @@ enum udgpu_field {
   UDGPU_RHS,                                 /* (imax,jmax,ktot) no halo (modpois.f90:84) */
   UDGPU_SV0, UDGPU_SVM,                      /* (ib-ihc:.., jb-jhc:.., kb-khc:ke+khc, nsv) */
   UDGPU_SVP,                                 /* (.., .., kb:ke+khc, nsv)                */
+  UDGPU_MOMFLUXB,                            /* as u0; allocated by udgpu_set_bottom (src/modfields.f90 momfluxb)  */
   UDGPU_NFIELDS
 };
 
@@ -162,6 +163,20 @@ int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax, int ladapt
  * tendencies first).  udgpu_substep calls it after subgrid once a forcing has been set. */
 int udgpu_set_forcing(udgpu_t *h, const double *dpdxl, const double *dpdyl);
 int udgpu_forces(udgpu_t *h);
+
+/* src/modibm.f90:1998 bottom with lbottom = .true., BCbotm = 3: wfmneutral(.., 91) (src/modwallfunctions.f90:307-349) on
+ * up, vp (k = kb) and momfluxb, plus the zero-flux scalar bottom correction (BCbots = 1, src/modibm.f90:2077-2091).
+ * udgpu_set_bottom takes the namelist values (z0, fkar = von Karman constant); udgpu_bottom is the call of
+ * src/program.f90:152; udgpu_substep calls it after subgrid once lbottom is set. */
+int udgpu_set_bottom(udgpu_t *h, int lbottom, int BCbotm, int BCbots, double z0, double fkar);
+int udgpu_bottom(udgpu_t *h);
+/* src/modforces.f90:328 masscorr, volume-flow branches (luvolflowr / lvvolflowr, :394-420 / :470-495): masked slab means of
+ * the tendency and of um / vm (avexy_ibm, src/modmpi.f90:623-664; summed over all ranks), def = flowrate - (rk3coef <up> + <um>),
+ * up += def / rk3coef.  The masks IIu / IIv are the interiors of mask_u / mask_v of udgpu_ibm_commit (all ones without
+ * IBM).  udef / vdef may be NULL (then the call does not synchronise the host).  udgpu_substep calls it between the
+ * IBM diffusion corrections and ibmnorm (src/program.f90:169) once a flow rate has been set. */
+int udgpu_set_masscorr(udgpu_t *h, int luvolflowr, int lvvolflowr, double uflowrate, double vflowrate);
+int udgpu_masscorr(udgpu_t *h, double dt, int rk3step, double *udef, double *vdef);
 
 /* ---- immersed-boundary masking (next tier; src/modibm.f90) ------------------------------- */
 /* point lists of modibm: kind 0-3 = solid_info_{u,v,w,c}%solpts_loc, 4-7 = bound_info_{u,v,w,c}%bndpts_loc; n points,

@@ -419,9 +419,89 @@ def case_forces(tag, shape=(8, 6, 7)):
     print(f"wrote ref_{tag}.npz")
 
 
+def case_channelglue(tag, shape=(10, 8, 6), nsv=1):
+    """bottom -> wfmneutral case 91 (src/modibm.f90:1998-2100, src/modwallfunctions.f90:262-352) and masscorr, volume-flow
+    branch (src/modforces.f90:394-420, 470-495), executed from the reference text: the rest of the resident-channel
+    glue of examples/999.  avexy_ibm (src/modmpi.f90:623-664) is an MPI helper and is given as a
+    single-pencil Python callback like the other MPI calls."""
+    I, J, K = shape
+    zf = stretched_zf(K, 0.5 * K * 1.1, 1.07)
+    w = World(I, J, K, xlen=0.55 * I, ylen=0.45 * J, zf=zf, nsv=nsv, iadv_sv=7)
+    g = w.g
+    ext = w.externals()
+
+    def avexy_ibm(it_, frame, vals, setters, kw_):
+        # aver, var, ib, ie, jb, je, kb, ke, kh, II, IIs, lnan
+        var, II, IIs, lnan = vals[1], vals[9], vals[10], vals[11]
+        nk = var.a.shape[2]
+        averl = np.array([np.sum(var.a[:, :, k] * II.a[:, :, k]) for k in range(nk)])
+        IId = np.array(IIs.a, copy=True)
+        if (not lnan) and IId[0] == 0:
+            averl[0] = np.sum(var.a[:, :, 0])
+            IId[0] = IId[nk - 2]            # IId(ke)
+        aver = np.where(IId == 0, -999.0, averl / np.where(IId == 0, 1, IId))
+        vals[0].a[...] = aver
+    ext["avexy_ibm"] = avexy_ibm
+    it = Interp(g, ext)
+    for f in ("modadvection.f90", "modsubgrid.f90", "modpois.f90", "modtstep.f90", "modboundary.f90", "modchecksim.f90"):
+        it.load(os.path.join(SRC, f))
+    it.load(os.path.join(SRC, "modibm.f90"), only=["bottom"])
+    it.load(os.path.join(SRC, "modwallfunctions.f90"), only=["wfmneutral"])
+    it.load(os.path.join(SRC, "modforces.f90"), only=["masscorr"])
+    rng = np.random.default_rng(31)
+    seed_fields(w, 29, nsv)
+    it.call("halos"); it.call("boundary")
+    for a, b in (("um", "u0"), ("vm", "v0"), ("wm", "w0")):
+        g[a].a[...] = g[b].a + 0.02 * rng.standard_normal(g[b].a.shape)
+    for nm in ("up", "vp", "wp", "svp"):
+        g[nm].a[...] = rng.standard_normal(g[nm].a.shape)
+    g["ekm"].a[...] = 1e-3 * (1.0 + rng.random(g["ekm"].a.shape))
+    g["ekh"].a[...] = 3e-3 * (1.0 + rng.random(g["ekh"].a.shape))
+    full = [(0, I + 1), (0, J + 1), (0, K + 1)]
+    tend = [(0, I + 1), (0, J + 1), (1, K + 1)]
+    hc = g["ihc"]
+    # IIu / IIv: 1 = fluid (createmasks, src/modibm.f90:2103-2160); a few "solid" points so that the masked means differ from plain ones
+    IIu = FArray.alloc([(1 - hc, I + hc), (1 - hc, J + hc), (1, K + hc)], int)
+    IIv = FArray.alloc([(1 - hc, I + hc), (1 - hc, J + hc), (1, K + hc)], int)
+    IIu.a[...] = 1; IIv.a[...] = 1
+    IIu.a[hc + 2:hc + 5, hc + 1:hc + 4, 0:2] = 0
+    IIv.a[hc + 2:hc + 4, hc + 1:hc + 5, 0:2] = 0
+    IIus = FArray(np.array([int(IIu.a[hc:hc + I, hc:hc + J, k].sum()) for k in range(K + hc)]), [1])
+    IIvs = FArray(np.array([int(IIv.a[hc:hc + I, hc:hc + J, k].sum()) for k in range(K + hc)]), [1])
+    g.update(iiu=IIu, iiv=IIv, iius=IIus, iivs=IIvs, uflowrate=1.37, vflowrate=-0.21, linoutflow=False,
+             luoutflowr=False, lvoutflowr=False, luvolflowr=True, lvvolflowr=True, udef=0.0, vdef=0.0,
+             uoutarea=1.0, voutarea=1.0, dxh=fa([(1, I + 1)], g["dx"]), dxhi=fa([(1, I + 1)], 1. / g["dx"]),
+             fkar=0.41, lbottom=True, bcbotm=3, bcbott=1, bcbotq=1, bcbots=1, z0=0.01, z0h=0.000067,
+             momfluxb=fa(full), tfluxb=fa(full), tau_x=fa(full), tau_y=fa(full), tau_z=fa(full), thl_flux=fa(full),
+             wtsurf=0.0, wqsurf=0.0, thls=300.0)
+    out = {"zf": zf, "shape": np.array([I, J, K]), "xlen": 0.55 * I, "ylen": 0.45 * J, "nsv": nsv, "z0": 0.01, "fkar": 0.41,
+           "uflowrate": 1.37, "vflowrate": -0.21, "IIu": np.array(IIu.a[hc:hc + I, hc:hc + J, :K + 1], dtype=np.int32),
+           "IIv": np.array(IIv.a[hc:hc + I, hc:hc + J, :K + 1], dtype=np.int32), "IIus": np.array(IIus.a[:K + 1], dtype=np.int32),
+           "IIvs": np.array(IIvs.a[:K + 1], dtype=np.int32)}
+    state = ["u0", "v0", "w0", "um", "vm", "wm", "up", "vp", "wp", "ekm", "ekh", "sv0", "svp"]
+    for k_, v_ in snapshot(w, state).items():
+        out["in_" + k_] = v_
+    it.call("bottom")
+    for k_, v_ in snapshot(w, ["up", "vp", "wp", "svp", "momfluxb"]).items():
+        out["bottom_" + k_] = v_
+    for rk in (1, 2, 3):
+        g["rk3step"] = rk; g["dt"] = 0.037
+        it.call("masscorr")
+        for k_, v_ in snapshot(w, ["up", "vp"]).items():
+            out[f"mc{rk}_" + k_] = v_
+        out[f"mc{rk}_udef"], out[f"mc{rk}_vdef"] = g["udef"], g["vdef"]
+    out["dt"] = 0.037
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, f"ref_{tag}.npz"), **out)
+    print(f"wrote ref_{tag}.npz  udef {out['mc1_udef']:.6e} {out['mc3_udef']:.6e} vdef {out['mc1_vdef']:.6e}")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "forces":
         case_forces("forces")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "channelglue":
+        case_channelglue("channelglue")
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ibm":
         case_ibm("ibm")
@@ -433,3 +513,4 @@ if __name__ == "__main__":
     case_substeps("cd2scalar", shape=(6, 8, 5), nsv=1, iadv_sv=2)
     case_ibm("ibm")
     case_forces("forces")
+    case_channelglue("channelglue")

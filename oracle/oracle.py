@@ -70,6 +70,13 @@ def lib():
         L.orc_rfft_packed.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
         L.orc_set_forcing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_forces.argtypes = [C.c_void_p]
+        L.orc_set_bottom.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.orc_bottom.argtypes = [C.c_void_p]
+        L.orc_momfluxb.restype = C.POINTER(C.c_double)
+        L.orc_momfluxb.argtypes = [C.c_void_p]
+        L.orc_set_masscorr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_masscorr.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.orc_masscorr_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_ibm_set_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_ibm_build_masks.argtypes = [C.c_void_p]
         L.orc_ibm_mask.restype = C.POINTER(C.c_double)
@@ -189,6 +196,29 @@ class Oracle:
         self.L.orc_set_forcing(self.h, a.ctypes.data, b.ctypes.data)
 
     def forces(self): self.L.orc_forces(self.h)
+
+    # bottom -> wfmneutral (src/modibm.f90:1998, src/modwallfunctions.f90:307) and masscorr (src/modforces.f90:328) ----
+    def set_bottom(self, z0, fkar=0.41, lbottom=True, BCbotm=3, BCbots=1):
+        self.L.orc_set_bottom(self.h, int(lbottom), BCbotm, BCbots, z0, fkar)
+
+    def bottom(self): self.L.orc_bottom(self.h)
+
+    def momfluxb(self):
+        shape = (self.itot + 2, self.jtot + 2, self.ktot + 2)
+        return np.ctypeslib.as_array(self.L.orc_momfluxb(self.h), shape=(int(np.prod(shape)),)).reshape(shape, order="F")
+
+    def set_masscorr(self, uflowrate=None, vflowrate=None, IIu=None, IIv=None):
+        """volume-flow forcing (luvolflowr / lvvolflowr); IIu, IIv: (itot, jtot, ktot+1) int arrays, 1 = fluid, or None"""
+        a = None if IIu is None else np.asfortranarray(IIu, dtype=np.int32)
+        b = None if IIv is None else np.asfortranarray(IIv, dtype=np.int32)
+        self.L.orc_set_masscorr(self.h, int(uflowrate is not None), int(vflowrate is not None), float(uflowrate or 0.0), float(vflowrate or 0.0),
+                                None if a is None else a.ctypes.data, None if b is None else b.ctypes.data)
+
+    def masscorr(self, dt, rk3step):
+        self.L.orc_masscorr(self.h, dt, rk3step)
+        u, v = C.c_double(), C.c_double()
+        self.L.orc_masscorr_get(self.h, C.byref(u), C.byref(v))
+        return u.value, v.value
 
     # immersed boundary masking (src/modibm.f90) ---------------------------------
     IBM_KINDS = ("solid_u", "solid_v", "solid_w", "solid_c", "bound_u", "bound_v", "bound_w", "bound_c")

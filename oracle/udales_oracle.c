@@ -48,6 +48,14 @@ struct orc {
   /* forces (src/modforces.f90:46): large-scale pressure gradient per level, kb:ke+kh */
   double *dpdxl, *dpdyl;
   int has_forcing;
+  /* bottom -> wfmneutral (src/modibm.f90:1998, src/modwallfunctions.f90:262) and masscorr (src/modforces.f90:328) */
+  int lbottom, BCbotm, BCbots;
+  double z0, fkar;
+  double *momfluxb;
+  int luvolflowr, lvvolflowr;
+  double uflowrate, vflowrate, udef, vdef;
+  int *IIu, *IIv;             /* (itot, jtot, ktot+1), 1 = fluid (createmasks, src/modibm.f90:2103); NULL = all fluid */
+  int *IIus, *IIvs;           /* fluid points per level, ktot+1 values */
 };
 
 #define MOFF 2
@@ -1366,12 +1374,128 @@ void orc_forces(orc_t *o) {
     }
 }
 
+/* ---- bottom -> wfmneutral(..., 91) ----------------------------------------------------------------------------
+ * src/modibm.f90:1998-2100 (lbottom branch: BCbotm = 3 -> wfmneutral; nsv > 0, BCbots = 1: zero-flux scalar
+ * correction :2077-2091) and src/modwallfunctions.f90:307-349.  dxf = dx, dxhi = dxi (x is uniform). */
+void orc_set_bottom(orc_t *o, int lbottom, int BCbotm, int BCbots, double z0, double fkar) {
+  o->lbottom = lbottom; o->BCbotm = BCbotm; o->BCbots = BCbots; o->z0 = z0; o->fkar = fkar;
+  if (!o->momfluxb) o->momfluxb = zalloc(nF(o));
+}
+double *orc_momfluxb(orc_t *o) { return o->momfluxb; }
+void orc_bottom(orc_t *o) {
+  if (!o->lbottom) return;
+  const int I = o->itot, J = o->jtot;
+  const double *u0 = o->u0, *v0 = o->v0, *ekm = o->ekm, *ekh = o->ekh;
+  if (o->BCbotm == 3) {
+    const int k = 1, km = 0;
+    const double fkar2 = o->fkar * o->fkar, umin = 0.0001;
+    const double delta = 0.5 * M(dzf, k);
+    const double lg = log(delta / o->z0);
+    const double logdz2 = lg * lg;
+    const double dx = o->dx, dxhi = o->dxi;
+    for (int j = 1; j <= J; j++)       /* u component, modwallfunctions.f90:318-332 */
+      for (int i = 1; i <= I; i++) {
+        const double utang1Int = F(u0, i, j, k);
+        const double utang2Int = (F(v0, i, j, k) + F(v0, i - 1, j, k) + F(v0, i, j + 1, k) + F(v0, i - 1, j + 1, k)) * 0.25;
+        const double utangInt = fmax(umin, (utang1Int * utang1Int + utang2Int * utang2Int));
+        const double ctm = fkar2 / (logdz2);
+        const double dummy = fabs(utang1Int) * sqrt(utangInt) * ctm;
+        const double bcmomflux = copysign(dummy, utang1Int);
+        F(o->momfluxb, i, j, k) = F(o->momfluxb, i, j, k) + bcmomflux * M(dzfi, k);
+        const double emom = (M(dzf, km) * (F(ekm, i, j, k) * dx + F(ekm, i - 1, j, k) * dx) +
+                             M(dzf, k) * (F(ekm, i, j, km) * dx + F(ekm, i - 1, j, km) * dx)) * dxhi * M(dzhiq, k);
+        T(o->up, i, j, k) = T(o->up, i, j, k) + (F(u0, i, j, k) - F(u0, i, j, km)) * emom * M(dzhi, k) * M(dzfi, k) - bcmomflux * M(dzfi, k);
+      }
+    for (int j = 1; j <= J; j++)       /* v component, :334-347 */
+      for (int i = 1; i <= I; i++) {
+        const double utang1Int = (F(u0, i, j, k) + F(u0, i, j - 1, k) + F(u0, i + 1, j - 1, k) + F(u0, i + 1, j, k)) * 0.25;
+        const double utang2Int = F(v0, i, j, k);
+        const double utangInt = fmax(umin, (utang1Int * utang1Int + utang2Int * utang2Int));
+        const double ctm = fkar2 / (logdz2);
+        const double dummy = fabs(utang2Int) * sqrt(utangInt) * ctm;
+        const double bcmomflux = copysign(dummy, utang2Int);
+        F(o->momfluxb, i, j, k) = F(o->momfluxb, i, j, k) + bcmomflux * M(dzfi, k);
+        const double eomm = (M(dzf, km) * (F(ekm, i, j, k) + F(ekm, i, j - 1, k)) + M(dzf, k) * (F(ekm, i, j, km) + F(ekm, i, j - 1, km))) * M(dzhiq, k);
+        T(o->vp, i, j, k) = T(o->vp, i, j, k) + (F(v0, i, j, k) - F(v0, i, j, km)) * eomm * M(dzhi, k) * M(dzfi, k) - bcmomflux * M(dzfi, k);
+      }
+  }
+  if (o->nsv > 0 && o->BCbots == 1) {  /* modibm.f90:2077-2091 */
+    const int kb = 1;
+    for (int n = 0; n < o->nsv; n++) {
+      const double *sv0 = o->sv0 + (size_t)n * nS(o);
+      double *svp = o->svp + (size_t)n * nST(o);
+      for (int j = 1; j <= J; j++)
+        for (int i = 1; i <= I; i++)
+          ST(svp, i, j, kb) = ST(svp, i, j, kb) + (0.5 * (M(dzf, kb - 1) * F(ekh, i, j, kb) + M(dzf, kb) * F(ekh, i, j, kb - 1)) *
+                                                   (S(sv0, i, j, kb) - S(sv0, i, j, kb - 1)) * M(dzh2i, kb) + 0.) * M(dzfi, kb);
+    }
+  }
+}
+
+/* ---- masscorr, volume-flow branches --------------------------------------------------------------------------
+ * src/modforces.f90:394-420 (u) and :470-495 (v) with avexy_ibm (src/modmpi.f90:623-664, lnan = .false.). */
+void orc_set_masscorr(orc_t *o, int luvolflowr, int lvvolflowr, double uflowrate, double vflowrate, const int *IIu, const int *IIv) {
+  const int I = o->itot, J = o->jtot, K = o->ktot;
+  const size_t n = (size_t)I * J * (K + 1);
+  o->luvolflowr = luvolflowr; o->lvvolflowr = lvvolflowr; o->uflowrate = uflowrate; o->vflowrate = vflowrate;
+  for (int c = 0; c < 2; c++) {
+    int **II = c ? &o->IIv : &o->IIu, **IIs = c ? &o->IIvs : &o->IIus;
+    const int *src = c ? IIv : IIu;
+    if (!*II) { *II = (int *)malloc(n * sizeof(int)); *IIs = (int *)malloc((K + 1) * sizeof(int)); }
+    for (size_t q = 0; q < n; q++) (*II)[q] = src ? src[q] : 1;
+    for (int k = 0; k <= K; k++) {
+      int s = 0;
+      for (size_t q = 0; q < (size_t)I * J; q++) s += (*II)[(size_t)k * I * J + q];
+      (*IIs)[k] = s;
+    }
+  }
+}
+static void avexy_ibm(const orc_t *o, double *aver, const double *var /* tendency-shaped or F-shaped */, int is_tend, const int *II, const int *IIs) {
+  const int I = o->itot, J = o->jtot, K = o->ktot;
+  for (int k = 1; k <= K + 1; k++) {
+    double s = 0., sall = 0.;
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++) {
+        const double v = is_tend ? T(var, i, j, k) : F(var, i, j, k);
+        s += v * II[(i - 1) + (size_t)I * ((j - 1) + (size_t)J * (k - 1))];
+        sall += v;
+      }
+    int d = IIs[k - 1];
+    if (k == 1 && d == 0) { s = sall; d = IIs[K - 1]; }   /* modmpi.f90:649-652 */
+    aver[k - 1] = d == 0 ? -999. : s / d;
+  }
+}
+void orc_masscorr(orc_t *o, double dt, int rk3step) {
+  const int I = o->itot, J = o->jtot, K = o->ktot;
+  const double rk3coef = dt / (4. - (double)rk3step), rk3coefi = 1 / rk3coef;
+  double *vol = (double *)malloc(2 * (K + 1) * sizeof(double)), *volold = vol + K + 1;
+  const double zhtop = M(zh, K + 1);
+  for (int c = 0; c < 2; c++) {
+    if (!(c ? o->lvvolflowr : o->luvolflowr)) continue;
+    double *tp = c ? o->vp : o->up;
+    avexy_ibm(o, vol, tp, 1, c ? o->IIv : o->IIu, c ? o->IIvs : o->IIus);
+    avexy_ibm(o, volold, c ? o->vm : o->um, 0, c ? o->IIv : o->IIu, c ? o->IIvs : o->IIus);
+    double s1 = 0., s2 = 0.;
+    for (int k = 1; k <= K; k++) { s1 += vol[k - 1] * M(dzf, k); s2 += volold[k - 1] * M(dzf, k); }
+    const double outflow = rk3coef * s1 / zhtop, flowrateold = s2 / zhtop;
+    const double def = (c ? o->vflowrate : o->uflowrate) - (outflow + flowrateold);
+    if (c) o->vdef = def; else o->udef = def;
+    for (int k = 1; k <= K; k++)
+      for (int j = 1; j <= J; j++)
+        for (int i = 1; i <= I; i++) T(tp, i, j, k) = T(tp, i, j, k) + def * rk3coefi;
+  }
+  free(vol);
+}
+void orc_masscorr_get(orc_t *o, double *udef, double *vdef) { *udef = o->udef; *vdef = o->vdef; }
+
 void orc_substep(orc_t *o, double *dt, int *rk3step, double dtmax, int ladaptive, double courant, double diffnr) {
   orc_tstep_update(o, dt, courant, diffnr, dtmax, ladaptive, rk3step, NULL, NULL);
   orc_advection(o);
   orc_subgrid(o);
+  orc_bottom(o);         /* src/program.f90:152 */
   orc_forces(o);         /* src/program.f90:158 */
   orc_ibm_diffcorr(o);   /* the in-scope part of ibmwallfun, src/program.f90:166 */
+  if (o->luvolflowr || o->lvvolflowr) orc_masscorr(o, *dt, *rk3step);   /* src/program.f90:169 */
   orc_ibmnorm(o);        /* src/program.f90:171 */
   orc_poisson(o, *dt, *rk3step);
   orc_tstep_integrate(o, *dt, *rk3step);

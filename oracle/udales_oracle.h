@@ -74,6 +74,16 @@ void orc_rfft_packed(int n, double *line, int inverse);  /* modpois.f90:478-490 
 void orc_set_forcing(orc_t *o, const double *dpdxl, const double *dpdyl);
 void orc_forces(orc_t *o);
 
+/* bottom -> wfmneutral case 91 (src/modibm.f90:1998, src/modwallfunctions.f90:307-349) and the zero-flux scalar
+ * correction (:2077-2091); masscorr, volume-flow branches (src/modforces.f90:394-420, 470-495).  IIu / IIv:
+ * (itot, jtot, ktot+1) ints, 1 = fluid, or NULL (no blocks). */
+void orc_set_bottom(orc_t *o, int lbottom, int BCbotm, int BCbots, double z0, double fkar);
+void orc_bottom(orc_t *o);
+double *orc_momfluxb(orc_t *o);
+void orc_set_masscorr(orc_t *o, int luvolflowr, int lvvolflowr, double uflowrate, double vflowrate, const int *IIu, const int *IIv);
+void orc_masscorr(orc_t *o, double dt, int rk3step);
+void orc_masscorr_get(orc_t *o, double *udef, double *vdef);
+
 /* immersed boundary masking: kind 0-3 = solid_u,v,w,c ; 4-7 = fluid-boundary points u,v,w,c;
  * ijk = n local 1-based (i,j,k) triples, point-major */
 void orc_ibm_set_points(orc_t *o, int kind, int n, const int *ijk);

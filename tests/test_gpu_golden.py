@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith(("ref_ibm.npz", "ref_restart102_block.npz", "ref_forces.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith(("ref_ibm.npz", "ref_restart102_block.npz", "ref_forces.npz", "ref_channelglue.npz")))
 GOLD_IBM = os.path.join(os.path.dirname(__file__), "golden", "ref_ibm.npz")
 
 
@@ -99,3 +99,35 @@ def test_cuda_forces_matches_reference_source():
     g.forces()
     for n in ("up", "vp", "wp"):
         assert np.array_equal(g.pull(n), d["out_" + n]), n      # one subtraction per cell: identical bits
+
+
+def test_cuda_bottom_and_masscorr_match_reference_source():
+    """udgpu_bottom (wfmneutral case 91 + scalar bottom correction) and udgpu_masscorr (volume-flow branches) against the vectors
+    produced by executing src/modibm.f90 / src/modwallfunctions.f90 / src/modforces.f90 (no oracle in between).  IIu / IIv of
+    the golden case become solid_u / solid_v lists, so the masks are the ones udgpu_ibm_commit builds."""
+    import udales_b200 as U
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_channelglue.npz"))
+    I, J, K = (int(x) for x in d["shape"])
+    nsv = int(d["nsv"])
+    g = U.UdalesGPU(I, J, K, xlen=float(d["xlen"]), ylen=float(d["ylen"]), zf=d["zf"], nsv=nsv)
+    for n in ("u0", "v0", "w0", "um", "vm", "wm", "up", "vp", "wp", "ekm", "ekh"):
+        g.push(n, d["in_" + n])
+    for n4 in range(nsv):
+        g.push("sv0", d["in_sv0"][..., n4], n4)
+        g.push("svp", d["in_svp"][..., n4], n4)
+    g.set_bottom(float(d["z0"]), float(d["fkar"]))
+    g.bottom()
+    for n in ("up", "vp", "wp"):
+        assert rel(g.pull(n), d["bottom_" + n]) < 1e-13, n
+    for n4 in range(nsv):
+        assert rel(g.pull("svp", n4), d["bottom_svp"][..., n4]) < 1e-13
+    assert rel(g.pull("momfluxb")[1:-1, 1:-1, 1], d["bottom_momfluxb"][1:-1, 1:-1, 1]) < 1e-13
+    pts = lambda II: (np.argwhere(II[:, :, :K] == 0) + 1).astype(np.int32)
+    g.ibm_set({"solid_u": pts(d["IIu"]), "solid_v": pts(d["IIv"])})
+    g.set_masscorr(float(d["uflowrate"]), float(d["vflowrate"]))
+    for rk in (1, 2, 3):
+        udef, vdef = g.masscorr(float(d["dt"]), rk)
+        assert udef == pytest.approx(float(d[f"mc{rk}_udef"]), rel=1e-12)
+        assert vdef == pytest.approx(float(d[f"mc{rk}_vdef"]), rel=1e-12)
+        assert rel(g.pull("up")[1:-1, 1:-1, :-1], d[f"mc{rk}_up"][1:-1, 1:-1, :-1]) < 1e-12
+        assert rel(g.pull("vp")[1:-1, 1:-1, :-1], d[f"mc{rk}_vp"][1:-1, 1:-1, :-1]) < 1e-12

@@ -447,3 +447,41 @@ def test_full_size_256_against_the_oracle_directly():
     dmax, dtot, drms = g.divergence()
     omax, otot, orms = o.chkdiv()
     assert drms < 1e-12 and abs(dmax - omax) < 1e-11
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 24, 20)])
+@pytest.mark.parametrize("flags", [0, F_NO_LAZY, F_NO_HALO])
+@pytest.mark.parametrize("case", ["channel999", "u_only", "ibm"])
+def test_resident_channel_glue_in_the_substep(shape, flags, case):
+    """examples/999 physics resident on the device: bottom -> wfmneutral, forces, masscorr (volume flow) inside the substep
+    (src/program.f90:152,158,169), lazily folded into the fused tderive+integrate kernel (flags 0) or eager (NO_LAZY / with IBM
+    masking, where ibmnorm follows masscorr).  Six substeps against the oracle, whole arrays."""
+    nsv = 1 if case != "u_only" else 0
+    o, g = make_pair(*shape, gpu_flags=flags, nsv=nsv)
+    K = shape[2]
+    rng = np.random.default_rng(4)
+    fx, fy = -1e-3 * (1 + rng.random(K + 1)), 2e-4 * rng.standard_normal(K + 1)
+    for x in (o, g):
+        x.set_bottom(0.01, 0.41)
+        if case == "u_only":
+            x.set_masscorr(uflowrate=1.1)
+        else:
+            x.set_masscorr(uflowrate=1.1, vflowrate=0.05)
+            x.set_forcing(fx, fy)
+    if case == "ibm":
+        lists = ibm_lists(*shape, IBM_BOXES[shape])
+        g.ibm_set(lists); o.ibm_set(lists)
+        I, J = shape[:2]
+        o.set_masscorr(1.1, 0.05, o.ibm_mask(0)[1:-1, 1:-1, 1:].astype(np.int32), o.ibm_mask(1)[1:-1, 1:-1, 1:].astype(np.int32))
+    dt = 0.02
+    o.dt = g.dt = dt
+    hc = o.ihc
+    for s in range(6):
+        o.substep(dt); g.substep(dt)
+        for n in ("u0", "v0", "w0", "um", "vm", "wm"):
+            assert relerr(g.pull(n), getattr(o, n)) < 1e-11, (s, n)
+        for n4 in range(nsv):
+            assert relerr(g.pull("sv0", n4)[:, :, hc:-hc], o.sv0[:, :, hc:-hc, n4]) < 1e-11, s
+        assert g.divergence()[2] < 1e-12
+    # the bulk velocity is what masscorr was told to hold (fluid volume mean of u after a full RK3 step)
+    assert relerr(interior(g.pull("momfluxb"))[:, :, 0], interior(o.momfluxb())[:, :, 0]) < 1e-11

@@ -11,7 +11,7 @@ import pytest
 
 from oracle.oracle import Oracle
 
-GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith(("ref_ibm.npz", "ref_restart102_block.npz", "ref_forces.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith(("ref_ibm.npz", "ref_restart102_block.npz", "ref_forces.npz", "ref_channelglue.npz")))
 GOLD_IBM = os.path.join(os.path.dirname(__file__), "golden", "ref_ibm.npz")
 TOL = 2e-13      # same arithmetic order, no FMA on either side; FFT library and pow() rounding differ
 
@@ -134,3 +134,39 @@ def test_oracle_forces_matches_reference_source():
     for n in ("up", "vp", "wp"):
         assert np.array_equal(getattr(o, n), d["out_" + n]), n
     assert np.abs(d["out_up"] - d["in_up"]).max() > 1e-4
+
+
+GOLD_GLUE = os.path.join(os.path.dirname(__file__), "golden", "ref_channelglue.npz")
+
+
+def build_glue(d, cls=Oracle, **kw):
+    """state of tests/golden/ref_channelglue.npz in an Oracle (or, with cls = UdalesGPU-like factory, in the CUDA library)"""
+    I, J, K = (int(x) for x in d["shape"])
+    nsv = int(d["nsv"])
+    o = cls(I, J, K, xlen=float(d["xlen"]), ylen=float(d["ylen"]), zf=d["zf"], nsv=nsv, **kw)
+    return o, nsv
+
+
+def test_oracle_bottom_and_masscorr_match_reference_source():
+    """bottom -> wfmneutral(91) + scalar bottom correction (src/modibm.f90:1998-2100, src/modwallfunctions.f90:307-349) and
+    masscorr's volume-flow branches (src/modforces.f90:394-420, 470-495) against vectors produced by executing the
+    reference text (make_golden.py channelglue)."""
+    d = np.load(GOLD_GLUE)
+    o, nsv = build_glue(d)
+    for n in ("u0", "v0", "w0", "um", "vm", "wm", "up", "vp", "wp", "ekm", "ekh"):
+        getattr(o, n)[...] = d["in_" + n]
+    o.sv0[...] = d["in_sv0"][..., :nsv]
+    o.svp[...] = d["in_svp"][..., :nsv]
+    o.set_bottom(float(d["z0"]), float(d["fkar"]))
+    o.bottom()
+    for n in ("up", "vp", "wp"):
+        assert rel(getattr(o, n), d["bottom_" + n]) < 1e-15, n           # same operation order, no FMA: bit-level agreement
+    assert rel(o.svp, d["bottom_svp"][..., :nsv]) < 1e-15
+    assert rel(o.momfluxb()[1:-1, 1:-1, 1], d["bottom_momfluxb"][1:-1, 1:-1, 1]) < 1e-15
+    o.set_masscorr(float(d["uflowrate"]), float(d["vflowrate"]), d["IIu"], d["IIv"])
+    for rk in (1, 2, 3):
+        udef, vdef = o.masscorr(float(d["dt"]), rk)
+        assert udef == pytest.approx(float(d[f"mc{rk}_udef"]), rel=1e-13)  # slab sums: summation order differs (numpy pairwise)
+        assert vdef == pytest.approx(float(d[f"mc{rk}_vdef"]), rel=1e-13)
+        assert rel(o.up[1:-1, 1:-1, :-1], d[f"mc{rk}_up"][1:-1, 1:-1, :-1]) < 1e-13
+        assert rel(o.vp[1:-1, 1:-1, :-1], d[f"mc{rk}_vp"][1:-1, 1:-1, :-1]) < 1e-13

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libudales_gpu.so")
 ABI_VERSION = 1
 
 FIELD_IDS = {"u0": 0, "v0": 1, "w0": 2, "um": 3, "vm": 4, "wm": 5, "up": 6, "vp": 7, "wp": 8,
-             "pres0": 9, "p": 10, "ekm": 11, "ekh": 12, "rhs": 13, "sv0": 14, "svm": 15, "svp": 16}
+             "pres0": 9, "p": 10, "ekm": 11, "ekh": 12, "rhs": 13, "sv0": 14, "svm": 15, "svp": 16, "momfluxb": 17}
 
 EXPORTS = [
     "udgpu_nccl_unique_id", "udgpu_init", "udgpu_finalize", "udgpu_last_error", "udgpu_abi_version",
@@ -31,7 +31,7 @@ EXPORTS = [
     "udgpu_tstep_update", "udgpu_advection", "udgpu_subgrid", "udgpu_closure", "udgpu_poisson",
     "udgpu_poisson_solve", "udgpu_poisson_solve_resident", "udgpu_fillps", "udgpu_tderive",
     "udgpu_tstep_integrate", "udgpu_halos", "udgpu_boundary", "udgpu_divergence", "udgpu_substep",
-    "udgpu_rk3_step_host", "udgpu_set_forcing", "udgpu_forces", "udgpu_ibm_set_points", "udgpu_ibm_commit", "udgpu_ibm_pull_mask", "udgpu_ibmnorm", "udgpu_ibm_diffcorr",
+    "udgpu_rk3_step_host", "udgpu_set_forcing", "udgpu_forces", "udgpu_set_bottom", "udgpu_bottom", "udgpu_set_masscorr", "udgpu_masscorr", "udgpu_ibm_set_points", "udgpu_ibm_commit", "udgpu_ibm_pull_mask", "udgpu_ibmnorm", "udgpu_ibm_diffcorr",
     "udgpu_profile_enable", "udgpu_profile_get", "udgpu_profile_reset", "udgpu_launch_count", "udgpu_stream", "udgpu_trace_dump",
 ]
 
@@ -107,6 +107,10 @@ def lib():
                                                                               C.c_double, C.c_double]
         L.udgpu_set_forcing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.udgpu_forces.argtypes = [C.c_void_p]
+        L.udgpu_set_bottom.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.udgpu_bottom.argtypes = [C.c_void_p]
+        L.udgpu_set_masscorr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.udgpu_masscorr.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.udgpu_ibm_set_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.udgpu_ibm_commit.argtypes = [C.c_void_p]
         L.udgpu_ibm_pull_mask.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -306,6 +310,22 @@ class UdalesGPU:
         self._chk(self.L.udgpu_set_forcing(self.h, a.ctypes.data, b.ctypes.data))
 
     def forces(self): self._chk(self.L.udgpu_forces(self.h))
+
+    # bottom -> wfmneutral (src/modibm.f90:1998, src/modwallfunctions.f90:307) and masscorr (src/modforces.f90:328) --------
+    def set_bottom(self, z0, fkar=0.41, lbottom=True, BCbotm=3, BCbots=1):
+        self._chk(self.L.udgpu_set_bottom(self.h, int(lbottom), BCbotm, BCbots, z0, fkar))
+
+    def bottom(self): self._chk(self.L.udgpu_bottom(self.h))
+
+    def set_masscorr(self, uflowrate=None, vflowrate=None):
+        """volume-flow forcing: luvolflowr / lvvolflowr are on for the components whose flow rate is given"""
+        self._chk(self.L.udgpu_set_masscorr(self.h, int(uflowrate is not None), int(vflowrate is not None), float(uflowrate or 0.0),
+                                            float(vflowrate or 0.0)))
+
+    def masscorr(self, dt, rk3step, want_def=True):
+        u, v = C.c_double(), C.c_double()
+        self._chk(self.L.udgpu_masscorr(self.h, dt, rk3step, C.byref(u) if want_def else None, C.byref(v) if want_def else None))
+        return u.value, v.value
 
     # immersed boundary masking (src/modibm.f90) ----------------------------------------
     IBM_KINDS = ("solid_u", "solid_v", "solid_w", "solid_c", "bound_u", "bound_v", "bound_w", "bound_c")

@@ -1,0 +1,148 @@
+// channel_glue.cuh — the rest of the resident-channel glue of examples/999:
+//   bottom -> wfmneutral(.., 91)   src/modibm.f90:1998-2100, src/modwallfunctions.f90:307-349 (+ the zero-flux scalar
+//                                  bottom correction, src/modibm.f90:2077-2091)
+//   masscorr, volume-flow branches src/modforces.f90:394-420 (u), :470-495 (v) with avexy_ibm (src/modmpi.f90:623-664)
+#pragma once
+#include "common.cuh"
+
+namespace udg {
+
+// wfmneutral case 91 on the plane k = kb: one thread per (i,j) does the u and the v update of its cell.  dxf = dx,
+// dxhi = dxi (x uniform).  momfluxb accumulates both contributions like the reference (:326, :343).
+__global__ void __launch_bounds__(256) k_bottom_wfmneutral(Geo g, double z0, double fkar, const double *__restrict__ u0, const double *__restrict__ v0,
+                                                           const double *__restrict__ ekm, double *__restrict__ up, double *__restrict__ vp,
+                                                           double *__restrict__ momfluxb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const int k = 1, km = 0;
+  const long long c = offF(g, i, j, k), t = offT(g, i, j, k), sj = g.pi, sk = g.pk;
+  const double fkar2 = fkar * fkar, umin = 0.0001;
+  const double dzfk = g.dzf[k], dzfkm = g.dzf[km], dzfik = g.dzfi[k], dzhik = g.dzhi[k], dzhiqk = g.dzhiq[k];
+  const double delta = 0.5 * dzfk;
+  const double lg = log(delta / z0);
+  const double ctm = fkar2 / (lg * lg);
+  double mf = momfluxb[c];
+  {
+    const double ut1 = u0[c];
+    const double ut2 = (v0[c] + v0[c - 1] + v0[c + sj] + v0[c - 1 + sj]) * 0.25;
+    const double utang = fmax(umin, (ut1 * ut1 + ut2 * ut2));
+    const double bcmomflux = copysign(fabs(ut1) * sqrt(utang) * ctm, ut1);
+    mf = mf + bcmomflux * dzfik;
+    const double emom = (dzfkm * (ekm[c] * g.dx + ekm[c - 1] * g.dx) + dzfk * (ekm[c - sk] * g.dx + ekm[c - 1 - sk] * g.dx)) * g.dxi * dzhiqk;
+    up[t] = up[t] + (ut1 - u0[c - sk]) * emom * dzhik * dzfik - bcmomflux * dzfik;
+  }
+  {
+    const double ut1 = (u0[c] + u0[c - sj] + u0[c + 1 - sj] + u0[c + 1]) * 0.25;
+    const double ut2 = v0[c];
+    const double utang = fmax(umin, (ut1 * ut1 + ut2 * ut2));
+    const double bcmomflux = copysign(fabs(ut2) * sqrt(utang) * ctm, ut2);
+    mf = mf + bcmomflux * dzfik;
+    const double eomm = (dzfkm * (ekm[c] + ekm[c - sj]) + dzfk * (ekm[c - sk] + ekm[c - sj - sk])) * dzhiqk;
+    vp[t] = vp[t] + (ut2 - v0[c - sk]) * eomm * dzhik * dzfik - bcmomflux * dzfik;
+  }
+  momfluxb[c] = mf;
+}
+// src/modibm.f90:2077-2091 (BCbots = 1, zero surface flux): blockIdx.z = scalar index
+__global__ void __launch_bounds__(256) k_bottom_scalar(Geo g, const double *__restrict__ ekh, const double *__restrict__ sv0, long long ssl,
+                                                       double *__restrict__ svp, long long tsl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const int kb = 1;
+  const double *s = sv0 + blockIdx.z * ssl;
+  double *sp = svp + blockIdx.z * tsl;
+  const long long c = offS(g, i, j, kb), t = offST(g, i, j, kb), m = offF(g, i, j, kb);
+  sp[t] = sp[t] + (0.5 * (g.dzf[kb - 1] * ekh[m] + g.dzf[kb] * ekh[m - g.pk]) * (s[c] - s[c - g.pkc]) * g.dzh2i[kb] + 0.) * g.dzfi[kb];
+}
+
+// ---- masscorr ---------------------------------------------------------------------------------------------------
+// Masked plane sums in a fixed order (reproducible run to run): block b of level k sums its strided share of the
+// plane, k_masscorr_finish adds the nblk partials in index order.  slot = 2*comp + (0: tendency, 1: m-field).
+// mask: momentum-halo shaped real mask (1 fluid / 0 solid; mask_u / mask_v of the IBM path) or nullptr = all fluid.
+constexpr int MC_NBLK = 32;
+__global__ void __launch_bounds__(256) k_slab_partial(Geo g, const double *__restrict__ tend, const double *__restrict__ mfld,
+                                                      const double *__restrict__ mask, int unmask_k1, double *__restrict__ part /* [2][K][MC_NBLK] */) {
+  const int k = blockIdx.y + 1, b = blockIdx.x;
+  const long long n = (long long)g.imax * g.jmax;
+  double s0 = 0., s1 = 0.;
+  for (long long q = (long long)b * blockDim.x + threadIdx.x; q < n; q += (long long)MC_NBLK * blockDim.x) {
+    const int j = (int)(q / g.imax) + 1, i = (int)(q - (long long)(j - 1) * g.imax) + 1;
+    const long long c = offF(g, i, j, k);
+    const double m = (mask && !(unmask_k1 && k == 1)) ? mask[c] : 1.0;
+    s0 += tend[offT(g, i, j, k)] * m;
+    s1 += mfld[c] * m;
+  }
+  __shared__ double sh0[256], sh1[256];
+  sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o) { sh0[threadIdx.x] += sh0[threadIdx.x + o]; sh1[threadIdx.x] += sh1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    part[((long long)0 * g.ktot + (k - 1)) * MC_NBLK + b] = sh0[0];
+    part[((long long)1 * g.ktot + (k - 1)) * MC_NBLK + b] = sh1[0];
+  }
+}
+// plane sums -> vol[slot][k] (before the cross-rank sum)
+__global__ void k_masscorr_reduce(int K, const double *__restrict__ part, double *__restrict__ vol /* [2][K] */) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 2 * K) return;
+  double s = 0.;
+  for (int b = 0; b < MC_NBLK; b++) s += part[(long long)q * MC_NBLK + b];
+  vol[q] = s;
+}
+// the scalar part of masscorr for one component (single thread): def = flowrate - (rk3coef <tend> + <m>), volume
+// means with dzf weights over zh(ke+1) (src/modforces.f90:408-413).  fpend: a lazily pending forces() has to be part of
+// the tendency mean (its profile is uniform in x, y: the masked plane mean of it is the profile itself).
+// Writes def and the effective per-level table the fused tderive+integrate kernel subtracts: fe[k] = fpend*f[k] - def/rk3coef.
+__global__ void k_masscorr_final(int K, const double *__restrict__ vol, const double *__restrict__ cnt /* fluid points per level, K */,
+                                 double cnt_ke, int unmask_k1, const double *__restrict__ dzf, double zhtop, double rk3coef, double flowrate,
+                                 const double *__restrict__ f /* forcing table, index k */, int fpend, double *__restrict__ def_out,
+                                 double *__restrict__ fe) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s1 = 0., s2 = 0.;
+  for (int k = 1; k <= K; k++) {
+    double d = cnt[k - 1];
+    if (k == 1 && unmask_k1) d = cnt_ke;                      // src/modmpi.f90:649-652
+    double a = d == 0. ? -999. : vol[k - 1] / d, bm = d == 0. ? -999. : vol[K + k - 1] / d;
+    if (fpend && d != 0.) a = a - f[k];
+    s1 += a * dzf[k];
+    s2 += bm * dzf[k];
+  }
+  const double outflow = rk3coef * s1 / zhtop, old = s2 / zhtop;
+  const double def = flowrate - (outflow + old);
+  *def_out = def;
+  const double add = def * (1 / rk3coef);
+  for (int k = 0; k <= K + 1; k++) fe[k] = (fpend ? f[k] : 0.) - add;
+}
+// up(i,j,k) = up(i,j,k) - fe(k) on the interior of one tendency (eager form of the masscorr / forces shift)
+__global__ void __launch_bounds__(256) k_tend_sub_table(Geo g, const double *__restrict__ fe, double *__restrict__ tp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long t = offT(g, i, j, k);
+  tp[t] = tp[t] - fe[k];
+}
+// fluid points per level of a real mask (interior), as doubles (summed across ranks with ncclSum afterwards)
+__global__ void k_mask_count(Geo g, const double *__restrict__ mask, double *__restrict__ cnt) {
+  const int k = blockIdx.x + 1;
+  double s = 0.;
+  const long long n = (long long)g.imax * g.jmax;
+  for (long long q = threadIdx.x; q < n; q += blockDim.x) {
+    const int j = (int)(q / g.imax) + 1, i = (int)(q - (long long)(j - 1) * g.imax) + 1;
+    s += mask ? mask[offF(g, i, j, k)] : 1.0;
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cnt[k - 1] = sh[0];
+}
+
+}  // namespace udg

@@ -21,6 +21,7 @@
 #include "stencil_v1.cuh"
 #include "scalar_v1.cuh"
 #include "ibm.cuh"
+#include "channel_glue.cuh"
 
 using namespace udg;
 
@@ -182,6 +183,18 @@ struct udgpu {
   double *d_fx = nullptr, *d_fy = nullptr, *d_fzero = nullptr;
   std::vector<double> fx_host, fy_host;   // what the device tables hold (udgpu_set_forcing is a no-op for unchanged profiles)
   bool has_forcing = false, forces_pending = false;
+  // bottom -> wfmneutral (src/modibm.f90:1998, src/modwallfunctions.f90:307) and masscorr (src/modforces.f90:328)
+  bool lbottom = false;
+  int BCbots = 1;
+  double z0 = 0., fkar = 0.41;
+  bool mc_on[2] = {false, false};        // luvolflowr, lvvolflowr
+  double mc_flow[2] = {0., 0.};          // uflowrate, vflowrate
+  double *d_mc_part = nullptr, *d_mc_vol = nullptr, *d_mc_cnt = nullptr, *d_mc_def = nullptr, *d_fxe = nullptr, *d_fye = nullptr;
+  std::vector<double> mc_cnt_host[2];    // fluid points per level (global), host copy
+  bool mc_counts_valid = false;
+  bool mc_pending = false;               // the uniform shift of masscorr is folded into the next tderive+integrate (tables d_fxe, d_fye)
+  bool mc_forces_folded = false;         // ... and those tables already contain a pending forces()
+  double zh_top = 0.;
   // immersed boundary (src/modibm.f90): point lists, masks
   int ibm_n[8] = {};
   int *ibm_pts[8] = {};
@@ -480,6 +493,7 @@ static int init_impl(udgpu *h, const udgpu_cfg *c, const void *nccl_uid, int nde
   g.dzfiq = MP(tDZFIQ); g.dzh2i = MP(tDZH2I); g.dzf2 = MP(tDZF2); g.dzfi5 = MP(tDZFI5); g.delta = MP(tDELTA);
   g.dzfc = MP(tDZFC); g.dzfci = MP(tDZFCI); g.dzhci = MP(tDZHCI);
 
+  for (int k = 1; k <= K; k++) h->zh_top += c->dzf[k];   // zh(ke+1), src/modglobal.f90:747-749
   // ---- fields ----
   const size_t nF = (size_t)g.pi * g.pj * (K + 2 * g.kh), nT = (size_t)g.pi * g.pj * (K + g.kh);
   const size_t nR = (size_t)g.imax * g.jmax * K;
@@ -506,11 +520,12 @@ static int init_impl(udgpu *h, const udgpu_cfg *c, const void *nccl_uid, int nde
       default: n = nF; d3 = K + 2 * g.kh; break;
     }
     h->cnt[f] = n; h->nslices[f] = sl;
+    const bool lazy_field = (f == UDGPU_MOMFLUXB);   // allocated by udgpu_set_bottom
     const bool scal = (f == UDGPU_SV0 || f == UDGPU_SVM || f == UDGPU_SVP);
     h->dims[f][0] = (f == UDGPU_RHS) ? g.imax : scal ? g.pic : g.pi;
     h->dims[f][1] = (f == UDGPU_RHS) ? g.jmax : scal ? g.pjc : g.pj;
     h->dims[f][2] = d3;
-    if (n) RET(dev_alloc(h, (void **)&h->f[f], n * sl * sizeof(double)));
+    if (n && !lazy_field) RET(dev_alloc(h, (void **)&h->f[f], n * sl * sizeof(double)));
   }
   RET(dev_alloc(h, (void **)&h->d_red, 16 * sizeof(double)));
   for (double **t : {&h->d_fx, &h->d_fy, &h->d_fzero}) RET(dev_alloc(h, (void **)t, (K + 2) * sizeof(double)));
@@ -907,17 +922,36 @@ static int launch_scalars(udgpu *h, bool acc) {
 static int tderive_now(udgpu *h);
 template <class After> static int slab_backward(udgpu *h, double *work, double *p_halo, bool carry, After &&after);
 static int forces_now(udgpu *h) {
-  h->forces_pending = false;
+  // materialise what is lazily pending on the tendencies: forces() and / or the uniform shift of masscorr()
   const Geo &g = h->g;
   RET(materialize_zero_tend(h));
-  k_forces<<<grid3(g, B3), B3, 0, h->st>>>(g, h->d_fx, h->d_fy, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP]);
-  KCHECK();
-  h->launches++;
+  const bool f = h->forces_pending, m = h->mc_pending;
+  h->forces_pending = false; h->mc_pending = false;
+  if (f && !(m && h->mc_forces_folded)) {
+    k_forces<<<grid3(g, B3), B3, 0, h->st>>>(g, h->d_fx, h->d_fy, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP]);
+    KCHECK();
+    h->launches++;
+  }
+  if (m) {
+    // tables fe = [forces] - def/rk3coef (k_masscorr_final); a component without masscorr has fe = [forces] or 0
+    if (h->mc_forces_folded) {   // forces included: one pass that also sets wp(kb) = 0
+      k_forces<<<grid3(g, B3), B3, 0, h->st>>>(g, h->d_fxe, h->d_fye, h->f[UDGPU_UP], h->f[UDGPU_VP], h->f[UDGPU_WP]);
+      KCHECK();
+      h->launches++;
+    } else {
+      for (int c = 0; c < 2; c++)
+        if (h->mc_on[c]) {
+          k_tend_sub_table<<<grid3(g, B3), B3, 0, h->st>>>(g, c ? h->d_fye : h->d_fxe, h->f[c ? UDGPU_VP : UDGPU_UP]);
+          KCHECK();
+          h->launches++;
+        }
+    }
+  }
   h->tend_zero = false;
   return UDGPU_OK;
 }
 static int flush_pending(udgpu *h, bool keep_forces) {
-  if (h->forces_pending && !keep_forces) RET(forces_now(h));   // adv_pending cannot be set here: forces() flushed it
+  if ((h->forces_pending || h->mc_pending) && !keep_forces) RET(forces_now(h));   // adv_pending cannot be set here: forces() flushed it
   if (h->bwd_pending) {   // the inverse half of a pipelined slab solve, on its own
     h->bwd_pending = false;
     ProfScope ps(h, PROF_POIS);
@@ -1529,14 +1563,18 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
     ProfScope ps(h, h->bwd_pending ? PROF_BWDPIPE : PROF_INTEG);
     if (own) {
       // one pass: bcp (periodic index / slab exchange of p), tderive, integrate, pres0 += p, halos, boundary
-      const bool fp = h->forces_pending;
-      h->forces_pending = false;
+      // pending forces() and / or masscorr(): subtracted per level inside the kernel (tables; wp(kb) = 0 only from forces)
+      const bool fp = h->forces_pending || h->mc_pending;
+      const double *tfx = h->mc_pending ? h->d_fxe : h->d_fx, *tfy = h->mc_pending ? h->d_fye : h->d_fy;
+      const int fz = (h->forces_pending && (!h->mc_pending || h->mc_forces_folded)) ? 1 : 0;
+      if (h->mc_pending && h->forces_pending && !h->mc_forces_folded) return set_err(UDGPU_ESTATE, "forces() after masscorr() within one substep is not the reference's order (src/program.f90:158,169)");
+      h->forces_pending = false; h->mc_pending = false;
       auto integ = [&](int k0, int kc) -> int {   // 0-based levels k0 .. k0+kc-1
         dim3 gr = grid3(g, B3);
         gr.z = kc;
 #define TI_(S3, XS, FO) k_tderive_integrate_halo<S3, XS, FO><<<gr, B3, 0, h->st>>>(g, rk3coef, f[UDGPU_P], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_WP], f[UDGPU_UM], \
                                                                        f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_PRES0], \
-                                                                       h->d_fx, h->d_fy, 1, k0)
+                                                                       tfx, tfy, fz, k0)
 #define TI2_(S3, XS) do { if (fp) TI_(S3, XS, true); else TI_(S3, XS, false); } while (0)
         if (rk3step == 3) { if (h->P > 1) TI2_(true, 1); else TI2_(true, 0); }
         else { if (h->P > 1) TI2_(false, 1); else TI2_(false, 0); }
@@ -1559,7 +1597,7 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
       h->halo_x_pending = h->P > 1;
       if (rk3step == 3) h->m_changed = true;
     } else {
-      if (h->forces_pending) RET(forces_now(h));
+      if (h->forces_pending || h->mc_pending) RET(forces_now(h));
       RET(wrap_xy(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
       h->p_halo_valid = true;
       if (rk3step == 3)
@@ -1705,11 +1743,11 @@ extern "C" int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax,
   RET(udgpu_tstep_update(h, dt, courant, diffnr, dtmax, ladaptive, rk3step, nullptr, nullptr));
   RET(udgpu_advection(h));
   RET(udgpu_subgrid(h));
+  if (h->lbottom) RET(udgpu_bottom(h));       // src/program.f90:152
   if (h->has_forcing) RET(udgpu_forces(h));   // src/program.f90:158
-  if (h->libm) {
-    RET(udgpu_ibm_diffcorr(h));   // the resident part of ibmwallfun, src/program.f90:166
-    RET(udgpu_ibmnorm(h));        // src/program.f90:171
-  }
+  if (h->libm) RET(udgpu_ibm_diffcorr(h));    // the resident part of ibmwallfun, src/program.f90:166
+  if (h->mc_on[0] || h->mc_on[1]) RET(udgpu_masscorr(h, *dt, *rk3step, nullptr, nullptr));   // src/program.f90:169
+  if (h->libm) RET(udgpu_ibmnorm(h));         // src/program.f90:171
   RET(udgpu_poisson(h, *dt, *rk3step));
   RET(udgpu_tstep_integrate(h, *dt, *rk3step));
   RET(udgpu_halos(h));
@@ -1741,8 +1779,130 @@ extern "C" int udgpu_forces(udgpu_t *h) {
   if (!h->has_forcing) return UDGPU_OK;
   RET(flush_pending(h));
   // with IBM masking the order matters (ibmnorm zeroes the tendencies of solid points after forces, src/program.f90:158,171)
-  if (h->libm || (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION)) return forces_now(h);
   h->forces_pending = true;
+  if (h->libm || (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION)) return forces_now(h);
+  return UDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// bottom -> wfmneutral case 91 (src/modibm.f90:1998-2100, src/modwallfunctions.f90:307-349)
+extern "C" int udgpu_set_bottom(udgpu_t *h, int lbottom, int BCbotm, int BCbots, double z0, double fkar) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (lbottom && BCbotm != 3) return set_err(UDGPU_EINVAL, "BCbotm=%d: only the neutral wall function (3, wfmneutral) is on the resident path", BCbotm);
+  if (lbottom && h->cfg.nsv > 0 && BCbots != 1) return set_err(UDGPU_EINVAL, "BCbots=%d: only the zero-flux scalar bottom (1) exists in the reference (src/modibm.f90:2092-2095)", BCbots);
+  if (lbottom && !(z0 > 0.)) return set_err(UDGPU_EINVAL, "z0 must be positive");
+  h->lbottom = lbottom != 0; h->BCbots = BCbots; h->z0 = z0; h->fkar = fkar;
+  if (h->lbottom && !h->f[UDGPU_MOMFLUXB]) RET(dev_alloc(h, (void **)&h->f[UDGPU_MOMFLUXB], h->cnt[UDGPU_MOMFLUXB] * sizeof(double)));
+  return UDGPU_OK;
+}
+extern "C" int udgpu_bottom(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (!h->lbottom) return UDGPU_OK;
+  RET(flush_pending(h));
+  RET(materialize_zero_tend(h));
+  const Geo &g = h->g;
+  double **f = h->f;
+  ProfScope ps(h, PROF_MOM);
+  const dim3 gr((g.imax + B3.x - 1) / B3.x, (g.jmax + B3.y - 1) / B3.y, 1);
+  k_bottom_wfmneutral<<<gr, B3, 0, h->st>>>(g, h->z0, h->fkar, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_EKM], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_MOMFLUXB]);
+  KCHECK();
+  h->launches++;
+  if (h->cfg.nsv > 0) {
+    k_bottom_scalar<<<dim3(gr.x, gr.y, h->cfg.nsv), B3, 0, h->st>>>(g, f[UDGPU_EKH], f[UDGPU_SV0], (long long)h->cnt[UDGPU_SV0], f[UDGPU_SVP], (long long)h->cnt[UDGPU_SVP]);
+    KCHECK();
+    h->launches++;
+  }
+  h->tend_zero = false;
+  return UDGPU_OK;
+}
+
+// masscorr, volume-flow branches (src/modforces.f90:394-420, 470-495).  IIu / IIv of the reference are 1 except at the
+// solid_u / solid_v points (createmasks, src/modibm.f90:2103-2160), i.e. the interior of mask_u / mask_v built by
+// udgpu_ibm_commit; without IBM every point counts.
+extern "C" int udgpu_set_masscorr(udgpu_t *h, int luvolflowr, int lvvolflowr, double uflowrate, double vflowrate) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  const int K = h->g.ktot;
+  h->mc_on[0] = luvolflowr != 0; h->mc_on[1] = lvvolflowr != 0;
+  h->mc_flow[0] = uflowrate; h->mc_flow[1] = vflowrate;
+  if ((h->mc_on[0] || h->mc_on[1]) && !h->d_mc_part) {
+    RET(dev_alloc(h, (void **)&h->d_mc_part, (size_t)2 * 2 * K * MC_NBLK * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_mc_vol, (size_t)2 * 2 * K * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_mc_cnt, (size_t)2 * K * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_mc_def, 2 * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_fxe, (K + 2) * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_fye, (K + 2) * sizeof(double)));
+  }
+  h->mc_counts_valid = false;
+  return UDGPU_OK;
+}
+static int masscorr_counts(udgpu *h) {
+  // IIus, IIvs: fluid points per level over all ranks (src/modibm.f90:2176-2190)
+  const Geo &g = h->g;
+  const int K = g.ktot;
+  for (int c = 0; c < 2; c++) {
+    k_mask_count<<<K, 256, 0, h->st>>>(g, h->libm ? h->ibm_mask[c] : nullptr, h->d_mc_cnt + (size_t)c * K);
+    KCHECK();
+    h->launches++;
+  }
+  if (h->P > 1) NC(ncclAllReduce(h->d_mc_cnt, h->d_mc_cnt, 2 * K, ncclDouble, ncclSum, h->comm, h->st));
+  for (int c = 0; c < 2; c++) {
+    h->mc_cnt_host[c].resize(K);
+    CU(cudaMemcpyAsync(h->mc_cnt_host[c].data(), h->d_mc_cnt + (size_t)c * K, K * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  }
+  RET(sync_check(h));
+  h->mc_counts_valid = true;
+  return UDGPU_OK;
+}
+extern "C" int udgpu_masscorr(udgpu_t *h, double dt, int rk3step, double *udef, double *vdef) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (!h->mc_on[0] && !h->mc_on[1]) return UDGPU_OK;
+  RET(flush_pending(h, true));              // a pending forces() is accounted for analytically (k_masscorr_final)
+  if (h->mc_pending) RET(forces_now(h));    // a second masscorr() before the integration: apply the first one
+  RET(materialize_zero_tend(h));
+  if (!h->mc_counts_valid) RET(masscorr_counts(h));
+  const Geo &g = h->g;
+  const int K = g.ktot;
+  const double rk3coef = dt / (4. - (double)rk3step);
+  double **f = h->f;
+  ProfScope ps(h, PROF_MOM);
+  const bool fpend = h->forces_pending;
+  for (int c = 0; c < 2; c++) {
+    if (!h->mc_on[c]) continue;
+    const int unmask = h->mc_cnt_host[c][0] == 0. ? 1 : 0;
+    k_slab_partial<<<dim3(MC_NBLK, K), 256, 0, h->st>>>(g, f[c ? UDGPU_VP : UDGPU_UP], f[c ? UDGPU_VM : UDGPU_UM], h->libm ? h->ibm_mask[c] : nullptr,
+                                                         unmask, h->d_mc_part + (size_t)c * 2 * K * MC_NBLK);
+    KCHECK();
+    k_masscorr_reduce<<<(2 * K + 127) / 128, 128, 0, h->st>>>(K, h->d_mc_part + (size_t)c * 2 * K * MC_NBLK, h->d_mc_vol + (size_t)c * 2 * K);
+    KCHECK();
+    h->launches += 2;
+  }
+  if (h->P > 1) NC(ncclAllReduce(h->d_mc_vol, h->d_mc_vol, 4 * K, ncclDouble, ncclSum, h->comm, h->st));   // MPI_ALLREDUCE of avexy_ibm, src/modmpi.f90:654
+  for (int c = 0; c < 2; c++) {
+    double *fe = c ? h->d_fye : h->d_fxe;
+    const double *ft = c ? h->d_fy : h->d_fx;
+    if (!h->mc_on[c]) {   // this component has no flow-rate forcing: its table only carries a pending forces()
+      if (fpend) CU(cudaMemcpyAsync(fe, ft, (K + 2) * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+      else CU(cudaMemsetAsync(fe, 0, (K + 2) * sizeof(double), h->st));
+      continue;
+    }
+    const int unmask = h->mc_cnt_host[c][0] == 0. ? 1 : 0;
+    k_masscorr_final<<<1, 32, 0, h->st>>>(K, h->d_mc_vol + (size_t)c * 2 * K, h->d_mc_cnt + (size_t)c * K, h->mc_cnt_host[c][K - 1], unmask, g.dzf, h->zh_top,
+                                          rk3coef, h->mc_flow[c], ft, fpend ? 1 : 0, h->d_mc_def + c, fe);
+    KCHECK();
+    h->launches++;
+  }
+  h->mc_pending = true;
+  h->mc_forces_folded = fpend;
+  // ibmnorm zeroes the tendencies of solid points AFTER masscorr (src/program.f90:169,171): with IBM masking, or when
+  // every call is eager, the shift is applied now
+  if (h->libm || (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION)) RET(forces_now(h));
+  if (udef || vdef) {
+    double d[2];
+    CU(cudaMemcpyAsync(d, h->d_mc_def, sizeof(d), cudaMemcpyDeviceToHost, h->st));
+    RET(sync_check(h));
+    if (udef) *udef = d[0];
+    if (vdef) *vdef = d[1];
+  }
   return UDGPU_OK;
 }
 
@@ -1786,6 +1946,7 @@ extern "C" int udgpu_ibm_commit(udgpu_t *h) {
   // exchange_halo_z(mask_*): periodic wrap / slab exchange
   RET(wrap_xy(h, {h->ibm_mask[0], h->ibm_mask[1], h->ibm_mask[2], h->ibm_mask[3]}, g.ktot + 2 * g.kh));
   h->libm = true;
+  h->mc_counts_valid = false;
   return UDGPU_OK;
 }
 
