@@ -57,6 +57,14 @@ def main():
     blk = {nm: np.ascontiguousarray(glob[nm][i0 - 1:i0 + n + 1, j0 - 1:j0 + n + 1, 0:n + 1]) for nm in ("u0", "v0", "w0")}
     np.savez_compressed(OUT, i0=i0, j0=j0, n=n, timee=meta[0], dt=meta[1], divmax_global=np.abs(div).max(), **blk)
     print("wrote", OUT, os.path.getsize(OUT) // 1024, "KiB")
+    # a 32^3 block (with its neighbour columns / rows and level k+1) of the real turbulent state incl. pres0: input of a
+    # closure + substep parity run on real LES data instead of synthetic noise (tests/test_gpu_parity.py)
+    m = 32
+    i1, j1 = 17, 9
+    turb = {nm: np.ascontiguousarray(glob[nm][i1 - 1:i1 + m + 1, j1 - 1:j1 + m + 1, 0:m + 1]) for nm in ("u0", "v0", "w0", "pres0")}
+    out2 = OUT.replace("ref_restart102_block", "ref_restart102_turb32")
+    np.savez_compressed(out2, i0=i1, j0=j1, n=m, timee=meta[0], dt=meta[1], **turb)
+    print("wrote", out2, os.path.getsize(out2) // 1024, "KiB")
 
 
 if __name__ == "__main__":
