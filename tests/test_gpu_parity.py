@@ -485,3 +485,21 @@ def test_resident_channel_glue_in_the_substep(shape, flags, case):
         assert g.divergence()[2] < 1e-12
     # the bulk velocity is what masscorr was told to hold (fluid volume mean of u after a full RK3 step)
     assert relerr(interior(g.pull("momfluxb"))[:, :, 0], interior(o.momfluxb())[:, :, 0]) < 1e-11
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 16), (128, 64, 9), (256, 64, 8), (64, 128, 5)])
+@pytest.mark.parametrize("rk3step", [1, 3])
+def test_fillps_fused_into_the_first_transform_is_bitwise_neutral(shape, rk3step, monkeypatch):
+    """poisson() with fillps + bcpup evaluated inside the first forward transform (no rhs array traffic) against the
+    separate k_fillps pass: the same expression in the same order, so p, the projected tendencies and pres0 are the
+    same bits; and against the oracle."""
+    monkeypatch.setenv("UDGPU_FILL_FUSED", "1")
+    o, ga = make_pair(*shape)
+    monkeypatch.setenv("UDGPU_FILL_FUSED", "0")
+    _, gb = make_pair(*shape)
+    dt = 0.03
+    for x in (o, ga, gb):
+        x.advection(); x.subgrid(); x.poisson(dt, rk3step)
+    for n in ("p", "up", "vp", "wp", "pres0"):
+        assert np.array_equal(ga.pull(n), gb.pull(n)), n
+    assert relerr(interior(ga.pull("p")), interior(o.p)) < TOL_PRES

@@ -80,16 +80,45 @@ struct BlkDesc {
   int halo, nblk;
 };
 
+// Source of a FILL launch: the forward transform of the first pass evaluates the right-hand side of the Poisson equation
+// itself while it loads its lines — fillps + bcpup (src/modpois.f90:911-973, src/modboundary.f90:1191-1255) fused into
+// the transform: p = d/dx(up + um/c) + d/dy(vp + vm/c) + d/dz(wp + wm/c), pwp(kb) = pwp(ke+1) = 0, same expression and
+// operation order as k_fillps, so the transformed data are the same bits as with the separate kernel.  The rhs array
+// is never written nor read (16 B/cell less traffic), and in the slab solve the six input streams keep HBM busy while
+// the transform's output is waiting for NVLink.
+struct FillSrc {
+  const double *up, *vp, *wp, *um, *vm, *wm;
+  const double *dzfi;
+  double rk3coefi, dxi, dyi;
+  long long pi, pk;        // row and level pitch of the halo'd arrays (ih = jh = kh = 1)
+  int imax, jmax, ktot;
+  int xwrap;               // x unsplit: the +1 neighbour of the last column is the periodic image (else the halo column)
+  int k0;                  // 0-based level of outer batch index 0 (k-chunks)
+};
+__device__ __forceinline__ double fill_rhs(const FillSrc &f, int i, int j, int k) {   // 1-based cell
+  const int ip = (f.xwrap && i == f.imax) ? 1 : i + 1, jp = (j == f.jmax) ? 1 : j + 1;
+  const long long t = (long long)i + f.pi * (j + 0ll) + f.pk * (k - 1), c = t + f.pk;     // offT / offF with halo 1
+  const long long tx = (long long)ip + f.pi * (j + 0ll) + f.pk * (k - 1), ty = (long long)i + f.pi * (jp + 0ll) + f.pk * (k - 1);
+  const double pu0 = f.up[t] + f.um[c] * f.rk3coefi;
+  const double pu1 = f.up[tx] + f.um[tx + f.pk] * f.rk3coefi;
+  const double pv0 = f.vp[t] + f.vm[c] * f.rk3coefi;
+  const double pv1 = f.vp[ty] + f.vm[ty + f.pk] * f.rk3coefi;
+  const double pw0 = (k == 1) ? 0.0 : f.wp[t] + f.wm[c] * f.rk3coefi;
+  const double pw1 = (k == f.ktot) ? 0.0 : f.wp[t + f.pk] + f.wm[c + f.pk] * f.rk3coefi;
+  return (pu1 - pu0) * f.dxi + (pv1 - pv0) * f.dyi + (pw1 - pw0) * f.dzfi[k];
+}
+
 template <int R1, int R2, int LANES, bool XDIR>
 struct RfftCfg {
   static constexpr int H = R1 * R2, N = 2 * H, NT = LANES * R2;
   static constexpr int SMEM = XDIR ? LANES * (H + 1) * 16 : LANES * H * 16;
 };
 
-template <int R1, int R2, int LANES, bool XDIR, bool INV, bool IBLK = false, bool OBLK = false>
+template <int R1, int R2, int LANES, bool XDIR, bool INV, bool IBLK = false, bool OBLK = false, bool FILL = false>
 __global__ void __launch_bounds__(LANES *R2, (R1 <= 16 ? 2 : 1)) k_rfft_fast(const double2 *__restrict__ tw, const double *__restrict__ in, LineDesc di,
                                                          double *__restrict__ out, LineDesc dd, double fac,
-                                                         BlkDesc ib = BlkDesc(), BlkDesc ob = BlkDesc()) {
+                                                         BlkDesc ib = BlkDesc(), BlkDesc ob = BlkDesc(), FillSrc fs = FillSrc()) {
+  static_assert(!FILL || (!INV && !IBLK), "FILL: forward transform reading the tendencies");
   constexpr int H = R1 * R2, N = 2 * H, NT = LANES * R2;
   constexpr int NK1 = R1 / R2;            // pass-2 DFTs per thread
   constexpr int NPAIR = (H / 2) / R2 + 1;  // split/merge pairs per thread (k = j, j+R2, ... <= H/2)
@@ -117,6 +146,11 @@ __global__ void __launch_bounds__(LANES *R2, (R1 <= 16 ? 2 : 1)) k_rfft_fast(con
     if (q == 0) { const int dl = d == 0 ? ob.nblk - 1 : d - 1; ob.base[dl][obase + loff + (long long)(ob.mask + 2) * dd.sp] = val; }
     if (q == ob.mask) { const int dr = d == ob.nblk - 1 ? 0 : d + 1; ob.base[dr][obase + loff] = val; }
   };
+  // FILL: value of point pt of line b of this CTA's batch = rhs(i, j, k) evaluated on the fly
+  auto RHS = [&](int b, int pt) -> double {
+    const int k = fs.k0 + kb + 1;
+    return XDIR ? fill_rhs(fs, pt + 1, b0 + b + 1, k) : fill_rhs(fs, b0 + b + 1, pt + 1, k);
+  };
   // x lines: global -> padded shared tile.  All of a thread's loads are issued before the first use (R1
   // independent 16-byte requests in flight per thread); 128-bit accesses when the lines are 16-byte aligned.
   constexpr int NIT = (LANES * H) / NT;   // = R1
@@ -134,8 +168,11 @@ __global__ void __launch_bounds__(LANES *R2, (R1 <= 16 ? 2 : 1)) k_rfft_fast(con
         const int idx = tid + (i0 + it) * NT;
         if (idx < nb * H) {
           const int b = idx / H, m = idx - b * H;
-          const double *q = IN((long long)b * di.s1, 2 * m);
-          st[it] = al_in ? *reinterpret_cast<const double2 *>(q) : make_double2(q[0], q[1]);
+          if (FILL) st[it] = make_double2(RHS(b, 2 * m), RHS(b, 2 * m + 1));
+          else {
+            const double *q = IN((long long)b * di.s1, 2 * m);
+            st[it] = al_in ? *reinterpret_cast<const double2 *>(q) : make_double2(q[0], q[1]);
+          }
         }
       }
 #pragma unroll
@@ -190,7 +227,7 @@ __global__ void __launch_bounds__(LANES *R2, (R1 <= 16 ? 2 : 1)) k_rfft_fast(con
 #pragma unroll
       for (int q = 0; q < R1; q++) {
         const int m = j + R2 * q;
-        v[q] = make_double2(*IN(lo, 2 * m), *IN(lo, 2 * m + 1));
+        v[q] = FILL ? make_double2(RHS(lane, 2 * m), RHS(lane, 2 * m + 1)) : make_double2(*IN(lo, 2 * m), *IN(lo, 2 * m + 1));
       }
     }
   } else {

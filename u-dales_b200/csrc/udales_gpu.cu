@@ -113,6 +113,7 @@ struct udgpu {
   FftPlan px, py;
   bool fast_x = false, fast_y = false, fast_z = false;
   int zu = 8, fft_lanes = 32;
+  int fill_fused = -1;        // fillps evaluated inside the first forward transform (UDGPU_FILL_FUSED=0/1; default: set at init, see there)
   int fft_rev = 1;            // consecutive kernels alternate their level direction for L2 reuse (UDGPU_FFT_REV=0: all upwards)
   double *d_zt = nullptr, *d_xd = nullptr, *d_yd = nullptr;
   int nxh = 0, nyh = 0;
@@ -148,6 +149,7 @@ struct udgpu {
   cudaEvent_t ev_c[8] = {};
   int xstreams = 8;           // UDGPU_XSTREAMS=1: all copies of a chunk on one stream
   cudaEvent_t ev_f[16] = {}, ev_r[16] = {};   // chunk c: local wire data ready (main -> copy) / all blocks have landed (copy -> main)
+  bool p_xhalo_carried = false;   // the last inverse half delivered p's x-halo columns together with the blocks
   bool bwd_pending = false;   // poisson() ran the forward half and the z solve; the inverse half is pipelined with tstep_integrate()
   double *bwd_work = nullptr, *bwd_phalo = nullptr;
   int *d_status = nullptr;   // device view of h_status
@@ -1003,14 +1005,20 @@ extern "C" int udgpu_subgrid(udgpu_t *h) {
 // fast power-of-two FFT dispatch: n -> (R1, R2, LANES)
 template <int R1, int R2, int LANES, bool XDIR>
 static int rfft_fast_launch(udgpu *h, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl,
-                            const BlkDesc *ib, const BlkDesc *ob) {
+                            const BlkDesc *ib, const BlkDesc *ob, const FillSrc *fs) {
   using C = RfftCfg<R1, R2, LANES, XDIR>;
   const dim3 grid((di.nb1 + LANES - 1) / LANES, di.nb2), block(LANES, R2);
   const BlkDesc z = BlkDesc();
 #define GO(INV, IB_, OB_) k_rfft_fast<R1, R2, LANES, XDIR, INV, IB_, OB_><<<grid, block, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac, ib ? *ib : z, ob ? *ob : z)
-  if (inverse) { if (ib) GO(true, true, false); else if (ob) GO(true, false, true); else GO(true, false, false); }
+#define GOF(OB_) k_rfft_fast<R1, R2, LANES, XDIR, false, false, OB_, true><<<grid, block, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac, z, ob ? *ob : z, *fs)
+  if (fs) {   // forward transform that evaluates the right-hand side itself (fillps fused in)
+    if (inverse || ib) return set_err(UDGPU_ESTATE, "FILL is a forward, non-blocked-input transform");
+    if (ob) GOF(true); else GOF(false);
+  }
+  else if (inverse) { if (ib) GO(true, true, false); else if (ob) GO(true, false, true); else GO(true, false, false); }
   else { if (ib) GO(false, true, false); else if (ob) GO(false, false, true); else GO(false, false, false); }
 #undef GO
+#undef GOF
   KCHECK();
   h->launches++;
   return UDGPU_OK;
@@ -1021,19 +1029,21 @@ static int rfft_fast_attr() {
 #define SA_(INV, IB_, OB_) CU(cudaFuncSetAttribute(k_rfft_fast<R1, R2, LANES, XDIR, INV, IB_, OB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM))
   SA_(true, false, false); SA_(false, false, false); SA_(true, true, false); SA_(false, true, false); SA_(true, false, true); SA_(false, false, true);
 #undef SA_
+  CU(cudaFuncSetAttribute(k_rfft_fast<R1, R2, LANES, XDIR, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  CU(cudaFuncSetAttribute(k_rfft_fast<R1, R2, LANES, XDIR, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   return UDGPU_OK;
 }
 static bool fast_len(int n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024; }
 template <bool XDIR>
 static int rfft_fast(udgpu *h, int n, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl,
-                     const BlkDesc *ib = nullptr, const BlkDesc *ob = nullptr) {
+                     const BlkDesc *ib = nullptr, const BlkDesc *ob = nullptr, const FillSrc *fs = nullptr) {
   switch (n) {
-    case 64: return rfft_fast_launch<8, 4, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
-    case 128: return rfft_fast_launch<8, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
-    case 256: if (h->fft_lanes == 16) return rfft_fast_launch<16, 8, 16, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
-              return rfft_fast_launch<16, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
-    case 512: return rfft_fast_launch<16, 16, 16, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
-    case 1024: return rfft_fast_launch<32, 16, 8, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob);
+    case 64: return rfft_fast_launch<8, 4, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob, fs);
+    case 128: return rfft_fast_launch<8, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob, fs);
+    case 256: if (h->fft_lanes == 16) return rfft_fast_launch<16, 8, 16, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob, fs);
+              return rfft_fast_launch<16, 8, 32, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob, fs);
+    case 512: return rfft_fast_launch<16, 16, 16, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob, fs);
+    case 1024: return rfft_fast_launch<32, 16, 8, XDIR>(h, inverse, in, di, out, dd, pl, ib, ob, fs);
   }
   return set_err(UDGPU_EINVAL, "no fast FFT for n=%d", n);
 }
@@ -1056,6 +1066,12 @@ static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, cons
     return dev_alloc(h, (void **)&h->d_scr, (size_t)g.imax * g.jmax * g.ktot * sizeof(double));
   }
   { const char *e = getenv("UDGPU_ZU"); if (e && atoi(e) == 16) h->zu = 16; }
+  // One GPU, 256^3 (profiles/r2_ab2_ztile_fill.jsonl): the fused x pass takes 0.27 ms against 0.172 + 0.085 ms for k_fillps
+  // + plain x pass although it moves 16 B/cell less — the transform kernel runs 512 threads per SM and cannot keep
+  // twelve input streams in flight like the 64 %-occupancy fillps kernel does.  So it is off at one GPU; in the slab solve
+  // the first transform waits for NVLink anyway and the fused loads fill that time.
+  h->fill_fused = h->P > 1 ? 1 : 0;
+  { const char *e = getenv("UDGPU_FILL_FUSED"); if (e) h->fill_fused = atoi(e) != 0; }
   { const char *e = getenv("UDGPU_FFT_LANES"); if (e && atoi(e) == 16) h->fft_lanes = 16; }
   { const char *e = getenv("UDGPU_FFT_REV"); if (e) h->fft_rev = atoi(e) != 0; }
   h->fast_x = fast_len(g.itot);
@@ -1081,8 +1097,39 @@ static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, cons
   return UDGPU_OK;
 }
 
+// tridiagonal z solve of one (halo-free) pencil with the tabulated factors (streaming two-sweep kernel, one thread per
+// column).  Measured and dropped in round 2 (profiles/r2_ab1_ztile.jsonl, r2_ab2_ztile_fill.jsonl, r2_ab3_zsplit.jsonl):
+// a shared-memory tile kernel that crosses HBM once (16 instead of 32 B/cell; 246 MB of DRAM traffic in ncu) took 128 us
+// against 94 us — with a 2 KB column per thread only ~100 recurrences fit on an SM and the dependent fp64 chain (one FMA
+// per level, ~25-30 cycles each) cannot be hidden; L2-sized sub-launches of this kernel were slower as well (0.41 ms
+// per solve with 2 launches, 0.68 ms with 8: each launch is latency-bound on its own).
+static int zsolve_fast(udgpu *h, const Geo &gg, double *x) {
+  if (h->zu == 16) k_zsolve<16><<<dim3((gg.imax + 127) / 128, gg.jmax), 128, 0, h->st>>>(gg, h->nxh, h->nyh, x, h->d_zt, h->d_a, h->d_c);
+  else k_zsolve<8><<<dim3((gg.imax + 127) / 128, gg.jmax), 128, 0, h->st>>>(gg, h->nxh, h->nyh, x, h->d_zt, h->d_a, h->d_c);
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+
+// the six input streams of fillps for a FILL transform (k0 = first 0-based level of the launch)
+static FillSrc fill_src(udgpu *h, double dt, int rk3step, int k0) {
+  const Geo &g = h->g;
+  FillSrc f;
+  f.up = h->f[UDGPU_UP]; f.vp = h->f[UDGPU_VP]; f.wp = h->f[UDGPU_WP];
+  f.um = h->f[UDGPU_UM]; f.vm = h->f[UDGPU_VM]; f.wm = h->f[UDGPU_WM];
+  f.dzfi = g.dzfi;
+  const double rk3coef = (rk3step == 0) ? 1. : dt / (4. - (double)rk3step);
+  f.rk3coefi = 1. / rk3coef;
+  f.dxi = g.dxi; f.dyi = g.dyi;
+  f.pi = g.pi; f.pk = g.pk;
+  f.imax = g.imax; f.jmax = g.jmax; f.ktot = g.ktot;
+  f.xwrap = h->P == 1 ? 1 : 0;
+  f.k0 = k0;
+  return f;
+}
+
 // ------------------------------------------------------------------------------------------
-static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *out, bool out_halo) {
+static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *out, bool out_halo, const FillSrc *fs = nullptr) {
   const Geo &g = h->g;
   LineDesc di, dd;
   const long long pr = g.imax, pp = (long long)g.imax * g.jmax;
@@ -1095,7 +1142,8 @@ static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *
     di = {1, pr, pp, g.jmax, g.ktot, rev};
     dd = di;
     if (out_halo) { dd.s1 = g.pi; dd.s2 = g.pk; }
-    if (h->fast_x) return rfft_fast<true>(h, g.itot, inverse, in, di, out, dd, h->px);
+    if (h->fast_x) return rfft_fast<true>(h, g.itot, inverse, in, di, out, dd, h->px, nullptr, nullptr, fs);
+    if (fs) return set_err(UDGPU_ESTATE, "FILL needs the register FFT");
     const size_t smem = (size_t)h->px.h * FFT_BP * sizeof(double2);
     k_rfft<true><<<dim3((g.jmax + FFT_B - 1) / FFT_B, g.ktot), dim3(FFT_B, FFT_TY), smem, h->st>>>(h->px, inverse, in, di, out, dd);
   } else {
@@ -1122,12 +1170,16 @@ static int setup_p2p(udgpu *h, size_t nR) {
   h->p2p = false;
   h->xmode = 0; h->xchunks = 1; h->xk0[0] = 0; h->xk0[1] = h->g.ktot;
   const int P = h->P;
-  // default transport by size (measured on 8 x B200, profiles/r2_trace_*: copy-engine transfers carry ~17 us of fixed
-  // cost each and run one after the other, so 8 MB copies reach 290 GB/s in aggregate, 270 MB copies 770 GB/s; the
-  // FFT kernels' own peer stores reach ~640 GB/s at any size but occupy the SMs while they wait for the link):
-  // per-peer blocks >= 64 MiB -> copy-engine pipeline (2), smaller -> peer stores from the transform kernels (1)
+  // default transport: the transform kernels store their output blocks straight into the peers' windows (1), with fillps
+  // fused into the forward y transform so that its six input streams keep HBM busy while the stores wait for NVLink.
+  // The copy-engine pipeline (2, UDGPU_XMODE=ce: local wire-format buffer, k-chunks moved by cudaMemcpyAsync on side
+  // streams under the neighbouring compute) was measured against it and is slower at every size tried, because copy-engine
+  // transfers carry ~17 us of fixed cost each and run one after the other (8 MB copies: 290 GB/s in aggregate; 270 MB
+  // copies: 770 GB/s) while the fused kernel already overlaps the transfer with fillps:
+  //   8 x B200, 1024^3 : stores + fused fillps 13.56 ms / substep, copy engines 13.96, stores without the fusion 14.72
+  //   2 x B200, 1024^3 : 48.88 vs 49.56 ms;   8 x B200, 512^3 (weak): 1.92 vs 2.14 ms      (profiles/r2_ab4_n8_*, r2_trace_*)
   const size_t blk_bytes = (size_t)h->IB * h->JB * h->g.ktot * sizeof(double);
-  int want_mode = blk_bytes >= ((size_t)64 << 20) ? 2 : 1;
+  int want_mode = 1;
   { const char *e = getenv("UDGPU_XMODE"); if (e) want_mode = !strcmp(e, "nccl") ? 0 : !strcmp(e, "store") ? 1 : !strcmp(e, "ce") ? 2 : want_mode; }
   if (h->cfg.flags & UDGPU_F_NCCL_TRANSPOSE) want_mode = 0;
   int want_chunks = 0;
@@ -1199,8 +1251,8 @@ static int setup_p2p(udgpu *h, size_t nR) {
   if (h->xmode == 2) {
     // k-chunks: per-peer copies of >= ~8 MiB keep the copy engines near their large-transfer rate
     const int K = h->g.ktot;
-    // k-chunks of >= 16 MiB per peer, at most 8
-    int C = want_chunks ? want_chunks : (int)std::min<size_t>(8, std::max<size_t>(1, blk_bytes / ((size_t)16 << 20)));
+    // k-chunks of >= 32 MiB per peer, at most 8
+    int C = want_chunks ? want_chunks : (int)std::min<size_t>(8, std::max<size_t>(1, blk_bytes / ((size_t)32 << 20)));
     C = std::max(1, std::min(C, std::min(16, K)));
     h->xchunks = C;
     for (int c = 0; c <= C; c++) h->xk0[c] = (int)(((long long)K * c) / C);
@@ -1333,7 +1385,7 @@ static int slab_landed(udgpu *h, int c) {
 }
 // forward half + z solve.  fill(k0, kc): producer of the right-hand side levels k0 .. k0+kc-1 (fillps), may be empty
 template <class Fill>
-static int slab_forward(udgpu *h, double *work, Fill &&fill) {
+static int slab_forward(udgpu *h, double *work, Fill &&fill, const FillSrc *fs0 = nullptr) {
   const Geo &g = h->g;
   const SlabGeo s = slab_geo(h, work, nullptr, false);
   const int C = h->xchunks;
@@ -1344,7 +1396,9 @@ static int slab_forward(udgpu *h, double *work, Fill &&fill) {
     BlkDesc bs, br;
     slab_bases(h, s, false, k0, bs, br);
     bs.shift = ilog2(s.JB); bs.mask = s.JB - 1;
-    RET(rfft_fast<false>(h, g.jtot, 0, work + k0 * s.yA0.s2, with_k(s.yA0, kc), nullptr, with_k(s.yW0, kc), h->py, nullptr, &bs));
+    FillSrc fsc;
+    if (fs0) { fsc = *fs0; fsc.k0 = k0; }
+    RET(rfft_fast<false>(h, g.jtot, 0, work + k0 * s.yA0.s2, with_k(s.yA0, kc), nullptr, with_k(s.yW0, kc), h->py, nullptr, &bs, fs0 ? &fsc : nullptr));
     trace_mark(h, "yfft", c);
     RET(slab_ship(h, s, false, c));
   }
@@ -1357,10 +1411,7 @@ static int slab_forward(udgpu *h, double *work, Fill &&fill) {
     RET(rfft_fast<true>(h, g.itot, 0, nullptr, with_k(s.xW0, kc), h->workB + k0 * s.xB0.s2, with_k(s.xB0, kc), h->px, &br, nullptr));
     trace_mark(h, "xfft", c);
   }
-  if (h->zu == 16) k_zsolve<16><<<dim3((g.itot + 127) / 128, s.JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
-  else k_zsolve<8><<<dim3((g.itot + 127) / 128, s.JB), 128, 0, h->st>>>(h->gB, h->nxh, h->nyh, h->workB, h->d_zt, h->d_a, h->d_c);
-  KCHECK();
-  h->launches++;
+  RET(zsolve_fast(h, h->gB, h->workB));
   trace_mark(h, "zsolve");
   return UDGPU_OK;
 }
@@ -1371,7 +1422,8 @@ static int slab_forward(udgpu *h, double *work, Fill &&fill) {
 template <class After>
 static int slab_backward(udgpu *h, double *work, double *p_halo, bool carry, After &&after) {
   const Geo &g = h->g;
-  carry = carry && p_halo && h->xmode == 2;
+  carry = carry && p_halo && h->p2p;   // peer-memory transports (the NCCL path keeps its plain blocks and the bcp exchange)
+  h->p_xhalo_carried = carry;
   const SlabGeo s = slab_geo(h, work, p_halo, carry);
   const int C = h->xchunks;
   auto xinv = [&](int c) -> int {
@@ -1405,17 +1457,18 @@ static int poisson_core_slab(udgpu *h, double *work, double *p_halo) {
   return slab_backward(h, work, p_halo, false, nop);
 }
 
-static int poisson_core(udgpu *h, double *work, double *p_halo) {
+static int poisson_core(udgpu *h, double *work, double *p_halo, const FillSrc *fs = nullptr) {
   const Geo &g = h->g;
   if (h->P > 1) return poisson_core_slab(h, work, p_halo);
   ProfScope ps(h, PROF_POIS);
-  RET(fft_pass(h, true, 0, work, work, false));
+  RET(fft_pass(h, true, 0, work, work, false, fs));   // fs: the right-hand side is evaluated by the transform itself
   RET(fft_pass(h, false, 0, work, work, false));
-  if (h->fast_z) { if (h->zu == 16) k_zsolve<16><<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, h->nxh, h->nyh, work, h->d_zt, h->d_a, h->d_c);
-    else k_zsolve<8><<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, h->nxh, h->nyh, work, h->d_zt, h->d_a, h->d_c); }
-  else k_solmpj<<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, work, h->d_scr, h->d_xrt, h->d_yrt, h->d_a, h->d_b, h->d_c, h->b_top_D);
-  KCHECK();
-  h->launches++;
+  if (h->fast_z) RET(zsolve_fast(h, g, work));
+  else {
+    k_solmpj<<<dim3((g.imax + 127) / 128, g.jmax), 128, 0, h->st>>>(g, work, h->d_scr, h->d_xrt, h->d_yrt, h->d_a, h->d_b, h->d_c, h->b_top_D);
+    KCHECK();
+    h->launches++;
+  }
   RET(fft_pass(h, false, 1, work, work, false));
   if (p_halo) RET(fft_pass(h, true, 1, work, p_halo + offF(g, 1, 1, 1), true));
   else RET(fft_pass(h, true, 1, work, work, false));
@@ -1512,24 +1565,40 @@ static int tderive_now(udgpu *h) {
 
 extern "C" int udgpu_poisson(udgpu_t *h, double dt, int rk3step) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
-  if (h->P > 1 && h->xmode == 2 && !(h->cfg.flags & UDGPU_F_NO_LAZY_FUSION)) {
-    // pipelined slab solve: fillps and the forward y transform run chunk by chunk under the copy-engine transfers of
-    // the previous chunk; the inverse half is left pending so that tstep_integrate() can run it chunk by chunk
-    // together with tderive + integrate (any other access finishes it first, see flush_pending)
+  const bool lazy = !(h->cfg.flags & UDGPU_F_NO_LAZY_FUSION);
+  // fillps fused into the first forward transform (x at one GPU, y in the slab solve): needs the register FFT for that length
+  const bool fuse_fill = lazy && h->fill_fused > 0 && (h->P > 1 ? h->fast_y : h->fast_x);
+  if (h->P > 1 && lazy && (h->xmode == 2 || fuse_fill)) {
+    // slab solve with the right-hand side produced on the way in (fused into the forward y transform, or chunk by
+    // chunk in front of it).  Copy-engine transport: the inverse half is left pending so that tstep_integrate() can run
+    // it chunk by chunk together with tderive + integrate (any other access finishes it first, see flush_pending)
     RET(fillps_prepare(h));
+    const FillSrc fs = fill_src(h, dt, rk3step, 0);
     {
       ProfScope ps(h, PROF_POIS);
-      RET(slab_forward(h, h->f[UDGPU_RHS], [&](int k0, int kc) -> int { return fillps_launch(h, dt, rk3step, k0, kc); }));
+      if (fuse_fill) RET(slab_forward(h, h->f[UDGPU_RHS], [](int, int) -> int { return UDGPU_OK; }, &fs));
+      else RET(slab_forward(h, h->f[UDGPU_RHS], [&](int k0, int kc) -> int { return fillps_launch(h, dt, rk3step, k0, kc); }));
     }
-    h->bwd_pending = true; h->bwd_work = h->f[UDGPU_RHS]; h->bwd_phalo = h->f[UDGPU_P];
+    if (h->xmode == 2) {
+      h->bwd_pending = true; h->bwd_work = h->f[UDGPU_RHS]; h->bwd_phalo = h->f[UDGPU_P];
+    } else {
+      ProfScope ps(h, PROF_POIS);
+      RET(slab_backward(h, h->f[UDGPU_RHS], h->f[UDGPU_P], true, [](int, int) -> int { return UDGPU_OK; }));
+    }
     h->p_halo_valid = false;
     h->tder_pending = true;
     return UDGPU_OK;
   }
-  RET(udgpu_fillps(h, dt, rk3step));
-  RET(poisson_core(h, h->f[UDGPU_RHS], h->f[UDGPU_P]));
+  if (h->P == 1 && fuse_fill) {
+    RET(fillps_prepare(h));
+    const FillSrc fs = fill_src(h, dt, rk3step, 0);
+    RET(poisson_core(h, h->f[UDGPU_RHS], h->f[UDGPU_P], &fs));
+  } else {
+    RET(udgpu_fillps(h, dt, rk3step));
+    RET(poisson_core(h, h->f[UDGPU_RHS], h->f[UDGPU_P]));
+  }
   h->p_halo_valid = false;
-  if (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION) return tderive_now(h);
+  if (!lazy) return tderive_now(h);
   h->tder_pending = true;   // fused with tstep_integrate(); flushed on any other access
   return UDGPU_OK;
 }
@@ -1590,7 +1659,7 @@ extern "C" int udgpu_tstep_integrate(udgpu_t *h, double dt, int rk3step) {
         // p's halo columns arrive with the blocks of the second exchange: no bcp exchange
         RET(slab_backward(h, h->bwd_work, h->bwd_phalo, true, [&](int k0, int kc) -> int { return integ(k0, kc); }));
       } else {
-        if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));
+        if (h->P > 1 && !h->p_xhalo_carried) RET(halo_x_exchange(h, {f[UDGPU_P]}, g.ktot + 2 * g.kh));   // bcp
         RET(integ(0, g.ktot));
       }
       h->halos_done = h->bc_done = true;
