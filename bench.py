@@ -401,11 +401,17 @@ def run_ours(args, rank, world):
     g.profile_enable(False)
     roof_all = {}
     bpc = dict(B_PER_CELL)
-    if world > 1:
-        # pipelined slab solve: "poisson_core" is the forward half + z solve (3 of the 5 passes), the inverse half runs
-        # chunk by chunk together with tderive+integrate in its own slot
-        bpc["poisson_core"] = 48.0
+    if world > 1 and fam.get(PROF_NAMES[6], 0) > 0:
+        # copy-engine pipeline (UDGPU_XMODE=ce): "poisson_core" is the forward half + z solve (fillps fused: 48 B read + 8 B
+        # written by the first transform, 32 B for the x transform and the z solve), the inverse half runs chunk by chunk
+        # together with tderive+integrate in its own slot
+        bpc["poisson_core"] = 56.0 + 32.0
         bpc[PROF_NAMES[6]] = 32.0 + 96.0
+    elif world > 1 and fam.get("fillps", 0) < 0.5 * 0.17 * ncell_loc / 256 ** 3:
+        # slab solve with fillps fused into the forward y transform: the rhs array is neither written nor read (16 B/cell
+        # less than fillps 56 + solve 80); what is left in the fillps slot is the slab exchange of up
+        bpc["poisson_core"] = 56.0 + 80.0 - 16.0
+        bpc["fillps"] = 0.0
     if nsv:   # K3: (4 + 2 n) * 8 B/cell for n fields in one pass; scalar integrate: svm, svp -> sv0 = 24 B/cell/field
         bpc["mom_tend"] += (4 + 2 * nsv) * 8.0
         bpc["tderive_integrate"] += 24.0 * nsv

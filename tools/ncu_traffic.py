@@ -23,7 +23,7 @@ def main(path, nsub):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     fam, per_kernel = {}, {}
     for r in rows[2:]:
-        name = r[ki].split("(")[0].split("<")[0].replace("udg::", "")
+        name = r[ki].split("(")[0].split("<")[0].replace("udg::", "").replace("void ", "").strip()
         tot = 0.0
         for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = h.index(m)

@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict
 // everything that is shared between consecutive levels in registers (the level-k and level-(k+1) operands of the
 // vertical derivatives, the w ring), so a level costs 17 loads instead of 30 and almost no address arithmetic.
 // Operand order inside each gradient is the reference's (src/modsubgrid.f90:271-327): differences to k_closure<1>
-// and to the oracle are FMA-contraction rounding only.
+// and to the oracle are FMA-contraction rounding only.  64 registers / 4 CTAs per SM is a measured optimum: 3 or 2 CTAs
+// with a two-level unrolled loop (more loads in flight per thread) ran 0.28 - 0.31 ms against 0.259 ms, 5 or 6 CTAs
+// spill and ran 0.40 - 0.52 ms (profiles/r2_ab6_closure.jsonl).
 template <int KC>
 __global__ void __launch_bounds__(256, 4) k_closure_vreman_march(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
                                                               const double *__restrict__ w0, double *__restrict__ ekm,

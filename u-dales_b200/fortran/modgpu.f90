@@ -21,7 +21,8 @@ module modgpu
   private
   public :: lgpu, gpu_init, gpu_exit, gpu_push_state, gpu_pull_state, gpu_push, gpu_pull, &
             gpu_tstep_update, gpu_advection, gpu_subgrid, gpu_poisson, gpu_tstep_integrate, &
-            gpu_halos, gpu_boundary, gpu_chkdiv, gpu_rk3_step_host, gpu_ibm_init, gpu_ibmnorm, gpu_ibm_diffcorr, gpu_forces
+            gpu_halos, gpu_boundary, gpu_chkdiv, gpu_rk3_step_host, gpu_ibm_init, gpu_ibmnorm, gpu_ibm_diffcorr, gpu_forces, &
+            gpu_bottom, gpu_masscorr
 
   logical :: lgpu = .false.            !< namelist RUN switch (the only new option)
   type(c_ptr) :: handle = c_null_ptr
@@ -29,7 +30,7 @@ module modgpu
   ! field ids = enum udgpu_field
   integer(c_int), parameter :: F_U0 = 0, F_V0 = 1, F_W0 = 2, F_UM = 3, F_VM = 4, F_WM = 5, &
                                F_UP = 6, F_VP = 7, F_WP = 8, F_PRES0 = 9, F_P = 10, F_EKM = 11, &
-                               F_EKH = 12, F_RHS = 13, F_SV0 = 14, F_SVM = 15, F_SVP = 16
+                               F_EKH = 12, F_RHS = 13, F_SV0 = 14, F_SVM = 15, F_SVP = 16, F_MOMFLUXB = 17
 
   type, bind(C) :: udgpu_cfg
     integer(c_int) :: abi_version
@@ -144,6 +145,29 @@ module modgpu
       import :: c_int, c_ptr
       type(c_ptr), value :: h
     end function
+    integer(c_int) function udgpu_set_bottom(h, lbottom, BCbotm, BCbots, z0, fkar) bind(C, name="udgpu_set_bottom")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: lbottom, BCbotm, BCbots
+      real(c_double), value :: z0, fkar
+    end function
+    integer(c_int) function udgpu_bottom(h) bind(C, name="udgpu_bottom")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    integer(c_int) function udgpu_set_masscorr(h, luvolflowr, lvvolflowr, uflowrate, vflowrate) bind(C, name="udgpu_set_masscorr")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: luvolflowr, lvvolflowr
+      real(c_double), value :: uflowrate, vflowrate
+    end function
+    integer(c_int) function udgpu_masscorr(h, dt, rk3step, udef, vdef) bind(C, name="udgpu_masscorr")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      real(c_double), value :: dt
+      integer(c_int), value :: rk3step
+      type(c_ptr), value :: udef, vdef       ! c_null_ptr: no host synchronisation
+    end function
     integer(c_int) function udgpu_ibm_set_points(h, kind, n, ijk, layout) bind(C, name="udgpu_ibm_set_points")
       import :: c_int, c_ptr
       type(c_ptr), value :: h
@@ -225,7 +249,15 @@ contains
     c%BCxm = BCxm; c%BCym = BCym; c%BCtopm = BCtopm; c%BCzp = BCzp
     c%ipoiss = ipoiss; c%iadv_mom = iadv_mom
     c%iadv_sv = 7
-    if (nsv > 0) c%iadv_sv = iadv_sv(1)
+    if (nsv > 0) then
+      ! the device path runs one advection scheme for all scalars (the reference forces kappa for every sv anyway,
+      ! src/modglobal.f90:556-559)
+      if (any(iadv_sv(1:nsv) /= iadv_sv(1))) then
+        write (0, *) 'ERROR: gpu_init: all scalars must use the same advection scheme, iadv_sv = ', iadv_sv(1:nsv)
+        stop 1
+      end if
+      c%iadv_sv = iadv_sv(1)
+    end if
     c%lles = l2i(lles); c%lvreman = l2i(lvreman); c%lsmagorinsky = l2i(lsmagorinsky); c%loneeqn = l2i(loneeqn)
     c%ltempeq = l2i(ltempeq); c%lmoist = l2i(lmoist)
     c%dx = dx; c%dy = dy
@@ -302,8 +334,8 @@ contains
     call chk(udgpu_tstep_update(handle, dt, courant, diffnr, dtmax, l2i(ladaptive), rk, ct, dn), 'tstep_update')
     rk3step = rk
     if (rk3step == 1) then          ! bookkeeping of src/modtstep.f90:136-147 stays on the host
+      if (ladaptive) dt_lim = timeleft     ! :136 (before timeleft is advanced; the non-adaptive branch :142-147 leaves dt_lim alone)
       timeleft = timeleft - dt
-      dt_lim = timeleft
       timee = timee + dt
       ntimee = ntimee + 1
       ntrun = ntrun + 1
@@ -357,20 +389,60 @@ contains
     integer(c_int) :: dummy(3)
     if (.not. libm) return
     dummy = 1
-    call chk(udgpu_ibm_set_points(handle, 0_c_int, int(solid_info_u%nsolptsrank, c_int), solid_info_u%solpts_loc, 1_c_int), 'ibm solid_u')
-    call chk(udgpu_ibm_set_points(handle, 1_c_int, int(solid_info_v%nsolptsrank, c_int), solid_info_v%solpts_loc, 1_c_int), 'ibm solid_v')
-    call chk(udgpu_ibm_set_points(handle, 2_c_int, int(solid_info_w%nsolptsrank, c_int), solid_info_w%solpts_loc, 1_c_int), 'ibm solid_w')
-    call chk(udgpu_ibm_set_points(handle, 4_c_int, int(bound_info_u%nbndptsrank, c_int), bound_info_u%bndpts_loc, 1_c_int), 'ibm bound_u')
-    call chk(udgpu_ibm_set_points(handle, 5_c_int, int(bound_info_v%nbndptsrank, c_int), bound_info_v%bndpts_loc, 1_c_int), 'ibm bound_v')
-    call chk(udgpu_ibm_set_points(handle, 6_c_int, int(bound_info_w%nbndptsrank, c_int), bound_info_w%bndpts_loc, 1_c_int), 'ibm bound_w')
+    ! a rank may own no point of a kind: its list is then zero-sized or not allocated at all, so a dummy goes in its place
+    call set_list(0_c_int, solid_info_u%nsolptsrank, solid_info_u%solpts_loc)
+    call set_list(1_c_int, solid_info_v%nsolptsrank, solid_info_v%solpts_loc)
+    call set_list(2_c_int, solid_info_w%nsolptsrank, solid_info_w%solpts_loc)
+    call set_list(4_c_int, bound_info_u%nbndptsrank, bound_info_u%bndpts_loc)
+    call set_list(5_c_int, bound_info_v%nbndptsrank, bound_info_v%bndpts_loc)
+    call set_list(6_c_int, bound_info_w%nbndptsrank, bound_info_w%bndpts_loc)
     if (nsv > 0) then
-      call chk(udgpu_ibm_set_points(handle, 3_c_int, int(solid_info_c%nsolptsrank, c_int), solid_info_c%solpts_loc, 1_c_int), 'ibm solid_c')
-      call chk(udgpu_ibm_set_points(handle, 7_c_int, int(bound_info_c%nbndptsrank, c_int), bound_info_c%bndpts_loc, 1_c_int), 'ibm bound_c')
+      call set_list(3_c_int, solid_info_c%nsolptsrank, solid_info_c%solpts_loc)
+      call set_list(7_c_int, bound_info_c%nbndptsrank, bound_info_c%bndpts_loc)
     else
       call chk(udgpu_ibm_set_points(handle, 3_c_int, 0_c_int, dummy, 1_c_int), 'ibm solid_c')
       call chk(udgpu_ibm_set_points(handle, 7_c_int, 0_c_int, dummy, 1_c_int), 'ibm bound_c')
     end if
     call chk(udgpu_ibm_commit(handle), 'ibm commit')
+  contains
+    subroutine set_list(kind, n, pts)
+      integer(c_int), intent(in) :: kind
+      integer, intent(in) :: n
+      integer, allocatable, intent(in) :: pts(:, :)
+      if (n > 0 .and. allocated(pts)) then
+        call chk(udgpu_ibm_set_points(handle, kind, int(n, c_int), pts, 1_c_int), 'ibm point list')
+      else
+        call chk(udgpu_ibm_set_points(handle, kind, 0_c_int, dummy, 1_c_int), 'ibm point list (empty)')
+      end if
+    end subroutine set_list
+  end subroutine
+  !> bottom (src/modibm.f90:1998, program.f90:152): wfmneutral case 91 + the zero-flux scalar bottom on the resident
+  !! tendencies.  The namelist values go down once (first call); BCbotm must be 3 (neutral wall function)
+  subroutine gpu_bottom
+    use modglobal, only: lbottom, BCbotm, BCbots, fkar
+    use modsurfdata, only: z0
+    logical, save :: first = .true.
+    if (first) then
+      call chk(udgpu_set_bottom(handle, l2i(lbottom), int(BCbotm, c_int), int(BCbots, c_int), z0, fkar), 'set_bottom')
+      first = .false.
+    end if
+    call chk(udgpu_bottom(handle), 'bottom')
+  end subroutine
+  !> masscorr (src/modforces.f90:328, program.f90:169), volume-flow branches; the outflow-rate branches (luoutflowr /
+  !! lvoutflowr) are for non-periodic domains and stay with the host.  udef / vdef are not needed by the host path.
+  subroutine gpu_masscorr
+    use modglobal, only: dt, rk3step, linoutflow, luoutflowr, lvoutflowr, luvolflowr, lvvolflowr, uflowrate, vflowrate
+    logical, save :: first = .true.
+    if (linoutflow) return
+    if (luoutflowr .or. lvoutflowr) then
+      write (0, *) 'ERROR: gpu_masscorr: luoutflowr / lvoutflowr are outside the GPU path (periodic domains use l[uv]volflowr)'
+      stop 1
+    end if
+    if (first) then
+      call chk(udgpu_set_masscorr(handle, l2i(luvolflowr), l2i(lvvolflowr), uflowrate, vflowrate), 'set_masscorr')
+      first = .false.
+    end if
+    call chk(udgpu_masscorr(handle, dt, int(rk3step, c_int), c_null_ptr, c_null_ptr), 'masscorr')
   end subroutine
   !> ibmnorm (src/modibm.f90:697) and the diff*_corr part of ibmwallfun (:1211-1213,1240-1242) on the resident fields
   subroutine gpu_ibmnorm
