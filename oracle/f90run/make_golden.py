@@ -496,7 +496,157 @@ def case_channelglue(tag, shape=(10, 8, 6), nsv=1):
     print(f"wrote ref_{tag}.npz  udef {out['mc1_udef']:.6e} {out['mc3_udef']:.6e} vdef {out['mc1_vdef']:.6e}")
 
 
+def _avexy_ibm_cb(it_, frame, vals, setters, kw_):
+    """avexy_ibm (src/modmpi.f90:623-664) on one pencil: an MPI helper, given as a callback like the other MPI calls.
+    args: aver, var, ib, ie, jb, je, kb, ke, kh, II, IIs, lnan"""
+    var, II, IIs, lnan = vals[1], vals[9], vals[10], vals[11]
+    nk = var.a.shape[2]
+    averl = np.array([np.sum(var.a[:, :, k] * II.a[:, :, k]) for k in range(nk)])
+    IId = np.array(IIs.a, copy=True)
+    if (not lnan) and IId[0] == 0:
+        averl[0] = np.sum(var.a[:, :, 0])
+        IId[0] = IId[nk - 2]            # IId(ke)
+    aver = np.where(IId == 0, -999.0, averl / np.where(IId == 0, 1, IId))
+    vals[0].a[...] = aver
+
+
+def case_thermo(tag, shape=(8, 6, 7), BCtopT=1, wttop=-0.01, wtsurf=0.01, with_ibm=False, nsub=3):
+    """Temperature on the resident path, dry: advecc_2nd + diffc on thl0, bottom (BCbotm = 3 wfmneutral +
+    fixed-flux temperature, src/modibm.f90:2033-2046), forces with buoyancy (src/modforces.f90:70-109), tstep_integrate,
+    halos, boundary (BCtopT), thermodynamics (src/modthermodynamics.f90:55-121 incl. diagfld, fromztop, calc_halflev, calthv),
+    executed from the reference text over `nsub` RK3 substeps in the order of src/program.f90:132-212.  With with_ibm the IBM
+    calls on temperature run too: diffc_corr(thl0, thlp) (ibmwallfun, :1225) and ibmnorm's solid(.., mask_c) +
+    advecc2nd_corr_liberal (:714-722)."""
+    I, J, K = shape
+    zf = stretched_zf(K, 0.5 * K * 1.1, 1.07)
+    w = World(I, J, K, xlen=0.55 * I, ylen=0.45 * J, zf=zf)
+    g = w.g
+    ext = w.externals()
+    ext["avexy_ibm"] = _avexy_ibm_cb
+    it = Interp(g, ext)
+    it.gtypes = {"sxfc": complex, "syfc": complex}
+    for f in ("modadvection.f90", "modsubgrid.f90", "modpois.f90", "modtstep.f90", "modboundary.f90", "modchecksim.f90"):
+        it.load(os.path.join(SRC, f))
+    it.load(os.path.join(SRC, "modthermodynamics.f90"), only=["thermodynamics", "diagfld", "fromztop", "calc_halflev", "calthv"])
+    it.load(os.path.join(SRC, "modforces.f90"), only=["forces"])
+    it.load(os.path.join(SRC, "modibm.f90"), only=["bottom", "solid", "diffu_corr", "diffv_corr", "diffw_corr", "diffc_corr", "ibmnorm",
+                                                   "advecc2nd_corr_liberal"])
+    it.load(os.path.join(SRC, "modwallfunctions.f90"), only=["wfmneutral"])
+    it.call("initpois")
+    full = [(0, I + 1), (0, J + 1), (0, K + 1)]
+    tend = [(0, I + 1), (0, J + 1), (1, K + 1)]
+    prof = [(1, K + 1)]
+    thls = 288.0
+    g.update(ltempeq=True, lbuoyancy=True, bctopt=BCtopT, wttop=wttop, thl_top=289.5, wtsurf=wtsurf, wqsurf=0.0, thls=thls, thvs=thls,
+             qts=0.0, ps=101500.0, pref0=1.e5, rd=287.04, rv=461.5, cp=1004., rlv=2.26e6, chi_half=0.5, khc=1,
+             lbottom=True, bcbotm=3, bcbott=1, bcbotq=1, bcbots=1, z0=0.01, z0h=0.000067, fkar=0.41,
+             dxh=fa([(1, I + 1)], g["dx"]), dxhi=fa([(1, I + 1)], 1. / g["dx"]),
+             momfluxb=fa(full), tfluxb=fa(full), tau_x=fa(full), tau_y=fa(full), tau_z=fa(full), thl_flux=fa(full),
+             thl0h=fa(full), qt0h=fa(full), ql0=fa(full), ql0h=fa(full), thv0h=fa(tend), thv0=fa([(1, I), (1, J), (1, K + 1)]),
+             th0av=fa(prof), thl0av=fa(prof), qt0av=fa(prof), ql0av=fa(prof), sv0av=fa([(1, K + 1), (1, 1)]),
+             thvh=fa(prof), thvf=fa(prof), presf=fa(prof), presh=fa(prof), exnf=fa(prof), exnh=fa(prof), rhof=fa(prof),
+             thlpcar=fa(prof), dpdyl=fa(prof), libm=with_ibm, lconservativeibm=False, lwritefac=False)
+    g["dthvdz"] = fa(tend)
+    rng = np.random.default_rng(41)
+    g["thlpcar"].a[...] = 1e-4 * rng.standard_normal(K + 1)
+    g["dpdxl"].a[...] = -1e-3 * (1.0 + rng.random(K + 1))
+    g["dpdyl"].a[...] = 2e-4 * rng.standard_normal(K + 1)
+    # masks / integer masks (createmasks, src/modibm.f90:2103-2190)
+    IIc = FArray.alloc([(1, I), (1, J), (1, K + 1)], int); IIc.a[...] = 1
+    IIu = FArray.alloc([(1, I), (1, J), (1, K + 1)], int); IIu.a[...] = 1
+    IIv = FArray.alloc([(1, I), (1, J), (1, K + 1)], int); IIv.a[...] = 1
+    IIw = FArray.alloc([(1, I), (1, J), (1, K + 1)], int); IIw.a[...] = 1
+    lists = None
+    if with_ibm:
+        lists = ibm_geometry(I, J, K, [(3, 4, 2, 3, 2), (6, 7, 5, 6, 3), (1, 1, 4, 5, 2)])
+        for nm in "uvwc":
+            pts = lists["solid_" + nm]
+            g["solid_info_" + nm] = {"nsolptsrank": int(pts.shape[0]), "solpts_loc": FArray(np.asfortranarray(pts.astype(int)), [1, 1])}
+            b = lists["bound_" + nm]
+            g["bound_info_" + nm] = {"nbndptsrank": int(b.shape[0]), "bndpts_loc": FArray(np.asfortranarray(b.astype(int)), [1, 1])}
+        dummy = fa(tend)
+        for nm, II in zip("uvwc", (IIu, IIv, IIw, IIc)):
+            m = fa(full, 1.0)
+            m.a[:, :, 0] = 0.0
+            if nm == "w":
+                m.a[:, :, 1] = 0.0
+            it.call("solid", g["solid_info_" + nm], m, dummy, 0.0, 1, 1, 1)
+            a = m.a
+            a[0] = a[I]; a[I + 1] = a[1]; a[:, 0] = a[:, J]; a[:, J + 1] = a[:, 1]
+            g["mask_" + nm] = m
+            for q in lists["solid_" + nm]:
+                II.a[q[0] - 1, q[1] - 1, q[2] - 1] = 0
+        IIw.a[:, :, 0] = 0
+    for nm, II in (("c", IIc), ("u", IIu), ("v", IIv), ("w", IIw)):
+        g["ii" + nm] = II
+        g["ii" + nm + "s"] = FArray(np.array([int(II.a[:, :, k].sum()) for k in range(K + 1)]), [1])
+    seed_fields(w, 37, 0)
+    g["thl0"].a[...] = 0.0
+    g["thl0"].a[1:-1, 1:-1, 1:-1] = thls + 0.05 * np.arange(1, K + 1)[None, None, :] + 0.3 * rng.standard_normal((I, J, K))
+    g["thl0"].a[:, :, 0] = g["thl0"].a[:, :, 1]                 # startup: thl0(kb-1) = thl0(kb), src/modstartup.f90:1208
+    g["ekm"].a[...] = g["numol"]
+    g["ekh"].a[...] = g["numol"] * g["prandtlmoli"]
+    it.call("halos"); it.call("boundary")
+    for a, b in (("um", "u0"), ("vm", "v0"), ("wm", "w0"), ("thlm", "thl0")):
+        g[a].a[...] = g[b].a
+    it.call("thermodynamics")
+    out = {"zf": zf, "shape": np.array([I, J, K]), "xlen": 0.55 * I, "ylen": 0.45 * J, "BCtopT": BCtopT, "wttop": wttop, "thl_top": 289.5,
+           "wtsurf": wtsurf, "thls": thls, "grav": g["grav"], "z0": 0.01, "fkar": 0.41, "with_ibm": int(with_ibm),
+           "thlpcar": np.array(g["thlpcar"].a), "dpdxl": np.array(g["dpdxl"].a), "dpdyl": np.array(g["dpdyl"].a)}
+    if lists:
+        for k_, v_ in lists.items():
+            out["pts_" + k_] = v_
+    state = ["u0", "v0", "w0", "um", "vm", "wm", "pres0", "thl0", "thlm"]
+    diag = ["thl0h", "thv0h", "dthvdz", "thvh", "thl0av", "th0av"]
+    for k_, v_ in snapshot(w, state + diag).items():
+        out["in_" + k_] = v_
+    dt = 0.03
+    g["dt"] = dt; g["dtmax"] = dt; g["ladaptive"] = False
+    for s in range(nsub):
+        it.call("tstep_update")
+        it.call("advection")
+        if s == 0:
+            out["adv_thlp"] = np.array(g["thlp"].a, copy=True)
+        it.call("subgrid")
+        if s == 0:
+            out["sub_thlp"] = np.array(g["thlp"].a, copy=True)
+        it.call("bottom")
+        if s == 0:
+            for k_, v_ in snapshot(w, ["up", "vp", "thlp"]).items():
+                out["bottom_" + k_] = v_
+        it.call("forces")
+        if s == 0:
+            for k_, v_ in snapshot(w, ["up", "vp", "wp", "thlp"]).items():
+                out["forces_" + k_] = v_
+        if with_ibm:
+            it.call("diffu_corr"); it.call("diffv_corr"); it.call("diffw_corr")
+            it.call("diffc_corr", g["thl0"], g["thlp"], 1, 1, 1)
+            if s == 0:
+                out["corr_thlp"] = np.array(g["thlp"].a, copy=True)
+            it.call("ibmnorm")
+            if s == 0:
+                for k_, v_ in snapshot(w, ["thlp", "thlm", "wp", "wm"]).items():
+                    out["norm_" + k_] = v_
+        it.call("poisson")
+        it.call("tstep_integrate")
+        it.call("halos")
+        it.call("boundary")
+        it.call("thermodynamics")
+        for k_, v_ in snapshot(w, state + diag).items():
+            out[f"s{s + 1}_" + k_] = v_
+    for k_, v_ in out.items():
+        if isinstance(v_, np.ndarray) and v_.dtype.kind == "f" and v_.ndim == 3 and not k_.startswith("in_"):
+            assert np.isfinite(v_[1:-1, 1:-1, 1:-1]).all(), k_
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, f"ref_{tag}.npz"), **out)
+    print(f"wrote ref_{tag}.npz ({len(out)} arrays) thvh {np.array(g['thvh'].a)[:3]} |w0|max {np.abs(g['w0'].a).max():.4f}")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "thermo":
+        case_thermo("thermo_flux")
+        case_thermo("thermo_value_ibm", shape=(8, 8, 6), BCtopT=2, wttop=0.0, wtsurf=-0.005, with_ibm=True)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "forces":
         case_forces("forces")
         sys.exit(0)
@@ -514,3 +664,7 @@ if __name__ == "__main__":
     case_ibm("ibm")
     case_forces("forces")
     case_channelglue("channelglue")
+    case_thermo("thermo_flux")
+    case_thermo("thermo_value_ibm", shape=(8, 8, 6), BCtopT=2, wttop=0.0, wtsurf=-0.005, with_ibm=True)
+    case_thermo("thermo_flux")
+    case_thermo("thermo_value_ibm", shape=(8, 8, 6), BCtopT=2, wttop=0.0, wtsurf=-0.005, with_ibm=True)

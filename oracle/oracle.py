@@ -83,6 +83,11 @@ def lib():
         L.orc_ibm_mask.argtypes = [C.c_void_p, C.c_int]
         L.orc_ibmnorm.argtypes = [C.c_void_p]
         L.orc_ibm_diffcorr.argtypes = [C.c_void_p]
+        L.orc_set_thermo.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+                                     C.c_int, C.c_double, C.c_void_p]
+        L.orc_thermodynamics.argtypes = [C.c_void_p]
+        L.orc_thermo_profile.restype = C.POINTER(C.c_double)
+        L.orc_thermo_profile.argtypes = [C.c_void_p, C.c_char_p]
         _LIB = L
     return _LIB
 
@@ -102,6 +107,7 @@ def stretched_zf(ktot: int, zsize: float, ratio: float = 1.03) -> np.ndarray:
 
 FIELDS = ("u0", "v0", "w0", "um", "vm", "wm", "pres0", "p", "ekm", "ekh",
           "up", "vp", "wp", "pup", "pvp", "pwp", "rhs", "sv0", "svm", "svp")
+THERMO_FIELDS = ("thl0", "thlm", "thlp", "thl0h", "thv0h", "dthvdz")
 
 
 class Oracle:
@@ -128,7 +134,13 @@ class Oracle:
         self.ih = self.jh = self.kh = 1
         self.ihc = self.jhc = self.khc = 2 if (nsv > 0 and iadv_sv == 7) else 1
         self.dx, self.dy = xlen / itot, ylen / jtot
-        for name in FIELDS:
+        self._map_fields(FIELDS)
+        self.ltempeq = False
+        self.rk3step = 0
+        self.dt = 0.0
+
+    def _map_fields(self, names):
+        for name in names:
             dims = (C.c_int * 4)()
             ptr = self.L.orc_field(self.h, name.encode(), dims)
             if not ptr:
@@ -138,8 +150,6 @@ class Oracle:
             n = int(np.prod(shape))
             arr = np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape, order="F")
             setattr(self, name, arr)
-        self.rk3step = 0
-        self.dt = 0.0
 
     def metric(self, name):
         lo, n = C.c_int(), C.c_int()
@@ -196,6 +206,21 @@ class Oracle:
         self.L.orc_set_forcing(self.h, a.ctypes.data, b.ctypes.data)
 
     def forces(self): self.L.orc_forces(self.h)
+
+    # temperature, dry -----------------------------------------------
+    def set_thermo(self, lbuoyancy=True, grav=9.81, thls=288.0, BCtopT=1, wttop=0.0, thl_top=288.0, BCbotT=1, wtsurf=0.0,
+                   thlpcar=None):
+        a = None if thlpcar is None else np.ascontiguousarray(thlpcar, dtype=np.float64)
+        assert a is None or a.size == self.ktot + 1
+        self.L.orc_set_thermo(self.h, int(lbuoyancy), grav, thls, BCtopT, wttop, thl_top, BCbotT, wtsurf,
+                              None if a is None else a.ctypes.data)
+        self._map_fields(THERMO_FIELDS)
+        self.ltempeq = True
+
+    def thermodynamics(self): self.L.orc_thermodynamics(self.h)
+
+    def thermo_profile(self, name):
+        return np.ctypeslib.as_array(self.L.orc_thermo_profile(self.h, name.encode()), shape=(self.ktot + 1,))
 
     # bottom -> wfmneutral (src/modibm.f90:1998, src/modwallfunctions.f90:307) and masscorr (src/modforces.f90:328) ----
     def set_bottom(self, z0, fkar=0.41, lbottom=True, BCbotm=3, BCbots=1):

@@ -56,6 +56,14 @@ struct orc {
   double uflowrate, vflowrate, udef, vdef;
   int *IIu, *IIv;             /* (itot, jtot, ktot+1), 1 = fluid (createmasks, src/modibm.f90:2103); NULL = all fluid */
   int *IIus, *IIvs;           /* fluid points per level, ktot+1 values */
+  /* temperature (ltempeq, dry: lmoist = .false.) */
+  int ltempeq, lbuoyancy, BCtopT, BCbotT;
+  double grav, thls, wttop, thl_top, wtsurf;
+  double *thl0, *thlm;        /* momentum-halo shape (alloc_z, src/modfields.f90:495-497) */
+  double *thlp;               /* tendency shape (src/modfields.f90:453) */
+  double *thl0h;              /* momentum-halo shape (:500); interior only is ever written */
+  double *thv0h, *dthvdz;     /* tendency shape (:464-465) */
+  double *thl0av, *thvh, *thlpcar; /* kb:ke+kh */
 };
 
 #define MOFF 2
@@ -193,7 +201,8 @@ void orc_destroy(orc_t *o) {
                    o->dzfc, o->dzfci, o->dzhci, o->delta, o->xrt, o->yrt, o->a, o->b, o->cc,
                    o->u0, o->v0, o->w0, o->um, o->vm, o->wm, o->pres0, o->p, o->ekm, o->ekh,
                    o->up, o->vp, o->wp, o->pup, o->pvp, o->pwp, o->rhs, o->d, o->sv0, o->svm, o->svp,
-                   o->dumu, o->duml, o->twx, o->twy};
+                   o->dumu, o->duml, o->twx, o->twy, o->thl0, o->thlm, o->thlp, o->thl0h, o->thv0h, o->dthvdz,
+                   o->thl0av, o->thvh, o->thlpcar};
   for (size_t n = 0; n < sizeof(all) / sizeof(all[0]); n++) free(all[n]);
   free(o);
 }
@@ -203,10 +212,13 @@ double *orc_field(orc_t *o, const char *name, int dims[4]) {
       {"u0", o->u0, 0}, {"v0", o->v0, 0}, {"w0", o->w0, 0}, {"um", o->um, 0}, {"vm", o->vm, 0}, {"wm", o->wm, 0},
       {"pres0", o->pres0, 0}, {"p", o->p, 0}, {"ekm", o->ekm, 0}, {"ekh", o->ekh, 0},
       {"up", o->up, 1}, {"vp", o->vp, 1}, {"wp", o->wp, 1}, {"pup", o->pup, 1}, {"pvp", o->pvp, 1}, {"pwp", o->pwp, 1},
-      {"rhs", o->rhs, 2}, {"sv0", o->sv0, 3}, {"svm", o->svm, 3}, {"svp", o->svp, 4}};
+      {"rhs", o->rhs, 2}, {"sv0", o->sv0, 3}, {"svm", o->svm, 3}, {"svp", o->svp, 4},
+      {"thl0", o->thl0, 0}, {"thlm", o->thlm, 0}, {"thl0h", o->thl0h, 0}, {"thlp", o->thlp, 1}, {"thv0h", o->thv0h, 1},
+      {"dthvdz", o->dthvdz, 1}};
   for (size_t n = 0; n < sizeof(tab) / sizeof(tab[0]); n++)
     if (!strcmp(tab[n].n, name)) {
       int kd = tab[n].kind;
+      if (!tab[n].p) return NULL;
       dims[3] = 1;
       if (kd <= 1) { dims[0] = PI_; dims[1] = PJ_; dims[2] = o->ktot + (kd == 0 ? 2 : 1) * o->kh; }
       else if (kd == 2) { dims[0] = o->itot; dims[1] = o->jtot; dims[2] = o->ktot; }
@@ -438,6 +450,12 @@ void orc_advection(orc_t *o) {
     if (o->c.iadv_sv == 7) advecc_kappa(o, o->sv0 + n * nS(o), o->svp + n * nST(o));
     else advecc_2nd(o, o->sv0 + n * nS(o), o->svp + n * nST(o));
   }
+  if (o->ltempeq) {      /* iadv_thl = cd2: advecc_2nd(ih, jh, kh, thl0, thlp), src/modadvection.f90:67-69 */
+    const int hc = o->ihc;
+    o->ihc = o->jhc = o->khc = 1;       /* thl carries the momentum halo: S / ST index like F / T */
+    advecc_2nd(o, o->thl0, o->thlp);
+    o->ihc = o->jhc = o->khc = hc;
+  }
 }
 
 /* ------------------------------------------------------------------------- */
@@ -446,6 +464,14 @@ static void fluxtop0(orc_t *o, double *f) {
   const int K = o->ktot;
   for (int j = 1 - o->jh; j <= o->jtot + o->jh; j++)
     for (int i = 1 - o->ih; i <= o->itot + o->ih; i++) F(f, i, j, K + 1) = F(f, i, j, K);
+}
+/* fluxtop with any flux: src/modboundary.f90:1494-1508 */
+static void fluxtop(orc_t *o, double *f, const double *ek, double flux) {
+  const int K = o->ktot;
+  if (fabs(flux) <= 1.e-10) { fluxtop0(o, f); return; }
+  for (int j = 1 - o->jh; j <= o->jtot + o->jh; j++)
+    for (int i = 1 - o->ih; i <= o->itot + o->ih; i++)
+      F(f, i, j, K + 1) = F(f, i, j, K) + M(dzh, K + 1) * flux / (M(dzhi, K + 1) * (0.5 * (M(dzf, K) * F(ek, i, j, K + 1) + M(dzf, K + 1) * F(ek, i, j, K))));
 }
 static void valuetop(orc_t *o, double *f, double val) {
   const int K = o->ktot;
@@ -494,6 +520,7 @@ static void closurebc(orc_t *o) {
   if (o->c.BCtopm == 1 || o->c.BCtopm == 3) {
     fluxtop0(o, o->um); fluxtop0(o, o->u0); fluxtop0(o, o->vm); fluxtop0(o, o->v0);
   }
+  if (o->ltempeq && o->BCtopT == 1) { fluxtop(o, o->thlm, o->ekh, o->wttop); fluxtop(o, o->thl0, o->ekh, o->wttop); }   /* :417-420 */
   /* nsv > 0 with BCtops flux (default, wsvtop = 0): fluxtopscal, see orc_boundary */
 }
 
@@ -753,6 +780,12 @@ void orc_subgrid(orc_t *o) {
   diffu(o, o->up);
   diffv(o, o->vp);
   diffw(o, o->wp);
+  if (o->ltempeq) {      /* diffc(ih, jh, kh, thl0, thlp), src/modsubgrid.f90:146 */
+    const int hc = o->ihc;
+    o->ihc = o->jhc = o->khc = 1;
+    diffc(o, o->thl0, o->thlp);
+    o->ihc = o->jhc = o->khc = hc;
+  }
   for (int n = 0; n < o->nsv; n++) diffc(o, o->sv0 + n * nS(o), o->svp + n * nST(o));
 }
 
@@ -1038,7 +1071,12 @@ void orc_tstep_integrate(orc_t *o, double dt, int rk3step) {
         F(o->w0, i, j, k) = F(o->wm, i, j, k) + rk3coef * T(o->wp, i, j, k);
         for (int n = 0; n < o->nsv; n++)
           S(o->sv0 + n * nS(o), i, j, k) = S(o->svm + n * nS(o), i, j, k) + rk3coef * ST(o->svp + n * nST(o), i, j, k);
+        if (o->ltempeq) F(o->thl0, i, j, k) = F(o->thlm, i, j, k) + rk3coef * T(o->thlp, i, j, k);   /* modtstep.f90:244 */
       }
+  if (o->ltempeq) {
+    memset(o->thlp, 0, nT(o) * sizeof(double));                         /* :325 */
+    if (rk3step == 3) memcpy(o->thlm, o->thl0, nF(o) * sizeof(double)); /* :334 */
+  }
   memset(o->up, 0, nT(o) * sizeof(double));
   memset(o->vp, 0, nT(o) * sizeof(double));
   memset(o->wp, 0, nT(o) * sizeof(double));
@@ -1054,8 +1092,9 @@ void orc_tstep_integrate(orc_t *o, double dt, int rk3step) {
 /* halos: src/modboundary.f90:67-109 -> xm_periodic :508-538, ym_periodic :596-626, xs/ys_periodic */
 void orc_halos(orc_t *o) {
   const int I = o->itot, J = o->jtot, K = o->ktot;
-  double *mom[6] = {o->u0, o->v0, o->w0, o->um, o->vm, o->wm};
-  for (int f = 0; f < 6; f++) {
+  double *mom[8] = {o->u0, o->v0, o->w0, o->um, o->vm, o->wm, o->thl0, o->thlm};   /* xT_periodic / yT_periodic :541-556, :628-647 */
+  const int nmom = o->ltempeq ? 8 : 6;
+  for (int f = 0; f < nmom; f++) {
     double *a = mom[f];
     for (int m = 1; m <= o->ih; m++)
       for (int k = 1 - o->kh; k <= K + o->kh; k++)
@@ -1073,7 +1112,7 @@ void orc_halos(orc_t *o) {
           S(a, I + m, j, k) = S(a, m, j, k);
         }
   }
-  for (int f = 0; f < 6; f++) {
+  for (int f = 0; f < nmom; f++) {
     double *a = mom[f];
     for (int m = 1; m <= o->ih; m++)                      /* the reference loops m to ih here too (:603) */
       for (int k = 1 - o->kh; k <= K + o->kh; k++)
@@ -1123,6 +1162,10 @@ void orc_boundary(orc_t *o) {
   }
   for (int j = 1 - o->jh; j <= J + o->jh; j++)
     for (int i = 1 - o->ih; i <= I + o->ih; i++) { F(o->w0, i, j, K + 1) = 0.; F(o->wm, i, j, K + 1) = 0.; }
+  if (o->ltempeq) {      /* modboundary.f90:208-221 */
+    if (o->BCtopT == 1) { fluxtop(o, o->thlm, o->ekh, o->wttop); fluxtop(o, o->thl0, o->ekh, o->wttop); }
+    else { valuetop(o, o->thlm, o->thl_top); valuetop(o, o->thl0, o->thl_top); }
+  }
   /* fluxtopscal with wsvtop = 0 (modboundary.f90:1521-1537): ghost levels ke+1..ke+khc over the
    * momentum-halo footprint (ib-ih:ie+ih, jb-jh:je+jh) copy level ke */
   for (int n = 0; n < o->nsv; n++) {
@@ -1239,12 +1282,50 @@ static void solid_scalar(orc_t *o, double *var, double *rhs, double val) {
     }
   }
 }
-/* ibmnorm :697-745 (neutral: momentum + scalars; kappa scalars need no advecc2nd correction) */
+/* advecc2nd_corr_liberal :936-987 on a momentum-halo scalar (thl with iadv_thl = cd2) */
+static void advecc2nd_corr_liberal(orc_t *o, const double *var, double *rhs) {
+  const double eps1 = 1.e-10;
+  const double *mk = o->mask[3], *u0 = o->u0, *v0 = o->v0, *w0 = o->w0;
+  const double dxi5 = o->dxi5, dyi5 = o->dyi5;
+  for (int n = 0; n < o->ibm_n[7]; n++) {
+    const int *q = o->ibm_pts[7] + 3 * n;
+    const int i = q[0], j = q[1], k = q[2];
+    if (fabs(F(mk, i + 1, j, k)) < eps1)
+      T(rhs, i, j, k) = T(rhs, i, j, k) + F(u0, i + 1, j, k) * (F(var, i + 1, j, k) + F(var, i, j, k)) * dxi5
+                                        - F(u0, i + 1, j, k) * (F(var, i, j, k) + F(var, i, j, k)) * dxi5;
+    if (fabs(F(mk, i - 1, j, k)) < eps1)
+      T(rhs, i, j, k) = T(rhs, i, j, k) - F(u0, i, j, k) * (F(var, i - 1, j, k) + F(var, i, j, k)) * dxi5
+                                        + F(u0, i, j, k) * (F(var, i, j, k) + F(var, i, j, k)) * dxi5;
+    if (fabs(F(mk, i, j + 1, k)) < eps1)
+      T(rhs, i, j, k) = T(rhs, i, j, k) + F(v0, i, j + 1, k) * (F(var, i, j + 1, k) + F(var, i, j, k)) * dyi5
+                                        - F(v0, i, j + 1, k) * (F(var, i, j, k) + F(var, i, j, k)) * dyi5;
+    if (fabs(F(mk, i, j - 1, k)) < eps1)
+      T(rhs, i, j, k) = T(rhs, i, j, k) - F(v0, i, j, k) * (F(var, i, j - 1, k) + F(var, i, j, k)) * dyi5
+                                        + F(v0, i, j, k) * (F(var, i, j, k) + F(var, i, j, k)) * dyi5;
+    if (fabs(F(mk, i, j, k + 1)) < eps1)
+      T(rhs, i, j, k) = T(rhs, i, j, k) + F(w0, i, j, k + 1) * (F(var, i, j, k + 1) * M(dzf, k) + F(var, i, j, k) * M(dzf, k + 1)) * M(dzhi, k + 1) * M(dzfi5, k)
+                                        - F(w0, i, j, k + 1) * (F(var, i, j, k) * M(dzf, k) + F(var, i, j, k) * M(dzf, k + 1)) * M(dzhi, k + 1) * M(dzfi5, k);
+    if (fabs(F(mk, i, j, k - 1)) < eps1)
+      T(rhs, i, j, k) = T(rhs, i, j, k) - F(w0, i, j, k) * (F(var, i, j, k - 1) * M(dzf, k) + F(var, i, j, k) * M(dzf, k - 1)) * M(dzhi, k) * M(dzfi5, k)
+                                        + F(w0, i, j, k) * (F(var, i, j, k) * M(dzf, k) + F(var, i, j, k) * M(dzf, k - 1)) * M(dzhi, k) * M(dzfi5, k);
+  }
+}
+/* ibmnorm :697-745 (momentum + temperature + scalars; kappa scalars need no advecc2nd correction) */
 void orc_ibmnorm(orc_t *o) {
   if (!o->libm) return;
   solid_mom(o, 0, o->um, o->up);
   solid_mom(o, 1, o->vm, o->vp);
   solid_mom(o, 2, o->wm, o->wp);
+  if (o->ltempeq) {      /* :714-722: solid(.., thlm, thlp, sum(thl0av dzf)/zh(ke+1), .., mask_c) + advecc2nd_corr_liberal */
+    const int hc = o->ihc, K = o->ktot;
+    double val = 0.;
+    for (int k = 1; k <= K; k++) val += o->thl0av[k - 1] * M(dzf, k);
+    val = val / M(zh, K + 1);
+    o->ihc = o->jhc = o->khc = 1;
+    solid_scalar(o, o->thlm, o->thlp, val);
+    o->ihc = o->jhc = o->khc = hc;
+    advecc2nd_corr_liberal(o, o->thl0, o->thlp);
+  }
   for (int n = 0; n < o->nsv; n++) solid_scalar(o, o->svm + n * nS(o), o->svp + n * nST(o), 0.);
 }
 /* diffu_corr / diffv_corr / diffw_corr / diffc_corr :990-1164: cancel the subgrid flux through solid neighbours */
@@ -1324,10 +1405,12 @@ void orc_ibm_diffcorr(orc_t *o) {
       T(o->wp, i, j, k) = T(o->wp, i, j, k) + eomm * (F(w0, i, j, k) - F(w0, i, j - 1, k)) * dy2i;
     }
   }
-  for (int s4 = 0; s4 < o->nsv; s4++) {
-    const double *var = o->sv0 + s4 * nS(o);
-    double *rhs = o->svp + s4 * nST(o);
+  const int hc_save = o->ihc;
+  for (int s4 = (o->ltempeq ? -1 : 0); s4 < o->nsv; s4++) {   /* s4 = -1: diffc_corr(thl0, thlp, ih, jh, kh), :1225 */
+    const double *var = s4 < 0 ? o->thl0 : o->sv0 + s4 * nS(o);
+    double *rhs = s4 < 0 ? o->thlp : o->svp + s4 * nST(o);
     const double *mk = o->mask[3];
+    o->ihc = o->jhc = o->khc = s4 < 0 ? 1 : hc_save;
     for (int n = 0; n < o->ibm_n[7]; n++) {
       const int *q = o->ibm_pts[7] + 3 * n;
       const int i = q[0], j = q[1], k = q[2];
@@ -1347,6 +1430,7 @@ void orc_ibm_diffcorr(orc_t *o) {
                                                   (S(var, i, j, k) - S(var, i, j, k - 1)) * M(dzh2i, k) * M(dzfi, k);
     }
   }
+  o->ihc = o->jhc = o->khc = hc_save;
 }
 
 /* forces, neutral branch: src/modforces.f90:88-125 */
@@ -1358,14 +1442,21 @@ void orc_set_forcing(orc_t *o, const double *dpdxl, const double *dpdyl) {
   o->has_forcing = 1;
 }
 void orc_forces(orc_t *o) {
-  if (!o->has_forcing) return;
+  if (!o->has_forcing && !o->ltempeq) return;
   const int I = o->itot, J = o->jtot, K = o->ktot;
+  if (!o->dpdxl) { o->dpdxl = zalloc(K + o->kh); o->dpdyl = zalloc(K + o->kh); }
   for (int k = 2; k <= K; k++)
     for (int j = 1; j <= J; j++)
       for (int i = 1; i <= I; i++) {
         T(o->up, i, j, k) = T(o->up, i, j, k) - o->dpdxl[k - 1];
         T(o->vp, i, j, k) = T(o->vp, i, j, k) - o->dpdyl[k - 1];
+        if (o->lbuoyancy)    /* src/modforces.f90:78 */
+          T(o->wp, i, j, k) = T(o->wp, i, j, k) + o->grav * (T(o->thv0h, i, j, k) - o->thvh[k - 1]) / o->thvh[k - 1];
       }
+  if (o->ltempeq)            /* radiative heating, :103-109 */
+    for (int k = 1; k <= K; k++)
+      for (int j = 1; j <= J; j++)
+        for (int i = 1; i <= I; i++) T(o->thlp, i, j, k) = T(o->thlp, i, j, k) + o->thlpcar[k - 1];
   for (int j = 1; j <= J; j++)
     for (int i = 1; i <= I; i++) {
       T(o->up, i, j, 1) = T(o->up, i, j, 1) - o->dpdxl[0];
@@ -1419,6 +1510,13 @@ void orc_bottom(orc_t *o) {
         T(o->vp, i, j, k) = T(o->vp, i, j, k) + (F(v0, i, j, k) - F(v0, i, j, km)) * eomm * M(dzhi, k) * M(dzfi, k) - bcmomflux * M(dzfi, k);
       }
   }
+  if (o->ltempeq && o->BCbotT == 1) {  /* fixed-flux bottom for temperature, modibm.f90:2033-2046 */
+    const int kb = 1;
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++)
+        T(o->thlp, i, j, kb) = T(o->thlp, i, j, kb) + (0.5 * (M(dzf, kb - 1) * F(ekh, i, j, kb) + M(dzf, kb) * F(ekh, i, j, kb - 1)) *
+                                                      (F(o->thl0, i, j, kb) - F(o->thl0, i, j, kb - 1)) * M(dzh2i, kb) - o->wtsurf) * M(dzfi, kb);
+  }
   if (o->nsv > 0 && o->BCbots == 1) {  /* modibm.f90:2077-2091 */
     const int kb = 1;
     for (int n = 0; n < o->nsv; n++) {
@@ -1430,6 +1528,78 @@ void orc_bottom(orc_t *o) {
                                                    (S(sv0, i, j, kb) - S(sv0, i, j, kb - 1)) * M(dzh2i, kb) + 0.) * M(dzfi, kb);
     }
   }
+}
+
+/* ---- temperature: set-up and thermodynamics (dry) ---------------------------------------------------------------
+ * src/modthermodynamics.f90:55-121 with lmoist = .false.: diagfld's slab mean of thl0 (:270, avexy_ibm with IIc),
+ * calc_halflev (:508-526), calthv (:213-235), thvh = avexy_ibm(thv0h, IIw) with the kb / kb+1 overrides (:76-90).
+ * Not restated: the hydrostatic pressure / exner / density profiles (fromztop, :338-420) and thvf; nothing on the
+ * dry path reads them (they feed the moist thermodynamics and the statistics). */
+void orc_set_thermo(orc_t *o, int lbuoyancy, double grav, double thls, int BCtopT, double wttop, double thl_top,
+                    int BCbotT, double wtsurf, const double *thlpcar) {
+  const int K = o->ktot;
+  if (!o->thl0) {
+    o->thl0 = zalloc(nF(o)); o->thlm = zalloc(nF(o)); o->thl0h = zalloc(nF(o));
+    o->thlp = zalloc(nT(o)); o->thv0h = zalloc(nT(o)); o->dthvdz = zalloc(nT(o));
+    o->thl0av = zalloc(K + 1); o->thvh = zalloc(K + 1); o->thlpcar = zalloc(K + 1);
+  }
+  o->ltempeq = 1; o->lbuoyancy = lbuoyancy; o->grav = grav; o->thls = thls;
+  o->BCtopT = BCtopT; o->wttop = wttop; o->thl_top = thl_top; o->BCbotT = BCbotT; o->wtsurf = wtsurf;
+  for (int k = 0; k <= K; k++) o->thlpcar[k] = thlpcar ? thlpcar[k] : 0.;
+}
+double *orc_thermo_profile(orc_t *o, const char *name) {
+  if (!strcmp(name, "thl0av")) return o->thl0av;
+  if (!strcmp(name, "thvh")) return o->thvh;
+  return NULL;
+}
+/* avexy_ibm (src/modmpi.f90:623-664, lnan = .false.) with a real mask array (1 fluid): II = interior of mask, all ones without IBM */
+static void avexy_mask(const orc_t *o, double *aver, const double *var, int is_tend, const double *mask, int w_kb_zero) {
+  const int I = o->itot, J = o->jtot, K = o->ktot;
+  long *cnt = (long *)calloc(K + 2, sizeof(long));
+  double *s = (double *)calloc(K + 2, sizeof(double)), *sall = (double *)calloc(K + 2, sizeof(double));
+  for (int k = 1; k <= K + 1; k++)
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++) {
+        const double v = is_tend ? T(var, i, j, k) : F(var, i, j, k);
+        int II = mask ? (F(mask, i, j, k) != 0.) : 1;
+        if (mask && w_kb_zero && k == 1) II = 0;           /* IIw(:,:,kb) = 0 with IBM (src/modibm.f90:2172) */
+        s[k] += v * II; sall[k] += v; cnt[k] += II;
+      }
+  for (int k = 1; k <= K + 1; k++) {
+    long d = cnt[k];
+    double a = s[k];
+    if (k == 1 && d == 0) { a = sall[k]; d = cnt[K]; }
+    aver[k - 1] = d == 0 ? -999. : a / (double)d;
+  }
+  free(cnt); free(s); free(sall);
+}
+void orc_thermodynamics(orc_t *o) {
+  if (!o->ltempeq) return;
+  const int I = o->itot, J = o->jtot, K = o->ktot;
+  const double eps1 = 1.e-10;
+  avexy_mask(o, o->thl0av, o->thl0, 0, o->libm ? o->mask[3] : NULL, 0);          /* diagfld :270 */
+  for (int k = 1; k <= K + 1; k++)                                               /* calc_halflev :518-526 */
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++)
+        F(o->thl0h, i, j, k) = (F(o->thl0, i, j, k) * M(dzf, k - 1) + F(o->thl0, i, j, k - 1) * M(dzf, k)) / (2 * M(dzh, k));
+  for (int j = 1; j <= J; j++)
+    for (int i = 1; i <= I; i++) F(o->thl0h, i, j, 1) = o->thls;
+  /* calthv, dry branch :213-235 */
+  memset(o->dthvdz, 0, nT(o) * sizeof(double));
+  for (int k = 1; k <= K + 1; k++)
+    for (int j = 1 - o->jh; j <= J + o->jh; j++)
+      for (int i = 1 - o->ih; i <= I + o->ih; i++) T(o->thv0h, i, j, k) = F(o->thl0h, i, j, k);
+  for (int k = 2; k <= K; k++)
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++)
+        T(o->dthvdz, i, j, k) = (F(o->thl0, i, j, k + 1) - F(o->thl0, i, j, k - 1)) / (M(dzh, k + 1) + M(dzh, k));
+  for (int k = 1; k <= K; k++)
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++)
+        if (fabs(T(o->dthvdz, i, j, k)) < eps1) T(o->dthvdz, i, j, k) = copysign(eps1, T(o->dthvdz, i, j, k));
+  avexy_mask(o, o->thvh, o->thv0h, 1, o->libm ? o->mask[2] : NULL, 1);           /* :76 */
+  o->thvh[0] = o->thl0av[0];                                                     /* :87: th0av(kb) * (1 + 0 - 0), dry */
+  if (fabs(o->thvh[1]) < eps1) o->thvh[1] = o->thl0av[1];                        /* :88-90 */
 }
 
 /* ---- masscorr, volume-flow branches --------------------------------------------------------------------------
@@ -1501,4 +1671,5 @@ void orc_substep(orc_t *o, double *dt, int *rk3step, double dtmax, int ladaptive
   orc_tstep_integrate(o, *dt, *rk3step);
   orc_halos(o);
   orc_boundary(o);
+  orc_thermodynamics(o); /* src/program.f90:212 */
 }

@@ -84,6 +84,16 @@ void orc_set_masscorr(orc_t *o, int luvolflowr, int lvvolflowr, double uflowrate
 void orc_masscorr(orc_t *o, double dt, int rk3step);
 void orc_masscorr_get(orc_t *o, double *udef, double *vdef);
 
+/* temperature, dry: ltempeq with iadv_thl = cd2 — advecc_2nd + diffc on thl0 (momentum halo), fixed-flux
+ * bottom (BCbotT = 1, src/modibm.f90:2033-2046), top flux / value (BCtopT = 1 / 2, src/modboundary.f90:208-221), buoyancy
+ * and radiative tendency in forces (src/modforces.f90:70-109), thermodynamics (src/modthermodynamics.f90:55-121, dry).
+ * Fields thl0 thlm thlp thl0h thv0h dthvdz through orc_field; profiles thl0av / thvh (ktot+1 values) through
+ * orc_thermo_profile.  thlpcar: ktot+1 values or NULL. */
+void orc_set_thermo(orc_t *o, int lbuoyancy, double grav, double thls, int BCtopT, double wttop, double thl_top,
+                    int BCbotT, double wtsurf, const double *thlpcar);
+void orc_thermodynamics(orc_t *o);
+double *orc_thermo_profile(orc_t *o, const char *name);
+
 /* immersed boundary masking: kind 0-3 = solid_u,v,w,c ; 4-7 = fluid-boundary points u,v,w,c;
  * ijk = n local 1-based (i,j,k) triples, point-major */
 void orc_ibm_set_points(orc_t *o, int kind, int n, const int *ijk);

@@ -503,3 +503,27 @@ def test_fillps_fused_into_the_first_transform_is_bitwise_neutral(shape, rk3step
     for n in ("p", "up", "vp", "wp", "pres0"):
         assert np.array_equal(ga.pull(n), gb.pull(n)), n
     assert relerr(interior(ga.pull("p")), interior(o.p)) < TOL_PRES
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 64), (32, 24, 16), (128, 64, 128), (64, 64, 256), (30, 18, 48), (64, 32, 512)])
+@pytest.mark.parametrize("variant", ["stream", "L8", "L16", "L32"])
+def test_one_pass_segmented_z_solve(shape, variant, monkeypatch):
+    """k_zsolve_seg (one pass over HBM, segments of the z recurrence combined through shared memory) against the oracle's
+    solmpj restatement (src/modpois.f90:1107-1166) and against the streaming two-sweep kernel, for every instantiated
+    segment length (levels per thread); shapes include tiles that run past the end of the plane (30 x 18)."""
+    if variant == "stream":
+        monkeypatch.setenv("UDGPU_ZSEG", "0")
+    else:
+        monkeypatch.setenv("UDGPU_ZSEG", "1")
+        monkeypatch.setenv("UDGPU_ZSEG_L", variant[1:])
+    st = shape[2] <= 256          # 1.04 ** 512: the stretched grid itself is ill-conditioned beyond 1e-10
+    o, g = make_pair(*shape, stretched=st)
+    rng = np.random.default_rng(11)
+    rhs = rng.standard_normal(shape)
+    rhs -= rhs.mean()
+    p_ref = o.poisson_solve(rhs)
+    p = g.poisson_solve(rhs)
+    assert relerr(p, p_ref) < TOL_PRES
+    monkeypatch.setenv("UDGPU_ZSEG", "0")
+    o2, g2 = make_pair(*shape, stretched=st)
+    assert relerr(p, g2.poisson_solve(rhs)) < 1e-11

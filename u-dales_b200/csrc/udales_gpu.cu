@@ -18,6 +18,7 @@
 #include "momtend_tma.cuh"
 #include "poisson_v1.cuh"
 #include "poisson_fast.cuh"
+#include "zsolve_seg.cuh"
 #include "stencil_v1.cuh"
 #include "scalar_v1.cuh"
 #include "ibm.cuh"
@@ -113,6 +114,7 @@ struct udgpu {
   FftPlan px, py;
   bool fast_x = false, fast_y = false, fast_z = false;
   int zu = 8, fft_lanes = 32;
+  int zseg = 1, zseg_L = 0;   // one-pass segmented z solve (k_zsolve_seg); UDGPU_ZSEG=0: streaming two-sweep kernel
   int fill_fused = -1;        // fillps evaluated inside the first forward transform (UDGPU_FILL_FUSED=0/1; default: set at init, see there)
   int fft_rev = 1;            // consecutive kernels alternate their level direction for L2 reuse (UDGPU_FFT_REV=0: all upwards)
   double *d_zt = nullptr, *d_xd = nullptr, *d_yd = nullptr;
@@ -1066,6 +1068,8 @@ static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, cons
     return dev_alloc(h, (void **)&h->d_scr, (size_t)g.imax * g.jmax * g.ktot * sizeof(double));
   }
   { const char *e = getenv("UDGPU_ZU"); if (e && atoi(e) == 16) h->zu = 16; }
+  { const char *e = getenv("UDGPU_ZSEG"); if (e) h->zseg = atoi(e) != 0; }
+  { const char *e = getenv("UDGPU_ZSEG_L"); if (e) h->zseg_L = atoi(e); }
   // One GPU, 256^3 (profiles/r2_ab2_ztile_fill.jsonl): the fused x pass takes 0.27 ms against 0.172 + 0.085 ms for k_fillps
   // + plain x pass although it moves 16 B/cell less — the transform kernel runs 512 threads per SM and cannot keep
   // twelve input streams in flight like the 64 %-occupancy fillps kernel does.  So it is off at one GPU; in the slab solve
@@ -1103,7 +1107,32 @@ static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, cons
 // against 94 us — with a 2 KB column per thread only ~100 recurrences fit on an SM and the dependent fp64 chain (one FMA
 // per level, ~25-30 cycles each) cannot be hidden; L2-sized sub-launches of this kernel were slower as well (0.41 ms
 // per solve with 2 launches, 0.68 ms with 8: each launch is latency-bound on its own).
+template <int L, int TW, int MAXT, int MINB>
+static int zsolve_seg_launch(udgpu *h, const Geo &gg, double *x) {
+  const int nseg = gg.ktot / L;
+  const long long plane = (long long)gg.imax * gg.jmax;
+  const size_t smem = ((size_t)4 * nseg * TW + 2 * gg.ktot) * sizeof(double);
+  k_zsolve_seg<L, TW, MAXT, MINB><<<(unsigned)((plane + TW - 1) / TW), nseg * TW, smem, h->st>>>(gg, h->nxh, h->nyh, nseg, x, h->d_zt, h->d_a, h->d_c);
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+
 static int zsolve_fast(udgpu *h, const Geo &gg, double *x) {
+  // one-pass segmented solve (zsolve_seg.cuh): K = nseg * L with 2 <= nseg <= 32 segments of L = 8 / 16 / 32 levels,
+  // 16-column tiles; every other K takes the streaming two-sweep kernel (as does UDGPU_ZSEG=0)
+  if (h->zseg) {
+    const int K = gg.ktot;
+    int L = h->zseg_L;
+    if (!L) L = K >= 256 ? 16 : 8;
+    const int nseg = K % L == 0 ? K / L : 0;
+    if (nseg >= 2 && nseg <= 32) {
+      if (L == 8) return zsolve_seg_launch<8, 16, 512, 2>(h, gg, x);
+      if (L == 16 && nseg <= 16) return zsolve_seg_launch<16, 16, 256, 2>(h, gg, x);
+      if (L == 16) return zsolve_seg_launch<16, 16, 512, 1>(h, gg, x);
+      if (L == 32 && nseg <= 16) return zsolve_seg_launch<32, 16, 256, 1>(h, gg, x);
+    }
+  }
   if (h->zu == 16) k_zsolve<16><<<dim3((gg.imax + 127) / 128, gg.jmax), 128, 0, h->st>>>(gg, h->nxh, h->nyh, x, h->d_zt, h->d_a, h->d_c);
   else k_zsolve<8><<<dim3((gg.imax + 127) / 128, gg.jmax), 128, 0, h->st>>>(gg, h->nxh, h->nyh, x, h->d_zt, h->d_a, h->d_c);
   KCHECK();
