@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define UDGPU_ABI_VERSION 1
+#define UDGPU_ABI_VERSION 2
 
 /* error codes */
 #define UDGPU_OK 0
@@ -57,6 +57,8 @@ enum udgpu_field {
   UDGPU_SV0, UDGPU_SVM,                      /* (ib-ihc:.., jb-jhc:.., kb-khc:ke+khc, nsv) */
   UDGPU_SVP,                                 /* (.., .., kb:ke+khc, nsv)                */
   UDGPU_MOMFLUXB,                            /* as u0; allocated by udgpu_set_bottom (src/modfields.f90 momfluxb)  */
+  UDGPU_THL0, UDGPU_THLM,                    /* as u0 (alloc_z, src/modfields.f90:495-497); with ltempeq only      */
+  UDGPU_THLP,                                /* as up (src/modfields.f90:453); with ltempeq only                   */
   UDGPU_NFIELDS
 };
 
@@ -79,7 +81,8 @@ typedef struct udgpu_cfg {
   int iadv_mom;                  /* 2 = cd2                (src/modglobal.f90:398)       */
   int iadv_sv;                   /* 7 kappa, 2 cd2         (src/modglobal.f90:397-399)   */
   int lles, lvreman, lsmagorinsky, loneeqn;  /* src/modsubgriddata.f90:39-42            */
-  int ltempeq, lmoist;           /* must be 0 (out of scope)              */
+  int ltempeq, lmoist;           /* ltempeq: dry temperature equation (thl0, thlm, thlp resident; udgpu_set_thermo);
+                                    lmoist must be 0 (out of scope)       */
   double dx, dy;                 /* src/modglobal.f90:710-711                            */
   const double *dzf;             /* dzf(kb-kh:ke+kh): ktot+2 values (src/modglobal.f90:751-755) */
   const double *dzh;             /* dzh(kb:ke+kh):   ktot+1 values (src/modglobal.f90:757-760)  */
@@ -90,6 +93,7 @@ typedef struct udgpu_cfg {
   double e12min;
   int device;                    /* CUDA device ordinal, -1 = LOCAL_RANK / current        */
   int flags;                     /* UDGPU_F_* */
+  int iadv_thl;                  /* 2 = cd2 (0 = unset -> iadv_mom, src/modglobal.f90:549); ABI 2 */
 } udgpu_cfg;
 
 #define UDGPU_F_NO_LAZY_FUSION 1  /* run every call eagerly as its own kernel(s) (debug / parity bisecting) */
@@ -151,8 +155,9 @@ int udgpu_halos(udgpu_t *h);
 int udgpu_boundary(udgpu_t *h);
 /* src/modchecksim.f90:161  chkdiv: max |div|, sum div*dV, and RMS(div) (parity metric) */
 int udgpu_divergence(udgpu_t *h, double *divmax, double *divtot, double *divrms);
-/* one pass of src/program.f90:132-207 restricted to the calls above, in the reference's order:
- * tstep_update, advection, subgrid, poisson, tstep_integrate, halos, boundary. */
+/* one pass of src/program.f90:132-212 restricted to the calls of this header, in the reference's order:
+ * tstep_update, advection, subgrid, [bottom, forces, ibm_diffcorr, masscorr, ibmnorm,] poisson, tstep_integrate, halos,
+ * boundary [, thermodynamics]. */
 int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax, int ladaptive,
                   double courant, double diffnr);
 
@@ -177,6 +182,28 @@ int udgpu_bottom(udgpu_t *h);
  * IBM diffusion corrections and ibmnorm (src/program.f90:169) once a flow rate has been set. */
 int udgpu_set_masscorr(udgpu_t *h, int luvolflowr, int lvvolflowr, double uflowrate, double vflowrate);
 int udgpu_masscorr(udgpu_t *h, double dt, int rk3step, double *udef, double *vdef);
+
+/* ---- temperature, dry (next tier; needs cfg.ltempeq = 1, iadv_thl = cd2) ----------------------------
+ * With ltempeq the library keeps thl0, thlm, thlp resident and the existing entry points do the temperature part of the
+ * reference procedures they replace: advection -> advecc_2nd(thl0, thlp) (src/modadvection.f90:67-69); subgrid ->
+ * diffc(thl0, thlp) (src/modsubgrid.f90:146) and closurebc's fluxtop on thl (src/modboundary.f90:417-420); bottom ->
+ * fixed-flux temperature branch (BCbotT = 1, src/modibm.f90:2033-2046); forces -> buoyancy on wp and thlp += thlpcar
+ * (src/modforces.f90:70-83, 103-109); ibm_diffcorr -> diffc_corr(thl0, thlp) (src/modibm.f90:1225); ibmnorm -> solid(..,
+ * thlm, thlp, <thl0av>, mask_c) + advecc2nd_corr_liberal (:714-722); tstep_integrate (src/modtstep.f90:244,325,334);
+ * halos (xT_periodic / yT_periodic, src/modboundary.f90:541-556) and boundary (BCtopT = 1 fluxtop(.., ekh, wttop) / 2
+ * valuetop(.., thl_top), :208-221).
+ * udgpu_set_thermo takes the namelist values (PHYSICS: lbuoyancy; BC: BCtopT, BCbotT, wttop, thl_top, wtsurf; thls) and the
+ * radiative tendency profile thlpcar(kb:ke+kh) (ktot+1 values, may be NULL = 0).  BCbotT = 2 (wfuno: stability functions)
+ * and the facet heat fluxes of wallfunheat stay with the host.
+ * udgpu_thermodynamics is the call of src/program.f90:212 (src/modthermodynamics.f90:55-121, lmoist = .false.): slab means
+ * thl0av (mask IIc) and thvh (thv0h = thl0h, mask IIw, kb / kb+1 overrides), summed over all ranks; the hydrostatic
+ * pressure / exner / density profiles (fromztop) are not on the dry path and are not computed.  It must follow every
+ * change of thl0 (as in the reference) and run once before the first forces(); udgpu_substep calls it last.
+ * udgpu_thermo_profile copies a profile to the host: which = 0 thl0av(kb:ke+kh), 1 thvh(kb:ke+kh) (ktot+1 values). */
+int udgpu_set_thermo(udgpu_t *h, int lbuoyancy, double grav, double thls, int BCtopT, double wttop, double thl_top,
+                     int BCbotT, double wtsurf, const double *thlpcar);
+int udgpu_thermodynamics(udgpu_t *h);
+int udgpu_thermo_profile(udgpu_t *h, int which, double *host);
 
 /* ---- immersed-boundary masking (next tier; src/modibm.f90) ------------------------------- */
 /* point lists of modibm: kind 0-3 = solid_info_{u,v,w,c}%solpts_loc, 4-7 = bound_info_{u,v,w,c}%bndpts_loc; n points,

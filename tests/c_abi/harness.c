@@ -17,7 +17,7 @@ static int layout(void) {
   OFF(abi_version); OFF(itot); OFF(imax); OFF(ih); OFF(ihc); OFF(nsv); OFF(zstart); OFF(nprocx); OFF(myidx); OFF(BCxm); OFF(BCtopm);
   OFF(BCzp); OFF(ipoiss); OFF(iadv_mom); OFF(iadv_sv); OFF(lles); OFF(loneeqn); OFF(ltempeq); OFF(lmoist); OFF(dx); OFF(dy); OFF(dzf);
   OFF(dzh); OFF(delta); OFF(numol); OFF(prandtlmoli); OFF(prandtli); OFF(c_vreman); OFF(cs); OFF(Uinf); OFF(Vinf); OFF(e12min);
-  OFF(device); OFF(flags);
+  OFF(device); OFF(flags); OFF(iadv_thl);
   printf("  \"abi\": %d,\n  \"nfields\": %d\n}\n", UDGPU_ABI_VERSION, (int)UDGPU_NFIELDS);
   return 0;
 }

@@ -6,12 +6,12 @@ from oracle.oracle import Oracle, stretched_zf
 STATE = ("u0", "v0", "w0", "um", "vm", "wm", "pres0")
 
 
-def make_pair(itot, jtot, ktot, stretched=True, seed_ir=43, gpu_flags=0, ubase=1.0, **kw):
+def make_pair(itot, jtot, ktot, stretched=True, seed_ir=43, gpu_flags=0, ubase=1.0, ltempeq_gpu=False, **kw):
     import udales_b200 as U
     zsize = ktot * (itot / 2.0) / itot
     zf = stretched_zf(ktot, zsize, 1.04) if stretched else None
     o = Oracle(itot, jtot, ktot, zf=zf, **kw)
-    g = U.UdalesGPU(itot, jtot, ktot, zf=o.zf, flags=gpu_flags, **kw)
+    g = U.UdalesGPU(itot, jtot, ktot, zf=o.zf, flags=gpu_flags, ltempeq=ltempeq_gpu, **kw)
     o.init_channel(ubase=ubase, ir=seed_ir)
     # a non-trivial pressure field with consistent periodic halos
     rng = np.random.default_rng(seed_ir)
@@ -86,3 +86,27 @@ def ibm_lists(I, J, K, boxes):
             pts = pts[pts[:, 2] >= 2]
         lists["bound_" + nm] = pts.astype(np.int32)
     return lists
+
+
+def add_thermo(o, g, seed=7, slab=None, **kw):
+    """switch the dry temperature tier on in a matching Oracle / UdalesGPU pair (g constructed with ltempeq=True): same
+    namelist values, a stably stratified thl0 with noise (deterministic in the GLOBAL index, so slabs agree), consistent
+    halos / ghost levels, thlm = thl0, and the first thermodynamics() as the reference's startup does.
+    slab: None, or (U.slab_of, world, rank) for an x-slab of the global oracle state."""
+    args = dict(lbuoyancy=True, grav=9.81, thls=288.0, BCtopT=1, wttop=-0.01, thl_top=289.0, BCbotT=1, wtsurf=0.01)
+    args.update(kw)
+    I, J, K = o.itot, o.jtot, o.ktot
+    rng = np.random.default_rng(seed)
+    car = 1e-4 * rng.standard_normal(K + 1)
+    o.set_thermo(thlpcar=car, **args)
+    g.set_thermo(thlpcar=car, **args)
+    o.ekm[...] = 1.5e-5; o.ekh[...] = 1.5e-5 / 0.71      # startup state: molecular values (fluxtop divides by ekh)
+    o.thl0[...] = 0.0
+    o.thl0[1:-1, 1:-1, 1:-1] = 288.0 + 0.02 * np.arange(1, K + 1)[None, None, :] + 0.2 * rng.standard_normal((I, J, K))
+    o.thl0[:, :, 0] = o.thl0[:, :, 1]                    # src/modstartup.f90:1208
+    o.halos(); o.boundary()
+    o.thlm[...] = o.thl0
+    cut = (lambda a: a) if slab is None else (lambda a: slab[0](a, slab[1], slab[2]))
+    for n in ("ekm", "ekh", "thl0", "thlm"):
+        g.push(n, cut(getattr(o, n)))
+    o.thermodynamics(); g.thermodynamics()

@@ -50,7 +50,7 @@ def main():
         for k in ENV_KEYS:
             os.environ.pop(k, None)
         os.environ.update(env)
-        cases = [("channel", s) for s in shapes] + [("scalars", (64, 64, 16)), ("ibm", (64, 64, 16))]
+        cases = [("channel", s) for s in shapes] + [("scalars", (64, 64, 16)), ("ibm", (64, 64, 16)), ("thermo", (64, 64, 16))]
         if name not in ("default", "ce", "nccl"):
             cases = cases[:1] + cases[2:3]
         for kind, shape in cases:

@@ -37,11 +37,12 @@ def run_case(U, Oracle, kind, shape, world, rank, dev, uid, flags=0, nsub=6, str
         failures.append(str(info))
     from helpers import ibm_lists
     I, J, K = shape
-    nsv = {"channel": 0, "scalars": 2, "ibm": 1}[kind]
+    nsv = {"channel": 0, "scalars": 2, "ibm": 1, "thermo": 0}[kind]
+    thermo = kind == "thermo"      # temperature + buoyancy + surface heat flux over IBM blocks (slab means through the allreduce)
     zf = stretched_zf(K, K * 0.5, 1.03) if stretched_zf else None
     o = Oracle(I, J, K, zf=zf, nsv=nsv)
     o.init_channel()
-    g = U.UdalesGPU(I, J, K, zf=o.zf, device=dev, nprocx=world, myidx=rank, nccl_uid=uid, flags=flags, nsv=nsv)
+    g = U.UdalesGPU(I, J, K, zf=o.zf, device=dev, nprocx=world, myidx=rank, nccl_uid=uid, flags=flags, nsv=nsv, ltempeq=thermo)
     hc = o.ihc
     for n in ("u0", "v0", "w0", "um", "vm", "wm", "pres0"):
         g.push(n, U.slab_of(getattr(o, n), world, rank))
@@ -50,7 +51,7 @@ def run_case(U, Oracle, kind, shape, world, rank, dev, uid, flags=0, nsub=6, str
         g.push("svm", U.slab_of(o.svm[..., n4], world, rank, halo=hc), n4)
     worst = 0.0
     imax = I // world
-    if kind == "ibm":
+    if kind in ("ibm", "thermo"):
         lists = ibm_lists(I, J, K, IBM_BOXES)
         o.ibm_set(lists)
         g.ibm_set(_slab_lists(lists, world, rank, I))
@@ -70,11 +71,24 @@ def run_case(U, Oracle, kind, shape, world, rank, dev, uid, flags=0, nsub=6, str
         g.push("rhs", np.asfortranarray(rhs[rank * imax:(rank + 1) * imax]))
         g.poisson_solve_resident()
         check(np.array_equal(g.pull("rhs"), p), ("poisson_solve_resident differs from poisson_solve", shape))
+    if thermo:
+        from helpers import add_thermo
+        add_thermo(o, g, slab=(U.slab_of, world, rank))
+        o.set_bottom(0.01); g.set_bottom(0.01)
     dt = 0.02
     o.dt = g.dt = dt
     for s in range(nsub):
         o.substep(dt)
         g.substep(dt)
+        if thermo:
+            for n in ("thl0", "thlm"):
+                a, b = g.pull(n), U.slab_of(getattr(o, n), world, rank)
+                e = np.abs(a[:, :, 1:] - b[:, :, 1:]).max() / 288.0
+                worst = max(worst, e)
+                check(e < TOL, (kind, n, s, shape, e))
+            e = np.abs(g.thermo_profile("thvh") - o.thermo_profile("thvh")).max() / 288.0
+            worst = max(worst, e)
+            check(e < 1e-12, (kind, "thvh", s, e))
         for n in ("u0", "v0", "w0", "um", "vm", "wm"):
             a, b = g.pull(n), U.slab_of(getattr(o, n), world, rank)
             e = np.abs(a - b).max()
@@ -104,9 +118,9 @@ def run_case(U, Oracle, kind, shape, world, rank, dev, uid, flags=0, nsub=6, str
 
 def bench_parity(U, Oracle, world, rank, dev, fresh_uid):
     """the bounded set bench.py runs before its timed region: channel (Poisson + 6 substeps), 2 kappa scalars, IBM blocks
-    (+1 scalar), all on 64x64xK grids split into `world` x-slabs.  Returns the JSON-able verdict."""
+    (+1 scalar), temperature with buoyancy over IBM blocks, all on 64x64xK grids split into `world` x-slabs.  Returns the JSON-able verdict."""
     from oracle.oracle import stretched_zf
-    cases = [("channel", (64, 64, 32), 6), ("scalars", (64, 64, 16), 3), ("ibm", (64, 64, 16), 3)]
+    cases = [("channel", (64, 64, 32), 6), ("scalars", (64, 64, 16), 3), ("ibm", (64, 64, 16), 3), ("thermo", (64, 64, 16), 3)]
     import os
     if world > 1:
         cases.append(("channel-ce", (64, 64, 32), 3))     # the copy-engine pipeline (default only for large blocks) forced on

@@ -120,3 +120,79 @@ def test_oracle_thermo_matches_reference_source(path):
         a, b = getattr(o, n), d["s3_" + n]
         k0 = 1 if n == "thl0h" else 0
         assert rel(a[1:-1, 1:-1, k0:], b[1:-1, 1:-1, k0:]) < 1e-11, n
+
+
+# ---- the CUDA library -------------------------------------------------------------------------------------------------
+F_NO_LAZY, F_V1, F_NO_HALO = 1, 8, 16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [0, F_NO_LAZY, F_NO_HALO, F_V1])
+@pytest.mark.parametrize("path", GOLD, ids=["flux", "value_ibm"])
+def test_cuda_thermo_matches_reference_source(path, flags):
+    """the same staged comparison, CUDA library against the vectors from the executed reference source (no oracle in between)"""
+    import udales_b200 as U
+    d = np.load(path)
+    I, J, K = (int(v) for v in d["shape"])
+    g = U.UdalesGPU(I, J, K, xlen=float(d["xlen"]), ylen=float(d["ylen"]), zf=d["zf"], ltempeq=True, flags=flags)
+    setup(d, g)
+    drive(d, g, 1e-12, 1e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(32, 24, 20), (64, 64, 16)])
+@pytest.mark.parametrize("case", ["plain", "value-top", "ibm", "scalars+masscorr"])
+@pytest.mark.parametrize("flags", [0, F_NO_LAZY])
+def test_cuda_thermo_substeps_track_oracle(shape, case, flags):
+    """six RK3 substeps through udgpu_substep with temperature, buoyancy, bottom (wall function + surface heat flux), forces
+    (+ IBM masking / kappa scalars and the volume-flow correction) against the oracle on whole arrays"""
+    from helpers import add_thermo, ibm_lists, make_pair
+    nsv = 2 if case.startswith("scalars") else 0
+    o, g = make_pair(*shape, nsv=nsv, ltempeq_gpu=True, gpu_flags=flags)
+    K = shape[2]
+    if case == "ibm":
+        lists = ibm_lists(*shape, [(5, 9, 4, 8, 5), (20, 24, 15, 20, 7), (shape[0] - 1, shape[0], 1, 3, 4)])
+        o.ibm_set(lists); g.ibm_set(lists)
+    kw = dict(BCtopT=2, wttop=0.0, wtsurf=-0.004) if case == "value-top" else {}
+    add_thermo(o, g, **kw)
+    prof = -1e-3 * (1.0 + 0.1 * np.arange(K + 1))
+    o.set_forcing(prof, 0.1 * prof); g.set_forcing(prof, 0.1 * prof)
+    o.set_bottom(0.01); g.set_bottom(0.01)
+    if case.startswith("scalars"):
+        o.set_masscorr(1.0, None, None, None); g.set_masscorr(1.0, None)
+    dt = 0.02
+    o.dt = g.dt = dt
+    for s in range(6):
+        o.substep(dt); g.substep(dt)
+        for n in ("u0", "v0", "w0", "um", "vm", "wm"):
+            assert rel(g.pull(n), getattr(o, n)) < 1e-11, (s, n)
+        for n in ("thl0", "thlm"):
+            assert rel(g.pull(n)[:, :, 1:], getattr(o, n)[:, :, 1:]) < 1e-12, (s, n)
+        for n in ("thvh", "thl0av"):
+            assert rel(g.thermo_profile(n), o.thermo_profile(n)) < 1e-12, (s, n)
+        for n4 in range(nsv):
+            hc = o.ihc
+            assert rel(g.pull("sv0", n4)[:, :, hc:-hc], o.sv0[:, :, hc:-hc, n4]) < 1e-11, (s, "sv0", n4)
+    assert g.divergence()[2] < 1e-12
+    assert np.abs(o.w0).max() > 1e-3 and np.abs(o.thl0[1:-1, 1:-1, 1:-1] - 288.0).max() > 0.1
+
+
+@pytest.mark.gpu
+def test_thermo_state_errors():
+    """forces / ibmnorm refuse to run on a stale thvh; set_thermo needs ltempeq; unsupported switches are EINVAL"""
+    import udales_b200 as U
+    g = U.UdalesGPU(16, 16, 8)
+    with pytest.raises(U.UdalesGPUError):
+        g.set_thermo()
+    g.close()
+    g = U.UdalesGPU(16, 16, 8, ltempeq=True)
+    with pytest.raises(U.UdalesGPUError):
+        g.set_thermo(BCbotT=2)
+    g.set_thermo()
+    g.advection(); g.subgrid()
+    with pytest.raises(U.UdalesGPUError):
+        g.forces()                       # no thermodynamics() since thl0 was (never) set
+    g.thermodynamics()
+    g.close()
+    with pytest.raises(U.UdalesGPUError):
+        U.UdalesGPU(16, 16, 8, ltempeq=True, iadv_thl=7)

@@ -19,10 +19,11 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libudales_gpu.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FIELD_IDS = {"u0": 0, "v0": 1, "w0": 2, "um": 3, "vm": 4, "wm": 5, "up": 6, "vp": 7, "wp": 8,
-             "pres0": 9, "p": 10, "ekm": 11, "ekh": 12, "rhs": 13, "sv0": 14, "svm": 15, "svp": 16, "momfluxb": 17}
+             "pres0": 9, "p": 10, "ekm": 11, "ekh": 12, "rhs": 13, "sv0": 14, "svm": 15, "svp": 16, "momfluxb": 17,
+             "thl0": 18, "thlm": 19, "thlp": 20}
 
 EXPORTS = [
     "udgpu_nccl_unique_id", "udgpu_init", "udgpu_finalize", "udgpu_last_error", "udgpu_abi_version",
@@ -32,6 +33,7 @@ EXPORTS = [
     "udgpu_poisson_solve", "udgpu_poisson_solve_resident", "udgpu_fillps", "udgpu_tderive",
     "udgpu_tstep_integrate", "udgpu_halos", "udgpu_boundary", "udgpu_divergence", "udgpu_substep",
     "udgpu_rk3_step_host", "udgpu_set_forcing", "udgpu_forces", "udgpu_set_bottom", "udgpu_bottom", "udgpu_set_masscorr", "udgpu_masscorr", "udgpu_ibm_set_points", "udgpu_ibm_commit", "udgpu_ibm_pull_mask", "udgpu_ibmnorm", "udgpu_ibm_diffcorr",
+    "udgpu_set_thermo", "udgpu_thermodynamics", "udgpu_thermo_profile",
     "udgpu_profile_enable", "udgpu_profile_get", "udgpu_profile_reset", "udgpu_launch_count", "udgpu_stream", "udgpu_trace_dump",
 ]
 
@@ -53,7 +55,7 @@ class Cfg(C.Structure):
                 ("dzf", C.POINTER(C.c_double)), ("dzh", C.POINTER(C.c_double)), ("delta", C.POINTER(C.c_double)),
                 ("numol", C.c_double), ("prandtlmoli", C.c_double), ("prandtli", C.c_double),
                 ("c_vreman", C.c_double), ("cs", C.c_double), ("Uinf", C.c_double), ("Vinf", C.c_double),
-                ("e12min", C.c_double), ("device", C.c_int), ("flags", C.c_int)]
+                ("e12min", C.c_double), ("device", C.c_int), ("flags", C.c_int), ("iadv_thl", C.c_int)]
 
 
 class UdalesGPUError(RuntimeError):
@@ -116,6 +118,10 @@ def lib():
         L.udgpu_ibm_pull_mask.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.udgpu_ibmnorm.argtypes = [C.c_void_p]
         L.udgpu_ibm_diffcorr.argtypes = [C.c_void_p]
+        L.udgpu_set_thermo.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
+                                       C.c_void_p]
+        L.udgpu_thermodynamics.argtypes = [C.c_void_p]
+        L.udgpu_thermo_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.udgpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.udgpu_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
         L.udgpu_profile_reset.argtypes = [C.c_void_p]
@@ -173,7 +179,7 @@ class UdalesGPU:
     def __init__(self, itot, jtot, ktot, xlen=None, ylen=None, zf=None, nsv=0, BCtopm=1,
                  lvreman=True, lsmagorinsky=False, lles=None, iadv_sv=7,
                  numol=1.5e-5, prandtlmol=0.71, prandtl=0.333, c_vreman=0.07, cs=-1.0,
-                 Uinf=0.0, Vinf=0.0, device=-1, flags=0, nprocx=1, myidx=0, nccl_uid=None):
+                 Uinf=0.0, Vinf=0.0, device=-1, flags=0, nprocx=1, myidx=0, nccl_uid=None, ltempeq=False, iadv_thl=2):
         self.L = lib()
         xlen = float(xlen if xlen is not None else itot / 2.0)
         ylen = float(ylen if ylen is not None else jtot / 2.0)
@@ -203,7 +209,7 @@ class UdalesGPU:
         c.iadv_mom = 2
         c.iadv_sv = iadv_sv
         c.lles, c.lvreman, c.lsmagorinsky, c.loneeqn = int(lles), int(lvreman), int(lsmagorinsky), 0
-        c.ltempeq = c.lmoist = 0
+        c.ltempeq, c.lmoist, c.iadv_thl = int(ltempeq), 0, iadv_thl
         c.dx, c.dy = xlen / itot, ylen / jtot
         c.dzf = self._dzf.ctypes.data_as(C.POINTER(C.c_double))
         c.dzh = self._dzh.ctypes.data_as(C.POINTER(C.c_double))
@@ -310,6 +316,21 @@ class UdalesGPU:
         self._chk(self.L.udgpu_set_forcing(self.h, a.ctypes.data, b.ctypes.data))
 
     def forces(self): self._chk(self.L.udgpu_forces(self.h))
+
+    # temperature, dry (construct with ltempeq=True) ---------------------------------------------------
+    def set_thermo(self, lbuoyancy=True, grav=9.81, thls=288.0, BCtopT=1, wttop=0.0, thl_top=288.0, BCbotT=1, wtsurf=0.0,
+                   thlpcar=None):
+        a = None if thlpcar is None else np.ascontiguousarray(thlpcar, dtype=np.float64)
+        assert a is None or a.size == self.ktot + 1
+        self._chk(self.L.udgpu_set_thermo(self.h, int(lbuoyancy), grav, thls, BCtopT, wttop, thl_top, BCbotT, wtsurf,
+                                          None if a is None else a.ctypes.data))
+
+    def thermodynamics(self): self._chk(self.L.udgpu_thermodynamics(self.h))
+
+    def thermo_profile(self, name):
+        out = np.empty(self.ktot + 1)
+        self._chk(self.L.udgpu_thermo_profile(self.h, {"thl0av": 0, "thvh": 1}[name], out.ctypes.data))
+        return out
 
     # bottom -> wfmneutral (src/modibm.f90:1998, src/modwallfunctions.f90:307) and masscorr (src/modforces.f90:328) --------
     def set_bottom(self, z0, fkar=0.41, lbottom=True, BCbotm=3, BCbots=1):

@@ -43,9 +43,10 @@ __global__ void __launch_bounds__(256) k_bottom_wfmneutral(Geo g, double z0, dou
   }
   momfluxb[c] = mf;
 }
-// src/modibm.f90:2077-2091 (BCbots = 1, zero surface flux): blockIdx.z = scalar index
+// src/modibm.f90:2077-2091 (BCbots = 1, zero surface flux: add = 0.) and :2033-2046 (BCbotT = 1: add = -wtsurf);
+// blockIdx.z = scalar index
 __global__ void __launch_bounds__(256) k_bottom_scalar(Geo g, const double *__restrict__ ekh, const double *__restrict__ sv0, long long ssl,
-                                                       double *__restrict__ svp, long long tsl) {
+                                                       double *__restrict__ svp, long long tsl, double add) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i > g.imax || j > g.jmax) return;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) k_bottom_scalar(Geo g, const double *__re
   const double *s = sv0 + blockIdx.z * ssl;
   double *sp = svp + blockIdx.z * tsl;
   const long long c = offS(g, i, j, kb), t = offST(g, i, j, kb), m = offF(g, i, j, kb);
-  sp[t] = sp[t] + (0.5 * (g.dzf[kb - 1] * ekh[m] + g.dzf[kb] * ekh[m - g.pk]) * (s[c] - s[c - g.pkc]) * g.dzh2i[kb] + 0.) * g.dzfi[kb];
+  sp[t] = sp[t] + (0.5 * (g.dzf[kb - 1] * ekh[m] + g.dzf[kb] * ekh[m - g.pk]) * (s[c] - s[c - g.pkc]) * g.dzh2i[kb] + add) * g.dzfi[kb];
 }
 
 // ---- masscorr ---------------------------------------------------------------------------------------------------

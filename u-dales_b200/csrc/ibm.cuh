@@ -35,11 +35,12 @@ __global__ void k_ibm_solid_mom(Geo g, int n, const int *__restrict__ pts, doubl
 }
 // solid() with mask on scalar-halo arrays (:772-822); blockIdx.y = scalar field
 __global__ void k_ibm_solid_scalar(Geo g, int n, const int *__restrict__ pts, const double *__restrict__ mk, double *__restrict__ var,
-                                   long long ssl, double *__restrict__ rhs, long long tsl, double val) {
+                                   long long ssl, double *__restrict__ rhs, long long tsl, double val_, const double *__restrict__ valp = nullptr) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   var += blockIdx.y * ssl;
   rhs += blockIdx.y * tsl;
+  const double val = valp ? *valp : val_;   // temperature: the value lives on the device (k_thermo_final)
   const double eps1 = 1.e-10;
   const int i = pts[3 * p], j = pts[3 * p + 1], k = pts[3 * p + 2];
   double v = val, r = 0., count = 0.;

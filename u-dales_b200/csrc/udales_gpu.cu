@@ -23,6 +23,7 @@
 #include "scalar_v1.cuh"
 #include "ibm.cuh"
 #include "channel_glue.cuh"
+#include "thermo.cuh"
 
 using namespace udg;
 
@@ -206,6 +207,13 @@ struct udgpu {
   bool libm = false;
   bool m_halo_stale = false;   // ibmnorm wrote um, vm, wm at solid points: their halo images are stale until halos()
   bool m_bc_stale = false;     // ... and their top ghost level until boundary()
+  // temperature, dry (thermo.cuh): namelist values of udgpu_set_thermo, per-level tables indexed by Fortran k
+  bool thermo_set = false, lbuoyancy = false, thermo_valid = false, th_counts_valid = false, thlpcar_nonzero = false;
+  int BCtopT = 1, BCbotT = 1;
+  double grav = 9.81, thls = 0., wttop = 0., thl_top = 0., wtsurf = 0.;
+  Geo gT;                      // geometry whose "scalar" halo is the momentum halo: the scalar kernels on thl0 / thlm / thlp
+  double *d_thlpcar = nullptr, *d_thl0av = nullptr, *d_thvh = nullptr, *d_th_part = nullptr, *d_th_sums = nullptr, *d_th_cnt = nullptr,
+         *d_th_solid = nullptr;
   bool prof = false;
   bool trace = false;          // udgpu_profile_enable(h, 2): event marks at every stage of the substep (udgpu_trace_dump)
   std::vector<TraceRec> tr;
@@ -369,7 +377,8 @@ static int validate_cfg(const udgpu_cfg *c, const void *nccl_uid) {
   if (c->BCxm != 1 || c->BCym != 1) return set_err(UDGPU_EINVAL, "only periodic lateral BCs (BCxm=BCym=1) are in scope");
   if (c->BCtopm != 1 && c->BCtopm != 2) return set_err(UDGPU_EINVAL, "BCtopm=%d: freeslip (1) / noslip (2) only", c->BCtopm);
   if (c->BCzp != 1) return set_err(UDGPU_EINVAL, "BCzp=%d: only the tridiagonal z solve (1) is in scope", c->BCzp);
-  if (c->ltempeq || c->lmoist || c->loneeqn) return set_err(UDGPU_EINVAL, "ltempeq/lmoist/loneeqn are out of scope (neutral configs)");
+  if (c->lmoist || c->loneeqn) return set_err(UDGPU_EINVAL, "lmoist/loneeqn are out of scope (dry LES with an eddy-viscosity closure)");
+  if (c->ltempeq && c->iadv_thl != 0 && c->iadv_thl != 2) return set_err(UDGPU_EINVAL, "iadv_thl=%d: only cd2 (2) is on the resident path", c->iadv_thl);
   if (c->ih != 1 || c->jh != 1 || c->kh != 1) return set_err(UDGPU_EINVAL, "momentum halo must be 1 (cd2, src/modglobal.f90:592-599)");
   if (c->nprocy != 1) return set_err(UDGPU_EINVAL, "only x-slab decompositions (nprocy = 1) are supported (nprocx x nprocy pencils: next)");
   if (c->nprocx < 1 || c->nprocx > 8) return set_err(UDGPU_EINVAL, "nprocx must be 1..8 (one NVSwitch box)");
@@ -518,6 +527,8 @@ static int init_impl(udgpu *h, const udgpu_cfg *c, const void *nccl_uid, int nde
     int d3 = 0, sl = 1;
     switch (f) {
       case UDGPU_UP: case UDGPU_VP: case UDGPU_WP: n = nT; d3 = K + g.kh; break;
+      case UDGPU_THLP: n = c->ltempeq ? nT : 0; d3 = K + g.kh; break;
+      case UDGPU_THL0: case UDGPU_THLM: n = c->ltempeq ? nF : 0; d3 = K + 2 * g.kh; break;
       case UDGPU_RHS: n = nR; d3 = K; break;
       case UDGPU_SV0: case UDGPU_SVM: n = c->nsv ? (size_t)g.pic * g.pjc * (K + 2 * g.khc) : 0; sl = c->nsv; d3 = K + 2 * g.khc; break;
       case UDGPU_SVP: n = c->nsv ? (size_t)g.pic * g.pjc * (K + g.khc) : 0; sl = c->nsv; d3 = K + g.khc; break;
@@ -531,6 +542,8 @@ static int init_impl(udgpu *h, const udgpu_cfg *c, const void *nccl_uid, int nde
     h->dims[f][2] = d3;
     if (n && !lazy_field) RET(dev_alloc(h, (void **)&h->f[f], n * sl * sizeof(double)));
   }
+  h->gT = g;
+  h->gT.ihc = g.ih; h->gT.jhc = g.jh; h->gT.khc = g.kh; h->gT.pic = g.pi; h->gT.pjc = g.pj; h->gT.pkc = g.pk;
   RET(dev_alloc(h, (void **)&h->d_red, 16 * sizeof(double)));
   for (double **t : {&h->d_fx, &h->d_fy, &h->d_fzero}) RET(dev_alloc(h, (void **)t, (K + 2) * sizeof(double)));
   CU(cudaMallocHost((void **)&h->h_red, 16 * sizeof(double)));
@@ -630,8 +643,9 @@ extern "C" int udgpu_field_count(udgpu_t *h, int field, size_t *count, int dims[
 extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
   RET(check_field(h, field, n4));
   RET(flush_pending(h));
-  const bool is_tend = (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP);
+  const bool is_tend = (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP || field == UDGPU_THLP);
   if (is_tend) { RET(materialize_zero_tend(h)); h->tend_pushed = true; }
+  if (field == UDGPU_THL0) h->thermo_valid = false;   // thvh belongs to the previous thl0 until thermodynamics() runs again
   if (field <= UDGPU_WP) { h->halo_dirty = h->bc_dirty = true; h->halos_done = h->bc_done = h->halo_x_pending = false; }
   if (field == UDGPU_P) h->p_halo_valid = true;   // the host's array is taken as is
   if (field == UDGPU_UM || field == UDGPU_VM || field == UDGPU_WM) h->m_changed = true;
@@ -645,7 +659,7 @@ extern "C" int udgpu_push(udgpu_t *h, int field, int n4, const double *host) {
 extern "C" int udgpu_pull(udgpu_t *h, int field, int n4, double *host) {
   RET(check_field(h, field, n4));
   RET(flush_pending(h));
-  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP) RET(materialize_zero_tend(h));
+  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP || field == UDGPU_THLP) RET(materialize_zero_tend(h));
   RET(settle_for_access(h, field));
   CU(cudaSetDevice(h->dev));
   CU(cudaMemcpyAsync(host, h->f[field] + (size_t)n4 * h->cnt[field], h->cnt[field] * sizeof(double), cudaMemcpyDeviceToHost, h->st));
@@ -657,10 +671,11 @@ extern "C" int udgpu_device_ptr(udgpu_t *h, int field, int n4, void **dptr) {
   RET(flush_pending(h));
   RET(settle_for_access(h, field));
   // the caller may write through the pointer: treat it like a push
-  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP) {
+  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP || field == UDGPU_THLP) {
     RET(materialize_zero_tend(h));
     h->tend_pushed = true; h->tend_zero = false;
   }
+  if (field == UDGPU_THL0) h->thermo_valid = false;
   if (field <= UDGPU_WP) { h->halo_dirty = h->bc_dirty = true; h->halos_done = h->bc_done = h->halo_x_pending = false; }
   *dptr = h->f[field] + (size_t)n4 * h->cnt[field];
   return UDGPU_OK;
@@ -817,6 +832,12 @@ extern "C" int udgpu_closure(udgpu_t *h) {
     KCHECK();
     h->launches++;
   }
+  // ... and fluxtop(thlm / thl0, ekh, wttop) with the NEW ekh (:417-420): changes the top ghost level whenever wttop /= 0
+  if (h->cfg.ltempeq && h->thermo_set && h->BCtopT == 1) {
+    k_thl_top<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, 1, h->wttop, 0., f[UDGPU_EKH], f[UDGPU_THL0], f[UDGPU_THLM]);
+    KCHECK();
+    h->launches++;
+  }
   return UDGPU_OK;
 }
 
@@ -867,9 +888,16 @@ template <bool ADV, bool DIFF>
 static int launch_scalars(udgpu *h, bool acc) {
   const Geo &g = h->g;
   const int nsv = h->cfg.nsv;
-  if (!nsv) return UDGPU_OK;
   const dim3 gr = grid3(g, B3);
   const bool les = g.lles != 0, kappa = h->cfg.iadv_sv == 7;
+  if (h->cfg.ltempeq) {   // advecc_2nd(ih, jh, kh, thl0, thlp) / diffc(ih, jh, kh, thl0, thlp)
+#define GT(ACC, LES) k_scalar_tend<2, ADV, DIFF, ACC, LES><<<gr, B3, 0, h->st>>>(h->gT, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKH], h->f[UDGPU_THL0], h->f[UDGPU_THLP])
+    if (acc) { if (les) GT(true, true); else GT(true, false); } else { if (les) GT(false, true); else GT(false, false); }
+#undef GT
+    KCHECK();
+    h->launches++;
+  }
+  if (!nsv) return UDGPU_OK;
   const long long ssl = (long long)h->cnt[UDGPU_SV0], tsl = (long long)h->cnt[UDGPU_SVP];
   // all fields in one pass, four at a time (the velocity / ekh loads are shared between the fields)
   const int nsmax = h->sc_nsmax;
@@ -1574,6 +1602,7 @@ static int materialize_zero_tend(udgpu *h) {
   if (!h->tend_lazy_zero) return UDGPU_OK;
   for (int f : {UDGPU_UP, UDGPU_VP, UDGPU_WP}) CU(cudaMemsetAsync(h->f[f], 0, h->cnt[f] * sizeof(double), h->st));
   if (h->cfg.nsv) CU(cudaMemsetAsync(h->f[UDGPU_SVP], 0, h->cnt[UDGPU_SVP] * h->cfg.nsv * sizeof(double), h->st));
+  if (h->cfg.ltempeq) CU(cudaMemsetAsync(h->f[UDGPU_THLP], 0, h->cnt[UDGPU_THLP] * sizeof(double), h->st));
   h->tend_lazy_zero = false;
   return UDGPU_OK;
 }
@@ -1634,6 +1663,13 @@ extern "C" int udgpu_poisson(udgpu_t *h, double dt, int rk3step) {
 
 static int integrate_scalars(udgpu *h, double rk3coef, int rk3step) {
   const Geo &g = h->g;
+  if (h->cfg.ltempeq) {   // src/modtstep.f90:244, 334 (thlp = 0 is lazy like the other tendencies)
+    if (rk3step == 3) k_scalar_integrate<true><<<grid3(g, B3), B3, 0, h->st>>>(h->gT, rk3coef, h->f[UDGPU_THL0], h->f[UDGPU_THLM], h->f[UDGPU_THLP]);
+    else k_scalar_integrate<false><<<grid3(g, B3), B3, 0, h->st>>>(h->gT, rk3coef, h->f[UDGPU_THL0], h->f[UDGPU_THLM], h->f[UDGPU_THLP]);
+    KCHECK();
+    h->launches++;
+    h->thermo_valid = false;
+  }
   for (int n = 0; n < h->cfg.nsv; n++) {
     double *s0 = h->f[UDGPU_SV0] + (size_t)n * h->cnt[UDGPU_SV0], *sm = h->f[UDGPU_SVM] + (size_t)n * h->cnt[UDGPU_SVM];
     const double *sp = h->f[UDGPU_SVP] + (size_t)n * h->cnt[UDGPU_SVP];
@@ -1759,6 +1795,7 @@ extern "C" int udgpu_halos(udgpu_t *h) {
     h->halo_dirty = false;
     h->m_changed = false;
   }
+  if (h->cfg.ltempeq) RET(wrap_xy(h, {f[UDGPU_THL0], f[UDGPU_THLM]}, g.ktot + 2 * g.kh));   // xT_periodic / yT_periodic (:541-556) or slab exchange
   if (h->cfg.nsv) {  // xs_periodic / ys_periodic (src/modboundary.f90:568-579,655-669) or exchange at level ihc
     std::vector<double *> sv;
     for (int n = 0; n < h->cfg.nsv; n++) {
@@ -1782,6 +1819,11 @@ extern "C" int udgpu_boundary(udgpu_t *h) {
     KCHECK();
     h->launches++;
     if (!h->halo_dirty) h->bc_dirty = false;   // planes are final only once the lateral halos under them are
+  }
+  if (h->cfg.ltempeq && h->thermo_set) {   // src/modboundary.f90:208-221
+    k_thl_top<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, h->BCtopT, h->wttop, h->thl_top, f[UDGPU_EKH], f[UDGPU_THL0], f[UDGPU_THLM]);
+    KCHECK();
+    h->launches++;
   }
   for (int n = 0; n < h->cfg.nsv; n++) {
     k_scalar_top<<<dim3((g.pi + 127) / 128, g.pj), 128, 0, h->st>>>(g, f[UDGPU_SV0] + (size_t)n * h->cnt[UDGPU_SV0], f[UDGPU_SVM] + (size_t)n * h->cnt[UDGPU_SVM]);
@@ -1842,7 +1884,7 @@ extern "C" int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax,
   RET(udgpu_advection(h));
   RET(udgpu_subgrid(h));
   if (h->lbottom) RET(udgpu_bottom(h));       // src/program.f90:152
-  if (h->has_forcing) RET(udgpu_forces(h));   // src/program.f90:158
+  if (h->has_forcing || h->thermo_set) RET(udgpu_forces(h));   // src/program.f90:158
   if (h->libm) RET(udgpu_ibm_diffcorr(h));    // the resident part of ibmwallfun, src/program.f90:166
   if (h->mc_on[0] || h->mc_on[1]) RET(udgpu_masscorr(h, *dt, *rk3step, nullptr, nullptr));   // src/program.f90:169
   if (h->libm) RET(udgpu_ibmnorm(h));         // src/program.f90:171
@@ -1850,6 +1892,7 @@ extern "C" int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax,
   RET(udgpu_tstep_integrate(h, *dt, *rk3step));
   RET(udgpu_halos(h));
   RET(udgpu_boundary(h));
+  if (h->thermo_set) RET(udgpu_thermodynamics(h));   // src/program.f90:212
   return UDGPU_OK;
 }
 
@@ -1874,8 +1917,31 @@ extern "C" int udgpu_set_forcing(udgpu_t *h, const double *dpdxl, const double *
 }
 extern "C" int udgpu_forces(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
-  if (!h->has_forcing) return UDGPU_OK;
+  if (!h->has_forcing && !h->thermo_set) return UDGPU_OK;
   RET(flush_pending(h));
+  if (h->thermo_set) {
+    // buoyancy and radiative tendency (src/modforces.f90:70-83, 103-109) are not uniform per level: applied at once; the
+    // per-level part (dpdxl, dpdyl, wp(kb) = 0; zero tables when no forcing was set) stays lazy as before
+    const Geo &g = h->g;
+    RET(materialize_zero_tend(h));
+    if (h->lbuoyancy) {
+      if (!h->thermo_valid) return set_err(UDGPU_ESTATE, "forces with lbuoyancy needs thvh: call udgpu_thermodynamics after thl0 changed (src/program.f90:212)");
+      if (g.ktot > 1) {
+        dim3 gr = grid3(g, B3);
+        gr.z = g.ktot - 1;
+        k_buoyancy<<<gr, B3, 0, h->st>>>(g, h->grav, h->f[UDGPU_THL0], h->d_thvh, h->f[UDGPU_WP]);
+        KCHECK();
+        h->launches++;
+      }
+    }
+    if (h->thlpcar_nonzero) {
+      k_tend_add_profile<<<grid3(g, B3), B3, 0, h->st>>>(g, h->d_thlpcar, h->f[UDGPU_THLP]);
+      KCHECK();
+      h->launches++;
+    }
+    h->tend_zero = false;
+    h->has_forcing = true;   // zero tables unless udgpu_set_forcing filled them
+  }
   // with IBM masking the order matters (ibmnorm zeroes the tendencies of solid points after forces, src/program.f90:158,171)
   h->forces_pending = true;
   if (h->libm || (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION)) return forces_now(h);
@@ -1905,8 +1971,13 @@ extern "C" int udgpu_bottom(udgpu_t *h) {
   k_bottom_wfmneutral<<<gr, B3, 0, h->st>>>(g, h->z0, h->fkar, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_EKM], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_MOMFLUXB]);
   KCHECK();
   h->launches++;
+  if (h->cfg.ltempeq && h->thermo_set) {   // BCbotT = 1: fixed temperature flux wtsurf (src/modibm.f90:2033-2046)
+    k_bottom_scalar<<<gr, B3, 0, h->st>>>(h->gT, f[UDGPU_EKH], f[UDGPU_THL0], 0, f[UDGPU_THLP], 0, -h->wtsurf);
+    KCHECK();
+    h->launches++;
+  }
   if (h->cfg.nsv > 0) {
-    k_bottom_scalar<<<dim3(gr.x, gr.y, h->cfg.nsv), B3, 0, h->st>>>(g, f[UDGPU_EKH], f[UDGPU_SV0], (long long)h->cnt[UDGPU_SV0], f[UDGPU_SVP], (long long)h->cnt[UDGPU_SVP]);
+    k_bottom_scalar<<<dim3(gr.x, gr.y, h->cfg.nsv), B3, 0, h->st>>>(g, f[UDGPU_EKH], f[UDGPU_SV0], (long long)h->cnt[UDGPU_SV0], f[UDGPU_SVP], (long long)h->cnt[UDGPU_SVP], 0.);
     KCHECK();
     h->launches++;
   }
@@ -2005,6 +2076,71 @@ extern "C" int udgpu_masscorr(udgpu_t *h, double dt, int rk3step, double *udef, 
 }
 
 // ------------------------------------------------------------------------------------------
+// temperature, dry (thermo.cuh)
+extern "C" int udgpu_set_thermo(udgpu_t *h, int lbuoyancy, double grav, double thls, int BCtopT, double wttop, double thl_top,
+                                int BCbotT, double wtsurf, const double *thlpcar) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (!h->cfg.ltempeq) return set_err(UDGPU_EINVAL, "udgpu_set_thermo needs cfg.ltempeq = 1 (thl0, thlm, thlp are allocated at init)");
+  if (BCtopT != 1 && BCtopT != 2) return set_err(UDGPU_EINVAL, "BCtopT=%d: flux (1) / value (2) only (src/modboundary.f90:208-221)", BCtopT);
+  if (BCbotT != 1) return set_err(UDGPU_EINVAL, "BCbotT=%d: only the fixed-flux bottom (1) is on the resident path (2 = wfuno stays with the host)", BCbotT);
+  RET(flush_pending(h));
+  const int K = h->g.ktot;
+  if (!h->d_thvh) {
+    for (double **t : {&h->d_thlpcar, &h->d_thl0av, &h->d_thvh}) RET(dev_alloc(h, (void **)t, (K + 2) * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_th_part, (size_t)3 * (K + 1) * TH_NBLK * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_th_sums, (size_t)3 * (K + 1) * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_th_cnt, (size_t)2 * (K + 1) * sizeof(double)));
+    RET(dev_alloc(h, (void **)&h->d_th_solid, sizeof(double)));
+  }
+  h->lbuoyancy = lbuoyancy != 0; h->grav = grav; h->thls = thls; h->BCtopT = BCtopT; h->wttop = wttop; h->thl_top = thl_top;
+  h->BCbotT = BCbotT; h->wtsurf = wtsurf;
+  h->thlpcar_nonzero = false;
+  CU(cudaSetDevice(h->dev));
+  CU(cudaMemsetAsync(h->d_thlpcar, 0, (K + 2) * sizeof(double), h->st));
+  if (thlpcar) {
+    for (int k = 0; k <= K; k++) if (thlpcar[k] != 0.) h->thlpcar_nonzero = true;
+    CU(cudaMemcpyAsync(h->d_thlpcar + 1, thlpcar, (K + 1) * sizeof(double), cudaMemcpyHostToDevice, h->st));   // table index = Fortran k
+    CU(cudaStreamSynchronize(h->st));
+  }
+  h->thermo_set = true;
+  h->thermo_valid = false;
+  return UDGPU_OK;
+}
+extern "C" int udgpu_thermodynamics(udgpu_t *h) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (!h->thermo_set) return UDGPU_OK;
+  RET(flush_pending(h));
+  const Geo &g = h->g;
+  const int K = g.ktot, K1 = K + 1;
+  ProfScope ps(h, PROF_HALO);
+  if (!h->th_counts_valid) {   // IIcs, IIws (src/modibm.f90:2176-2190): fluid points per level kb .. ke+kh over all ranks
+    k_mask_count<<<K1, 256, 0, h->st>>>(g, h->libm ? h->ibm_mask[3] : nullptr, h->d_th_cnt);
+    KCHECK();
+    k_mask_count<<<K1, 256, 0, h->st>>>(g, h->libm ? h->ibm_mask[2] : nullptr, h->d_th_cnt + K1);
+    KCHECK();
+    h->launches += 2;
+    if (h->P > 1) NC(ncclAllReduce(h->d_th_cnt, h->d_th_cnt, 2 * K1, ncclDouble, ncclSum, h->comm, h->st));
+    h->th_counts_valid = true;
+  }
+  k_thermo_partial<<<dim3(TH_NBLK, K1), 256, 0, h->st>>>(g, h->thls, h->f[UDGPU_THL0], h->libm ? h->ibm_mask[3] : nullptr, h->libm ? h->ibm_mask[2] : nullptr, h->d_th_part);
+  KCHECK();
+  k_thermo_reduce<<<(3 * K1 + 127) / 128, 128, 0, h->st>>>(3 * K1, h->d_th_part, h->d_th_sums);
+  KCHECK();
+  if (h->P > 1) NC(ncclAllReduce(h->d_th_sums, h->d_th_sums, 3 * K1, ncclDouble, ncclSum, h->comm, h->st));   // MPI_ALLREDUCE of avexy_ibm, src/modmpi.f90:654
+  k_thermo_final<<<1, 32, 0, h->st>>>(K, h->d_th_sums, h->d_th_cnt, h->d_th_cnt + K1, g.dzf, h->zh_top, h->d_thl0av, h->d_thvh, h->d_th_solid);
+  KCHECK();
+  h->launches += 3;
+  h->thermo_valid = true;
+  return UDGPU_OK;
+}
+extern "C" int udgpu_thermo_profile(udgpu_t *h, int which, double *host) {
+  if (!h || !host || which < 0 || which > 1) return set_err(UDGPU_EINVAL, "bad argument");
+  if (!h->thermo_set) return set_err(UDGPU_ESTATE, "udgpu_set_thermo first");
+  CU(cudaMemcpyAsync(host, (which ? h->d_thvh : h->d_thl0av) + 1, (h->g.ktot + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  return sync_check(h);
+}
+
+// ------------------------------------------------------------------------------------------
 // immersed-boundary masking (src/modibm.f90)
 extern "C" int udgpu_ibm_set_points(udgpu_t *h, int kind, int n, const int *ijk, int layout) {
   if (!h || kind < 0 || kind > 7 || n < 0 || (n > 0 && !ijk)) return set_err(UDGPU_EINVAL, "bad IBM point list");
@@ -2045,6 +2181,7 @@ extern "C" int udgpu_ibm_commit(udgpu_t *h) {
   RET(wrap_xy(h, {h->ibm_mask[0], h->ibm_mask[1], h->ibm_mask[2], h->ibm_mask[3]}, g.ktot + 2 * g.kh));
   h->libm = true;
   h->mc_counts_valid = false;
+  h->th_counts_valid = false;
   return UDGPU_OK;
 }
 
@@ -2068,6 +2205,10 @@ extern "C" int udgpu_ibm_diffcorr(udgpu_t *h) {
   if (n[4]) { k_ibm_diffcorr_mom<0><<<(n[4] + 127) / 128, 128, 0, h->st>>>(g, n[4], h->ibm_pts[4], h->ibm_mask[0], f[UDGPU_EKM], f[UDGPU_U0], f[UDGPU_UP]); KCHECK(); h->launches++; }
   if (n[5]) { k_ibm_diffcorr_mom<1><<<(n[5] + 127) / 128, 128, 0, h->st>>>(g, n[5], h->ibm_pts[5], h->ibm_mask[1], f[UDGPU_EKM], f[UDGPU_V0], f[UDGPU_VP]); KCHECK(); h->launches++; }
   if (n[6]) { k_ibm_diffcorr_mom<2><<<(n[6] + 127) / 128, 128, 0, h->st>>>(g, n[6], h->ibm_pts[6], h->ibm_mask[2], f[UDGPU_EKM], f[UDGPU_W0], f[UDGPU_WP]); KCHECK(); h->launches++; }
+  if (n[7] && h->cfg.ltempeq) {   // diffc_corr(thl0, thlp, ih, jh, kh), src/modibm.f90:1225
+    k_ibm_diffcorr_c<<<dim3((n[7] + 127) / 128, 1), 128, 0, h->st>>>(h->gT, n[7], h->ibm_pts[7], h->ibm_mask[3], f[UDGPU_EKH], f[UDGPU_THL0], 0, f[UDGPU_THLP], 0);
+    KCHECK(); h->launches++;
+  }
   if (n[7] && h->cfg.nsv) {
     k_ibm_diffcorr_c<<<dim3((n[7] + 127) / 128, h->cfg.nsv), 128, 0, h->st>>>(g, n[7], h->ibm_pts[7], h->ibm_mask[3], f[UDGPU_EKH], f[UDGPU_SV0],
                                                                              (long long)h->cnt[UDGPU_SV0], f[UDGPU_SVP], (long long)h->cnt[UDGPU_SVP]);
@@ -2089,6 +2230,17 @@ extern "C" int udgpu_ibmnorm(udgpu_t *h) {
   const int vm[3] = {UDGPU_UM, UDGPU_VM, UDGPU_WM}, vp[3] = {UDGPU_UP, UDGPU_VP, UDGPU_WP};
   for (int c = 0; c < 3; c++)
     if (n[c]) { k_ibm_solid_mom<<<(n[c] + 127) / 128, 128, 0, h->st>>>(g, n[c], h->ibm_pts[c], f[vm[c]], f[vp[c]]); KCHECK(); h->launches++; }
+  if (h->cfg.ltempeq) {   // :714-722: solid(.., thlm, thlp, sum(thl0av dzf) / zh(ke+1), .., mask_c), then advecc2nd_corr_liberal(thl0, thlp)
+    if (!h->thermo_valid) return set_err(UDGPU_ESTATE, "ibmnorm with ltempeq needs thl0av: call udgpu_thermodynamics after thl0 changed (src/program.f90:212)");
+    if (n[3]) {
+      k_ibm_solid_scalar<<<dim3((n[3] + 127) / 128, 1), 128, 0, h->st>>>(h->gT, n[3], h->ibm_pts[3], h->ibm_mask[3], f[UDGPU_THLM], 0, f[UDGPU_THLP], 0, 0., h->d_th_solid);
+      KCHECK(); h->launches++;
+    }
+    if (n[7]) {
+      k_ibm_advecc2nd_corr<<<(n[7] + 127) / 128, 128, 0, h->st>>>(g, n[7], h->ibm_pts[7], h->ibm_mask[3], f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_THL0], f[UDGPU_THLP]);
+      KCHECK(); h->launches++;
+    }
+  }
   if (n[3] && h->cfg.nsv) {
     k_ibm_solid_scalar<<<dim3((n[3] + 127) / 128, h->cfg.nsv), 128, 0, h->st>>>(g, n[3], h->ibm_pts[3], h->ibm_mask[3], f[UDGPU_SVM], (long long)h->cnt[UDGPU_SVM],
                                                                                f[UDGPU_SVP], (long long)h->cnt[UDGPU_SVP], 0.);

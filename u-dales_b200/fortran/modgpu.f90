@@ -22,7 +22,7 @@ module modgpu
   public :: lgpu, gpu_init, gpu_exit, gpu_push_state, gpu_pull_state, gpu_push, gpu_pull, &
             gpu_tstep_update, gpu_advection, gpu_subgrid, gpu_poisson, gpu_tstep_integrate, &
             gpu_halos, gpu_boundary, gpu_chkdiv, gpu_rk3_step_host, gpu_ibm_init, gpu_ibmnorm, gpu_ibm_diffcorr, gpu_forces, &
-            gpu_bottom, gpu_masscorr
+            gpu_bottom, gpu_masscorr, gpu_thermo_init, gpu_thermodynamics
 
   logical :: lgpu = .false.            !< namelist RUN switch (the only new option)
   type(c_ptr) :: handle = c_null_ptr
@@ -30,7 +30,8 @@ module modgpu
   ! field ids = enum udgpu_field
   integer(c_int), parameter :: F_U0 = 0, F_V0 = 1, F_W0 = 2, F_UM = 3, F_VM = 4, F_WM = 5, &
                                F_UP = 6, F_VP = 7, F_WP = 8, F_PRES0 = 9, F_P = 10, F_EKM = 11, &
-                               F_EKH = 12, F_RHS = 13, F_SV0 = 14, F_SVM = 15, F_SVP = 16, F_MOMFLUXB = 17
+                               F_EKH = 12, F_RHS = 13, F_SV0 = 14, F_SVM = 15, F_SVP = 16, F_MOMFLUXB = 17, &
+                               F_THL0 = 18, F_THLM = 19, F_THLP = 20
 
   type, bind(C) :: udgpu_cfg
     integer(c_int) :: abi_version
@@ -54,6 +55,7 @@ module modgpu
     real(c_double) :: e12min
     integer(c_int) :: device
     integer(c_int) :: flags
+    integer(c_int) :: iadv_thl
   end type udgpu_cfg
 
   interface
@@ -66,6 +68,24 @@ module modgpu
       type(udgpu_cfg), intent(in) :: cfg
       type(c_ptr), value :: uid
       type(c_ptr), intent(out) :: h
+    end function
+    integer(c_int) function udgpu_set_thermo(h, lbuoyancy, grav, thls, BCtopT, wttop, thl_top, BCbotT, wtsurf, thlpcar) &
+        bind(C, name="udgpu_set_thermo")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: lbuoyancy, BCtopT, BCbotT
+      real(c_double), value :: grav, thls, wttop, thl_top, wtsurf
+      real(c_double), intent(in) :: thlpcar(*)
+    end function
+    integer(c_int) function udgpu_thermodynamics(h) bind(C, name="udgpu_thermodynamics")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+    end function
+    integer(c_int) function udgpu_thermo_profile(h, which, host) bind(C, name="udgpu_thermo_profile")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: which
+      real(c_double), intent(inout) :: host(*)
     end function
     integer(c_int) function udgpu_finalize(h) bind(C, name="udgpu_finalize")
       import :: c_int, c_ptr
@@ -223,7 +243,7 @@ contains
   !> after initpois (src/program.f90:89): hand the grid, metrics and switches to the device library
   subroutine gpu_init
     use modglobal, only: itot, jtot, ktot, imax, jmax, kmax, ih, jh, kh, ihc, jhc, khc, nsv, dx, dy, dzf, dzh, &
-                         delta, BCxm, BCym, BCtopm, BCzp, ipoiss, iadv_mom, iadv_sv, lles, ltempeq, lmoist, &
+                         delta, BCxm, BCym, BCtopm, BCzp, ipoiss, iadv_mom, iadv_sv, iadv_thl, lles, ltempeq, lmoist, &
                          numol, prandtlmoli, Uinf, Vinf, e12min, ib, kb
     use modsubgriddata, only: lvreman, lsmagorinsky, loneeqn, prandtli, c_vreman, cs
     use modmpi, only: nprocx, nprocy, myidx, myidy, myid, comm3d, mpierr
@@ -238,7 +258,7 @@ contains
     dzh_c = dzh(kb:kb + ktot - 1 + kh)
     delta_c = delta(ib, kb:kb + ktot - 1 + kh)
 
-    c%abi_version = 1
+    c%abi_version = 2
     c%itot = itot; c%jtot = jtot; c%ktot = ktot
     c%imax = imax; c%jmax = jmax; c%kmax = kmax
     c%ih = ih; c%jh = jh; c%kh = kh
@@ -266,6 +286,7 @@ contains
     c%c_vreman = c_vreman; c%cs = cs; c%Uinf = Uinf; c%Vinf = Vinf; c%e12min = e12min
     c%device = -1          ! LOCAL_RANK (one rank per GPU)
     c%flags = 0
+    c%iadv_thl = iadv_thl
 
     if (nprocx*nprocy > 1) then
       if (myid == 0) call chk(udgpu_nccl_unique_id(uid), 'nccl_unique_id')
@@ -275,7 +296,36 @@ contains
       call chk(udgpu_init(c, c_null_ptr, handle), 'init')
     end if
     call gpu_push_state
+    if (ltempeq) call gpu_thermo_init
   end subroutine gpu_init
+
+  !> temperature, dry (ltempeq, lbuoyancy): namelist values and the radiative tendency profile go down once, thl0 / thlm
+  !! follow, and the first thermodynamics (src/modstartup.f90 calls it before the time loop) sets thvh for forces
+  subroutine gpu_thermo_init
+    use modglobal, only: lbuoyancy, grav, BCtopT, BCbotT, lmoist
+    use modfields, only: thl0, thlm, thlp, thlpcar
+    use modsurfdata, only: thls, wtsurf, wttop, thl_top
+    if (lmoist) then
+      write (0, *) 'ERROR: gpu_thermo_init: lmoist is outside the GPU path'
+      stop 1
+    end if
+    call chk(udgpu_set_thermo(handle, l2i(lbuoyancy), grav, thls, int(BCtopT, c_int), wttop, thl_top, int(BCbotT, c_int), &
+                              wtsurf, thlpcar), 'set_thermo')
+    call chk(udgpu_push(handle, F_THL0, 0_c_int, thl0), 'push thl0')
+    call chk(udgpu_push(handle, F_THLM, 0_c_int, thlm), 'push thlm')
+    call chk(udgpu_push(handle, F_THLP, 0_c_int, thlp), 'push thlp')
+    call chk(udgpu_thermodynamics(handle), 'thermodynamics')
+  end subroutine gpu_thermo_init
+  !> thermodynamics (src/modthermodynamics.f90:55, program.f90:212), dry: thl0av, thvh on the device; the host copies
+  !! of the two profiles are refreshed for the statistics
+  subroutine gpu_thermodynamics
+    use modglobal, only: ltempeq
+    use modfields, only: thl0av, thvh
+    if (.not. ltempeq) return
+    call chk(udgpu_thermodynamics(handle), 'thermodynamics')
+    call chk(udgpu_thermo_profile(handle, 0_c_int, thl0av), 'thl0av')
+    call chk(udgpu_thermo_profile(handle, 1_c_int, thvh), 'thvh')
+  end subroutine gpu_thermodynamics
 
   subroutine gpu_exit
     if (c_associated(handle)) call chk(udgpu_finalize(handle), 'finalize')
@@ -300,7 +350,8 @@ contains
 
   !> before writerestartfiles / fielddump / statistics (time-gated in program.f90:201-220)
   subroutine gpu_pull_state
-    use modfields, only: u0, v0, w0, um, vm, wm, pres0
+    use modglobal, only: ltempeq
+    use modfields, only: u0, v0, w0, um, vm, wm, pres0, thl0, thlm
     use modsubgriddata, only: ekm, ekh
     call chk(udgpu_pull(handle, F_U0, 0_c_int, u0), 'pull u0')
     call chk(udgpu_pull(handle, F_V0, 0_c_int, v0), 'pull v0')
@@ -311,6 +362,10 @@ contains
     call chk(udgpu_pull(handle, F_PRES0, 0_c_int, pres0), 'pull pres0')
     call chk(udgpu_pull(handle, F_EKM, 0_c_int, ekm), 'pull ekm')
     call chk(udgpu_pull(handle, F_EKH, 0_c_int, ekh), 'pull ekh')
+    if (ltempeq) then
+      call chk(udgpu_pull(handle, F_THL0, 0_c_int, thl0), 'pull thl0')
+      call chk(udgpu_pull(handle, F_THLM, 0_c_int, thlm), 'pull thlm')
+    end if
   end subroutine gpu_pull_state
 
   !> single-field variants for host add-ons that touch the tendencies between subgrid and poisson
@@ -371,19 +426,15 @@ contains
   !> forces (src/modforces.f90:46, neutral branch) on the resident tendencies; dpdxl/dpdyl (kb:ke+kh) are uploaded on
   !! every call (ktot+1 doubles each: negligible) so that fixuinf / time-dependent forcing on the host is picked up
   subroutine gpu_forces
-    use modglobal, only: lbuoyancy
     use modfields, only: dpdxl, dpdyl
-    if (lbuoyancy) then
-      write(0, *) 'gpu_forces: lbuoyancy is outside the GPU path'
-      stop 1
-    end if
+    ! lbuoyancy: the buoyancy term and thlpcar are applied by the library (udgpu_set_thermo, gpu_thermo_init)
     call chk(udgpu_set_forcing(handle, dpdxl, dpdyl), 'set_forcing')
     call chk(udgpu_forces(handle), 'forces')
   end subroutine
   !> hand modibm's local point lists to the device (call once after initibm, src/program.f90); the lists are the
   !! (n,3) integer arrays solid_info_*%solpts_loc / bound_info_*%bndpts_loc exactly as they lie in memory (layout 1)
   subroutine gpu_ibm_init
-    use modglobal, only: libm, nsv
+    use modglobal, only: libm, nsv, ltempeq
     use modibm, only: solid_info_u, solid_info_v, solid_info_w, solid_info_c, &
                       bound_info_u, bound_info_v, bound_info_w, bound_info_c
     integer(c_int) :: dummy(3)
@@ -396,7 +447,7 @@ contains
     call set_list(4_c_int, bound_info_u%nbndptsrank, bound_info_u%bndpts_loc)
     call set_list(5_c_int, bound_info_v%nbndptsrank, bound_info_v%bndpts_loc)
     call set_list(6_c_int, bound_info_w%nbndptsrank, bound_info_w%bndpts_loc)
-    if (nsv > 0) then
+    if (nsv > 0 .or. ltempeq) then
       call set_list(3_c_int, solid_info_c%nsolptsrank, solid_info_c%solpts_loc)
       call set_list(7_c_int, bound_info_c%nbndptsrank, bound_info_c%bndpts_loc)
     else
