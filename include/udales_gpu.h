@@ -203,6 +203,9 @@ int udgpu_masscorr(udgpu_t *h, double dt, int rk3step, double *udef, double *vde
 int udgpu_set_thermo(udgpu_t *h, int lbuoyancy, double grav, double thls, int BCtopT, double wttop, double thl_top,
                      int BCbotT, double wtsurf, const double *thlpcar);
 int udgpu_thermodynamics(udgpu_t *h);
+/* NAMSUBGRID lbuoycorr / Rigc: buoyancy correction of the Vreman eddy viscosity for stable stratification
+ * (src/modsubgrid.f90:332-354), active with lbuoyancy; applied by udgpu_closure / udgpu_subgrid */
+int udgpu_set_buoycorr(udgpu_t *h, int lbuoycorr, double Rigc);
 int udgpu_thermo_profile(udgpu_t *h, int which, double *host);
 
 /* ---- immersed-boundary masking (next tier; src/modibm.f90) ------------------------------- */

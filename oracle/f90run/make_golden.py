@@ -510,7 +510,7 @@ def _avexy_ibm_cb(it_, frame, vals, setters, kw_):
     vals[0].a[...] = aver
 
 
-def case_thermo(tag, shape=(8, 6, 7), BCtopT=1, wttop=-0.01, wtsurf=0.01, with_ibm=False, nsub=3):
+def case_thermo(tag, shape=(8, 6, 7), BCtopT=1, wttop=-0.01, wtsurf=0.01, with_ibm=False, nsub=3, lbuoycorr=False):
     """Temperature on the resident path, dry: advecc_2nd + diffc on thl0, bottom (BCbotm = 3 wfmneutral +
     fixed-flux temperature, src/modibm.f90:2033-2046), forces with buoyancy (src/modforces.f90:70-109), tstep_integrate,
     halos, boundary (BCtopT), thermodynamics (src/modthermodynamics.f90:55-121 incl. diagfld, fromztop, calc_halflev, calthv),
@@ -545,7 +545,7 @@ def case_thermo(tag, shape=(8, 6, 7), BCtopT=1, wttop=-0.01, wtsurf=0.01, with_i
              thl0h=fa(full), qt0h=fa(full), ql0=fa(full), ql0h=fa(full), thv0h=fa(tend), thv0=fa([(1, I), (1, J), (1, K + 1)]),
              th0av=fa(prof), thl0av=fa(prof), qt0av=fa(prof), ql0av=fa(prof), sv0av=fa([(1, K + 1), (1, 1)]),
              thvh=fa(prof), thvf=fa(prof), presf=fa(prof), presh=fa(prof), exnf=fa(prof), exnh=fa(prof), rhof=fa(prof),
-             thlpcar=fa(prof), dpdyl=fa(prof), libm=with_ibm, lconservativeibm=False, lwritefac=False)
+             thlpcar=fa(prof), dpdyl=fa(prof), libm=with_ibm, lconservativeibm=False, lwritefac=False, lbuoycorr=lbuoycorr)
     g["dthvdz"] = fa(tend)
     rng = np.random.default_rng(41)
     g["thlpcar"].a[...] = 1e-4 * rng.standard_normal(K + 1)
@@ -592,6 +592,7 @@ def case_thermo(tag, shape=(8, 6, 7), BCtopT=1, wttop=-0.01, wtsurf=0.01, with_i
     it.call("thermodynamics")
     out = {"zf": zf, "shape": np.array([I, J, K]), "xlen": 0.55 * I, "ylen": 0.45 * J, "BCtopT": BCtopT, "wttop": wttop, "thl_top": 289.5,
            "wtsurf": wtsurf, "thls": thls, "grav": g["grav"], "z0": 0.01, "fkar": 0.41, "with_ibm": int(with_ibm),
+           "lbuoycorr": int(lbuoycorr), "Rigc": g["rigc"],
            "thlpcar": np.array(g["thlpcar"].a), "dpdxl": np.array(g["dpdxl"].a), "dpdyl": np.array(g["dpdyl"].a)}
     if lists:
         for k_, v_ in lists.items():
@@ -610,6 +611,7 @@ def case_thermo(tag, shape=(8, 6, 7), BCtopT=1, wttop=-0.01, wtsurf=0.01, with_i
         it.call("subgrid")
         if s == 0:
             out["sub_thlp"] = np.array(g["thlp"].a, copy=True)
+            out["sub_ekm"] = np.array(g["ekm"].a, copy=True); out["sub_ekh"] = np.array(g["ekh"].a, copy=True)
         it.call("bottom")
         if s == 0:
             for k_, v_ in snapshot(w, ["up", "vp", "thlp"]).items():
@@ -646,6 +648,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "thermo":
         case_thermo("thermo_flux")
         case_thermo("thermo_value_ibm", shape=(8, 8, 6), BCtopT=2, wttop=0.0, wtsurf=-0.005, with_ibm=True)
+        case_thermo("thermo_buoycorr", shape=(6, 8, 8), lbuoycorr=True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "forces":
         case_forces("forces")
@@ -668,3 +671,4 @@ if __name__ == "__main__":
     case_thermo("thermo_value_ibm", shape=(8, 8, 6), BCtopT=2, wttop=0.0, wtsurf=-0.005, with_ibm=True)
     case_thermo("thermo_flux")
     case_thermo("thermo_value_ibm", shape=(8, 8, 6), BCtopT=2, wttop=0.0, wtsurf=-0.005, with_ibm=True)
+    case_thermo("thermo_buoycorr", shape=(6, 8, 8), lbuoycorr=True)

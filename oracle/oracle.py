@@ -86,6 +86,7 @@ def lib():
         L.orc_set_thermo.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                      C.c_int, C.c_double, C.c_void_p]
         L.orc_thermodynamics.argtypes = [C.c_void_p]
+        L.orc_set_buoycorr.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.orc_thermo_profile.restype = C.POINTER(C.c_double)
         L.orc_thermo_profile.argtypes = [C.c_void_p, C.c_char_p]
         _LIB = L
@@ -218,6 +219,7 @@ class Oracle:
         self.ltempeq = True
 
     def thermodynamics(self): self.L.orc_thermodynamics(self.h)
+    def set_buoycorr(self, lbuoycorr=True, Rigc=0.25): self.L.orc_set_buoycorr(self.h, int(lbuoycorr), Rigc)
 
     def thermo_profile(self, name):
         return np.ctypeslib.as_array(self.L.orc_thermo_profile(self.h, name.encode()), shape=(self.ktot + 1,))

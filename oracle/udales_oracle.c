@@ -57,8 +57,8 @@ struct orc {
   int *IIu, *IIv;             /* (itot, jtot, ktot+1), 1 = fluid (createmasks, src/modibm.f90:2103); NULL = all fluid */
   int *IIus, *IIvs;           /* fluid points per level, ktot+1 values */
   /* temperature (ltempeq, dry: lmoist = .false.) */
-  int ltempeq, lbuoyancy, BCtopT, BCbotT;
-  double grav, thls, wttop, thl_top, wtsurf;
+  int ltempeq, lbuoyancy, BCtopT, BCbotT, lbuoycorr;
+  double grav, thls, wttop, thl_top, wtsurf, Rigc;
   double *thl0, *thlm;        /* momentum-halo shape (alloc_z, src/modfields.f90:495-497) */
   double *thlp;               /* tendency shape (src/modfields.f90:453) */
   double *thl0h;              /* momentum-halo shape (:500); interior only is ever written */
@@ -609,6 +609,22 @@ void orc_closure(orc_t *o) {
           double bb = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
           if (bb < 1.e-8) F(ekm, i, j, k) = 0.;
           else F(ekm, i, j, k) = o->c.c_vreman * sqrt(bb / aa);
+        }
+      }
+    }
+    if (o->lbuoyancy && o->lbuoycorr) {   /* buoyancy correction of the Vreman model for stable stratification, :332-354 */
+      const double *thl0 = o->thl0, *dthvdz = o->dthvdz;
+      for (int k = 1; k <= o->ktot; k++) {
+        const int kp = k + 1, km = k - 1;
+        for (int j = 1; j <= o->jtot; j++) {
+          const int jp = j + 1;
+          for (int i = 1; i <= o->itot; i++) {
+            const int ip = i + 1;
+            const double du0dz = 0.5 * ((F(u0, i, j, kp) + F(u0, ip, j, kp)) - (F(u0, i, j, km) + F(u0, ip, j, km))) / (M(dzh, kp) + M(dzh, k));
+            const double dv0dz = 0.5 * ((F(v0, i, j, kp) + F(v0, i, jp, kp)) - (F(v0, i, j, km) + F(v0, i, jp, km))) / (M(dzh, kp) + M(dzh, k));
+            const double Rig = ((o->grav / F(thl0, i, j, k)) * T(dthvdz, i, j, k)) / (du0dz * du0dz + dv0dz * dv0dz + 1.e-10);
+            F(ekm, i, j, k) = F(ekm, i, j, k) * sqrt(1.0 - fmin(fmax(Rig, 0.0), o->Rigc) / o->Rigc);
+          }
         }
       }
     }
@@ -1547,6 +1563,7 @@ void orc_set_thermo(orc_t *o, int lbuoyancy, double grav, double thls, int BCtop
   o->BCtopT = BCtopT; o->wttop = wttop; o->thl_top = thl_top; o->BCbotT = BCbotT; o->wtsurf = wtsurf;
   for (int k = 0; k <= K; k++) o->thlpcar[k] = thlpcar ? thlpcar[k] : 0.;
 }
+void orc_set_buoycorr(orc_t *o, int lbuoycorr, double Rigc) { o->lbuoycorr = lbuoycorr; o->Rigc = Rigc; }   /* NAMSUBGRID, src/modsubgriddata.f90:41,44 */
 double *orc_thermo_profile(orc_t *o, const char *name) {
   if (!strcmp(name, "thl0av")) return o->thl0av;
   if (!strcmp(name, "thvh")) return o->thvh;

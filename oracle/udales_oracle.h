@@ -92,6 +92,9 @@ void orc_masscorr_get(orc_t *o, double *udef, double *vdef);
 void orc_set_thermo(orc_t *o, int lbuoyancy, double grav, double thls, int BCtopT, double wttop, double thl_top,
                     int BCbotT, double wtsurf, const double *thlpcar);
 void orc_thermodynamics(orc_t *o);
+/* lbuoycorr / Rigc (NAMSUBGRID): buoyancy correction of the Vreman eddy viscosity, src/modsubgrid.f90:332-354; reads the
+ * dthvdz of the last orc_thermodynamics */
+void orc_set_buoycorr(orc_t *o, int lbuoycorr, double Rigc);
 double *orc_thermo_profile(orc_t *o, const char *name);
 
 /* immersed boundary masking: kind 0-3 = solid_u,v,w,c ; 4-7 = fluid-boundary points u,v,w,c;

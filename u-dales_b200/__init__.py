@@ -33,7 +33,7 @@ EXPORTS = [
     "udgpu_poisson_solve", "udgpu_poisson_solve_resident", "udgpu_fillps", "udgpu_tderive",
     "udgpu_tstep_integrate", "udgpu_halos", "udgpu_boundary", "udgpu_divergence", "udgpu_substep",
     "udgpu_rk3_step_host", "udgpu_set_forcing", "udgpu_forces", "udgpu_set_bottom", "udgpu_bottom", "udgpu_set_masscorr", "udgpu_masscorr", "udgpu_ibm_set_points", "udgpu_ibm_commit", "udgpu_ibm_pull_mask", "udgpu_ibmnorm", "udgpu_ibm_diffcorr",
-    "udgpu_set_thermo", "udgpu_thermodynamics", "udgpu_thermo_profile",
+    "udgpu_set_thermo", "udgpu_thermodynamics", "udgpu_thermo_profile", "udgpu_set_buoycorr",
     "udgpu_profile_enable", "udgpu_profile_get", "udgpu_profile_reset", "udgpu_launch_count", "udgpu_stream", "udgpu_trace_dump",
 ]
 
@@ -121,6 +121,7 @@ def lib():
         L.udgpu_set_thermo.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
                                        C.c_void_p]
         L.udgpu_thermodynamics.argtypes = [C.c_void_p]
+        L.udgpu_set_buoycorr.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.udgpu_thermo_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.udgpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.udgpu_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
@@ -326,6 +327,7 @@ class UdalesGPU:
                                           None if a is None else a.ctypes.data))
 
     def thermodynamics(self): self._chk(self.L.udgpu_thermodynamics(self.h))
+    def set_buoycorr(self, lbuoycorr=True, Rigc=0.25): self._chk(self.L.udgpu_set_buoycorr(self.h, int(lbuoycorr), Rigc))
 
     def thermo_profile(self, name):
         out = np.empty(self.ktot + 1)

@@ -186,7 +186,7 @@ template <bool DIFF, bool ACC, bool LES, int NS>
 __global__ void __launch_bounds__(32 * SC_BY, 2) k_scalar_kappa_march(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
                                                                    const double *__restrict__ w0, const double *__restrict__ ekh,
                                                                    const double *__restrict__ sv, long long ssl, double *__restrict__ svp,
-                                                                   long long tsl) {
+                                                                   long long tsl, int pf) {
   const int lane = threadIdx.x;
   const int i = blockIdx.x * SC_WX + lane + 1;
   const int j = blockIdx.y * SC_BY + threadIdx.y + 1;
@@ -217,6 +217,14 @@ __global__ void __launch_bounds__(32 * SC_BY, 2) k_scalar_kappa_march(Geo g, con
   for (int n = 0; n < NS; n++)
     cz[n] = (k0 >= 2) ? kface(sm2[n], sm1[n], s0[n], sp1[n], wb, g.dzhci[k0 - 1], g.dzhci[k0], g.dzhci[k0 + 1], g.dzfc[k0]) : 0.0;
   for (int k = k0; k < k1; k++) {
+    if (pf > 0 && k + pf <= g.ktot) {   // planes pf levels ahead -> L2 (the kernel is latency-bound)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(u0 + m + pf * mk));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(v0 + m + pf * mk));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + m + (pf + 1) * mk));
+      if (DIFF && LES) asm volatile("prefetch.global.L2 [%0];" ::"l"(ekh + m + (pf + 1) * mk));
+#pragma unroll
+      for (int n = 0; n < NS; n++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + n * ssl + (pf + 2) * sk));
+    }
     const double ul = u0[m];
     const double ur = __shfl_down_sync(0xffffffffu, ul, 1);
     const double vl = v0[m], vr = v0[m + mj];

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) k_closure(Geo g, const double *__restrict
 // and to the oracle are FMA-contraction rounding only.  64 registers / 4 CTAs per SM is a measured optimum: 3 or 2 CTAs
 // with a two-level unrolled loop (more loads in flight per thread) ran 0.28 - 0.31 ms against 0.259 ms, 5 or 6 CTAs
 // spill and ran 0.40 - 0.52 ms (profiles/r2_ab6_closure.jsonl).
-template <int KC>
+template <int KC, int PF>
 __global__ void __launch_bounds__(256, 4) k_closure_vreman_march(Geo g, const double *__restrict__ u0, const double *__restrict__ v0,
                                                               const double *__restrict__ w0, double *__restrict__ ekm,
                                                               double *__restrict__ ekh, int halo, int rev) {
@@ -141,6 +141,11 @@ __global__ void __launch_bounds__(256, 4) k_closure_vreman_march(Geo g, const do
   double w_c = __ldg(pw), w_ip = __ldg(pw + 1), w_im = __ldg(pw - 1), w_jp = __ldg(pw + sj), w_jm = __ldg(pw - sj);
   for (int k = k0; k < k1; k++) {
     const int K = k + 1;
+    if (PF > 0 && k + PF <= g.ktot + 1) {   // pull the planes PF levels ahead into L2 while this level computes: the kernel is
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pu + PF * sk));   // latency-bound (ncu: long-scoreboard stalls, 33 % of DRAM),
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + PF * sk));   // 0.259 -> 0.245 ms at 256^3 with PF = 2 (profiles/r2_ab8_closure_pf.jsonl)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + PF * sk));
+    }
     const double u_ipjp = __ldg(pu + sj + 1), u_jp = __ldg(pu + sj), u_ipjm = __ldg(pu - sj + 1), u_jm = __ldg(pu - sj);
     const double v_ipjp = __ldg(pv + sj + 1), v_ip = __ldg(pv + 1), v_imjp = __ldg(pv + sj - 1), v_im = __ldg(pv - 1);
     const double uK_c = __ldg(pu + sk), uK_ip = __ldg(pu + sk + 1), vK_c = __ldg(pv + sk), vK_jp = __ldg(pv + sk + sj);

@@ -124,6 +124,30 @@ __global__ void k_thermo_final(int K, const double *__restrict__ sums /* [3][K+1
   *solid_val = s / zhtop;
 }
 
+// Buoyancy correction of the Vreman eddy viscosity for stable stratification (lbuoycorr, src/modsubgrid.f90:332-354), as a
+// pass over the interior after the closure kernel: ekm there is nu_t + numol and ekh = nu_t prandtli + numol prandtlmoli
+// (:356-360), so nu_t = ekm - numol is scaled by sqrt(1 - min(max(Rig, 0), Rigc) / Rigc) and both are rebuilt.  dthvdz is
+// calthv's (dry: centred difference of thl0, 0 at kb, floored at +-eps1; src/modthermodynamics.f90:213-235) evaluated in
+// place: thl0 has not changed since the last thermodynamics().
+__global__ void __launch_bounds__(256) k_vreman_buoycorr(Geo g, double grav, double Rigc, const double *__restrict__ u0, const double *__restrict__ v0,
+                                                         const double *__restrict__ thl0, double *__restrict__ ekm, double *__restrict__ ekh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const long long c = offF(g, i, j, k), sj = g.pi, sk = g.pk;
+  const double eps1 = 1.e-10;
+  double dth = k >= 2 ? (thl0[c + sk] - thl0[c - sk]) / (g.dzh[k + 1] + g.dzh[k]) : 0.;
+  if (fabs(dth) < eps1) dth = copysign(eps1, dth);
+  const double dzs = g.dzh[k + 1] + g.dzh[k];
+  const double du0dz = 0.5 * ((u0[c + sk] + u0[c + 1 + sk]) - (u0[c - sk] + u0[c + 1 - sk])) / dzs;
+  const double dv0dz = 0.5 * ((v0[c + sk] + v0[c + sj + sk]) - (v0[c - sk] + v0[c + sj - sk])) / dzs;
+  const double Rig = ((grav / thl0[c]) * dth) / (du0dz * du0dz + dv0dz * dv0dz + 1.e-10);
+  const double e = (ekm[c] - g.numol) * sqrt(1.0 - fmin(fmax(Rig, 0.0), Rigc) / Rigc);
+  ekh[c] = e * g.prandtli + g.numol * g.prandtlmoli;
+  ekm[c] = e + g.numol;
+}
+
 // advecc2nd_corr_liberal (src/modibm.f90:936-987) on a momentum-halo scalar: one thread per fluid-boundary point of c
 __global__ void k_ibm_advecc2nd_corr(Geo g, int n, const int *__restrict__ pts, const double *__restrict__ mk, const double *__restrict__ u0,
                                      const double *__restrict__ v0, const double *__restrict__ w0, const double *__restrict__ var,

@@ -168,6 +168,8 @@ struct udgpu {
   int mt_grid = 0;
   int sc_nsmax = 4;           // fields per scalar-tendency launch (UDGPU_SCALAR_NSMAX = 1..4)
   int sc_march = 1;           // kappa scalars: k-marching shuffle kernel (UDGPU_SCALAR_MARCH=0: one thread per cell)
+  int cl_pf = 2;              // marching closure: L2 prefetch two levels ahead (UDGPU_CLOSURE_PF=0: off)
+  int sc_pf = 0;              // marching kappa-scalar kernel: L2 prefetch distance in levels (UDGPU_SCALAR_PF)
   int cl_march = 1;           // Vreman closure: k-marching register-carry kernel (UDGPU_CLOSURE_MARCH=0: one thread per cell)
   int nsm = 148;
   // state
@@ -210,6 +212,8 @@ struct udgpu {
   // temperature, dry (thermo.cuh): namelist values of udgpu_set_thermo, per-level tables indexed by Fortran k
   bool thermo_set = false, lbuoyancy = false, thermo_valid = false, th_counts_valid = false, thlpcar_nonzero = false;
   int BCtopT = 1, BCbotT = 1;
+  bool lbuoycorr = false;      // NAMSUBGRID: buoyancy correction of the Vreman eddy viscosity (udgpu_set_buoycorr)
+  double Rigc = 0.25;
   double grav = 9.81, thls = 0., wttop = 0., thl_top = 0., wtsurf = 0.;
   Geo gT;                      // geometry whose "scalar" halo is the momentum halo: the scalar kernels on thl0 / thlm / thlp
   double *d_thlpcar = nullptr, *d_thl0av = nullptr, *d_thvh = nullptr, *d_th_part = nullptr, *d_th_sums = nullptr, *d_th_cnt = nullptr,
@@ -444,6 +448,8 @@ static int init_impl(udgpu *h, const udgpu_cfg *c, const void *nccl_uid, int nde
   if (h->P > 1) NC(ncclCommInitRank(&h->comm, h->P, *(const ncclUniqueId *)nccl_uid, h->rank));
 
   { const char *e = getenv("UDGPU_CLOSURE_MARCH"); if (e) h->cl_march = atoi(e); }
+  { const char *e = getenv("UDGPU_CLOSURE_PF"); if (e) h->cl_pf = atoi(e); }
+  { const char *e = getenv("UDGPU_SCALAR_PF"); if (e) h->sc_pf = atoi(e); }
   { const char *e = getenv("UDGPU_SCALAR_MARCH"); if (e) h->sc_march = atoi(e); }
   { const char *e = getenv("UDGPU_SCALAR_NSMAX"); if (e && atoi(e) >= 1 && atoi(e) <= 4) h->sc_nsmax = atoi(e); }
   if (c->flags & UDGPU_F_V1_KERNELS) h->cl_march = 0;
@@ -801,20 +807,29 @@ extern "C" int udgpu_closure(udgpu_t *h) {
   const Geo &g = h->g;
   ProfScope ps(h, PROF_CLOSURE);
   const dim3 gr = grid3(g, B3);
-  const int halo = h->fuse_halo ? 1 : 0;
+  // lbuoycorr rescales ekm after the closure kernel: its own halo / ghost writes would be stale, the generic closurebc runs
+  const bool buoycorr = h->lbuoycorr && h->lbuoyancy && h->thermo_set && h->cfg.lvreman && !h->cfg.lsmagorinsky;
+  const int halo = (h->fuse_halo && !buoycorr) ? 1 : 0;
   double **f = h->f;
   // model selection order of the reference: smagorinsky first, then vreman, else DNS (modsubgrid.f90:208,269,401)
   if (h->cfg.lsmagorinsky) k_closure<2><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
   else if (h->cfg.lvreman && h->cl_march > 0) {
     constexpr int KC = 16;
     const dim3 gm(gr.x, gr.y, (g.ktot + KC - 1) / KC);
-    k_closure_vreman_march<KC><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, h->fft_rev);
+    if (h->cl_pf > 0) k_closure_vreman_march<KC, 2><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, h->fft_rev);
+    else k_closure_vreman_march<KC, 0><<<gm, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo, h->fft_rev);
   }
   else if (h->cfg.lvreman) k_closure<1><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
   else k_closure<0><<<gr, B3, 0, h->st>>>(g, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_W0], f[UDGPU_EKM], f[UDGPU_EKH], halo);
   KCHECK();
   h->launches++;
   trace_mark(h, "closure");
+  if (buoycorr) {   // src/modsubgrid.f90:332-354
+    if (!h->thermo_valid) return set_err(UDGPU_ESTATE, "closure with lbuoycorr needs dthvdz: call udgpu_thermodynamics after thl0 changed (src/program.f90:212)");
+    k_vreman_buoycorr<<<gr, B3, 0, h->st>>>(g, h->grav, h->Rigc, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_THL0], f[UDGPU_EKM], f[UDGPU_EKH]);
+    KCHECK();
+    h->launches++;
+  }
   if (halo) {
     // closurebc's wraps and ghost levels were written by the closure kernel itself; a split x still needs its slab exchange
     if (h->P > 1) RET(halo_x_exchange(h, {f[UDGPU_EKM], f[UDGPU_EKH]}, g.ktot + 2 * g.kh));
@@ -923,7 +938,7 @@ static int launch_scalars(udgpu *h, bool acc) {
     }
     if (kappa && ADV && h->sc_march) {
       const dim3 gm((g.imax + SC_WX - 1) / SC_WX, (g.jmax + SC_BY - 1) / SC_BY, (g.ktot + SC_KC - 1) / SC_KC), bm(32, SC_BY);
-#define GM4(ACC, LES, NS) k_scalar_kappa_march<DIFF, ACC, LES, NS><<<gm, bm, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKH], sv, ssl, svp, tsl)
+#define GM4(ACC, LES, NS) k_scalar_kappa_march<DIFF, ACC, LES, NS><<<gm, bm, 0, h->st>>>(g, h->f[UDGPU_U0], h->f[UDGPU_V0], h->f[UDGPU_W0], h->f[UDGPU_EKH], sv, ssl, svp, tsl, h->sc_pf)
 #define GM3(ACC, LES) do { if (ns == 1) GM4(ACC, LES, 1); else if (ns == 2) GM4(ACC, LES, 2); else if (ns == 3) GM4(ACC, LES, 3); else GM4(ACC, LES, 4); } while (0)
       if (acc) { if (les) GM3(true, true); else GM3(true, false); }
       else { if (les) GM3(false, true); else GM3(false, false); }
@@ -2104,6 +2119,13 @@ extern "C" int udgpu_set_thermo(udgpu_t *h, int lbuoyancy, double grav, double t
   }
   h->thermo_set = true;
   h->thermo_valid = false;
+  return UDGPU_OK;
+}
+extern "C" int udgpu_set_buoycorr(udgpu_t *h, int lbuoycorr, double Rigc) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (lbuoycorr && !(Rigc > 0.)) return set_err(UDGPU_EINVAL, "Rigc must be positive");
+  if (lbuoycorr && !h->cfg.ltempeq) return set_err(UDGPU_EINVAL, "lbuoycorr needs cfg.ltempeq = 1");
+  h->lbuoycorr = lbuoycorr != 0; h->Rigc = Rigc;
   return UDGPU_OK;
 }
 extern "C" int udgpu_thermodynamics(udgpu_t *h) {

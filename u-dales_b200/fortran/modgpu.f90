@@ -77,6 +77,12 @@ module modgpu
       real(c_double), value :: grav, thls, wttop, thl_top, wtsurf
       real(c_double), intent(in) :: thlpcar(*)
     end function
+    integer(c_int) function udgpu_set_buoycorr(h, lbuoycorr, Rigc) bind(C, name="udgpu_set_buoycorr")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: lbuoycorr
+      real(c_double), value :: Rigc
+    end function
     integer(c_int) function udgpu_thermodynamics(h) bind(C, name="udgpu_thermodynamics")
       import :: c_int, c_ptr
       type(c_ptr), value :: h
@@ -305,12 +311,14 @@ contains
     use modglobal, only: lbuoyancy, grav, BCtopT, BCbotT, lmoist
     use modfields, only: thl0, thlm, thlp, thlpcar
     use modsurfdata, only: thls, wtsurf, wttop, thl_top
+    use modsubgriddata, only: lbuoycorr, Rigc
     if (lmoist) then
       write (0, *) 'ERROR: gpu_thermo_init: lmoist is outside the GPU path'
       stop 1
     end if
     call chk(udgpu_set_thermo(handle, l2i(lbuoyancy), grav, thls, int(BCtopT, c_int), wttop, thl_top, int(BCbotT, c_int), &
                               wtsurf, thlpcar), 'set_thermo')
+    call chk(udgpu_set_buoycorr(handle, l2i(lbuoycorr), Rigc), 'set_buoycorr')
     call chk(udgpu_push(handle, F_THL0, 0_c_int, thl0), 'push thl0')
     call chk(udgpu_push(handle, F_THLM, 0_c_int, thlm), 'push thlm')
     call chk(udgpu_push(handle, F_THLP, 0_c_int, thlp), 'push thlp')
