@@ -169,7 +169,7 @@ struct udgpu {
   int sc_nsmax = 4;           // fields per scalar-tendency launch (UDGPU_SCALAR_NSMAX = 1..4)
   int sc_march = 1;           // kappa scalars: k-marching shuffle kernel (UDGPU_SCALAR_MARCH=0: one thread per cell)
   int cl_pf = 2;              // marching closure: L2 prefetch two levels ahead (UDGPU_CLOSURE_PF=0: off)
-  int sc_pf = 0;              // marching kappa-scalar kernel: L2 prefetch distance in levels (UDGPU_SCALAR_PF)
+  int sc_pf = 2;              // marching kappa-scalar kernel: L2 prefetch distance in levels (UDGPU_SCALAR_PF)
   int cl_march = 1;           // Vreman closure: k-marching register-carry kernel (UDGPU_CLOSURE_MARCH=0: one thread per cell)
   int nsm = 148;
   // state
