@@ -154,6 +154,8 @@ def workload_config(args, world):
     what = {"channel": f"neutral periodic channel {I}x{J}x{K}, stencil+Poisson only, no IBM/scalars",
             "scalars": f"periodic channel {I}x{J}x{K} + 4 kappa-advected passive scalars",
             "ibm": f"periodic channel {I}x{J}x{K} + urban blocks (16x16x8 per 32x32 tile) masked by the IBM path",
+            "thermo": f"periodic channel {I}x{J}x{K} + urban blocks (IBM) + temperature equation with buoyancy, surface heat flux, bottom wall "
+                      "function, volume-flow forcing (the physics set of examples/102)",
             "poisson": f"Poisson solve only, {I}x{J}x{K}, rhs resident"}[args.workload]
     what += " (BASELINE config 2)" if (world == 1 and args.workload == "channel" and (I, J, K) == (256, 256, 256)) else \
             f" ({I * J * K // world} cells per GPU, x-slabs nprocx={world})"
@@ -312,7 +314,7 @@ def run_ours(args, rank, world):
     def make(I, J, K, nsv=0, on_device=False, workload="channel"):
         imax = I // world
         g = U.UdalesGPU(I, J, K, xlen=I / 2.0, ylen=J / 2.0, zf=(np.arange(K) + 0.5) * 0.5, device=dev,
-                        nprocx=world, myidx=rank, nccl_uid=fresh_uid(), nsv=nsv)
+                        nprocx=world, myidx=rank, nccl_uid=fresh_uid(), nsv=nsv, ltempeq=(workload == "thermo"))
         if on_device:
             init_state_on_device(g, torch, imax, J, K, 1234 + rank)
         else:
@@ -329,8 +331,18 @@ def run_ours(args, rank, world):
                 g.push(nm.replace("0", "m"), g.pull(nm))
             for n4 in range(nsv):
                 g.push("svm", g.pull("sv0", n4), n4)
-        if workload == "ibm":
+        if workload in ("ibm", "thermo"):
             g.ibm_set(urban_blocks(I, J, K, rank * imax, imax))
+        if workload == "thermo":
+            # examples/102: ltempeq, lbuoyancy, wtsurf = 0.01, wttop = -0.01, luvolflowr; stably stratified thl0 + noise
+            g.set_thermo(lbuoyancy=True, thls=288.0, BCtopT=1, wttop=-0.01, BCbotT=1, wtsurf=0.01)
+            g.set_bottom(0.01); g.set_masscorr(1.0, None)
+            rng = np.random.default_rng([11, rank])
+            th = np.zeros(g.shape("thl0"), order="F")
+            th[...] = 288.0 + 0.01 * np.arange(K + 2)[None, None, :] + 0.05 * rng.random(th.shape)
+            ek = np.full(g.shape("ekh"), 1.5e-5 / 0.71, order="F")
+            g.push("ekh", ek); g.push("thl0", th); g.halos(); g.boundary()
+            g.push("thlm", g.pull("thl0")); g.thermodynamics()
         g.dt = dt
         return g
 
@@ -529,7 +541,7 @@ def main():
     ap.add_argument("--no-1024", action="store_true", help="skip the north_star 1024^3 strong-scaling measurement")
     ap.add_argument("--size1024", type=int, default=1024, help=argparse.SUPPRESS)
     ap.add_argument("--grid", default="", help="explicit global grid I,J,K (e.g. 1024,1024,512 = BASELINE config 4) instead of the weak-scaling grid")
-    ap.add_argument("--workload", default="channel", choices=["channel", "scalars", "ibm", "poisson"],
+    ap.add_argument("--workload", default="channel", choices=["channel", "scalars", "ibm", "thermo", "poisson"],
                     help="channel = BASELINE config 2 (the headline); scalars = + 4 kappa scalars (config 5 style); "
                          "ibm = + urban blocks masked on the device (config 3 style); poisson = the solve alone (config 4 style)")
     args = ap.parse_args()

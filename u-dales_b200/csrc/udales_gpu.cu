@@ -19,6 +19,7 @@
 #include "poisson_v1.cuh"
 #include "poisson_fast.cuh"
 #include "zsolve_seg.cuh"
+#include "poisson_xline.cuh"
 #include "stencil_v1.cuh"
 #include "scalar_v1.cuh"
 #include "ibm.cuh"
@@ -117,6 +118,7 @@ struct udgpu {
   int zu = 8, fft_lanes = 32;
   int zseg = 1, zseg_L = 0;   // one-pass segmented z solve (k_zsolve_seg); UDGPU_ZSEG=0: streaming two-sweep kernel
   int fill_fused = -1;        // fillps evaluated inside the first forward transform (UDGPU_FILL_FUSED=0/1; default: set at init, see there)
+  int xline = 1;              // x transforms with a line's threads in neighbouring lanes (poisson_xline.cuh; UDGPU_XLINE=0: staged k_rfft_fast)
   int fft_rev = 1;            // consecutive kernels alternate their level direction for L2 reuse (UDGPU_FFT_REV=0: all upwards)
   double *d_zt = nullptr, *d_xd = nullptr, *d_yd = nullptr;
   int nxh = 0, nyh = 0;
@@ -1092,6 +1094,33 @@ static int rfft_fast(udgpu *h, int n, int inverse, const double *in, LineDesc di
   }
   return set_err(UDGPU_EINVAL, "no fast FFT for n=%d", n);
 }
+// x lines, threads of a line in neighbouring lanes (one GPU; the slab solve keeps the blocked / fused variants of k_rfft_fast)
+template <int R1, int R2>
+static int rfft_xline_launch(udgpu *h, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl) {
+  using C = XlineCfg<R1, R2>;
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k_rfft_xline<R1, R2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    CU(cudaFuncSetAttribute(k_rfft_xline<R1, R2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr = true;
+  }
+  const dim3 grid((di.nb1 + C::LPB - 1) / C::LPB, di.nb2);
+  if (inverse) k_rfft_xline<R1, R2, true><<<grid, C::NT, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac);
+  else k_rfft_xline<R1, R2, false><<<grid, C::NT, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac);
+  KCHECK();
+  h->launches++;
+  return UDGPU_OK;
+}
+static int rfft_xline(udgpu *h, int n, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl) {
+  switch (n) {
+    case 64: return rfft_xline_launch<8, 4>(h, inverse, in, di, out, dd, pl);
+    case 128: return rfft_xline_launch<8, 8>(h, inverse, in, di, out, dd, pl);
+    case 256: return rfft_xline_launch<16, 8>(h, inverse, in, di, out, dd, pl);
+    case 512: return rfft_xline_launch<16, 16>(h, inverse, in, di, out, dd, pl);
+    case 1024: return rfft_xline_launch<32, 16>(h, inverse, in, di, out, dd, pl);
+  }
+  return set_err(UDGPU_EINVAL, "no fast FFT for n=%d", n);
+}
 template <bool XDIR>
 static int rfft_fast_setattr(int n) {
   switch (n) {
@@ -1121,6 +1150,7 @@ static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, cons
   { const char *e = getenv("UDGPU_FILL_FUSED"); if (e) h->fill_fused = atoi(e) != 0; }
   { const char *e = getenv("UDGPU_FFT_LANES"); if (e && atoi(e) == 16) h->fft_lanes = 16; }
   { const char *e = getenv("UDGPU_FFT_REV"); if (e) h->fft_rev = atoi(e) != 0; }
+  { const char *e = getenv("UDGPU_XLINE"); if (e) h->xline = atoi(e) != 0; }
   h->fast_x = fast_len(g.itot);
   h->fast_y = fast_len(g.jtot);
   if (h->P > 1 && !(h->fast_x && h->fast_y))
@@ -1214,6 +1244,7 @@ static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *
     di = {1, pr, pp, g.jmax, g.ktot, rev};
     dd = di;
     if (out_halo) { dd.s1 = g.pi; dd.s2 = g.pk; }
+    if (h->fast_x && h->xline && !fs) return rfft_xline(h, g.itot, inverse, in, di, out, dd, h->px);
     if (h->fast_x) return rfft_fast<true>(h, g.itot, inverse, in, di, out, dd, h->px, nullptr, nullptr, fs);
     if (fs) return set_err(UDGPU_ESTATE, "FILL needs the register FFT");
     const size_t smem = (size_t)h->px.h * FFT_BP * sizeof(double2);
