@@ -33,13 +33,13 @@ def main():
     nx = ny = 2
     I = J = K = 64
     loc = 32
-    glob = {nm: np.zeros((I + 2, J + 2, K + 1)) for nm in ("u0", "v0", "w0", "pres0")}   # (0:I+1, 0:J+1, 1:K+1)
+    glob = {nm: np.zeros((I + 2, J + 2, K + 1)) for nm in ("u0", "v0", "w0", "pres0", "thl0")}   # (0:I+1, 0:J+1, 1:K+1)
     meta = None
     for px in range(nx):
         for py in range(ny):
             rec = records(os.path.join(D, f"initd00000267_{px:03d}_{py:03d}.102"))
             assert len(rec[0]) == loc * loc * K * 8 and len(rec[1]) == loc * loc * K * 5 * 4
-            for q, nm in enumerate(("u0", "v0", "w0", "pres0")):
+            for q, nm in enumerate(("u0", "v0", "w0", "pres0", "thl0")):
                 a = np.frombuffer(rec[2 + q], dtype="<f8").reshape((loc + 2, loc + 2, K + 1), order="F")
                 # interior of the rank; rank halos only where they are the global (periodic) halo
                 glob[nm][1 + px * loc:1 + (px + 1) * loc, 1 + py * loc:1 + (py + 1) * loc, :] = a[1:-1, 1:-1, :]
@@ -61,7 +61,7 @@ def main():
     # closure + substep parity run on real LES data instead of synthetic noise (tests/test_gpu_parity.py)
     m = 32
     i1, j1 = 17, 9
-    turb = {nm: np.ascontiguousarray(glob[nm][i1 - 1:i1 + m + 1, j1 - 1:j1 + m + 1, 0:m + 1]) for nm in ("u0", "v0", "w0", "pres0")}
+    turb = {nm: np.ascontiguousarray(glob[nm][i1 - 1:i1 + m + 1, j1 - 1:j1 + m + 1, 0:m + 1]) for nm in ("u0", "v0", "w0", "pres0", "thl0")}
     out2 = OUT.replace("ref_restart102_block", "ref_restart102_turb32")
     np.savez_compressed(out2, i0=i1, j0=j1, n=m, timee=meta[0], dt=meta[1], **turb)
     print("wrote", out2, os.path.getsize(out2) // 1024, "KiB")

@@ -102,3 +102,38 @@ def test_parity_on_the_reference_binarys_turbulent_field(kw):
         for nm in ("u0", "v0", "w0", "um"):
             assert rel(g.pull(nm), getattr(o, nm)) < 1e-11, (s, nm)
         assert g.divergence()[2] < 1e-12
+
+
+@pytest.mark.gpu
+def test_temperature_run_on_the_reference_binarys_turbulent_field(tmp_path):
+    """examples/102 is a temperature case (ltempeq, lbuoyancy, wtsurf = 0.01, wttop = -0.01): warm-start velocity AND thl0 of the
+    reference binary's own restart state (32^3 block), run three substeps with buoyancy, the surface heat flux and the wall
+    function on the device and in the oracle, write the rank file: thl0 is in it."""
+    from oracle.oracle import Oracle
+    fx = np.load(os.path.join(GOLD, "ref_restart102_turb32.npz"))
+    n = int(fx["n"])
+    zf = np.arange(n) + 0.5
+    g = U.UdalesGPU(n, n, n, xlen=float(n), ylen=float(n), zf=zf, ltempeq=True)
+    o = Oracle(n, n, n, xlen=float(n), ylen=float(n), zf=zf)
+    kw = dict(lbuoyancy=True, thls=288.0, BCtopT=1, wttop=-0.01, BCbotT=1, wtsurf=0.01)
+    g.set_thermo(**kw); o.set_thermo(**kw)
+    g.set_bottom(0.01); o.set_bottom(0.01)
+    R.load_into(g, {nm: fx[nm] for nm in ("u0", "v0", "w0", "pres0", "thl0")}, timee=float(fx["timee"]), dt=0.1)
+    for nm in ("u0", "v0", "w0", "um", "vm", "wm", "pres0", "thl0", "thlm", "ekm", "ekh"):
+        getattr(o, nm)[...] = g.pull(nm)
+    o.thermodynamics()
+    assert np.array_equal(g.pull("thl0")[1:-1, 1:-1, 1:-1], fx["thl0"][1:-1, 1:-1, :-1])
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    assert rel(g.thermo_profile("thvh"), o.thermo_profile("thvh")) < 1e-13
+    dt = 0.1
+    o.dt = g.dt = dt
+    for s in range(3):
+        o.substep(dt); g.substep(dt)
+        for nm in ("u0", "v0", "w0"):
+            assert rel(g.pull(nm), getattr(o, nm)) < 1e-11, (s, nm)
+        assert rel(g.pull("thl0")[:, :, 1:], o.thl0[:, :, 1:]) < 1e-13, s
+        assert g.divergence()[2] < 1e-12
+    assert np.abs(o.thl0[1:-1, 1:-1, 1:-1] - fx["thl0"][1:-1, 1:-1, :-1]).max() > 1e-3     # the temperature field moved
+    p = R.save_from(g, tmp_path, 268, 102, 100.6)
+    d = R.read_initd(p, n, n, n)
+    assert np.array_equal(d["thl0"], g.pull("thl0")[:, :, 1:])

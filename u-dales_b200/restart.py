@@ -92,7 +92,7 @@ def write_inits(path, sv0, timee):
     _write_records(path, [np.asarray(sv0, dtype="<f8"), struct.pack("<d", float(timee))])
 
 
-def assemble(directory, ntrun, expnr, itot, jtot, ktot, nprocx, nprocy, names=("u0", "v0", "w0", "pres0", "ekm")):
+def assemble(directory, ntrun, expnr, itot, jtot, ktot, nprocx, nprocy, names=("u0", "v0", "w0", "pres0", "ekm", "thl0")):
     """the files of an nprocx x nprocy reference run -> global arrays (itot+2, jtot+2, ktot+1) with the periodic /
     domain halo taken from the edge ranks (interior from every rank).  Returns (dict, timee, dt)."""
     imax, jmax = itot // nprocx, jtot // nprocy
@@ -118,15 +118,24 @@ def load_into(g, glob, timee=0.0, dt=0.0):
     level k = kb-1 is zero (never written by the reference either, src/modstartup.f90:1155-1176), halos() / boundary()
     re-establish the ghost cells, and um, vm, wm start as copies (src/modstartup.f90:1233-1244 after a warm start)."""
     imax, lo = g.imax, g.myidx * g.imax
-    for nm in ("u0", "v0", "w0", "pres0", "ekm"):
+    thermo = bool(g.cfg.ltempeq) and "thl0" in glob
+    for nm in ("u0", "v0", "w0", "pres0", "ekm") + (("thl0",) if thermo else ()):
         if nm not in glob:
             continue
         a = np.zeros(g.shape(nm), order="F")
         a[:, :, 1:] = glob[nm][lo:lo + imax + 2, :, :]
+        if nm == "thl0":
+            a[:, :, 0] = a[:, :, 1]       # thl0(kb-1) = thl0(kb), src/modstartup.f90:1208
         g.push(nm, a)
+    if thermo and "ekm" not in glob:
+        # boundary()'s fluxtop divides by ekh: the reference's startup has run closure by then; molecular values stand in
+        ek = np.full(g.shape("ekh"), float(g.cfg.numol) * float(g.cfg.prandtlmoli), order="F")
+        g.push("ekh", ek)
     g.halos(); g.boundary()
-    for nm in ("u0", "v0", "w0"):
+    for nm in ("u0", "v0", "w0") + (("thl0",) if thermo else ()):
         g.push(nm.replace("0", "m"), g.pull(nm))
+    if thermo:
+        g.thermodynamics()                # src/modstartup.f90 calls thermodynamics before the time loop
     g.dt = dt
     g.rk3step = 0
     return timee
@@ -135,7 +144,7 @@ def load_into(g, glob, timee=0.0, dt=0.0):
 def save_from(g, directory, ntrun, expnr, timee, extra=None):
     """write this rank's initd file (x-slab: myidy = 0) in the reference's layout; thl0, e120, qt0, ql0, ql0h are zeros
     (neutral run) unless given in `extra`"""
-    f = {nm: g.pull(nm)[:, :, 1:] for nm in ("u0", "v0", "w0", "pres0", "ekm")}
+    f = {nm: g.pull(nm)[:, :, 1:] for nm in ("u0", "v0", "w0", "pres0", "ekm") + (("thl0",) if g.cfg.ltempeq else ())}
     f.update(extra or {})
     os.makedirs(directory, exist_ok=True)
     path = os.path.join(directory, restart_name("d", ntrun, g.myidx, 0, expnr))
