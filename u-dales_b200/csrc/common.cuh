@@ -26,6 +26,7 @@ struct Geo {
   double Uinf, Vinf;
   int BCtopm, lles;
   int wrapx;             // 1: x is unsplit and kernels that own their halos write the periodic x images themselves
+  int xalt;              // 1: x-spectral slots between the two x transforms are aligned pairs (poisson_xline.cuh), not the packed order
 };
 
 // offset of Fortran element (i,j,k) in a momentum-halo array starting at k = 1-kh

@@ -435,8 +435,8 @@ __global__ void __launch_bounds__(128) k_zsolve(Geo g, int nxh, int nyh, double 
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i >= g.imax) return;
   const int K = g.ktot;
-  const int ig = g.i0g + i, jg = g.j0g + j;       // global packed slot (0-based) -> distinct-eigenvalue index
-  const int ix = (ig + 1) >> 1, jy = (jg + 1) >> 1;
+  const int ig = g.i0g + i, jg = g.j0g + j;       // global slot (0-based) -> distinct-eigenvalue index
+  const int ix = g.xalt ? (ig == 0 ? 0 : ig == 1 ? nxh - 1 : ig >> 1) : (ig + 1) >> 1, jy = (jg + 1) >> 1;
   const long long sk = (long long)g.imax * g.jmax, tk = (long long)nxh * nyh;
   double *xp = x + (long long)i + (long long)g.imax * j;
   const double *zp = zt + (long long)jy * nxh + ix;

@@ -15,6 +15,14 @@
 //   * the results leave in 8 / 16-byte stores straight from registers: consecutive lanes own consecutive output words.
 // The tile of a line in shared memory is padded by one word per R2 (pad(p) = p + p / R2) so that the pass-2 reads
 // (thread stride R2 words) fall into different banks.
+//
+// Spectral layout BETWEEN the two x passes.  The reference's packing [Re0, Re1, Im1, .., Re(n/2)] puts every complex
+// coefficient across a 16-byte boundary: 36 eight-byte stores / loads per thread, half a sector each (ncu: LSU data pipe
+// 69 % of its peak, the limiter of the first version of this kernel).  The work array is ours between the forward and
+// the inverse x pass, so the line is kept as aligned pairs instead: slots (0, 1) = (X0, X(n/2)) — both real — and slots
+// (2k, 2k+1) = (Re Xk, Im Xk), k = 1 .. n/2-1.  The y transforms treat every x slot as an independent column, and the z
+// solve only needs the slot -> eigenvalue map (Geo::xalt: slot 0 -> 0, slot 1 -> n/2, slots 2k, 2k+1 -> k; packed:
+// slot s -> (s+1)/2), so every number goes through the same arithmetic as before and the pressure is the same bits.
 #pragma once
 #include "common.cuh"
 #include "poisson_fast.cuh"
@@ -61,8 +69,17 @@ __global__ void __launch_bounds__(256, (R1 >= 32 ? 1 : 2)) k_rfft_xline(const do
       const int k = j + R2 * t;
       gx0[t] = gx1[t] = gy0[t] = gy1[t] = 0.;
       if (k <= H / 2 && act) {
-        if (k == 0) { gx0[t] = pin[0]; gy0[t] = pin[N - 1]; }
-        else { gx0[t] = pin[2 * k - 1]; gx1[t] = pin[2 * k]; gy0[t] = pin[2 * (H - k) - 1]; gy1[t] = pin[2 * (H - k)]; }
+        const double *sa = pin + 2 * k, *sb = pin + 2 * (H - k);     // aligned pairs (see the header): (X0, Xh) / (Re Xk, Im Xk)
+        if (al_in) {
+          const double2 a = *reinterpret_cast<const double2 *>(sa);
+          gx0[t] = a.x; gx1[t] = a.y;
+          if (k == 0) gy0[t] = a.y;
+          else { const double2 b = *reinterpret_cast<const double2 *>(sb); gy0[t] = b.x; gy1[t] = b.y; }
+        } else {
+          gx0[t] = sa[0]; gx1[t] = sa[1];
+          if (k == 0) gy0[t] = sa[1];
+          else { gy0[t] = sb[0]; gy1[t] = sb[1]; }
+        }
       }
     }
 #pragma unroll
@@ -126,7 +143,10 @@ __global__ void __launch_bounds__(256, (R1 >= 32 ? 1 : 2)) k_rfft_xline(const do
       if (k <= H / 2) {
         const double2 Zk = buf[SX(k)];
         if (k == 0) {
-          if (act) { pout[0] = (Zk.x + Zk.y) * fac; pout[N - 1] = (Zk.x - Zk.y) * fac; }   // (X0, Xh) both real
+          if (act) {   // (X0, Xh) both real: slots 0, 1
+            const double2 o = make_double2((Zk.x + Zk.y) * fac, (Zk.x - Zk.y) * fac);
+            if (al_out) *reinterpret_cast<double2 *>(pout) = o; else { pout[0] = o.x; pout[1] = o.y; }
+          }
         } else {
           const double2 Zc = cconj(buf[SX(H - k)]);
           const double2 E = make_double2(0.5 * (Zk.x + Zc.x), 0.5 * (Zk.y + Zc.y));
@@ -135,8 +155,10 @@ __global__ void __launch_bounds__(256, (R1 >= 32 ? 1 : 2)) k_rfft_xline(const do
           const double2 T = cmul(make_double2(0.5 * w.y, -0.5 * w.x), D);
           const double2 a = cadd(E, T), b = cconj(csub(E, T));
           if (act) {
-            pout[2 * k - 1] = a.x * fac; pout[2 * k] = a.y * fac;
-            pout[2 * (H - k) - 1] = b.x * fac; pout[2 * (H - k)] = b.y * fac;
+            const double2 oa = make_double2(a.x * fac, a.y * fac), ob = make_double2(b.x * fac, b.y * fac);
+            double *da = pout + 2 * k, *db = pout + 2 * (H - k);
+            if (al_out) { *reinterpret_cast<double2 *>(da) = oa; *reinterpret_cast<double2 *>(db) = ob; }
+            else { da[0] = oa.x; da[1] = oa.y; db[0] = ob.x; db[1] = ob.y; }
           }
         }
       }

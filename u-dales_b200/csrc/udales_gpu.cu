@@ -1171,6 +1171,7 @@ static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, cons
   KCHECK();
   CU(cudaStreamSynchronize(h->st));
   h->fast_z = true;
+  h->g.xalt = (h->P == 1 && h->fast_x && h->xline && !h->fill_fused) ? 1 : 0;
   return UDGPU_OK;
 }
 
@@ -1244,7 +1245,10 @@ static int fft_pass(udgpu *h, bool xdir, int inverse, const double *in, double *
     di = {1, pr, pp, g.jmax, g.ktot, rev};
     dd = di;
     if (out_halo) { dd.s1 = g.pi; dd.s2 = g.pk; }
-    if (h->fast_x && h->xline && !fs) return rfft_xline(h, g.itot, inverse, in, di, out, dd, h->px);
+    if (g.xalt) {   // both x passes of a solve use the line-local kernel and its aligned-pair spectral layout, or neither
+      if (fs) return set_err(UDGPU_ESTATE, "FILL and the line-local x transform are exclusive");
+      return rfft_xline(h, g.itot, inverse, in, di, out, dd, h->px);
+    }
     if (h->fast_x) return rfft_fast<true>(h, g.itot, inverse, in, di, out, dd, h->px, nullptr, nullptr, fs);
     if (fs) return set_err(UDGPU_ESTATE, "FILL needs the register FFT");
     const size_t smem = (size_t)h->px.h * FFT_BP * sizeof(double2);

@@ -34,7 +34,9 @@ k_zsolve_seg(Geo g, int nxh, int nyh, int nseg, double *__restrict__ x, const do
   const bool act = q0 < plane;
   const long long q = act ? q0 : plane - 1;
   const int i = (int)(q % g.imax), j = (int)(q / g.imax);
-  const int ix = (g.i0g + i + 1) >> 1, jy = (g.j0g + j + 1) >> 1;   // packed slot -> distinct eigenvalue
+  const int ig = g.i0g + i;
+  const int ix = g.xalt ? (ig == 0 ? 0 : ig == 1 ? nxh - 1 : ig >> 1) : (ig + 1) >> 1;   // x slot -> distinct eigenvalue
+  const int jy = (g.j0g + j + 1) >> 1;                                                   // packed y slot -> distinct eigenvalue
   const int k0 = s * L;
   double *xp = x + q + (long long)k0 * plane;
   const double *zp = zt + (long long)jy * nxh + ix + (long long)k0 * tk;
