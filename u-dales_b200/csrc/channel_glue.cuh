@@ -98,13 +98,15 @@ __global__ void k_masscorr_reduce(int K, const double *__restrict__ part, double
 // means with dzf weights over zh(ke+1) (src/modforces.f90:408-413).  fpend: a lazily pending forces() has to be part of
 // the tendency mean (its profile is uniform in x, y: the masked plane mean of it is the profile itself).
 // Writes def and the effective per-level table the fused tderive+integrate kernel subtracts: fe[k] = fpend*f[k] - def/rk3coef.
-__global__ void k_masscorr_final(int K, const double *__restrict__ vol, const double *__restrict__ cnt /* fluid points per level, K */,
+__global__ void __launch_bounds__(256) k_masscorr_final(int K, const double *__restrict__ vol, const double *__restrict__ cnt /* fluid points per level, K */,
                                  double cnt_ke, int unmask_k1, const double *__restrict__ dzf, double zhtop, double rk3coef, double flowrate,
                                  const double *__restrict__ f /* forcing table, index k */, int fpend, double *__restrict__ def_out,
                                  double *__restrict__ fe) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one block of 256 threads: a thread per level and a fixed shared-memory tree for the two dzf-weighted sums (a single
+  // thread walking the levels pays one dependent global load per level: ~90 us at K = 256)
+  __shared__ double sh1[256], sh2[256];
   double s1 = 0., s2 = 0.;
-  for (int k = 1; k <= K; k++) {
+  for (int k = threadIdx.x + 1; k <= K; k += blockDim.x) {
     double d = cnt[k - 1];
     if (k == 1 && unmask_k1) d = cnt_ke;                      // src/modmpi.f90:649-652
     double a = d == 0. ? -999. : vol[k - 1] / d, bm = d == 0. ? -999. : vol[K + k - 1] / d;
@@ -112,11 +114,17 @@ __global__ void k_masscorr_final(int K, const double *__restrict__ vol, const do
     s1 += a * dzf[k];
     s2 += bm * dzf[k];
   }
-  const double outflow = rk3coef * s1 / zhtop, old = s2 / zhtop;
+  sh1[threadIdx.x] = s1; sh2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o) { sh1[threadIdx.x] += sh1[threadIdx.x + o]; sh2[threadIdx.x] += sh2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const double outflow = rk3coef * sh1[0] / zhtop, old = sh2[0] / zhtop;
   const double def = flowrate - (outflow + old);
-  *def_out = def;
+  if (threadIdx.x == 0) *def_out = def;
   const double add = def * (1 / rk3coef);
-  for (int k = 0; k <= K + 1; k++) fe[k] = (fpend ? f[k] : 0.) - add;
+  for (int k = threadIdx.x; k <= K + 1; k += blockDim.x) fe[k] = (fpend ? f[k] : 0.) - add;
 }
 // up(i,j,k) = up(i,j,k) - fe(k) on the interior of one tendency (eager form of the masscorr / forces shift)
 __global__ void __launch_bounds__(256) k_tend_sub_table(Geo g, const double *__restrict__ fe, double *__restrict__ tp) {

@@ -69,20 +69,22 @@ __global__ void k_thl_top(Geo g, int mode, double flux, double val, const double
 //   slot 0: sum thl0 * mask_c     (diagfld: thl0av, avexy_ibm with IIc)
 //   slot 1: sum thl0              (the kb fallback of avexy_ibm when every cell of kb is solid, src/modmpi.f90:649-652)
 //   slot 2: sum thl0h * mask_w    (thvh = avexy_ibm(thv0h, IIw); thl0h(kb) = thls)
-constexpr int TH_NBLK = 32;
+constexpr int TH_NBLK = 64;
 __global__ void __launch_bounds__(256) k_thermo_partial(Geo g, double thls, const double *__restrict__ thl0, const double *__restrict__ mask_c,
                                                         const double *__restrict__ mask_w, double *__restrict__ part /* [3][K+1][TH_NBLK] */) {
   const int k = blockIdx.y + 1, b = blockIdx.x, K1 = g.ktot + 1;
-  const long long n = (long long)g.imax * g.jmax;
   double s0 = 0., s1 = 0., s2 = 0.;
-  for (long long q = (long long)b * blockDim.x + threadIdx.x; q < n; q += (long long)TH_NBLK * blockDim.x) {
-    const int j = (int)(q / g.imax) + 1, i = (int)(q - (long long)(j - 1) * g.imax) + 1;
-    const long long c = offF(g, i, j, k);
-    const double v = thl0[c];
-    s0 += v * (mask_c ? mask_c[c] : 1.0);
-    s1 += v;
-    const double vh = k == 1 ? thls : thl_half(g, thl0, c, k);
-    s2 += vh * (mask_w ? mask_w[c] : 1.0);
+  // block b takes rows j = b+1, b+1+TH_NBLK, ..; threads run along i (coalesced); the order of the additions is fixed
+  for (int j = b + 1; j <= g.jmax; j += TH_NBLK) {
+    const long long row = offF(g, 1, j, k);
+    for (int i = threadIdx.x; i < g.imax; i += blockDim.x) {
+      const long long c = row + i;
+      const double v = thl0[c];
+      s0 += v * (mask_c ? mask_c[c] : 1.0);
+      s1 += v;
+      const double vh = k == 1 ? thls : thl_half(g, thl0, c, k);
+      s2 += vh * (mask_w ? mask_w[c] : 1.0);
+    }
   }
   __shared__ double sh[3][256];
   sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
@@ -103,25 +105,36 @@ __global__ void k_thermo_reduce(int n, const double *__restrict__ part, double *
 }
 // profiles from the (cross-rank) sums: thl0av(k), thvh(k), k = 1 .. K+1 (tables indexed by k), and the value ibmnorm
 // gives solid temperature points, sum(thl0av(kb:ke) dzf(kb:ke)) / zh(ke+1) (src/modibm.f90:715).
-// cnt_c / cnt_w: fluid points per level of mask_c / mask_w over all ranks (IIcs, IIws).
-__global__ void k_thermo_final(int K, const double *__restrict__ sums /* [3][K+1] */, const double *__restrict__ cnt_c, const double *__restrict__ cnt_w,
-                               const double *__restrict__ dzf, double zhtop, double *__restrict__ thl0av, double *__restrict__ thvh,
-                               double *__restrict__ solid_val) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// cnt_c / cnt_w: fluid points per level of mask_c / mask_w over all ranks (IIcs, IIws).  One block of 256 threads: a
+// thread per level (a single thread walking the levels pays one dependent global load per level, ~100 us at K = 256),
+// the weighted sum through a fixed shared-memory tree.
+__global__ void __launch_bounds__(256) k_thermo_final(int K, const double *__restrict__ sums /* [3][K+1] */, const double *__restrict__ cnt_c,
+                                                      const double *__restrict__ cnt_w, const double *__restrict__ dzf, double zhtop,
+                                                      double *__restrict__ thl0av, double *__restrict__ thvh, double *__restrict__ solid_val) {
   const int K1 = K + 1;
   const double eps1 = 1.e-10;
-  for (int k = 1; k <= K1; k++) {
+  __shared__ double sh[256];
+  double ws = 0.;
+  for (int k = threadIdx.x + 1; k <= K1; k += blockDim.x) {
     double d = cnt_c[k - 1], a = sums[k - 1];
     if (k == 1 && d == 0.) { a = sums[K1 + k - 1]; d = cnt_c[K - 1]; }
-    thl0av[k] = d == 0. ? -999. : a / d;
-    double dw = cnt_w[k - 1];
+    const double av = d == 0. ? -999. : a / d;
+    thl0av[k] = av;
+    const double dw = cnt_w[k - 1];
     thvh[k] = dw == 0. ? -999. : sums[2 * K1 + k - 1] / dw;
+    if (k <= K) ws += av * dzf[k];
   }
-  thvh[1] = thl0av[1];                                   // :87  th0av(kb) (1 + 0 - 0), dry
-  if (fabs(thvh[2]) < eps1) thvh[2] = thl0av[2];         // :88-90
-  double s = 0.;
-  for (int k = 1; k <= K; k++) s += thl0av[k] * dzf[k];
-  *solid_val = s / zhtop;
+  sh[threadIdx.x] = ws;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    thvh[1] = thl0av[1];                                   // :87  th0av(kb) (1 + 0 - 0), dry
+    if (K1 >= 2 && fabs(thvh[2]) < eps1) thvh[2] = thl0av[2];   // :88-90
+    *solid_val = sh[0] / zhtop;
+  }
 }
 
 // Buoyancy correction of the Vreman eddy viscosity for stable stratification (lbuoycorr, src/modsubgrid.f90:332-354), as a

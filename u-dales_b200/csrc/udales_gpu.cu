@@ -2105,7 +2105,7 @@ extern "C" int udgpu_masscorr(udgpu_t *h, double dt, int rk3step, double *udef, 
       continue;
     }
     const int unmask = h->mc_cnt_host[c][0] == 0. ? 1 : 0;
-    k_masscorr_final<<<1, 32, 0, h->st>>>(K, h->d_mc_vol + (size_t)c * 2 * K, h->d_mc_cnt + (size_t)c * K, h->mc_cnt_host[c][K - 1], unmask, g.dzf, h->zh_top,
+    k_masscorr_final<<<1, 256, 0, h->st>>>(K, h->d_mc_vol + (size_t)c * 2 * K, h->d_mc_cnt + (size_t)c * K, h->mc_cnt_host[c][K - 1], unmask, g.dzf, h->zh_top,
                                           rk3coef, h->mc_flow[c], ft, fpend ? 1 : 0, h->d_mc_def + c, fe);
     KCHECK();
     h->launches++;
@@ -2184,7 +2184,7 @@ extern "C" int udgpu_thermodynamics(udgpu_t *h) {
   k_thermo_reduce<<<(3 * K1 + 127) / 128, 128, 0, h->st>>>(3 * K1, h->d_th_part, h->d_th_sums);
   KCHECK();
   if (h->P > 1) NC(ncclAllReduce(h->d_th_sums, h->d_th_sums, 3 * K1, ncclDouble, ncclSum, h->comm, h->st));   // MPI_ALLREDUCE of avexy_ibm, src/modmpi.f90:654
-  k_thermo_final<<<1, 32, 0, h->st>>>(K, h->d_th_sums, h->d_th_cnt, h->d_th_cnt + K1, g.dzf, h->zh_top, h->d_thl0av, h->d_thvh, h->d_th_solid);
+  k_thermo_final<<<1, 256, 0, h->st>>>(K, h->d_th_sums, h->d_th_cnt, h->d_th_cnt + K1, g.dzf, h->zh_top, h->d_thl0av, h->d_thvh, h->d_th_solid);
   KCHECK();
   h->launches += 3;
   h->thermo_valid = true;
