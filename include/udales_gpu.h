@@ -169,11 +169,16 @@ int udgpu_substep(udgpu_t *h, double *dt, int *rk3step, double dtmax, int ladapt
 int udgpu_set_forcing(udgpu_t *h, const double *dpdxl, const double *dpdyl);
 int udgpu_forces(udgpu_t *h);
 
-/* src/modibm.f90:1998 bottom with lbottom = .true., BCbotm = 3: wfmneutral(.., 91) (src/modwallfunctions.f90:307-349) on
+/* src/modibm.f90:1998 bottom with lbottom = .true.; BCbotm = 3: wfmneutral(.., 91) (src/modwallfunctions.f90:307-349) on
  * up, vp (k = kb) and momfluxb, plus the zero-flux scalar bottom correction (BCbots = 1, src/modibm.f90:2077-2091).
  * udgpu_set_bottom takes the namelist values (z0, fkar = von Karman constant); udgpu_bottom is the call of
  * src/program.f90:152; udgpu_substep calls it after subgrid once lbottom is set. */
 int udgpu_set_bottom(udgpu_t *h, int lbottom, int BCbotm, int BCbots, double z0, double fkar);
+/* BCbotm = 2 (the namelist default) / BCbotT = 2: wfuno cases 91 / 92 with the stability functions unom / unoh
+ * (src/modwallfunctions.f90:24-260).  z0h, prandtlturb (src/modglobal.f90:304), grav, thls = wall temperature; tcell = the
+ * uniform thl0(kb) of a run WITHOUT temperature equation (the reference evaluates the stability correction with
+ * thl0 = thlprof and thls even then); with ltempeq the resident thl0 is used. */
+int udgpu_set_wfuno(udgpu_t *h, double z0h, double prandtlturb, double grav, double thls, double tcell);
 int udgpu_bottom(udgpu_t *h);
 /* src/modforces.f90:328 masscorr, volume-flow branches (luvolflowr / lvvolflowr, :394-420 / :470-495): masked slab means of
  * the tendency and of um / vm (avexy_ibm, src/modmpi.f90:623-664; summed over all ranks), def = flowrate - (rk3coef <up> + <um>),
@@ -193,8 +198,8 @@ int udgpu_masscorr(udgpu_t *h, double dt, int rk3step, double *udef, double *vde
  * halos (xT_periodic / yT_periodic, src/modboundary.f90:541-556) and boundary (BCtopT = 1 fluxtop(.., ekh, wttop) / 2
  * valuetop(.., thl_top), :208-221).
  * udgpu_set_thermo takes the namelist values (PHYSICS: lbuoyancy; BC: BCtopT, BCbotT, wttop, thl_top, wtsurf; thls) and the
- * radiative tendency profile thlpcar(kb:ke+kh) (ktot+1 values, may be NULL = 0).  BCbotT = 2 (wfuno: stability functions)
- * and the facet heat fluxes of wallfunheat stay with the host.
+ * radiative tendency profile thlpcar(kb:ke+kh) (ktot+1 values, may be NULL = 0).  BCbotT = 2 needs udgpu_set_wfuno; the
+ * facet heat fluxes of wallfunheat stay with the host.
  * udgpu_thermodynamics is the call of src/program.f90:212 (src/modthermodynamics.f90:55-121, lmoist = .false.): slab means
  * thl0av (mask IIc) and thvh (thv0h = thl0h, mask IIw, kb / kb+1 overrides), summed over all ranks; the hydrostatic
  * pressure / exner / density profiles (fromztop) are not on the dry path and are not computed.  It must follow every

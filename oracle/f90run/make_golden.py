@@ -510,7 +510,7 @@ def _avexy_ibm_cb(it_, frame, vals, setters, kw_):
     vals[0].a[...] = aver
 
 
-def case_thermo(tag, shape=(8, 6, 7), BCtopT=1, wttop=-0.01, wtsurf=0.01, with_ibm=False, nsub=3, lbuoycorr=False):
+def case_thermo(tag, shape=(8, 6, 7), BCtopT=1, wttop=-0.01, wtsurf=0.01, with_ibm=False, nsub=3, lbuoycorr=False, wfuno=False):
     """Temperature on the resident path, dry: advecc_2nd + diffc on thl0, bottom (BCbotm = 3 wfmneutral +
     fixed-flux temperature, src/modibm.f90:2033-2046), forces with buoyancy (src/modforces.f90:70-109), tstep_integrate,
     halos, boundary (BCtopT), thermodynamics (src/modthermodynamics.f90:55-121 incl. diagfld, fromztop, calc_halflev, calthv),
@@ -531,15 +531,16 @@ def case_thermo(tag, shape=(8, 6, 7), BCtopT=1, wttop=-0.01, wtsurf=0.01, with_i
     it.load(os.path.join(SRC, "modforces.f90"), only=["forces"])
     it.load(os.path.join(SRC, "modibm.f90"), only=["bottom", "solid", "diffu_corr", "diffv_corr", "diffw_corr", "diffc_corr", "ibmnorm",
                                                    "advecc2nd_corr_liberal"])
-    it.load(os.path.join(SRC, "modwallfunctions.f90"), only=["wfmneutral"])
+    it.load(os.path.join(SRC, "modwallfunctions.f90"), only=["wfmneutral", "wfuno", "unom", "unoh"])
     it.call("initpois")
     full = [(0, I + 1), (0, J + 1), (0, K + 1)]
     tend = [(0, I + 1), (0, J + 1), (1, K + 1)]
     prof = [(1, K + 1)]
-    thls = 288.0
+    thls = 288.1 if wfuno else 288.0      # wfuno: wall temperature inside the range of thl0(kb): stable and unstable points
     g.update(ltempeq=True, lbuoyancy=True, bctopt=BCtopT, wttop=wttop, thl_top=289.5, wtsurf=wtsurf, wqsurf=0.0, thls=thls, thvs=thls,
              qts=0.0, ps=101500.0, pref0=1.e5, rd=287.04, rv=461.5, cp=1004., rlv=2.26e6, chi_half=0.5, khc=1,
-             lbottom=True, bcbotm=3, bcbott=1, bcbotq=1, bcbots=1, z0=0.01, z0h=0.000067, fkar=0.41,
+             lbottom=True, bcbotm=2 if wfuno else 3, bcbott=2 if wfuno else 1, bcbotq=1, bcbots=1, z0=0.01, z0h=0.000067, fkar=0.41,
+             prandtlturb=0.71, bctfluxa=0.0,
              dxh=fa([(1, I + 1)], g["dx"]), dxhi=fa([(1, I + 1)], 1. / g["dx"]),
              momfluxb=fa(full), tfluxb=fa(full), tau_x=fa(full), tau_y=fa(full), tau_z=fa(full), thl_flux=fa(full),
              thl0h=fa(full), qt0h=fa(full), ql0=fa(full), ql0h=fa(full), thv0h=fa(tend), thv0=fa([(1, I), (1, J), (1, K + 1)]),
@@ -592,7 +593,7 @@ def case_thermo(tag, shape=(8, 6, 7), BCtopT=1, wttop=-0.01, wtsurf=0.01, with_i
     it.call("thermodynamics")
     out = {"zf": zf, "shape": np.array([I, J, K]), "xlen": 0.55 * I, "ylen": 0.45 * J, "BCtopT": BCtopT, "wttop": wttop, "thl_top": 289.5,
            "wtsurf": wtsurf, "thls": thls, "grav": g["grav"], "z0": 0.01, "fkar": 0.41, "with_ibm": int(with_ibm),
-           "lbuoycorr": int(lbuoycorr), "Rigc": g["rigc"],
+           "lbuoycorr": int(lbuoycorr), "Rigc": g["rigc"], "wfuno": int(wfuno), "z0h": 0.000067, "prandtlturb": 0.71,
            "thlpcar": np.array(g["thlpcar"].a), "dpdxl": np.array(g["dpdxl"].a), "dpdyl": np.array(g["dpdyl"].a)}
     if lists:
         for k_, v_ in lists.items():
@@ -649,6 +650,7 @@ if __name__ == "__main__":
         case_thermo("thermo_flux")
         case_thermo("thermo_value_ibm", shape=(8, 8, 6), BCtopT=2, wttop=0.0, wtsurf=-0.005, with_ibm=True)
         case_thermo("thermo_buoycorr", shape=(6, 8, 8), lbuoycorr=True)
+        case_thermo("thermo_wfuno", shape=(8, 6, 6), wfuno=True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "forces":
         case_forces("forces")
@@ -672,3 +674,4 @@ if __name__ == "__main__":
     case_thermo("thermo_flux")
     case_thermo("thermo_value_ibm", shape=(8, 8, 6), BCtopT=2, wttop=0.0, wtsurf=-0.005, with_ibm=True)
     case_thermo("thermo_buoycorr", shape=(6, 8, 8), lbuoycorr=True)
+    case_thermo("thermo_wfuno", shape=(8, 6, 6), wfuno=True)

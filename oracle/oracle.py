@@ -72,6 +72,7 @@ def lib():
         L.orc_forces.argtypes = [C.c_void_p]
         L.orc_set_bottom.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
         L.orc_bottom.argtypes = [C.c_void_p]
+        L.orc_set_wfuno.argtypes = [C.c_void_p] + [C.c_double] * 5
         L.orc_momfluxb.restype = C.POINTER(C.c_double)
         L.orc_momfluxb.argtypes = [C.c_void_p]
         L.orc_set_masscorr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
@@ -227,6 +228,10 @@ class Oracle:
     # bottom -> wfmneutral (src/modibm.f90:1998, src/modwallfunctions.f90:307) and masscorr (src/modforces.f90:328) ----
     def set_bottom(self, z0, fkar=0.41, lbottom=True, BCbotm=3, BCbots=1):
         self.L.orc_set_bottom(self.h, int(lbottom), BCbotm, BCbots, z0, fkar)
+
+    def set_wfuno(self, z0h=0.00035, prandtlturb=0.71, grav=9.81, thls=288.0, tcell=288.0):
+        """parameters of the wall functions with stability correction (BCbotm = 2, BCbotT = 2)"""
+        self.L.orc_set_wfuno(self.h, z0h, prandtlturb, grav, thls, tcell)
 
     def bottom(self): self.L.orc_bottom(self.h)
 

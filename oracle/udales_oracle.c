@@ -59,6 +59,9 @@ struct orc {
   /* temperature (ltempeq, dry: lmoist = .false.) */
   int ltempeq, lbuoyancy, BCtopT, BCbotT, lbuoycorr;
   double grav, thls, wttop, thl_top, wtsurf, Rigc;
+  /* wfuno (BCbotm = 2 / BCbotT = 2): z0h, prandtlturb, gravity, wall temperature; tcell = the uniform thl0(kb) of a run
+   * without temperature equation (thl0 stays at thlprof there) */
+  double wf_z0h, wf_prandtlturb, wf_grav, wf_twall, wf_tcell;
   double *thl0, *thlm;        /* momentum-halo shape (alloc_z, src/modfields.f90:495-497) */
   double *thlp;               /* tendency shape (src/modfields.f90:453) */
   double *thl0h;              /* momentum-halo shape (:500); interior only is ever written */
@@ -1489,10 +1492,95 @@ void orc_set_bottom(orc_t *o, int lbottom, int BCbotm, int BCbots, double z0, do
   if (!o->momfluxb) o->momfluxb = zalloc(nF(o));
 }
 double *orc_momfluxb(orc_t *o) { return o->momfluxb; }
+/* unom / unoh: src/modwallfunctions.f90:226-260 / :176-223 (Uno 1995 stability functions) */
+static double unom(double logdz, double logzh, double sqdz, double Ribl0, double fkar2, double prandtlturb) {
+  const double b1 = 9.4, b2 = 4.7, dm = 7.4, dh = 5.3;
+  double Fm, Fh, cm, ch;
+  if (Ribl0 > 0.) { Fm = 1. / ((1. + b2 * Ribl0) * (1. + b2 * Ribl0)); Fh = Fm; }
+  else {
+    cm = (dm * fkar2) / (logdz * logdz) * b1 * sqdz;
+    ch = (dh * fkar2) / (logdz * logdz) * b1 * sqdz;
+    Fm = 1. - (b1 * Ribl0) / (1. + cm * sqrt(fabs(Ribl0)));
+    Fh = 1. - (b1 * Ribl0) / (1. + ch * sqrt(fabs(Ribl0)));
+  }
+  const double M = prandtlturb * logdz * sqrt(Fm) / Fh;
+  const double Ribl1 = Ribl0 - Ribl0 * prandtlturb * logzh / (prandtlturb * logzh + M);
+  if (Ribl1 > 0.) Fm = 1. / ((1. + b2 * Ribl1) * (1. + b2 * Ribl1));
+  else {
+    cm = (dm * fkar2) / (logdz * logdz) * b1 * sqdz;
+    Fm = 1. - (b1 * Ribl1) / (1. + cm * sqrt(fabs(Ribl1)));
+  }
+  return fkar2 / (logdz * logdz) * Fm;
+}
+static double unoh(double logdz, double logzh, double sqdz, double utangInt, double dT, double Ribl0, double fkar2, double prandtlturb) {
+  const double b1 = 9.4, b2 = 4.7, dm = 7.4, dh = 5.3;
+  double Fm, Fh, cm, ch;
+  if (Ribl0 > 0.) { Fm = 1. / ((1. + b2 * Ribl0) * (1. + b2 * Ribl0)); Fh = Fm; }
+  else {
+    cm = (dm * fkar2) / (logdz * logdz) * b1 * sqdz;
+    ch = (dh * fkar2) / (logdz * logdz) * b1 * sqdz;
+    Fm = 1. - (b1 * Ribl0) / (1. + cm * sqrt(fabs(Ribl0)));
+    Fh = 1. - (b1 * Ribl0) / (1. + ch * sqrt(fabs(Ribl0)));
+  }
+  double M = prandtlturb * logdz * sqrt(Fm) / Fh;
+  const double Ribl1 = Ribl0 - Ribl0 * prandtlturb * logzh / (prandtlturb * logzh + M);
+  if (Ribl1 > 0.) { Fm = 1. / ((1. + b2 * Ribl1) * (1. + b2 * Ribl1)); Fh = Fm; }
+  else {
+    cm = (dm * fkar2) / (logdz * logdz) * b1 * sqdz;
+    ch = (dh * fkar2) / (logdz * logdz) * b1 * sqdz;
+    Fm = 1. - (b1 * Ribl1) / (1. + cm * sqrt(fabs(Ribl1)));
+    Fh = 1. - (b1 * Ribl1) / (1. + ch * sqrt(fabs(Ribl1)));
+  }
+  M = prandtlturb * logdz * sqrt(Fm) / Fh;
+  const double dTrough = dT * 1. / (prandtlturb * logzh / M + 1.);
+  const double octh = sqrt(utangInt) * fkar2 / (logdz * logdz) * Fh / prandtlturb;
+  return octh * dTrough;
+}
+void orc_set_wfuno(orc_t *o, double z0h, double prandtlturb, double grav, double thls, double tcell) {
+  o->wf_z0h = z0h; o->wf_prandtlturb = prandtlturb; o->wf_grav = grav; o->wf_twall = thls; o->wf_tcell = tcell;
+}
 void orc_bottom(orc_t *o) {
   if (!o->lbottom) return;
   const int I = o->itot, J = o->jtot;
   const double *u0 = o->u0, *v0 = o->v0, *ekm = o->ekm, *ekh = o->ekh;
+  if (o->BCbotm == 2) {   /* wfuno(.., 91): src/modwallfunctions.f90:79-128; Tcell = thl0 (uniform without temperature equation) */
+    const int k = 1, km = 0;
+    const double fkar2 = o->fkar * o->fkar, umin = 0.0001, Twall = o->wf_twall, grav = o->wf_grav, pt = o->wf_prandtlturb;
+    const double delta = 0.5 * M(dzf, k);
+    const double logdz = log(delta / o->z0), logzh = log(o->z0 / o->wf_z0h), sqdz = sqrt(delta / o->z0);
+    const double dx = o->dx, dxhi = o->dxi;
+#define TC(i, j) (o->ltempeq ? F(o->thl0, i, j, k) : o->wf_tcell)
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++) {
+        const double utang1Int = F(u0, i, j, k);
+        const double utang2Int = (F(v0, i, j, k) + F(v0, i - 1, j, k) + F(v0, i, j + 1, k) + F(v0, i - 1, j + 1, k)) * 0.25;
+        const double utangInt = fmax(umin, (utang1Int * utang1Int + utang2Int * utang2Int));
+        const double dT = ((TC(i, j) + TC(i - 1, j)) - (Twall + Twall)) * 0.5;
+        const double Ribl0 = grav * delta * dT * 2 / ((Twall + Twall) * utangInt);
+        const double ctm = unom(logdz, logzh, sqdz, Ribl0, fkar2, pt);
+        const double dummy = fabs(utang1Int) * sqrt(utangInt) * ctm;
+        const double bcmomflux = copysign(dummy, utang1Int);
+        F(o->momfluxb, i, j, k) = F(o->momfluxb, i, j, k) + bcmomflux * M(dzfi, k);
+        const double emom = (M(dzf, km) * (F(ekm, i, j, k) * dx + F(ekm, i - 1, j, k) * dx) +
+                             M(dzf, k) * (F(ekm, i, j, km) * dx + F(ekm, i - 1, j, km) * dx)) * dxhi * M(dzhiq, k);
+        T(o->up, i, j, k) = T(o->up, i, j, k) + (F(u0, i, j, k) - F(u0, i, j, km)) * emom * M(dzhi, k) * M(dzfi, k) - bcmomflux * M(dzfi, k);
+      }
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++) {
+        const double utang1Int = (F(u0, i, j, k) + F(u0, i, j - 1, k) + F(u0, i + 1, j - 1, k) + F(u0, i + 1, j, k)) * 0.25;
+        const double utang2Int = F(v0, i, j, k);
+        const double utangInt = fmax(umin, (utang1Int * utang1Int + utang2Int * utang2Int));
+        const double dT = ((TC(i, j) + TC(i, j - 1)) - (Twall + Twall)) * 0.5;
+        const double Ribl0 = grav * delta * dT * 2 / ((Twall + Twall) * utangInt);
+        const double ctm = unom(logdz, logzh, sqdz, Ribl0, fkar2, pt);
+        const double dummy = fabs(utang2Int) * sqrt(utangInt) * ctm;
+        const double bcmomflux = copysign(dummy, utang2Int);
+        F(o->momfluxb, i, j, k) = F(o->momfluxb, i, j, k) + bcmomflux * M(dzfi, k);
+        const double eomm = (M(dzf, km) * (F(ekm, i, j, k) + F(ekm, i, j - 1, k)) + M(dzf, k) * (F(ekm, i, j, km) + F(ekm, i, j - 1, km))) * M(dzhiq, k);
+        T(o->vp, i, j, k) = T(o->vp, i, j, k) + (F(v0, i, j, k) - F(v0, i, j, km)) * eomm * M(dzhi, k) * M(dzfi, k) - bcmomflux * M(dzfi, k);
+      }
+#undef TC
+  }
   if (o->BCbotm == 3) {
     const int k = 1, km = 0;
     const double fkar2 = o->fkar * o->fkar, umin = 0.0001;
@@ -1524,6 +1612,23 @@ void orc_bottom(orc_t *o) {
         F(o->momfluxb, i, j, k) = F(o->momfluxb, i, j, k) + bcmomflux * M(dzfi, k);
         const double eomm = (M(dzf, km) * (F(ekm, i, j, k) + F(ekm, i, j - 1, k)) + M(dzf, k) * (F(ekm, i, j, km) + F(ekm, i, j - 1, km))) * M(dzhiq, k);
         T(o->vp, i, j, k) = T(o->vp, i, j, k) + (F(v0, i, j, k) - F(v0, i, j, km)) * eomm * M(dzhi, k) * M(dzfi, k) - bcmomflux * M(dzfi, k);
+      }
+  }
+  if (o->ltempeq && o->BCbotT == 2) {  /* wfuno(.., 92): fixed wall temperature, src/modwallfunctions.f90:131-161 */
+    const int k = 1;
+    const double fkar2 = o->fkar * o->fkar, umin = 0.0001, Twall = o->wf_twall, grav = o->wf_grav, pt = o->wf_prandtlturb;
+    const double delta = M(dzf, k) * 0.5;
+    const double logdz = log(delta / o->z0), logzh = log(o->z0 / o->wf_z0h), sqdz = sqrt(delta / o->z0);
+    for (int j = 1; j <= J; j++)
+      for (int i = 1; i <= I; i++) {
+        const double utang1Int = (F(u0, i, j, k) + F(u0, i + 1, j, k)) * 0.5;
+        const double utang2Int = (F(v0, i, j, k) + F(v0, i, j + 1, k)) * 0.5;
+        const double utangInt = fmax(umin, (utang1Int * utang1Int + utang2Int * utang2Int));
+        const double dT = (F(o->thl0, i, j, k) - Twall);
+        const double Ribl0 = grav * delta * dT / (Twall * utangInt);
+        const double bcTflux = unoh(logdz, logzh, sqdz, utangInt, dT, Ribl0, fkar2, pt);
+        T(o->thlp, i, j, k) = T(o->thlp, i, j, k) + 0.5 * (M(dzf, k - 1) * F(ekh, i, j, k) + M(dzf, k) * F(ekh, i, j, k - 1)) *
+                              (F(o->thl0, i, j, k) - F(o->thl0, i, j, k - 1)) * M(dzh2i, k) * M(dzfi, k) - bcTflux * M(dzfi, k);
       }
   }
   if (o->ltempeq && o->BCbotT == 1) {  /* fixed-flux bottom for temperature, modibm.f90:2033-2046 */

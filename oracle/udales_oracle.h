@@ -79,6 +79,9 @@ void orc_forces(orc_t *o);
  * (itot, jtot, ktot+1) ints, 1 = fluid, or NULL (no blocks). */
 void orc_set_bottom(orc_t *o, int lbottom, int BCbotm, int BCbots, double z0, double fkar);
 void orc_bottom(orc_t *o);
+/* BCbotm = 2 / BCbotT = 2: wfuno cases 91 / 92 with the stability functions unom / unoh (src/modwallfunctions.f90:24-260).
+ * tcell: the uniform thl0(kb) of a run without temperature equation (Tcell of case 91 then). */
+void orc_set_wfuno(orc_t *o, double z0h, double prandtlturb, double grav, double thls, double tcell);
 double *orc_momfluxb(orc_t *o);
 void orc_set_masscorr(orc_t *o, int luvolflowr, int lvvolflowr, double uflowrate, double vflowrate, const int *IIu, const int *IIv);
 void orc_masscorr(orc_t *o, double dt, int rk3step);

@@ -11,7 +11,7 @@ import pytest
 
 from oracle.oracle import Oracle
 
-GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith(("ref_ibm.npz", "ref_restart102_block.npz", "ref_restart102_turb32.npz", "ref_forces.npz", "ref_channelglue.npz", "ref_thermo_flux.npz", "ref_thermo_value_ibm.npz", "ref_thermo_buoycorr.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")) if not p.endswith(("ref_ibm.npz", "ref_restart102_block.npz", "ref_restart102_turb32.npz", "ref_forces.npz", "ref_channelglue.npz", "ref_thermo_flux.npz", "ref_thermo_value_ibm.npz", "ref_thermo_buoycorr.npz", "ref_thermo_wfuno.npz")))
 GOLD_IBM = os.path.join(os.path.dirname(__file__), "golden", "ref_ibm.npz")
 TOL = 2e-13      # same arithmetic order, no FMA on either side; FFT library and pow() rounding differ
 

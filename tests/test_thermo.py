@@ -14,7 +14,7 @@ import pytest
 
 from oracle.oracle import Oracle
 
-GOLD = [os.path.join(os.path.dirname(__file__), "golden", f"ref_thermo_{t}.npz") for t in ("flux", "value_ibm", "buoycorr")]
+GOLD = [os.path.join(os.path.dirname(__file__), "golden", f"ref_thermo_{t}.npz") for t in ("flux", "value_ibm", "buoycorr", "wfuno")]
 STATE = ("u0", "v0", "w0", "um", "vm", "wm", "pres0", "thl0", "thlm")
 
 
@@ -43,12 +43,17 @@ class OracleView:
 
 def setup(d, x):
     K = int(d["shape"][2])
+    wf = int(d["wfuno"]) if "wfuno" in d.files else 0
     x.set_thermo(lbuoyancy=True, grav=float(d["grav"]), thls=float(d["thls"]), BCtopT=int(d["BCtopT"]), wttop=float(d["wttop"]),
-                 thl_top=float(d["thl_top"]), BCbotT=1, wtsurf=float(d["wtsurf"]), thlpcar=d["thlpcar"])
+                 thl_top=float(d["thl_top"]), BCbotT=2 if wf else 1, wtsurf=float(d["wtsurf"]), thlpcar=d["thlpcar"])
     if int(d["lbuoycorr"]):
         x.set_buoycorr(True, float(d["Rigc"]))
     x.set_forcing(d["dpdxl"], d["dpdyl"])
-    x.set_bottom(float(d["z0"]), float(d["fkar"]))
+    if wf:       # BCbotm = 2 / BCbotT = 2: wfuno cases 91 / 92 (src/modwallfunctions.f90:24-260)
+        x.set_wfuno(z0h=float(d["z0h"]), prandtlturb=float(d["prandtlturb"]), grav=float(d["grav"]), thls=float(d["thls"]))
+        x.set_bottom(float(d["z0"]), float(d["fkar"]), BCbotm=2)
+    else:
+        x.set_bottom(float(d["z0"]), float(d["fkar"]))
     if int(d["with_ibm"]):
         x.ibm_set({k[4:]: d[k] for k in d.files if k.startswith("pts_")})
     ekm = np.full(d["in_u0"].shape, 1.5e-5, order="F")
@@ -111,7 +116,7 @@ def drive(d, x, tol, tol_p):
     assert np.abs(d["forces_wp"])[ti].max() > 1e-3
 
 
-@pytest.mark.parametrize("path", GOLD, ids=["flux", "value_ibm", "buoycorr"])
+@pytest.mark.parametrize("path", GOLD, ids=["flux", "value_ibm", "buoycorr", "wfuno"])
 def test_oracle_thermo_matches_reference_source(path):
     d = np.load(path)
     I, J, K = (int(v) for v in d["shape"])
@@ -132,7 +137,7 @@ F_NO_LAZY, F_V1, F_NO_HALO = 1, 8, 16
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("flags", [0, F_NO_LAZY, F_NO_HALO, F_V1])
-@pytest.mark.parametrize("path", GOLD, ids=["flux", "value_ibm", "buoycorr"])
+@pytest.mark.parametrize("path", GOLD, ids=["flux", "value_ibm", "buoycorr", "wfuno"])
 def test_cuda_thermo_matches_reference_source(path, flags):
     """the same staged comparison, CUDA library against the vectors from the executed reference source (no oracle in between)"""
     import udales_b200 as U
@@ -193,7 +198,7 @@ def test_thermo_state_errors():
     g.close()
     g = U.UdalesGPU(16, 16, 8, ltempeq=True)
     with pytest.raises(U.UdalesGPUError):
-        g.set_thermo(BCbotT=2)
+        g.set_thermo(BCbotT=3)
     g.set_thermo()
     g.advection(); g.subgrid()
     with pytest.raises(U.UdalesGPUError):
@@ -214,3 +219,31 @@ def test_buoycorr_golden_exercises_the_correction():
     o.set_buoycorr(False)
     o.thermodynamics(); o.advection(); o.subgrid()
     assert rel(o.ekm, d["sub_ekm"]) > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ltempeq", [False, True])
+def test_cuda_wfuno_bottom_tracks_oracle(ltempeq):
+    """BCbotm = 2 is the namelist default: wfuno case 91 (stability-corrected momentum wall function) in a run WITHOUT
+    temperature equation evaluates its Richardson number with the uniform thl0 = thlprof and thls (examples/999: lbottom, no
+    thls given) — and with ltempeq case 92 (BCbotT = 2) on top; six substeps against the oracle"""
+    from helpers import add_thermo, make_pair
+    shape = (32, 24, 20)
+    o, g = make_pair(*shape, ltempeq_gpu=ltempeq)
+    kw = dict(z0h=0.00035, prandtlturb=0.71, grav=9.81, thls=287.6 if ltempeq else -1.0, tcell=288.0)
+    o.set_wfuno(**kw); g.set_wfuno(**kw)
+    if ltempeq:
+        add_thermo(o, g, BCbotT=2, thls=287.6)
+    o.set_bottom(0.05, BCbotm=2); g.set_bottom(0.05, BCbotm=2)
+    dt = 0.02
+    o.dt = g.dt = dt
+    for s in range(6):
+        o.substep(dt); g.substep(dt)
+        for n in ("u0", "v0", "w0"):
+            assert rel(g.pull(n), getattr(o, n)) < 1e-11, (s, n)
+        if ltempeq:
+            assert rel(g.pull("thl0")[:, :, 1:], o.thl0[:, :, 1:]) < 1e-12, s
+    assert rel(g.pull("momfluxb")[1:-1, 1:-1, 1], o.momfluxb()[1:-1, 1:-1, 1]) < 1e-11
+    with pytest.raises(Exception):
+        g2 = make_pair(16, 16, 8)[1]
+        g2.set_bottom(0.05, BCbotm=2); g2.advection(); g2.subgrid(); g2.bottom()      # wfuno without its parameters

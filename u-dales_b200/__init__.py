@@ -32,7 +32,7 @@ EXPORTS = [
     "udgpu_tstep_update", "udgpu_advection", "udgpu_subgrid", "udgpu_closure", "udgpu_poisson",
     "udgpu_poisson_solve", "udgpu_poisson_solve_resident", "udgpu_fillps", "udgpu_tderive",
     "udgpu_tstep_integrate", "udgpu_halos", "udgpu_boundary", "udgpu_divergence", "udgpu_substep",
-    "udgpu_rk3_step_host", "udgpu_set_forcing", "udgpu_forces", "udgpu_set_bottom", "udgpu_bottom", "udgpu_set_masscorr", "udgpu_masscorr", "udgpu_ibm_set_points", "udgpu_ibm_commit", "udgpu_ibm_pull_mask", "udgpu_ibmnorm", "udgpu_ibm_diffcorr",
+    "udgpu_rk3_step_host", "udgpu_set_forcing", "udgpu_forces", "udgpu_set_bottom", "udgpu_set_wfuno", "udgpu_bottom", "udgpu_set_masscorr", "udgpu_masscorr", "udgpu_ibm_set_points", "udgpu_ibm_commit", "udgpu_ibm_pull_mask", "udgpu_ibmnorm", "udgpu_ibm_diffcorr",
     "udgpu_set_thermo", "udgpu_thermodynamics", "udgpu_thermo_profile", "udgpu_set_buoycorr",
     "udgpu_profile_enable", "udgpu_profile_get", "udgpu_profile_reset", "udgpu_launch_count", "udgpu_stream", "udgpu_trace_dump",
 ]
@@ -111,6 +111,7 @@ def lib():
         L.udgpu_forces.argtypes = [C.c_void_p]
         L.udgpu_set_bottom.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
         L.udgpu_bottom.argtypes = [C.c_void_p]
+        L.udgpu_set_wfuno.argtypes = [C.c_void_p] + [C.c_double] * 5
         L.udgpu_set_masscorr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
         L.udgpu_masscorr.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.udgpu_ibm_set_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
@@ -337,6 +338,10 @@ class UdalesGPU:
     # bottom -> wfmneutral (src/modibm.f90:1998, src/modwallfunctions.f90:307) and masscorr (src/modforces.f90:328) --------
     def set_bottom(self, z0, fkar=0.41, lbottom=True, BCbotm=3, BCbots=1):
         self._chk(self.L.udgpu_set_bottom(self.h, int(lbottom), BCbotm, BCbots, z0, fkar))
+
+    def set_wfuno(self, z0h=0.00035, prandtlturb=0.71, grav=9.81, thls=288.0, tcell=288.0):
+        """parameters of the wall functions with stability correction (BCbotm = 2, BCbotT = 2)"""
+        self._chk(self.L.udgpu_set_wfuno(self.h, z0h, prandtlturb, grav, thls, tcell))
 
     def bottom(self): self._chk(self.L.udgpu_bottom(self.h))
 

@@ -57,6 +57,95 @@ __global__ void __launch_bounds__(256) k_bottom_scalar(Geo g, const double *__re
   sp[t] = sp[t] + (0.5 * (g.dzf[kb - 1] * ekh[m] + g.dzf[kb] * ekh[m - g.pk]) * (s[c] - s[c - g.pkc]) * g.dzh2i[kb] + add) * g.dzfi[kb];
 }
 
+// ---- wfuno: wall functions with stability correction (Uno 1995 / Cai 2012), src/modwallfunctions.f90:24-260 ----------
+// unom (:226-260) and unoh (:176-223); logdz = log(delta / z0), logzh = log(z0 / z0h), sqdz = sqrt(delta / z0) come from
+// the host (the same libm the reference uses)
+__device__ __forceinline__ void uno_f(double Ri, double fkar2, double logdz, double sqdz, double &Fm, double &Fh) {
+  const double b1 = 9.4, b2 = 4.7, dm = 7.4, dh = 5.3;
+  if (Ri > 0.) { Fm = 1. / ((1. + b2 * Ri) * (1. + b2 * Ri)); Fh = Fm; }
+  else {
+    const double cm = (dm * fkar2) / (logdz * logdz) * b1 * sqdz, ch = (dh * fkar2) / (logdz * logdz) * b1 * sqdz;
+    const double sr = sqrt(fabs(Ri));
+    Fm = 1. - (b1 * Ri) / (1. + cm * sr);
+    Fh = 1. - (b1 * Ri) / (1. + ch * sr);
+  }
+}
+__device__ __forceinline__ double unom(double logdz, double logzh, double sqdz, double Ribl0, double fkar2, double pt) {
+  double Fm, Fh;
+  uno_f(Ribl0, fkar2, logdz, sqdz, Fm, Fh);
+  const double M = pt * logdz * sqrt(Fm) / Fh;
+  const double Ribl1 = Ribl0 - Ribl0 * pt * logzh / (pt * logzh + M);
+  uno_f(Ribl1, fkar2, logdz, sqdz, Fm, Fh);
+  return fkar2 / (logdz * logdz) * Fm;
+}
+__device__ __forceinline__ double unoh(double logdz, double logzh, double sqdz, double utangInt, double dT, double Ribl0, double fkar2, double pt) {
+  double Fm, Fh;
+  uno_f(Ribl0, fkar2, logdz, sqdz, Fm, Fh);
+  double M = pt * logdz * sqrt(Fm) / Fh;
+  const double Ribl1 = Ribl0 - Ribl0 * pt * logzh / (pt * logzh + M);
+  uno_f(Ribl1, fkar2, logdz, sqdz, Fm, Fh);
+  M = pt * logdz * sqrt(Fm) / Fh;
+  const double dTrough = dT * 1. / (pt * logzh / M + 1.);
+  const double octh = sqrt(utangInt) * fkar2 / (logdz * logdz) * Fh / pt;
+  return octh * dTrough;
+}
+struct WfunoPar { double fkar, logdz, logzh, sqdz, delta, grav, twall, pt, tcell; };
+// case 91 (:79-128): surface momentum flux on the plane k = kb.  thl0 == nullptr: no temperature equation, Tcell = tcell
+__global__ void __launch_bounds__(256) k_bottom_wfuno_mom(Geo g, WfunoPar w, const double *__restrict__ u0, const double *__restrict__ v0,
+                                                          const double *__restrict__ thl0, const double *__restrict__ ekm, double *__restrict__ up,
+                                                          double *__restrict__ vp, double *__restrict__ momfluxb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const int k = 1, km = 0;
+  const long long c = offF(g, i, j, k), t = offT(g, i, j, k), sj = g.pi, sk = g.pk;
+  const double fkar2 = w.fkar * w.fkar, umin = 0.0001, Twall = w.twall;
+  const double dzfk = g.dzf[k], dzfkm = g.dzf[km], dzfik = g.dzfi[k], dzhik = g.dzhi[k], dzhiqk = g.dzhiq[k];
+  const double tc = thl0 ? thl0[c] : w.tcell;
+  double mf = momfluxb[c];
+  {
+    const double ut1 = u0[c];
+    const double ut2 = (v0[c] + v0[c - 1] + v0[c + sj] + v0[c - 1 + sj]) * 0.25;
+    const double utang = fmax(umin, (ut1 * ut1 + ut2 * ut2));
+    const double dT = ((tc + (thl0 ? thl0[c - 1] : w.tcell)) - (Twall + Twall)) * 0.5;
+    const double Ribl0 = w.grav * w.delta * dT * 2 / ((Twall + Twall) * utang);
+    const double ctm = unom(w.logdz, w.logzh, w.sqdz, Ribl0, fkar2, w.pt);
+    const double bcmomflux = copysign(fabs(ut1) * sqrt(utang) * ctm, ut1);
+    mf = mf + bcmomflux * dzfik;
+    const double emom = (dzfkm * (ekm[c] * g.dx + ekm[c - 1] * g.dx) + dzfk * (ekm[c - sk] * g.dx + ekm[c - 1 - sk] * g.dx)) * g.dxi * dzhiqk;
+    up[t] = up[t] + (ut1 - u0[c - sk]) * emom * dzhik * dzfik - bcmomflux * dzfik;
+  }
+  {
+    const double ut1 = (u0[c] + u0[c - sj] + u0[c + 1 - sj] + u0[c + 1]) * 0.25;
+    const double ut2 = v0[c];
+    const double utang = fmax(umin, (ut1 * ut1 + ut2 * ut2));
+    const double dT = ((tc + (thl0 ? thl0[c - sj] : w.tcell)) - (Twall + Twall)) * 0.5;
+    const double Ribl0 = w.grav * w.delta * dT * 2 / ((Twall + Twall) * utang);
+    const double ctm = unom(w.logdz, w.logzh, w.sqdz, Ribl0, fkar2, w.pt);
+    const double bcmomflux = copysign(fabs(ut2) * sqrt(utang) * ctm, ut2);
+    mf = mf + bcmomflux * dzfik;
+    const double eomm = (dzfkm * (ekm[c] + ekm[c - sj]) + dzfk * (ekm[c - sk] + ekm[c - sj - sk])) * dzhiqk;
+    vp[t] = vp[t] + (ut2 - v0[c - sk]) * eomm * dzhik * dzfik - bcmomflux * dzfik;
+  }
+  momfluxb[c] = mf;
+}
+// case 92 (:131-161): surface temperature flux for a wall at fixed temperature (BCbotT = 2)
+__global__ void __launch_bounds__(256) k_bottom_wfuno_thl(Geo g, WfunoPar w, const double *__restrict__ u0, const double *__restrict__ v0,
+                                                          const double *__restrict__ thl0, const double *__restrict__ ekh, double *__restrict__ thlp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > g.imax || j > g.jmax) return;
+  const int k = 1;
+  const long long c = offF(g, i, j, k), t = offT(g, i, j, k), sj = g.pi, sk = g.pk;
+  const double fkar2 = w.fkar * w.fkar, umin = 0.0001, Twall = w.twall;
+  const double ut1 = (u0[c] + u0[c + 1]) * 0.5, ut2 = (v0[c] + v0[c + sj]) * 0.5;
+  const double utang = fmax(umin, (ut1 * ut1 + ut2 * ut2));
+  const double dT = (thl0[c] - Twall);
+  const double Ribl0 = w.grav * w.delta * dT / (Twall * utang);
+  const double bcTflux = unoh(w.logdz, w.logzh, w.sqdz, utang, dT, Ribl0, fkar2, w.pt);
+  thlp[t] = thlp[t] + 0.5 * (g.dzf[k - 1] * ekh[c] + g.dzf[k] * ekh[c - sk]) * (thl0[c] - thl0[c - sk]) * g.dzh2i[k] * g.dzfi[k] - bcTflux * g.dzfi[k];
+}
+
 // ---- masscorr ---------------------------------------------------------------------------------------------------
 // Masked plane sums in a fixed order (reproducible run to run): block b of level k sums its strided share of the
 // plane, k_masscorr_finish adds the nblk partials in index order.  slot = 2*comp + (0: tendency, 1: m-field).

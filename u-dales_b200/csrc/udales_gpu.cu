@@ -194,7 +194,9 @@ struct udgpu {
   bool has_forcing = false, forces_pending = false;
   // bottom -> wfmneutral (src/modibm.f90:1998, src/modwallfunctions.f90:307) and masscorr (src/modforces.f90:328)
   bool lbottom = false;
-  int BCbots = 1;
+  int BCbots = 1, BCbotm = 3;
+  bool wf_set = false;         // udgpu_set_wfuno: z0h, prandtlturb, grav, thls, tcell for BCbotm = 2 / BCbotT = 2
+  double wf_z0h = 0., wf_pt = 0.71, wf_grav = 9.81, wf_twall = 0., wf_tcell = 0.;
   double z0 = 0., fkar = 0.41;
   bool mc_on[2] = {false, false};        // luvolflowr, lvvolflowr
   double mc_flow[2] = {0., 0.};          // uflowrate, vflowrate
@@ -203,7 +205,7 @@ struct udgpu {
   bool mc_counts_valid = false;
   bool mc_pending = false;               // the uniform shift of masscorr is folded into the next tderive+integrate (tables d_fxe, d_fye)
   bool mc_forces_folded = false;         // ... and those tables already contain a pending forces()
-  double zh_top = 0.;
+  double zh_top = 0., dzf_kb = 0.;   // zh(ke+1), dzf(kb)
   // immersed boundary (src/modibm.f90): point lists, masks
   int ibm_n[8] = {};
   int *ibm_pts[8] = {};
@@ -515,6 +517,7 @@ static int init_impl(udgpu *h, const udgpu_cfg *c, const void *nccl_uid, int nde
   g.dzfc = MP(tDZFC); g.dzfci = MP(tDZFCI); g.dzhci = MP(tDZHCI);
 
   for (int k = 1; k <= K; k++) h->zh_top += c->dzf[k];   // zh(ke+1), src/modglobal.f90:747-749
+  h->dzf_kb = c->dzf[1];
   // ---- fields ----
   const size_t nF = (size_t)g.pi * g.pj * (K + 2 * g.kh), nT = (size_t)g.pi * g.pj * (K + g.kh);
   const size_t nR = (size_t)g.imax * g.jmax * K;
@@ -2002,11 +2005,18 @@ extern "C" int udgpu_forces(udgpu_t *h) {
 // bottom -> wfmneutral case 91 (src/modibm.f90:1998-2100, src/modwallfunctions.f90:307-349)
 extern "C" int udgpu_set_bottom(udgpu_t *h, int lbottom, int BCbotm, int BCbots, double z0, double fkar) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
-  if (lbottom && BCbotm != 3) return set_err(UDGPU_EINVAL, "BCbotm=%d: only the neutral wall function (3, wfmneutral) is on the resident path", BCbotm);
+  if (lbottom && BCbotm != 3 && BCbotm != 2) return set_err(UDGPU_EINVAL, "BCbotm=%d: wall function (2, wfuno) or neutral wall function (3, wfmneutral)", BCbotm);
   if (lbottom && h->cfg.nsv > 0 && BCbots != 1) return set_err(UDGPU_EINVAL, "BCbots=%d: only the zero-flux scalar bottom (1) exists in the reference (src/modibm.f90:2092-2095)", BCbots);
   if (lbottom && !(z0 > 0.)) return set_err(UDGPU_EINVAL, "z0 must be positive");
-  h->lbottom = lbottom != 0; h->BCbots = BCbots; h->z0 = z0; h->fkar = fkar;
+  h->lbottom = lbottom != 0; h->BCbots = BCbots; h->BCbotm = BCbotm; h->z0 = z0; h->fkar = fkar;
   if (h->lbottom && !h->f[UDGPU_MOMFLUXB]) RET(dev_alloc(h, (void **)&h->f[UDGPU_MOMFLUXB], h->cnt[UDGPU_MOMFLUXB] * sizeof(double)));
+  return UDGPU_OK;
+}
+extern "C" int udgpu_set_wfuno(udgpu_t *h, double z0h, double prandtlturb, double grav, double thls, double tcell) {
+  if (!h) return set_err(UDGPU_ESTATE, "null handle");
+  if (!(z0h > 0.) || !(prandtlturb > 0.) || thls == 0.) return set_err(UDGPU_EINVAL, "z0h, prandtlturb must be positive and thls non-zero");
+  h->wf_z0h = z0h; h->wf_pt = prandtlturb; h->wf_grav = grav; h->wf_twall = thls; h->wf_tcell = tcell;
+  h->wf_set = true;
   return UDGPU_OK;
 }
 extern "C" int udgpu_bottom(udgpu_t *h) {
@@ -2018,10 +2028,26 @@ extern "C" int udgpu_bottom(udgpu_t *h) {
   double **f = h->f;
   ProfScope ps(h, PROF_MOM);
   const dim3 gr((g.imax + B3.x - 1) / B3.x, (g.jmax + B3.y - 1) / B3.y, 1);
-  k_bottom_wfmneutral<<<gr, B3, 0, h->st>>>(g, h->z0, h->fkar, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_EKM], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_MOMFLUXB]);
+  WfunoPar wp;
+  memset(&wp, 0, sizeof(wp));
+  if (h->BCbotm == 2 || (h->cfg.ltempeq && h->thermo_set && h->BCbotT == 2)) {
+    if (!h->wf_set) return set_err(UDGPU_ESTATE, "BCbotm = 2 / BCbotT = 2 (wfuno) need udgpu_set_wfuno (z0h, prandtlturb, grav, thls)");
+    const double delta = 0.5 * h->dzf_kb;
+    wp.fkar = h->fkar; wp.delta = delta; wp.logdz = log(delta / h->z0); wp.logzh = log(h->z0 / h->wf_z0h); wp.sqdz = sqrt(delta / h->z0);
+    wp.grav = h->wf_grav; wp.twall = h->wf_twall; wp.pt = h->wf_pt; wp.tcell = h->wf_tcell;
+  }
+  if (h->BCbotm == 2)   // wfuno(.., 91), src/modibm.f90:2024
+    k_bottom_wfuno_mom<<<gr, B3, 0, h->st>>>(g, wp, f[UDGPU_U0], f[UDGPU_V0], h->cfg.ltempeq ? f[UDGPU_THL0] : nullptr, f[UDGPU_EKM], f[UDGPU_UP], f[UDGPU_VP],
+                                              f[UDGPU_MOMFLUXB]);
+  else
+    k_bottom_wfmneutral<<<gr, B3, 0, h->st>>>(g, h->z0, h->fkar, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_EKM], f[UDGPU_UP], f[UDGPU_VP], f[UDGPU_MOMFLUXB]);
   KCHECK();
   h->launches++;
-  if (h->cfg.ltempeq && h->thermo_set) {   // BCbotT = 1: fixed temperature flux wtsurf (src/modibm.f90:2033-2046)
+  if (h->cfg.ltempeq && h->thermo_set && h->BCbotT == 2) {   // wfuno(.., 92): wall at fixed temperature thls (src/modibm.f90:2047)
+    k_bottom_wfuno_thl<<<gr, B3, 0, h->st>>>(g, wp, f[UDGPU_U0], f[UDGPU_V0], f[UDGPU_THL0], f[UDGPU_EKH], f[UDGPU_THLP]);
+    KCHECK();
+    h->launches++;
+  } else if (h->cfg.ltempeq && h->thermo_set) {   // BCbotT = 1: fixed temperature flux wtsurf (src/modibm.f90:2033-2046)
     k_bottom_scalar<<<gr, B3, 0, h->st>>>(h->gT, f[UDGPU_EKH], f[UDGPU_THL0], 0, f[UDGPU_THLP], 0, -h->wtsurf);
     KCHECK();
     h->launches++;
@@ -2132,7 +2158,7 @@ extern "C" int udgpu_set_thermo(udgpu_t *h, int lbuoyancy, double grav, double t
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
   if (!h->cfg.ltempeq) return set_err(UDGPU_EINVAL, "udgpu_set_thermo needs cfg.ltempeq = 1 (thl0, thlm, thlp are allocated at init)");
   if (BCtopT != 1 && BCtopT != 2) return set_err(UDGPU_EINVAL, "BCtopT=%d: flux (1) / value (2) only (src/modboundary.f90:208-221)", BCtopT);
-  if (BCbotT != 1) return set_err(UDGPU_EINVAL, "BCbotT=%d: only the fixed-flux bottom (1) is on the resident path (2 = wfuno stays with the host)", BCbotT);
+  if (BCbotT != 1 && BCbotT != 2) return set_err(UDGPU_EINVAL, "BCbotT=%d: fixed flux (1) or wall function at fixed temperature (2, wfuno)", BCbotT);
   RET(flush_pending(h));
   const int K = h->g.ktot;
   if (!h->d_thvh) {

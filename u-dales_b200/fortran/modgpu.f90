@@ -69,6 +69,11 @@ module modgpu
       type(c_ptr), value :: uid
       type(c_ptr), intent(out) :: h
     end function
+    integer(c_int) function udgpu_set_wfuno(h, z0h, prandtlturb, grav, thls, tcell) bind(C, name="udgpu_set_wfuno")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h
+      real(c_double), value :: z0h, prandtlturb, grav, thls, tcell
+    end function
     integer(c_int) function udgpu_set_thermo(h, lbuoyancy, grav, thls, BCtopT, wttop, thl_top, BCbotT, wtsurf, thlpcar) &
         bind(C, name="udgpu_set_thermo")
       import :: c_int, c_ptr, c_double
@@ -310,12 +315,15 @@ contains
   subroutine gpu_thermo_init
     use modglobal, only: lbuoyancy, grav, BCtopT, BCbotT, lmoist
     use modfields, only: thl0, thlm, thlp, thlpcar
-    use modsurfdata, only: thls, wtsurf, wttop, thl_top
+    use modglobal, only: prandtlturb, kb
+    use modfields, only: thlprof
+    use modsurfdata, only: thls, wtsurf, wttop, thl_top, z0h
     use modsubgriddata, only: lbuoycorr, Rigc
     if (lmoist) then
       write (0, *) 'ERROR: gpu_thermo_init: lmoist is outside the GPU path'
       stop 1
     end if
+    call chk(udgpu_set_wfuno(handle, z0h, prandtlturb, grav, thls, thlprof(kb)), 'set_wfuno')   ! BCbotT = 2 reads it
     call chk(udgpu_set_thermo(handle, l2i(lbuoyancy), grav, thls, int(BCtopT, c_int), wttop, thl_top, int(BCbotT, c_int), &
                               wtsurf, thlpcar), 'set_thermo')
     call chk(udgpu_set_buoycorr(handle, l2i(lbuoycorr), Rigc), 'set_buoycorr')
@@ -475,13 +483,17 @@ contains
       end if
     end subroutine set_list
   end subroutine
-  !> bottom (src/modibm.f90:1998, program.f90:152): wfmneutral case 91 + the zero-flux scalar bottom on the resident
-  !! tendencies.  The namelist values go down once (first call); BCbotm must be 3 (neutral wall function)
+  !> bottom (src/modibm.f90:1998, program.f90:152): wfuno case 91 (BCbotm = 2, the default) or wfmneutral case 91
+  !! (BCbotm = 3), the temperature bottom (BCbotT = 1 flux / 2 wfuno case 92) and the zero-flux scalar bottom on the resident
+  !! tendencies.  The namelist values go down once (first call)
   subroutine gpu_bottom
-    use modglobal, only: lbottom, BCbotm, BCbots, fkar
-    use modsurfdata, only: z0
+    use modglobal, only: lbottom, BCbotm, BCbots, fkar, grav, prandtlturb, kb
+    use modsurfdata, only: z0, z0h, thls
+    use modfields, only: thlprof
     logical, save :: first = .true.
     if (first) then
+      ! wfuno's stability correction: wall temperature thls; without temperature equation thl0 stays at thlprof
+      call chk(udgpu_set_wfuno(handle, z0h, prandtlturb, grav, thls, thlprof(kb)), 'set_wfuno')
       call chk(udgpu_set_bottom(handle, l2i(lbottom), int(BCbotm, c_int), int(BCbots, c_int), z0, fkar), 'set_bottom')
       first = .false.
     end if
