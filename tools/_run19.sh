@@ -1,0 +1,8 @@
+python -m pytest tests/test_multigpu.py -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/r2_pytest_mgpu2_final.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+$TR bench.py --gpus 2 --no-cpu > gpurun_out/r2_bench_final_n2.json 2> gpurun_out/r2_bench_final_n2.err
+tail -c 300 gpurun_out/r2_bench_final_n2.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r2_bench_final_n2.json').read().strip().split('\n')[-1])
+print(d['value'], d['ms_per_step'], d['parity']['ok'], d['grid1024']['value'], d['grid1024']['ms_per_step'])"
