@@ -25,13 +25,17 @@ __global__ void k_ibm_mask_solid(Geo g, int n, const int *__restrict__ pts, doub
   mk[offF(g, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2])] = 0.;
 }
 
-// solid() without mask (:762-770)
-__global__ void k_ibm_solid_mom(Geo g, int n, const int *__restrict__ pts, double *__restrict__ var, double *__restrict__ rhs) {
+// solid() without mask (:762-770).  pend != nullptr: a per-level table (forces / masscorr, index k) is still to be
+// subtracted from this tendency inside the fused tderive+integrate kernel; the solid point gets the table value so that
+// the subtraction leaves exactly the 0 the reference stores (x - x), and every other reader of the tendency in between
+// (fillps: differences within a level) sees all points of a level carrying the same offset.
+__global__ void k_ibm_solid_mom(Geo g, int n, const int *__restrict__ pts, double *__restrict__ var, double *__restrict__ rhs,
+                                const double *__restrict__ pend) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const int i = pts[3 * p], j = pts[3 * p + 1], k = pts[3 * p + 2];
   var[offF(g, i, j, k)] = 0.;
-  rhs[offT(g, i, j, k)] = 0.;
+  rhs[offT(g, i, j, k)] = pend ? pend[k] : 0.;
 }
 // solid() with mask on scalar-halo arrays (:772-822); blockIdx.y = scalar field
 __global__ void k_ibm_solid_scalar(Geo g, int n, const int *__restrict__ pts, const double *__restrict__ mk, double *__restrict__ var,

@@ -1997,7 +1997,8 @@ extern "C" int udgpu_forces(udgpu_t *h) {
   }
   // with IBM masking the order matters (ibmnorm zeroes the tendencies of solid points after forces, src/program.f90:158,171)
   h->forces_pending = true;
-  if (h->libm || (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION)) return forces_now(h);
+  // IBM masking keeps the lazy form too: ibmnorm gives solid points the pending table value (k_ibm_solid_mom)
+  if (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION) return forces_now(h);
   return UDGPU_OK;
 }
 
@@ -2140,7 +2141,7 @@ extern "C" int udgpu_masscorr(udgpu_t *h, double dt, int rk3step, double *udef, 
   h->mc_forces_folded = fpend;
   // ibmnorm zeroes the tendencies of solid points AFTER masscorr (src/program.f90:169,171): with IBM masking, or when
   // every call is eager, the shift is applied now
-  if (h->libm || (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION)) RET(forces_now(h));
+  if (h->cfg.flags & UDGPU_F_NO_LAZY_FUSION) RET(forces_now(h));
   if (udef || vdef) {
     double d[2];
     CU(cudaMemcpyAsync(d, h->d_mc_def, sizeof(d), cudaMemcpyDeviceToHost, h->st));
@@ -2279,7 +2280,7 @@ extern "C" int udgpu_ibm_pull_mask(udgpu_t *h, int m, double *host) {
 extern "C" int udgpu_ibm_diffcorr(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
   if (!h->libm) return UDGPU_OK;
-  RET(flush_pending(h));
+  RET(flush_pending(h, true));   // additive corrections at fluid points commute with a pending per-level table
   RET(materialize_zero_tend(h));
   const Geo &g = h->g;
   double **f = h->f;
@@ -2304,15 +2305,22 @@ extern "C" int udgpu_ibm_diffcorr(udgpu_t *h) {
 extern "C" int udgpu_ibmnorm(udgpu_t *h) {
   if (!h) return set_err(UDGPU_ESTATE, "null handle");
   if (!h->libm) return UDGPU_OK;
-  RET(flush_pending(h));
+  // forces() after masscorr() is not the reference's order: apply both now instead of guessing which table holds what
+  if (h->mc_pending && h->forces_pending && !h->mc_forces_folded) RET(forces_now(h));
+  RET(flush_pending(h, true));
   RET(materialize_zero_tend(h));
   const Geo &g = h->g;
   double **f = h->f;
   ProfScope ps(h, PROF_MOM);
   const int *n = h->ibm_n;
   const int vm[3] = {UDGPU_UM, UDGPU_VM, UDGPU_WM}, vp[3] = {UDGPU_UP, UDGPU_VP, UDGPU_WP};
+  // pending per-level tables (subtracted later inside the fused tderive+integrate kernel): masscorr's tables carry a
+  // pending forces() as well (or zeros for a component without flow-rate forcing); w has no table (forces: wp(kb) = 0 only)
+  const double *pend[3] = {nullptr, nullptr, nullptr};
+  if (h->mc_pending) { pend[0] = h->d_fxe; pend[1] = h->d_fye; }
+  else if (h->forces_pending) { pend[0] = h->d_fx; pend[1] = h->d_fy; }
   for (int c = 0; c < 3; c++)
-    if (n[c]) { k_ibm_solid_mom<<<(n[c] + 127) / 128, 128, 0, h->st>>>(g, n[c], h->ibm_pts[c], f[vm[c]], f[vp[c]]); KCHECK(); h->launches++; }
+    if (n[c]) { k_ibm_solid_mom<<<(n[c] + 127) / 128, 128, 0, h->st>>>(g, n[c], h->ibm_pts[c], f[vm[c]], f[vp[c]], pend[c]); KCHECK(); h->launches++; }
   if (h->cfg.ltempeq) {   // :714-722: solid(.., thlm, thlp, sum(thl0av dzf) / zh(ke+1), .., mask_c), then advecc2nd_corr_liberal(thl0, thlp)
     if (!h->thermo_valid) return set_err(UDGPU_ESTATE, "ibmnorm with ltempeq needs thl0av: call udgpu_thermodynamics after thl0 changed (src/program.f90:212)");
     if (n[3]) {
