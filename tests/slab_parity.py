@@ -75,6 +75,11 @@ def run_case(U, Oracle, kind, shape, world, rank, dev, uid, flags=0, nsub=6, str
         from helpers import add_thermo
         add_thermo(o, g, slab=(U.slab_of, world, rank))
         o.set_bottom(0.01); g.set_bottom(0.01)
+        # pressure-gradient forcing + volume-flow correction over the IBM masks: both stay lazily pending through ibmnorm
+        prof = -1e-3 * (1.0 + 0.1 * np.arange(K + 1))
+        o.set_forcing(prof, 0.1 * prof); g.set_forcing(prof, 0.1 * prof)
+        IIu = np.asfortranarray((o.ibm_mask(0)[1:-1, 1:-1, 1:K + 2] != 0.0).astype(np.int32))
+        o.set_masscorr(1.0, None, IIu, None); g.set_masscorr(1.0, None)
     dt = 0.02
     o.dt = g.dt = dt
     for s in range(nsub):

@@ -549,3 +549,16 @@ def test_x_transform_with_line_local_threads_is_bitwise_neutral(shape, monkeypat
     q0 = g2.pull("p")
     assert np.array_equal(p1, p0)
     assert np.array_equal(interior(q1), interior(q0))
+
+
+@pytest.mark.parametrize("kind", ["channel", "scalars", "ibm", "thermo"])
+def test_slab_parity_cases_on_one_gpu(kind):
+    """the cases of tests/slab_parity.py (what tests/mgpu_worker.py runs on 2+ GPUs and bench.py runs before its timed
+    region) with a single slab: channel incl. Poisson alone and adaptive dt, 2 kappa scalars, IBM blocks across the
+    periodic seam, temperature + buoyancy + forcing + volume-flow correction over IBM blocks"""
+    import udales_b200 as U
+    from oracle.oracle import Oracle, stretched_zf
+    from slab_parity import TOL, run_case
+    shape = (64, 64, 32) if kind == "channel" else (64, 64, 16)
+    e = run_case(U, Oracle, kind, shape, 1, 0, 0, None, nsub=3, stretched_zf=stretched_zf)
+    assert e < TOL
