@@ -124,6 +124,13 @@ int udgpu_push(udgpu_t *h, int field, int n4, const double *host);
 int udgpu_pull(udgpu_t *h, int field, int n4, double *host);
 int udgpu_field_count(udgpu_t *h, int field, size_t *count, int dims[3]);
 int udgpu_device_ptr(udgpu_t *h, int field, int n4, void **dptr);   /* zero-copy interop */
+/* sparse residency for host add-ons that touch few cells per substep (the facet wall functions of ibmwallfun,
+ * src/modibm.f90:1286-1860: they read u0 v0 w0 thl0 next to the walls and add to up vp wp thlp at the fluid-boundary
+ * points).  offsets: n 0-based linear offsets into the field's Fortran array (halos included, as udgpu_field_count
+ * describes it).  pull: out[q] = field(offsets[q]).  add: field(offsets[q]) += vals[q], tendencies only; a point may occur
+ * several times.  Both synchronise; both leave a lazily pending forces / masscorr pending. */
+int udgpu_pull_points(udgpu_t *h, int field, int n4, long long n, const long long *offsets, double *out);
+int udgpu_add_points(udgpu_t *h, int field, int n4, long long n, const long long *offsets, const double *vals);
 int udgpu_sync(udgpu_t *h);
 int udgpu_host_register(void *ptr, size_t bytes);    /* pin a Fortran array once (cudaHostRegister) */
 int udgpu_host_unregister(void *ptr);

@@ -562,3 +562,32 @@ def test_slab_parity_cases_on_one_gpu(kind):
     shape = (64, 64, 32) if kind == "channel" else (64, 64, 16)
     e = run_case(U, Oracle, kind, shape, 1, 0, 0, None, nsub=3, stretched_zf=stretched_zf)
     assert e < TOL
+
+
+def test_sparse_pull_and_add_points():
+    """udgpu_pull_points / udgpu_add_points: what a host-side wall function needs instead of whole arrays — values of u0 at a
+    point list equal the pulled array, additions to a tendency land where they should (duplicates accumulate), a lazily
+    pending forces() survives the addition, and out-of-range offsets are refused"""
+    import udales_b200 as U
+    o, g = make_pair(32, 24, 20)
+    rng = np.random.default_rng(4)
+    pts = np.stack([rng.integers(0, 34, 500), rng.integers(0, 26, 500), rng.integers(0, 22, 500)], axis=1)
+    u = g.pull("u0")
+    assert np.array_equal(g.pull_points("u0", pts), u[pts[:, 0], pts[:, 1], pts[:, 2]])
+    g.advection(); g.subgrid()
+    prof = -1e-3 * np.ones(21)
+    g.set_forcing(prof, 0.0 * prof)
+    g.forces()                                           # stays lazily pending
+    tp = pts.copy(); tp[:, 2] = np.minimum(tp[:, 2], 20)  # tendency arrays have ktot + 1 levels
+    tp = np.concatenate([tp, tp[:50]])                   # duplicates
+    vals = rng.standard_normal(tp.shape[0])
+    g2 = make_pair(32, 24, 20)[1]
+    g2.advection(); g2.subgrid(); g2.set_forcing(prof, 0.0 * prof); g2.forces()
+    ref = g2.pull("up")
+    np.add.at(ref, (tp[:, 0], tp[:, 1], tp[:, 2]), vals)
+    g.add_points("up", tp, vals)
+    assert np.abs(g.pull("up") - ref).max() < 1e-13
+    with pytest.raises(U.UdalesGPUError):
+        g.add_points("u0", tp, vals)                     # not a tendency
+    with pytest.raises(U.UdalesGPUError):
+        g.pull_points("u0", np.array([[0, 0, 23]]))      # level beyond the array: offset past the end

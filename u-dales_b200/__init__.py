@@ -27,7 +27,7 @@ FIELD_IDS = {"u0": 0, "v0": 1, "w0": 2, "um": 3, "vm": 4, "wm": 5, "up": 6, "vp"
 
 EXPORTS = [
     "udgpu_nccl_unique_id", "udgpu_init", "udgpu_finalize", "udgpu_last_error", "udgpu_abi_version",
-    "udgpu_push", "udgpu_pull", "udgpu_field_count", "udgpu_device_ptr", "udgpu_sync",
+    "udgpu_push", "udgpu_pull", "udgpu_pull_points", "udgpu_add_points", "udgpu_field_count", "udgpu_device_ptr", "udgpu_sync",
     "udgpu_host_register", "udgpu_host_unregister",
     "udgpu_tstep_update", "udgpu_advection", "udgpu_subgrid", "udgpu_closure", "udgpu_poisson",
     "udgpu_poisson_solve", "udgpu_poisson_solve_resident", "udgpu_fillps", "udgpu_tderive",
@@ -92,6 +92,8 @@ def lib():
         L.udgpu_field_count.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
         L.udgpu_device_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.udgpu_sync.argtypes = [C.c_void_p]
+        L.udgpu_pull_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]
+        L.udgpu_add_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]
         L.udgpu_host_register.argtypes = [C.c_void_p, C.c_size_t]
         L.udgpu_host_unregister.argtypes = [C.c_void_p]
         L.udgpu_tstep_update.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double,
@@ -265,6 +267,26 @@ class UdalesGPU:
 
     def pull_raw(self, name, ptr, n4=0):
         self._chk(self.L.udgpu_pull(self.h, FIELD_IDS[name], n4, ptr))
+
+    def _offsets(self, name, ijk):
+        """(n,3) 0-based storage indices (halo cells included) -> linear Fortran offsets into the field"""
+        d = self.shape(name)
+        ijk = np.asarray(ijk, dtype=np.int64).reshape(-1, 3)
+        return np.ascontiguousarray(ijk[:, 0] + d[0] * (ijk[:, 1] + d[1] * ijk[:, 2]))
+
+    def pull_points(self, name, ijk, n4=0):
+        """values of a field at a list of points (sparse residency for host add-ons such as the facet wall functions)"""
+        off = self._offsets(name, ijk)
+        out = np.empty(off.size)
+        self._chk(self.L.udgpu_pull_points(self.h, FIELD_IDS[name], n4, off.size, off.ctypes.data, out.ctypes.data))
+        return out
+
+    def add_points(self, name, ijk, vals, n4=0):
+        """tendency(name) += vals at a list of points"""
+        off = self._offsets(name, ijk)
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        assert v.size == off.size
+        self._chk(self.L.udgpu_add_points(self.h, FIELD_IDS[name], n4, off.size, off.ctypes.data, v.ctypes.data))
 
     def sync(self): self._chk(self.L.udgpu_sync(self.h))
 

@@ -222,6 +222,9 @@ struct udgpu {
   Geo gT;                      // geometry whose "scalar" halo is the momentum halo: the scalar kernels on thl0 / thlm / thlp
   double *d_thlpcar = nullptr, *d_thl0av = nullptr, *d_thvh = nullptr, *d_th_part = nullptr, *d_th_sums = nullptr, *d_th_cnt = nullptr,
          *d_th_solid = nullptr;
+  long long *d_pts_off = nullptr;   // staging of udgpu_pull_points / udgpu_add_points
+  double *d_pts_val = nullptr;
+  size_t pts_cap = 0;
   bool prof = false;
   bool trace = false;          // udgpu_profile_enable(h, 2): event marks at every stage of the substep (udgpu_trace_dump)
   std::vector<TraceRec> tr;
@@ -689,6 +692,59 @@ extern "C" int udgpu_device_ptr(udgpu_t *h, int field, int n4, void **dptr) {
   if (field == UDGPU_THL0) h->thermo_valid = false;
   if (field <= UDGPU_WP) { h->halo_dirty = h->bc_dirty = true; h->halos_done = h->bc_done = h->halo_x_pending = false; }
   *dptr = h->f[field] + (size_t)n4 * h->cnt[field];
+  return UDGPU_OK;
+}
+// sparse residency: values at a list of points instead of whole arrays, for host add-ons that only touch a few cells per
+// substep (the facet wall functions of ibmwallfun read u0 v0 w0 (thl0) near the walls and add to up vp wp (thlp) at the
+// fluid-boundary points: ~1e4-1e5 points against 1.7e7 cells)
+__global__ void k_gather_points(long long n, const long long *__restrict__ off, const double *__restrict__ a, double *__restrict__ out) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q < n) out[q] = a[off[q]];
+}
+__global__ void k_add_points(long long n, const long long *__restrict__ off, const double *__restrict__ v, double *__restrict__ a) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q < n) atomicAdd(a + off[q], v[q]);      // a point may be listed more than once (several facet sections per cell)
+}
+static int points_stage(udgpu *h, int field, int n4, long long n, const long long *offsets) {
+  RET(check_field(h, field, n4));
+  if (n < 0 || (n > 0 && !offsets)) return set_err(UDGPU_EINVAL, "bad point list");
+  for (long long q = 0; q < n; q++)
+    if (offsets[q] < 0 || (size_t)offsets[q] >= h->cnt[field]) return set_err(UDGPU_EINVAL, "point %lld: offset %lld outside field %d", q, offsets[q], field);
+  if ((size_t)n > h->pts_cap) {
+    h->pts_cap = (size_t)n + (size_t)n / 2 + 1024;
+    RET(dev_alloc(h, (void **)&h->d_pts_off, h->pts_cap * sizeof(long long)));    // the old buffers stay in the allocation list until finalize
+    RET(dev_alloc(h, (void **)&h->d_pts_val, h->pts_cap * sizeof(double)));
+  }
+  CU(cudaMemcpyAsync(h->d_pts_off, offsets, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, h->st));
+  return UDGPU_OK;
+}
+extern "C" int udgpu_pull_points(udgpu_t *h, int field, int n4, long long n, const long long *offsets, double *out) {
+  if (!h || (n > 0 && !out)) return set_err(UDGPU_EINVAL, "null argument");
+  RET(flush_pending(h));
+  if (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP || field == UDGPU_THLP) RET(materialize_zero_tend(h));
+  RET(settle_for_access(h, field));
+  RET(points_stage(h, field, n4, n, offsets));
+  if (n == 0) return UDGPU_OK;
+  k_gather_points<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(n, h->d_pts_off, h->f[field] + (size_t)n4 * h->cnt[field], h->d_pts_val);
+  KCHECK();
+  h->launches++;
+  CU(cudaMemcpyAsync(out, h->d_pts_val, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  return sync_check(h);
+}
+extern "C" int udgpu_add_points(udgpu_t *h, int field, int n4, long long n, const long long *offsets, const double *vals) {
+  if (!h || (n > 0 && !vals)) return set_err(UDGPU_EINVAL, "null argument");
+  const bool is_tend = (field == UDGPU_UP || field == UDGPU_VP || field == UDGPU_WP || field == UDGPU_SVP || field == UDGPU_THLP);
+  if (!is_tend) return set_err(UDGPU_EINVAL, "udgpu_add_points adds to tendencies only (up vp wp svp thlp)");
+  RET(flush_pending(h, true));     // an addition commutes with a pending per-level table
+  RET(materialize_zero_tend(h));
+  RET(points_stage(h, field, n4, n, offsets));
+  if (n == 0) return UDGPU_OK;
+  CU(cudaMemcpyAsync(h->d_pts_val, vals, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  k_add_points<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(n, h->d_pts_off, h->d_pts_val, h->f[field] + (size_t)n4 * h->cnt[field]);
+  KCHECK();
+  h->launches++;
+  h->tend_zero = false;
+  CU(cudaStreamSynchronize(h->st));   // the host buffers may be reused by the caller right away
   return UDGPU_OK;
 }
 // cudaStreamSynchronize + the peer-rendezvous verdict: every entry point that hands results to the host goes through here

@@ -22,7 +22,7 @@ module modgpu
   public :: lgpu, gpu_init, gpu_exit, gpu_push_state, gpu_pull_state, gpu_push, gpu_pull, &
             gpu_tstep_update, gpu_advection, gpu_subgrid, gpu_poisson, gpu_tstep_integrate, &
             gpu_halos, gpu_boundary, gpu_chkdiv, gpu_rk3_step_host, gpu_ibm_init, gpu_ibmnorm, gpu_ibm_diffcorr, gpu_forces, &
-            gpu_bottom, gpu_masscorr, gpu_thermo_init, gpu_thermodynamics
+            gpu_bottom, gpu_masscorr, gpu_thermo_init, gpu_thermodynamics, gpu_pull_points, gpu_add_points
 
   logical :: lgpu = .false.            !< namelist RUN switch (the only new option)
   type(c_ptr) :: handle = c_null_ptr
@@ -97,6 +97,22 @@ module modgpu
       type(c_ptr), value :: h
       integer(c_int), value :: which
       real(c_double), intent(inout) :: host(*)
+    end function
+    integer(c_int) function udgpu_pull_points(h, field, n4, n, offsets, out) bind(C, name="udgpu_pull_points")
+      import :: c_int, c_ptr, c_double, c_long_long
+      type(c_ptr), value :: h
+      integer(c_int), value :: field, n4
+      integer(c_long_long), value :: n
+      integer(c_long_long), intent(in) :: offsets(*)
+      real(c_double), intent(inout) :: out(*)
+    end function
+    integer(c_int) function udgpu_add_points(h, field, n4, n, offsets, vals) bind(C, name="udgpu_add_points")
+      import :: c_int, c_ptr, c_double, c_long_long
+      type(c_ptr), value :: h
+      integer(c_int), value :: field, n4
+      integer(c_long_long), value :: n
+      integer(c_long_long), intent(in) :: offsets(*)
+      real(c_double), intent(in) :: vals(*)
     end function
     integer(c_int) function udgpu_finalize(h) bind(C, name="udgpu_finalize")
       import :: c_int, c_ptr
@@ -396,6 +412,36 @@ contains
     real(c_double), intent(inout) :: a(*)
     call chk(udgpu_pull(handle, field, 0_c_int, a), 'pull')
   end subroutine gpu_pull
+
+  !> sparse residency for host add-ons that touch few cells (the facet wall functions): values of a resident field at
+  !! the points (i,j,k) of a list, and additions to a resident tendency at such points.  ijk(n,3): Fortran indices of the
+  !! reference arrays (halo cells allowed); klo = lower k bound of the array (kb-kh for fields, kb for tendencies)
+  subroutine gpu_pull_points(field, n, ijk, klo, vals)
+    use modglobal, only: ib, jb, ih, jh, imax, jmax
+    integer(c_int), intent(in) :: field
+    integer, intent(in) :: n, ijk(n, 3), klo
+    real(c_double), intent(out) :: vals(n)
+    integer(c_long_long) :: off(max(n, 1))
+    integer :: q
+    do q = 1, n
+      off(q) = int(ijk(q, 1) - (ib - ih), c_long_long) + int(imax + 2*ih, c_long_long)*(int(ijk(q, 2) - (jb - jh), c_long_long) &
+               + int(jmax + 2*jh, c_long_long)*int(ijk(q, 3) - klo, c_long_long))
+    end do
+    call chk(udgpu_pull_points(handle, field, 0_c_int, int(n, c_long_long), off, vals), 'pull_points')
+  end subroutine gpu_pull_points
+  subroutine gpu_add_points(field, n, ijk, klo, vals)
+    use modglobal, only: ib, jb, ih, jh, imax, jmax
+    integer(c_int), intent(in) :: field
+    integer, intent(in) :: n, ijk(n, 3), klo
+    real(c_double), intent(in) :: vals(n)
+    integer(c_long_long) :: off(max(n, 1))
+    integer :: q
+    do q = 1, n
+      off(q) = int(ijk(q, 1) - (ib - ih), c_long_long) + int(imax + 2*ih, c_long_long)*(int(ijk(q, 2) - (jb - jh), c_long_long) &
+               + int(jmax + 2*jh, c_long_long)*int(ijk(q, 3) - klo, c_long_long))
+    end do
+    call chk(udgpu_add_points(handle, field, 0_c_int, int(n, c_long_long), off, vals), 'add_points')
+  end subroutine gpu_add_points
 
   subroutine gpu_tstep_update
     use modglobal, only: dt, courant, diffnr, dtmax, ladaptive, rk3step, timee, timeleft, ntimee, ntrun, dt_lim
