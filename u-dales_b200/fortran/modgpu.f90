@@ -339,7 +339,7 @@ contains
       write (0, *) 'ERROR: gpu_thermo_init: lmoist is outside the GPU path'
       stop 1
     end if
-    call chk(udgpu_set_wfuno(handle, z0h, prandtlturb, grav, thls, thlprof(kb)), 'set_wfuno')   ! BCbotT = 2 reads it
+    if (BCbotT == 2) call chk(udgpu_set_wfuno(handle, z0h, prandtlturb, grav, thls, thlprof(kb)), 'set_wfuno')   ! wfuno case 92
     call chk(udgpu_set_thermo(handle, l2i(lbuoyancy), grav, thls, int(BCtopT, c_int), wttop, thl_top, int(BCbotT, c_int), &
                               wtsurf, thlpcar), 'set_thermo')
     call chk(udgpu_set_buoycorr(handle, l2i(lbuoycorr), Rigc), 'set_buoycorr')
@@ -533,13 +533,13 @@ contains
   !! (BCbotm = 3), the temperature bottom (BCbotT = 1 flux / 2 wfuno case 92) and the zero-flux scalar bottom on the resident
   !! tendencies.  The namelist values go down once (first call)
   subroutine gpu_bottom
-    use modglobal, only: lbottom, BCbotm, BCbots, fkar, grav, prandtlturb, kb
+    use modglobal, only: lbottom, BCbotm, BCbotT, BCbots, fkar, grav, prandtlturb, kb
     use modsurfdata, only: z0, z0h, thls
     use modfields, only: thlprof
     logical, save :: first = .true.
     if (first) then
       ! wfuno's stability correction: wall temperature thls; without temperature equation thl0 stays at thlprof
-      call chk(udgpu_set_wfuno(handle, z0h, prandtlturb, grav, thls, thlprof(kb)), 'set_wfuno')
+      if (BCbotm == 2 .or. BCbotT == 2) call chk(udgpu_set_wfuno(handle, z0h, prandtlturb, grav, thls, thlprof(kb)), 'set_wfuno')
       call chk(udgpu_set_bottom(handle, l2i(lbottom), int(BCbotm, c_int), int(BCbots, c_int), z0, fkar), 'set_bottom')
       first = .false.
     end if
