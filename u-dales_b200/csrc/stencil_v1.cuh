@@ -661,18 +661,21 @@ __device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
 
 // tstep_update maxima: src/modtstep.f90:113-127.  out[0] = courant, out[1] = diffusion number
 // (both divided by dt later on the host side: they are linear in dt).
+constexpr int CFL_KC = 16;   // levels per thread: 16 times fewer block reductions and atomics than one cell per thread
 __global__ void __launch_bounds__(256) k_cfl(Geo g, const double *__restrict__ um, const double *__restrict__ vm,
                                              const double *__restrict__ wm, const double *__restrict__ ekm,
                                              const double *__restrict__ ekh, double dt, double *__restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  const int k = blockIdx.z + 1;
+  const int k0 = blockIdx.z * CFL_KC + 1, k1 = min(k0 + CFL_KC, g.ktot + 1);
   double c = 0., d = 0.;
   if (i <= g.imax && j <= g.jmax) {
-    const long long q = offF(g, i, j, k);
-    c = (fabs(um[q]) * g.dxi + fabs(vm[q]) * g.dyi + fabs(wm[q]) / g.dzh[k]) * dt;
-    const double m = (g.dzh2i[k] + g.dx2i + g.dy2i) * dt;
-    d = fmax(ekm[q] * m, ekh[q] * m);
+    long long q = offF(g, i, j, k0);
+    for (int k = k0; k < k1; k++, q += g.pk) {       // maxima: any order gives the same bits
+      c = fmax(c, (fabs(um[q]) * g.dxi + fabs(vm[q]) * g.dyi + fabs(wm[q]) / g.dzh[k]) * dt);
+      const double m = (g.dzh2i[k] + g.dx2i + g.dy2i) * dt;
+      d = fmax(d, fmax(ekm[q] * m, ekh[q] * m));
+    }
   }
   c = warp_max(c); d = warp_max(d);
   __shared__ double sc[8], sd[8];

@@ -1951,7 +1951,9 @@ extern "C" int udgpu_tstep_update(udgpu_t *h, double *dt, double courant, double
   if (ladaptive) {
     double **f = h->f;
     CU(cudaMemsetAsync(h->d_red, 0, 2 * sizeof(double), h->st));
-    k_cfl<<<grid3(g, B3), B3, 0, h->st>>>(g, f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_EKM], f[UDGPU_EKH], *dt, h->d_red);
+    dim3 gc = grid3(g, B3);
+    gc.z = (g.ktot + CFL_KC - 1) / CFL_KC;
+    k_cfl<<<gc, B3, 0, h->st>>>(g, f[UDGPU_UM], f[UDGPU_VM], f[UDGPU_WM], f[UDGPU_EKM], f[UDGPU_EKH], *dt, h->d_red);
     KCHECK();
     h->launches++;
     if (h->P > 1) NC(ncclAllReduce(h->d_red, h->d_red, 2, ncclDouble, ncclMax, h->comm, h->st));  // MPI_ALLREDUCE(MAX), src/modtstep.f90:131-132
