@@ -44,8 +44,10 @@ def test_reads_the_reference_binarys_own_restart_files():
     assert timee == pytest.approx(100.2639, abs=1e-3) and dt == pytest.approx(0.42978, abs=1e-4)
     fx = np.load(os.path.join(GOLD, "ref_restart102_turb32.npz"))
     i0, j0, n = int(fx["i0"]), int(fx["j0"]), int(fx["n"])
-    for nm in ("u0", "v0", "w0", "pres0"):
+    for nm in ("u0", "v0", "w0", "pres0", "thl0"):
         assert np.array_equal(glob[nm][i0 - 1:i0 + n + 1, j0 - 1:j0 + n + 1, 0:n + 1], fx[nm]), nm
+    th = glob["thl0"][1:-1, 1:-1, :-1]
+    assert 287.0 < th.min() and th.max() < 289.5 and th.std() > 0.01          # examples/102: thl0 = 288 K plus the heated-surface signal
     u, v, w = glob["u0"], glob["v0"], glob["w0"]
     div = (u[2:, 1:-1, :-1] - u[1:-1, 1:-1, :-1]) + (v[1:-1, 2:, :-1] - v[1:-1, 1:-1, :-1]) + (w[1:-1, 1:-1, 1:] - w[1:-1, 1:-1, :-1])
     assert np.abs(div).max() < 5e-15
