@@ -218,7 +218,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "cflags": flags,
                          "sample": f"{args.steps} RK3 substeps on a {n}^3 block of the workload (the whole workload at N=1; cell-updates/s "
                                    "is intensive), C/OpenMP restatement of the reference loops on all host cores of ONE box "
-                                   "(not the Fortran/MPI binary: no Fortran/MPI/FFTW in the image; in-tree iterative radix-2 FFT instead of FFTW)"},
+                                   "(not the Fortran/MPI binary: no Fortran/MPI/FFTW in the image; in-tree radix-2 real FFT (half-length complex transform + split) instead of FFTW)"},
         "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -509,7 +509,7 @@ def run_ours(args, rank, world):
         val, el, cores, flags = cpu_arm(n, nsub, dt)
         cpu = {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "cflags": flags,
                "sample": f"{nsub} RK3 substeps of the same {n}^3 workload; C/OpenMP restatement of the reference loops, "
-                         "in-tree iterative radix-2 FFT (FFTW absent) — not the Fortran/MPI binary"}
+                         "in-tree radix-2 real FFT (half-length complex transform + split; FFTW absent) — not the Fortran/MPI binary"}
 
     line = {
         "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,

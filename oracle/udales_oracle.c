@@ -878,7 +878,7 @@ static void cfft_rec(int n, int s, const double *in, double *out, int sign, doub
 }
 
 /* iterative power-of-two complex FFT with a twiddle table (fast path for the CPU baseline) */
-static void cfft_pow2(int n, double *x, int sign, const double *tw /* n/2 complex, forward */) {
+static void cfft_pow2(int n, double *x, int sign, const double *tw /* (n tws)/2 complex, forward, table of length n * tws */, int tws) {
   for (int i = 1, j = 0; i < n; i++) {
     int bit = n >> 1;
     for (; j & bit; bit >>= 1) j ^= bit;
@@ -889,7 +889,7 @@ static void cfft_pow2(int n, double *x, int sign, const double *tw /* n/2 comple
     const int half = len >> 1, step = n / len;
     for (int i = 0; i < n; i += len)
       for (int k = 0; k < half; k++) {
-        double wr = tw[2 * k * step], wi = sign < 0 ? tw[2 * k * step + 1] : -tw[2 * k * step + 1];
+        double wr = tw[2 * k * step * tws], wi = sign < 0 ? tw[2 * k * step * tws + 1] : -tw[2 * k * step * tws + 1];
         double *a = x + 2 * (i + k), *b = x + 2 * (i + k + half);
         double tr = b[0] * wr - b[1] * wi, ti = b[0] * wi + b[1] * wr;
         b[0] = a[0] - tr; b[1] = a[1] - ti; a[0] += tr; a[1] += ti;
@@ -910,9 +910,45 @@ static int is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 static void rfft_packed(int n, double *line, int inverse, double *work, const double *tw) {
   const double fac = 1. / sqrt(n * 1.);
   double *z = work, *scr = work + 2 * n;
+  if (is_pow2(n) && n >= 4) {
+    /* what an r2c / c2r plan does (the reference calls FFTW's, src/modpois.f90:110-111, 481, 676): a real line of n points
+     * is a complex FFT of h = n/2 points z[m] = x[2m] + i x[2m+1] plus a split (forward) or merge (inverse) pass.
+     * w^k = exp(-2 pi i k / n) = tw[k]. */
+    const int h = n / 2;
+    if (!inverse) {
+      for (int m = 0; m < 2 * h; m++) z[m] = line[m];                 /* (Re, Im) pairs are the line itself */
+      cfft_pow2(h, z, -1, tw, 2);
+      line[0] = (z[0] + z[1]) * fac;
+      line[n - 1] = (z[0] - z[1]) * fac;
+      for (int k = 1; k <= h / 2; k++) {
+        const double zr = z[2 * k], zi = z[2 * k + 1], cr = z[2 * (h - k)], ci = -z[2 * (h - k) + 1];   /* Zk, conj(Z(h-k)) */
+        const double er = 0.5 * (zr + cr), ei = 0.5 * (zi + ci), dr = zr - cr, di = zi - ci;
+        const double wr = tw[2 * k], wi = tw[2 * k + 1];
+        /* T = (-i/2) w^k D = (0.5 wi, -0.5 wr) * (dr, di) */
+        const double ar = 0.5 * wi, ai = -0.5 * wr;
+        const double tr = ar * dr - ai * di, ti = ar * di + ai * dr;
+        line[2 * k - 1] = (er + tr) * fac; line[2 * k] = (ei + ti) * fac;                               /* X[k] = E + T */
+        line[2 * (h - k) - 1] = (er - tr) * fac; line[2 * (h - k)] = -(ei - ti) * fac;                  /* X[h-k] = conj(E - T) */
+      }
+    } else {
+      z[0] = line[0] + line[n - 1]; z[1] = line[0] - line[n - 1];
+      for (int k = 1; k <= h / 2; k++) {
+        const double xr = line[2 * k - 1], xi = line[2 * k], yr = line[2 * (h - k) - 1], yi = -line[2 * (h - k)];   /* Xk, conj(X(h-k)) */
+        const double ar = xr + yr, ai = xi + yi, br = xr - yr, bi = xi - yi;
+        const double wr = tw[2 * k], wi = tw[2 * k + 1];
+        /* T = i conj(w^k) B = (wi, wr) * (br, bi) */
+        const double tr = wi * br - wr * bi, ti = wi * bi + wr * br;
+        z[2 * k] = ar + tr; z[2 * k + 1] = ai + ti;                                                     /* Z[k] = A + T */
+        z[2 * (h - k)] = ar - tr; z[2 * (h - k) + 1] = -(ai - ti);                                      /* Z[h-k] = conj(A - T) */
+      }
+      cfft_pow2(h, z, +1, tw, 2);
+      for (int m = 0; m < 2 * h; m++) line[m] = z[m] * fac;
+    }
+    return;
+  }
   if (!inverse) {
     for (int i = 0; i < n; i++) { z[2 * i] = line[i]; z[2 * i + 1] = 0.; }
-    if (is_pow2(n)) cfft_pow2(n, z, -1, tw);
+    if (is_pow2(n)) cfft_pow2(n, z, -1, tw, 1);
     else { double *out = (double *)malloc(sizeof(double) * 2 * n); cfft_rec(n, 1, z, out, -1, scr); memcpy(z, out, sizeof(double) * 2 * n); free(out); }
     line[0] = z[0];
     for (int i = 1; i <= n / 2 - 1; i++) { line[2 * i - 1] = z[2 * i]; line[2 * i] = z[2 * i + 1]; }
@@ -925,7 +961,7 @@ static void rfft_packed(int n, double *line, int inverse, double *work, const do
       z[2 * (n - i)] = line[2 * i - 1]; z[2 * (n - i) + 1] = -line[2 * i];   /* Hermitian extension = what c2r implies */
     }
     z[2 * (n / 2)] = line[n - 1]; z[2 * (n / 2) + 1] = 0.;
-    if (is_pow2(n)) cfft_pow2(n, z, +1, tw);
+    if (is_pow2(n)) cfft_pow2(n, z, +1, tw, 1);
     else { double *out = (double *)malloc(sizeof(double) * 2 * n); cfft_rec(n, 1, z, out, +1, scr); memcpy(z, out, sizeof(double) * 2 * n); free(out); }
     for (int i = 0; i < n; i++) line[i] = z[2 * i] * fac;
   }
