@@ -1157,17 +1157,29 @@ static int rfft_fast(udgpu *h, int n, int inverse, const double *in, LineDesc di
 template <int R1, int R2>
 static int rfft_xline_launch(udgpu *h, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl) {
   using C = XlineCfg<R1, R2>;
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k_rfft_xline<R1, R2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    CU(cudaFuncSetAttribute(k_rfft_xline<R1, R2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr = true;
-  }
   const dim3 grid((di.nb1 + C::LPB - 1) / C::LPB, di.nb2);
   if (inverse) k_rfft_xline<R1, R2, true><<<grid, C::NT, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac);
   else k_rfft_xline<R1, R2, false><<<grid, C::NT, C::SMEM, h->st>>>(pl.tw, in, di, out, dd, pl.fac);
   KCHECK();
   h->launches++;
+  return UDGPU_OK;
+}
+// dynamic shared memory opt-in of both directions, on the handle's device, at init (like rfft_fast_setattr)
+template <int R1, int R2>
+static int rfft_xline_attr() {
+  using C = XlineCfg<R1, R2>;
+  CU(cudaFuncSetAttribute(k_rfft_xline<R1, R2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  CU(cudaFuncSetAttribute(k_rfft_xline<R1, R2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  return UDGPU_OK;
+}
+static int rfft_xline_setattr(int n) {
+  switch (n) {
+    case 64: return rfft_xline_attr<8, 4>();
+    case 128: return rfft_xline_attr<8, 8>();
+    case 256: return rfft_xline_attr<16, 8>();
+    case 512: return rfft_xline_attr<16, 16>();
+    case 1024: return rfft_xline_attr<32, 16>();
+  }
   return UDGPU_OK;
 }
 static int rfft_xline(udgpu *h, int n, int inverse, const double *in, LineDesc di, double *out, LineDesc dd, const FftPlan &pl) {
@@ -1231,6 +1243,7 @@ static int setup_poisson_fast_fwd(udgpu *h, const std::vector<double> &xrt, cons
   CU(cudaStreamSynchronize(h->st));
   h->fast_z = true;
   h->g.xalt = (h->P == 1 && h->fast_x && h->xline && !h->fill_fused) ? 1 : 0;
+  if (h->g.xalt) RET(rfft_xline_setattr(g.itot));
   return UDGPU_OK;
 }
 
